@@ -1,0 +1,85 @@
+"""ctypes binding of libb200nlp.so (the C-ABI declared in include/b200nlp.h).
+
+There is deliberately NO fallback: if the shared library is missing or a kernel launch fails, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200nlp.so")
+
+_lib = None
+
+P = c_void_p
+I64 = c_int64
+I = c_int
+F = c_float
+
+# name -> argtypes; every function returns int unless listed in _RESTYPE.
+_SIGNATURES = {
+    "b200_last_error": [],
+    "b200_abi_version": [],
+    "b200_device_check": [],
+    "b200_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, P],
+    "b200_gemm_bf16_ex": [P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, I, I, P],
+}
+_RESTYPE = {"b200_last_error": c_char_p}
+
+
+def exported_symbols():
+    """Names include/b200nlp.h declares (kept in sync by tests/test_abi.py)."""
+    return sorted(_SIGNATURES)
+
+
+def register(name, argtypes, restype=None):
+    _SIGNATURES[name] = argtypes
+    if restype is not None:
+        _RESTYPE[name] = restype
+
+
+def load():
+    """Load the library (building it first if it is absent and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def call(name, *args):
+    """Call an int-returning entry point; raise B200Error with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.b200_last_error()
+        raise B200Error(f"{name} failed (rc={rc}): {msg.decode() if msg else '?'}")
+    return rc
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

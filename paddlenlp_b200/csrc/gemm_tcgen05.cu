@@ -1,0 +1,397 @@
+// bf16 GEMM on 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+//   C[M,N] (+)= op(A)[M,K] * op(B)[K,N] (+ bias[N])      bf16 in, fp32 accumulate, one rounding to bf16.
+//
+// Replaces the cuBLAS(Lt) calls under paddle `nn.Linear` on the Llama/Qwen2 hot path
+// (reference: paddlenlp/transformers/llama/modeling.py:771-799 q/k/v/o, :627-630 gate/up/down, :1894-1921 lm_head;
+//  weights are stored [in,out] = "B is [K,N] row-major" = MN-major B operand) and the dX / dW GEMMs of their backward.
+//
+// Design (one persistent kernel, warp-specialised, 192 threads):
+//   warp 0      TMA producer   : global -> 128B-swizzled smem ring, STAGES deep, BK = 64
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (UMMA M=128*CG, N=256, K=16); tcgen05.commit
+//                                releases smem stages and publishes the finished accumulator
+//   warps 2..5  epilogue       : tcgen05.ld (TMEM -> regs), (+bias, +C_old), round to bf16, swizzled smem staging,
+//                                per-warp TMA store of 32x64 boxes
+//   TMEM        2 accumulator stages x 256 fp32 columns = all 512 columns, so the epilogue of tile i overlaps the
+//               main loop of tile i+1.
+//   CG = 2      CTA pair (cluster of 2, cta_group::2): each CTA loads its 128 rows of A and its 128 columns of B;
+//               the pair computes a 256x256 tile, halving per-SM shared-memory operand traffic.
+//   Operand majors: both K-major (contraction dim contiguous) and MN-major operands are fed straight from their
+//   row-major global layout through TMA; no transposes are materialised.
+#include "../../include/b200nlp.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+namespace gemm {
+
+constexpr int BM = 128;   // rows of the tile owned by one CTA
+constexpr int BN = 256;   // tile columns (UMMA N)
+constexpr int BK = 64;    // K per pipeline stage (= one 128-byte swizzle row of bf16)
+constexpr int UK = 16;    // UMMA K for 16-bit inputs
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_BOX_ROWS = 32;
+constexpr int EPI_BOX_COLS = 64;
+constexpr int EPI_BUF_BYTES = EPI_BOX_ROWS * EPI_BOX_COLS * 2;  // 4 KB
+constexpr int TMEM_COLS = 512;
+
+template <int CG>
+struct Cfg {
+  static constexpr int B_COLS = BN / CG;                       // B columns staged per CTA
+  static constexpr int A_BYTES = BM * BK * 2;                  // 16 KB
+  static constexpr int B_BYTES = B_COLS * BK * 2;              // 32 KB (CG=1) / 16 KB (CG=2)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (CG == 2) ? 6 : 4;
+  static constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;  // 32 KB
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+};
+
+struct Params {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles;
+  int accumulate;          // C += result
+  const float* bias;       // [N] fp32 or nullptr
+};
+
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
+  // Grouped ordering: GM consecutive m-tiles share each n-tile column so that concurrently running CTAs reuse
+  // A and B tiles out of L2.
+  constexpr int GM = 8;
+  const int per_group = GM * num_n;
+  const int g = t / per_group;
+  const int first_m = g * GM;
+  const int gsize = min(GM, num_m - first_m);
+  const int r = t - g * per_group;
+  m_blk = first_m + (r % gsize);
+  n_blk = r / gsize;
+}
+
+template <int CG, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const Params p) {
+  using C = Cfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_smem = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + C::EPI_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * C::STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint64_t* epi_bar = tmem_empty + 2;              // [EPI_WARPS]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_bar + EPI_WARPS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int pair_id = blockIdx.x / CG;
+  const int num_pairs = gridDim.x / CG;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], CG * EPI_WARPS);
+    }
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&epi_bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<CG>(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair_id; t < num_tiles; t += num_pairs) {
+        int m_blk, n_blk;
+        tile_coords(t, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
+        const int m0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM;   // this CTA's A rows
+        const int n0 = n_blk * BN + static_cast<int>(cta_rank) * C::B_COLS;   // this CTA's B columns
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          const int k0 = kb * BK;
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * CG);
+          auto load = [&](const CUtensorMap* tm, void* dst, int c0, int c1) {
+            if constexpr (CG == 2) tma_load_2d_pair(tm, &full_bar[stage], dst, c0, c1);
+            else tma_load_2d(tm, &full_bar[stage], dst, c0, c1);
+          };
+          if constexpr (A_MN) {
+            // A stored [K, M] row-major: boxes of 64 (M) x 64 (K), one per 64 rows of the tile.
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) load(&tmA, sa + c * (64 * BK * 2), m0 + c * 64, k0);
+          } else {
+            load(&tmA, sa, k0, m0);  // A stored [M, K] row-major: one 64 (K) x 128 (M) box
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int c = 0; c < C::B_COLS / 64; ++c) load(&tmB, sb + c * (64 * BK * 2), n0 + c * 64, k0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < C::B_COLS / 128; ++c) load(&tmB, sb + c * (128 * BK * 2), k0, n0 + c * 128);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (is_leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, A_MN, B_MN);
+      // K-major  : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.       K advance = 32 B
+      // MN-major : 64-element chunks along M/N 8 KB apart (LBO), 8-k groups 1024 B.  K advance = 16 rows = 2 KB
+      constexpr uint32_t a_lbo = A_MN ? 64 * BK * 2 : 16, a_adv = A_MN ? UK * 128 : UK * 2;
+      constexpr uint32_t b_lbo = B_MN ? 64 * BK * 2 : 16, b_adv = B_MN ? UK * 128 : UK * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = pair_id; t < num_tiles; t += num_pairs) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * a_adv, a_lbo, 1024);
+            const uint64_t db = umma_desc_sw128(sb + k * b_adv, b_lbo, 1024);
+            umma_ss<CG>(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if constexpr (CG == 2) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================================== epilogue =====================================
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    uint8_t* my_buf = epi_smem + q * 2 * EPI_BUF_BYTES;
+    const uint32_t my_buf_s = smem_u32(my_buf);
+    uint32_t ephase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    int buf = 0;
+    for (int t = pair_id; t < num_tiles; t += num_pairs) {
+      int m_blk, n_blk;
+      tile_coords(t, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
+      const int row0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM + q * 32;
+      const int col0 = n_blk * BN;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int slab = 0; slab < BN / EPI_BOX_COLS; ++slab) {
+        const int c0 = col0 + slab * EPI_BOX_COLS;
+        const uint32_t sbuf = my_buf_s + buf * EPI_BUF_BYTES;
+        // the TMA store issued two slabs ago from this buffer must have finished reading it
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        const bool live = (row0 < p.M) && (c0 < p.N);
+        if (p.accumulate && live && lane == 0) {
+          mbar_arrive_expect_tx(&epi_bar[q], EPI_BUF_BYTES);
+          tma_load_2d(&tmC, &epi_bar[q], my_buf + buf * EPI_BUF_BYTES, c0, row0);
+        }
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr + slab * EPI_BOX_COLS, v0);
+        tmem_ld32(taddr + slab * EPI_BOX_COLS + 32, v1);
+        tmem_ld_wait();
+        if (slab == BN / EPI_BOX_COLS - 1) {
+          // accumulator fully read: hand the TMEM stage back to the MMA warp of the leader CTA
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+        }
+        if (live) {
+          if (p.accumulate) { mbar_wait(&epi_bar[q], ephase); }
+          const uint32_t row_s = sbuf + lane * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int idx = ch * 8 + j;
+              f[j] = __uint_as_float(idx < 32 ? v0[idx] : v1[idx - 32]);
+            }
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int col = c0 + ch * 8 + j;
+                f[j] += (col < p.N) ? __ldg(p.bias + col) : 0.f;
+              }
+            }
+            const uint32_t addr = row_s + ((ch ^ (lane & 7)) << 4);
+            if (p.accumulate) {
+              const uint4 old = ld_shared_v4(addr);
+              const float2 o0 = unpack_bf16x2(old.x), o1 = unpack_bf16x2(old.y), o2 = unpack_bf16x2(old.z),
+                           o3 = unpack_bf16x2(old.w);
+              f[0] += o0.x; f[1] += o0.y; f[2] += o1.x; f[3] += o1.y;
+              f[4] += o2.x; f[5] += o2.y; f[6] += o3.x; f[7] += o3.y;
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            st_shared_v4(addr, o);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, my_buf + buf * EPI_BUF_BYTES, c0, row0);
+            tma_store_commit();
+          }
+          if (p.accumulate) ephase ^= 1u;
+        }
+        buf ^= 1;
+      }
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  // ===================================== teardown =====================================
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int CG, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p,
+                  int max_ctas, cudaStream_t stream) {
+  using C = Cfg<CG>;
+  auto kern = gemm_bf16_kernel<CG, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(gemm smem=%d): %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  int sms = sm_count();
+  if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+  int pairs = sms / CG;
+  if (pairs > num_tiles) pairs = num_tiles;
+  if (pairs < 1) pairs = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pairs * CG);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p);
+  if (e != cudaSuccess) {
+    set_last_error("gemm launch: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+}  // namespace gemm
+}  // namespace b200
+
+extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N,
+                                 int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major,
+                                 int accumulate, int cta_group, int max_ctas, cudaStream_t stream) {
+  using namespace b200;
+  using namespace b200::gemm;
+  B200_CHECK_ARG(A && B && C, "gemm: null pointer");
+  B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: non-positive dimension M=%lld N=%lld K=%lld", (long long)M,
+                 (long long)N, (long long)K);
+  B200_CHECK_ARG(K % 8 == 0 && N % 8 == 0 && M % 8 == 0,
+                 "gemm: M, N, K must be multiples of 8 (got %lld, %lld, %lld)", (long long)M, (long long)N,
+                 (long long)K);
+  B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "gemm: leading dimensions must be multiples of 8");
+  B200_CHECK_ARG(cta_group == 1 || cta_group == 2, "gemm: cta_group must be 1 or 2");
+  B200_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
+
+  CUtensorMap tmA, tmB, tmC;
+  int rc;
+  {
+    // A: K-major  -> stored [M, K], dims {K, M}, box {64, 128}
+    //    MN-major -> stored [K, M], dims {M, K}, box {64, 64}
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (a_mn_major) { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = BK; }
+    else            { dims[0] = K; dims[1] = M; box[0] = BK; box[1] = 128; }
+    strides[0] = static_cast<uint64_t>(lda) * 2;
+    if ((rc = encode_tmap_bf16(&tmA, A, 2, dims, strides, box)) != 0) return rc;
+  }
+  {
+    // B: K-major  -> stored [N, K], dims {K, N}, box {64, 128}
+    //    MN-major -> stored [K, N], dims {N, K}, box {64, 64}
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (b_mn_major) { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
+    else            { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = 128; }
+    strides[0] = static_cast<uint64_t>(ldb) * 2;
+    if ((rc = encode_tmap_bf16(&tmB, B, 2, dims, strides, box)) != 0) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldc) * 2};
+    uint32_t box[2] = {EPI_BOX_COLS, EPI_BOX_ROWS};
+    if ((rc = encode_tmap_bf16(&tmC, C, 2, dims, strides, box)) != 0) return rc;
+  }
+  Params p;
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.K = static_cast<int>(K);
+  p.num_m_tiles = static_cast<int>((M + BM * cta_group - 1) / (BM * cta_group));
+  p.num_n_tiles = static_cast<int>((N + BN - 1) / BN);
+  p.accumulate = accumulate;
+  p.bias = bias;
+
+#define B200_GEMM_DISPATCH(CG)                                                                          \
+  do {                                                                                                  \
+    if (a_mn_major && b_mn_major) return launch<CG, true, true>(tmA, tmB, tmC, p, max_ctas, stream);    \
+    if (a_mn_major) return launch<CG, true, false>(tmA, tmB, tmC, p, max_ctas, stream);                 \
+    if (b_mn_major) return launch<CG, false, true>(tmA, tmB, tmC, p, max_ctas, stream);                 \
+    return launch<CG, false, false>(tmA, tmB, tmC, p, max_ctas, stream);                                \
+  } while (0)
+  if (cta_group == 2) B200_GEMM_DISPATCH(2);
+  B200_GEMM_DISPATCH(1);
+#undef B200_GEMM_DISPATCH
+}
+
+extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N, int64_t K,
+                              int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int accumulate,
+                              cudaStream_t stream) {
+  return b200_gemm_bf16_ex(A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn_major, b_mn_major, accumulate,
+                           /*cta_group=*/2, /*max_ctas=*/0, stream);
+}

@@ -1,0 +1,32 @@
+// Host-side helpers shared by the C-ABI translation units: thread-local error string, CUtensorMap encoding
+// through the driver entry point (no link-time dependency on libcuda), device attribute cache.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace b200 {
+
+// Error convention of the C-ABI (include/b200nlp.h): 0 ok, <0 argument error, >0 cudaError_t.
+void set_last_error(const char* fmt, ...);
+int fail_arg(const char* fmt, ...);   // records message, returns -1
+int check_launch(const char* what);  // cudaGetLastError() -> return code
+
+int sm_count();  // multiprocessors of the current device (cached per device)
+
+// Encode a 2-D or 3-D bf16 (2-byte element) tiled tensor map with 128-byte swizzle.
+//   dims[i]    extent of dimension i in elements (dimension 0 is contiguous)
+//   strides[i] byte stride of dimension i+1 (i < rank-1); must be multiples of 16
+//   box[i]     box extent in elements; box[0]*2 must be <= 128 for SWIZZLE_128B
+// Returns 0 on success, <0 on failure (message recorded).
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box);
+
+}  // namespace b200
+
+#define B200_CHECK_ARG(cond, ...)                  \
+  do {                                             \
+    if (!(cond)) return b200::fail_arg(__VA_ARGS__); \
+  } while (0)
