@@ -55,6 +55,78 @@ int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const float* bias, 
                       int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int accumulate,
                       int cta_group, int max_ctas, cudaStream_t stream);
 
+/* ---- RMSNorm: replaces fused_ln.fused_rms_norm / fast_ln (apex-derived custom ops) --------------------------
+ * fwd : y = bf16( bf16(x * rstd) * w ), rstd[row] = rsqrt(mean(x^2) + eps) in fp32 (saved for the backward).
+ * bwd : dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) (+ dres, the gradient arriving through the residual branch);
+ *       dw (+)= sum_rows dy * bf16(xhat).   workspace: b200_rmsnorm_bwd_workspace_bytes(rows, h) bytes.
+ * Reference: llama/modeling.py:352-386; fusion_ops.py:119-144; legacy/model_zoo/gpt-3/external_ops/fused_ln/
+ * layer_norm_cuda.cu:47-66 (fwd), :164-183 (bwd); layer_norm_cuda.h:447-531, 1190-1260.
+ */
+int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t rows, int64_t h, float eps,
+                     cudaStream_t stream);
+int64_t b200_rmsnorm_bwd_workspace_bytes(int64_t rows, int64_t h);
+int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+                     void* dw, int accumulate_dw, void* workspace, int64_t rows, int64_t h, cudaStream_t stream);
+
+/* Column sums of a bf16 [rows, n] matrix (leading dimension ld) into a bf16 vector: bias gradients of Qwen2 q/k/v
+ * (qwen2/modeling.py:478-480).  workspace: b200_colsum_workspace_bytes(rows, n). */
+int64_t b200_colsum_workspace_bytes(int64_t rows, int64_t n);
+int b200_colsum_bf16(const void* a, void* out, int accumulate, void* workspace, int64_t rows, int64_t n, int64_t ld,
+                     cudaStream_t stream);
+
+/* ---- RoPE (rotate-half), in place on `num_heads` consecutive heads starting at x: replaces Paddle-core
+ * fused_rotary_position_embedding(use_neox_rotary_style=False) (fusion_ops.py:57-116; llama/modeling.py:557-577).
+ * cos/sin tables: fp32 [max_pos, head_dim/2]; position of token t = position_ids[t] or t %% seq_len.
+ * backward != 0 applies the transposed rotation (sin -> -sin). */
+int b200_rope_inplace(void* x, const float* cos_table, const float* sin_table, const int32_t* position_ids,
+                      int64_t tokens, int64_t seq_len, int64_t ld, int64_t num_heads, int64_t head_dim, int backward,
+                      cudaStream_t stream);
+
+/* ---- SwiGLU on a packed [rows, 2*inter] = [gate | up] buffer: replaces Paddle-core swiglu
+ * (llama/modeling.py:38-45, 648-650).  bwd writes [dgate | dup] packed the same way. */
+int b200_swiglu_fwd(const void* gate_up, void* out, int64_t rows, int64_t inter, cudaStream_t stream);
+int b200_swiglu_bwd(const void* gate_up, const void* dout, void* dgate_up, int64_t rows, int64_t inter,
+                    cudaStream_t stream);
+
+/* ---- Embedding gather / scatter-add (nn.Embedding, llama/modeling.py:1465-1468, 1634). ids are int64. */
+int b200_embedding_fwd(const int64_t* ids, const void* table, void* out, int64_t tokens, int64_t h, int64_t vocab,
+                       cudaStream_t stream);
+int b200_embedding_bwd(const int64_t* ids, const void* dout, void* dtable, int64_t tokens, int64_t h, int64_t vocab,
+                       cudaStream_t stream);
+
+/* ---- Flash attention, causal, GQA, head_dim 128: replaces F.scaled_dot_product_attention(is_causal=True)
+ * (fusion_ops.py:147-267; Paddle-vendored FlashAttention-2) and its gradient (csrc/gpu/flash_attn_bwd.cc:22-92).
+ * q [B,S,nh,128], k/v [B,S,kvh,128], o [B,S,nh,128]; ld* = token stride in elements (the tensors may be views into a
+ * packed QKV projection).  lse [B,nh,S] fp32 (natural log).  Backward workspace: b200_fa_bwd_workspace_bytes(). */
+int b200_fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int64_t B, int64_t S,
+                int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv,
+                int64_t ldo, float softmax_scale, cudaStream_t stream);
+int64_t b200_fa_bwd_workspace_bytes(int64_t B, int64_t S, int64_t num_heads, int64_t head_dim);
+int b200_fa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t S, int64_t num_heads,
+                int64_t num_kv_heads, int64_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv, float softmax_scale, cudaStream_t stream);
+
+/* ---- Criterion: LlamaPretrainingCriterion (llama/modeling.py:1799-1825) on bf16 logits [tokens, vocab] (ld).
+ * fwd : loss_tok[i] = fp32 CE (0 for ignore_index), lse[i]; loss_out[0] = sum(l_i [l_i>0]) / count, loss_out[1] = count.
+ * bwd : logits are overwritten by dlogits = (softmax - onehot) * [l_i>0] * grad_scale / count (bf16). */
+int b200_ce_fwd(const void* logits, const int64_t* labels, float* loss_tok, float* lse, float* loss_out, int64_t tokens,
+                int64_t vocab, int64_t ld, int64_t ignore_index, cudaStream_t stream);
+int b200_ce_bwd(void* logits_inout, const int64_t* labels, const float* loss_tok, const float* lse,
+                const float* loss_out, float grad_scale, int64_t tokens, int64_t vocab, int64_t ld, cudaStream_t stream);
+/* Greedy token choice: first maximal index of each bf16 row (generation_utils.py:291-363 with top_p = 0). */
+int b200_argmax_bf16(const void* logits, int64_t* out, int64_t rows, int64_t vocab, int64_t ld, cudaStream_t stream);
+
+/* ---- Optimizer on the flat parameter buffer: ClipGradByGlobalNorm + AdamW(multi_precision)
+ * (trainer.py:1717-1750).  Elements [0, decay_end) receive weight decay.
+ * grad_sqnorm: out[0] = || scale * g ||^2 ; adamw: g_eff = g * grad_scale * max_norm / max(||.||, max_norm). */
+int64_t b200_grad_sqnorm_workspace_bytes(void);
+int b200_grad_sqnorm(const void* grads, float* out, void* workspace, int64_t n, float scale, cudaStream_t stream);
+int b200_adamw_step(void* params_bf16, const void* grads_bf16, float* master, float* exp_avg, float* exp_avg_sq,
+                    const float* grad_sqnorm, int64_t n, int64_t decay_end, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int64_t step, float grad_scale, float max_grad_norm, cudaStream_t stream);
+int b200_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,13 +126,13 @@ def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float, mode: str) -> to
     return rnd(y * weight, mode)
 
 
-def rope_tables(head_dim: int, seq_len: int, theta: float):
+def rope_tables(head_dim: int, seq_len: int, theta: float, device="cpu"):
     # modeling.py:409-423: inv_freq = 1 / base**(arange(0,dim,2)/dim); emb = concat([freqs, freqs]); cos/sin fp32.
     inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
     t = torch.arange(seq_len, dtype=torch.float32)
     freqs = torch.einsum("i,j->ij", t, inv_freq)
     emb = torch.cat([freqs, freqs], dim=-1)
-    return emb.cos(), emb.sin()  # [S, d]
+    return emb.cos().to(device), emb.sin().to(device)  # [S, d]; always computed on the CPU first
 
 
 def rotate_half(x: torch.Tensor) -> torch.Tensor:
@@ -164,7 +164,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mode: str) -> t
     v = v[:, :, :, None, :].expand(b, s, kvh, rep, d).reshape(b, s, nh, d)
     qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
     scores = torch.matmul(qt, kt.transpose(-1, -2)) / math.sqrt(d)
-    mask = torch.full((s, s), float("-inf")).triu(1)
+    mask = torch.full((s, s), float("-inf"), device=q.device).triu(1)
     p = torch.softmax(scores + mask, dim=-1)
     p = rnd(p, mode)
     out = torch.matmul(p, vt).transpose(1, 2).reshape(b, s, nh * d)
@@ -212,7 +212,7 @@ def model_forward(input_ids: torch.Tensor, w: Dict[str, torch.Tensor], cfg: RefC
     pre = cfg.model_type
     x = w[f"{pre}.embed_tokens.weight"][input_ids]
     cos, sin = rope_tables(cfg.head_dim, max(input_ids.shape[1], int(position_ids.max()) + 1 if position_ids is not None else 0),
-                           cfg.rope_theta)
+                           cfg.rope_theta, x.device)
     for i in range(cfg.num_hidden_layers):
         x = decoder_layer(x, w, f"{pre}.layers.{i}.", cfg, cos, sin, mode, position_ids)
     hf = rms_norm(x, w[f"{pre}.norm.weight"], cfg.rms_norm_eps, mode)

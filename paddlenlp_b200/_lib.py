@@ -25,8 +25,34 @@ _SIGNATURES = {
     "b200_device_check": [],
     "b200_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, P],
     "b200_gemm_bf16_ex": [P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, I, I, P],
+    "b200_rmsnorm_fwd": [P, P, P, P, I64, I64, F, P],
+    "b200_rmsnorm_bwd_workspace_bytes": [I64, I64],
+    "b200_rmsnorm_bwd": [P, P, P, P, P, P, P, I, P, I64, I64, P],
+    "b200_colsum_workspace_bytes": [I64, I64],
+    "b200_colsum_bf16": [P, P, I, P, I64, I64, I64, P],
+    "b200_rope_inplace": [P, P, P, P, I64, I64, I64, I64, I64, I, P],
+    "b200_swiglu_fwd": [P, P, I64, I64, P],
+    "b200_swiglu_bwd": [P, P, P, I64, I64, P],
+    "b200_embedding_fwd": [P, P, P, I64, I64, I64, P],
+    "b200_embedding_bwd": [P, P, P, I64, I64, I64, P],
+    "b200_fa_fwd": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, I64, F, P],
+    "b200_fa_bwd_workspace_bytes": [I64, I64, I64, I64],
+    "b200_fa_bwd": [P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, I64, I64, I64, I64, I64, F, P],
+    "b200_ce_fwd": [P, P, P, P, P, I64, I64, I64, I64, P],
+    "b200_ce_bwd": [P, P, P, P, P, F, I64, I64, I64, P],
+    "b200_argmax_bf16": [P, P, I64, I64, I64, P],
+    "b200_grad_sqnorm_workspace_bytes": [],
+    "b200_grad_sqnorm": [P, P, P, I64, F, P],
+    "b200_adamw_step": [P, P, P, P, P, P, I64, I64, F, F, F, F, F, I64, F, F, P],
+    "b200_bf16_to_f32": [P, P, I64, P],
 }
-_RESTYPE = {"b200_last_error": c_char_p}
+_RESTYPE = {
+    "b200_last_error": c_char_p,
+    "b200_rmsnorm_bwd_workspace_bytes": c_int64,
+    "b200_colsum_workspace_bytes": c_int64,
+    "b200_fa_bwd_workspace_bytes": c_int64,
+    "b200_grad_sqnorm_workspace_bytes": c_int64,
+}
 
 
 def exported_symbols():

@@ -1,0 +1,379 @@
+// Causal GQA flash-attention backward on tcgen05 (head_dim 128).
+//
+//   inputs : q, k, v, o, do, lse            outputs: dq (fp32 accumulation buffer), dk, dv (bf16)
+//   P = exp(S*scale - lse) ; dP = dO V^T ; dS = P o (dP - D) * scale, D = rowsum(dO o O)
+//   dV = P^T dO ; dK = dS^T Q ; dQ = dS K
+//
+// Replaces Paddle-core flash_attn_grad (reference: fusion_ops.py:240-246 backward of scaled_dot_product_attention;
+// wrapper shape in csrc/gpu/flash_attn_bwd.cc:22-92).
+//
+// One CTA = one (batch, kv-head, 128-row kv tile); it loops over the q-heads of the GQA group and the q tiles
+// i >= j, so dK/dV are accumulated in TMEM without atomics; dQ tiles are reduced into an fp32 buffer with vector
+// red.global.add (converted to bf16 by b200_fa_bwd_dq_finish, fused with nothing else so that RoPE-backward can
+// run on the bf16 result in place).
+//   warp 0       TMA producer (K_j, V_j once; Q_i, dO_i per iteration)
+//   warp 1       MMA issuer   (5 UMMA GEMMs per iteration, operands K-major or MN-major straight from the same
+//                              swizzled tiles: Q and dO are consumed both ways)
+//   warps 2..5   one thread per q row: P and dS from TMEM S / dP, written as bf16 to swizzled smem; dQ read-out
+//   TMEM: S|dQ [0,128)  dP [128,256)  dV [256,384)  dK [384,512)
+#include "../../include/b200nlp.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+namespace fab {
+
+constexpr int TILE_BYTES = 128 * 128 * 2;
+constexpr int HALF_BYTES = TILE_BYTES / 2;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = 6 * TILE_BYTES + 256 + 1024;   // K, V, Q, dO, P, dS
+
+struct Params {
+  int S, B, nh, kvh;
+  float scale, scale_log2;
+  const float* lse;     // [B, nh, S]  natural log
+  const float* delta;   // [B, nh, S]  rowsum(dO o O)
+  float* dq_acc;        // [B, S, nh, 128] fp32
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+              const __grid_constant__ CUtensorMap tmdK, const __grid_constant__ CUtensorMap tmdV, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + TILE_BYTES;
+  uint8_t* sQ = smem + 2 * TILE_BYTES;
+  uint8_t* sdO = smem + 3 * TILE_BYTES;
+  uint8_t* sP = smem + 4 * TILE_BYTES;
+  uint8_t* sdS = smem + 5 * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;
+  uint64_t* qdo_empty = bars + 2;
+  uint64_t* s_full = bars + 3;
+  uint64_t* pds_full = bars + 4;
+  uint64_t* dq_full = bars + 5;
+  uint64_t* dq_empty = bars + 6;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (p.S + 127) / 128;
+  const int jt = static_cast<int>(blockIdx.x);     // kv tile; tile 0 has the most work and is scheduled first
+  const int kv_head = blockIdx.y, batch = blockIdx.z;
+  const int group = p.nh / p.kvh;
+  const int n_q = num_tiles - jt;                  // q tiles jt .. num_tiles-1
+  const int n_iter = group * n_q;
+  const int kv0 = jt * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(kv_full, 1);
+    mbar_init(qdo_full, 1);
+    mbar_init(qdo_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
+      tma_load_4d(&tmK, kv_full, sK, 0, kv_head, kv0, batch);
+      tma_load_4d(&tmK, kv_full, sK + HALF_BYTES, 64, kv_head, kv0, batch);
+      tma_load_4d(&tmV, kv_full, sV, 0, kv_head, kv0, batch);
+      tma_load_4d(&tmV, kv_full, sV + HALF_BYTES, 64, kv_head, kv0, batch);
+      for (int n = 0; n < n_iter; ++n) {
+        const int hq = kv_head * group + n / n_q;
+        const int q0 = (jt + n % n_q) * 128;
+        mbar_wait(qdo_empty, (n & 1) ^ 1u);
+        mbar_arrive_expect_tx(qdo_full, 2 * TILE_BYTES);
+        tma_load_4d(&tmQ, qdo_full, sQ, 0, hq, q0, batch);
+        tma_load_4d(&tmQ, qdo_full, sQ + HALF_BYTES, 64, hq, q0, batch);
+        tma_load_4d(&tmdO, qdo_full, sdO, 0, hq, q0, batch);
+        tma_load_4d(&tmdO, qdo_full, sdO + HALF_BYTES, 64, hq, q0, batch);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t id_kk = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t id_mm = umma_idesc_bf16(128, 128, true, true);
+      constexpr uint32_t id_km = umma_idesc_bf16(128, 128, false, true);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO), aP = smem_u32(sP),
+                     adS = smem_u32(sdS);
+      auto kmaj = [](uint32_t base, int kk) {   // K-major operand, k-step kk (16 elements of the contiguous dim)
+        return umma_desc_sw128(base + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
+      };
+      auto mnmaj = [](uint32_t base, int kk) {  // MN-major operand, k-step kk (16 rows of the tile)
+        return umma_desc_sw128(base + kk * 2048, HALF_BYTES, 1024);
+      };
+      mbar_wait(kv_full, 0);
+      for (int n = 0; n < n_iter; ++n) {
+        mbar_wait(qdo_full, n & 1);
+        mbar_wait(dq_empty, (n & 1) ^ 1u);     // S/dQ columns drained by the previous iteration's read-out
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tS, kmaj(aQ, kk), kmaj(aK, kk), id_kk, kk > 0);      // S = Q K^T
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tdP, kmaj(adO, kk), kmaj(aV, kk), id_kk, kk > 0);    // dP = dO V^T
+        umma_commit(s_full);
+        mbar_wait(pds_full, n & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)                                                                  // dV += P^T dO
+          umma_ss<1>(tdV, mnmaj(aP, kk), mnmaj(adO, kk), id_mm, (n > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)                                                                  // dK += dS^T Q
+          umma_ss<1>(tdK, mnmaj(adS, kk), mnmaj(aQ, kk), id_mm, (n > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tS, kmaj(adS, kk), mnmaj(aK, kk), id_km, kk > 0);     // dQ = dS K
+        umma_commit(qdo_empty);
+        umma_commit(dq_full);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
+    for (int n = 0; n < n_iter; ++n) {
+      const int hq = kv_head * group + n / n_q;
+      const int qt = jt + n % n_q;
+      const int q0 = qt * 128;
+      const bool row_ok = (q0 + r) < p.S;
+      const size_t stat_idx = (static_cast<size_t>(batch) * p.nh + hq) * p.S + q0 + r;
+      const float lse2 = row_ok ? p.lse[stat_idx] * 1.4426950408889634f : 0.f;
+      const float drow = row_ok ? p.delta[stat_idx] : 0.f;
+      const bool diag = (qt == jt);
+      mbar_wait(s_full, n & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tS + lane_off + ch * 32, sv);
+        tmem_ld32(tdP + lane_off + ch * 32, dv);
+        tmem_ld_wait();
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int col = ch * 32 + 2 * c;
+          float p0 = exp2f(__uint_as_float(sv[2 * c]) * p.scale_log2 - lse2);
+          float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) * p.scale_log2 - lse2);
+          if (!row_ok || (diag && col > r)) p0 = 0.f;
+          if (!row_ok || (diag && col + 1 > r)) p1 = 0.f;
+          const float d0 = p0 * (__uint_as_float(dv[2 * c]) - drow) * p.scale;
+          const float d1 = p1 * (__uint_as_float(dv[2 * c + 1]) - drow) * p.scale;
+          pp[c] = pack_bf16x2(p0, p1);
+          dd[c] = pack_bf16x2(d0, d1);
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int c16 = ch * 4 + k4;
+          const uint32_t off = (c16 >> 3) * HALF_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4);
+          st_shared_v4(aP + off, make_uint4(pp[4 * k4], pp[4 * k4 + 1], pp[4 * k4 + 2], pp[4 * k4 + 3]));
+          st_shared_v4(adS + off, make_uint4(dd[4 * k4], dd[4 * k4 + 1], dd[4 * k4 + 2], dd[4 * k4 + 3]));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+      // dQ tile read-out and reduction into the fp32 buffer
+      mbar_wait(dq_full, n & 1);
+      tc_fence_after();
+      float* dq_row = p.dq_acc + ((static_cast<size_t>(batch) * p.S + q0 + r) * p.nh + hq) * 128;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(tS + lane_off + ch * 32, o);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            red_add_v4(dq_row + ch * 32 + c * 4, __uint_as_float(o[4 * c]), __uint_as_float(o[4 * c + 1]),
+                       __uint_as_float(o[4 * c + 2]), __uint_as_float(o[4 * c + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_empty);
+    }
+    // epilogue: dK, dV -> bf16 -> smem (reuse Q / dO tiles) -> TMA store
+    const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO);
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t tsrc = which == 0 ? tdK : tdV;
+      const uint32_t sdst = which == 0 ? aQ : adO;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(tsrc + lane_off + ch * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const int c16 = ch * 4 + c8;
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[c8 * 8 + 0]), __uint_as_float(o[c8 * 8 + 1]));
+          v.y = pack_bf16x2(__uint_as_float(o[c8 * 8 + 2]), __uint_as_float(o[c8 * 8 + 3]));
+          v.z = pack_bf16x2(__uint_as_float(o[c8 * 8 + 4]), __uint_as_float(o[c8 * 8 + 5]));
+          v.w = pack_bf16x2(__uint_as_float(o[c8 * 8 + 6]), __uint_as_float(o[c8 * 8 + 7]));
+          st_shared_v4(sdst + (c16 >> 3) * HALF_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4), v);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (warp == 2 && lane == 0) {
+      tma_store_4d(&tmdK, sQ, 0, kv_head, kv0, batch);
+      tma_store_4d(&tmdK, sQ + HALF_BYTES, 64, kv_head, kv0, batch);
+      tma_store_4d(&tmdV, sdO, 0, kv_head, kv0, batch);
+      tma_store_4d(&tmdV, sdO + HALF_BYTES, 64, kv_head, kv0, batch);
+      tma_store_commit();
+      tma_store_wait<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// delta[b, h, s] = sum_d dO[b,s,h,d] * O[b,s,h,d]      (16 lanes per row of 128)
+__global__ void fa_bwd_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
+                                    int B, int S, int nh, int64_t ldo, int64_t lddo) {
+  const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 4;   // (b, s, h) flattened
+  const int sub = threadIdx.x & 15;
+  const int64_t total = static_cast<int64_t>(B) * S * nh;
+  float acc = 0.f;
+  int b = 0, s = 0, h = 0;
+  if (row < total) {
+    h = static_cast<int>(row % nh);
+    const int64_t tok = row / nh;
+    s = static_cast<int>(tok % S);
+    b = static_cast<int>(tok / S);
+    const uint4 ov = ld_nc_v4(reinterpret_cast<const uint4*>(o + tok * ldo + h * 128) + sub);
+    const uint4 dv = ld_nc_v4(reinterpret_cast<const uint4*>(dout + tok * lddo + h * 128) + sub);
+    const uint32_t* oi = reinterpret_cast<const uint32_t*>(&ov);
+    const uint32_t* di = reinterpret_cast<const uint32_t*>(&dv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16x2(oi[j]), d = unpack_bf16x2(di[j]);
+      acc += a.x * d.x + a.y * d.y;
+    }
+  }
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (row < total && sub == 0) delta[(static_cast<size_t>(b) * nh + h) * S + s] = acc;
+}
+
+// dq (bf16, token stride lddq) = bf16(dq_acc fp32 [B*S, nh*128])
+__global__ void fa_bwd_dq_finish_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, int64_t tokens, int width,
+                                        int64_t lddq) {
+  const int64_t nchunk_row = width >> 3;
+  const int64_t total = tokens * nchunk_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = i / nchunk_row, c = i % nchunk_row;
+    const float4* src = reinterpret_cast<const float4*>(acc + t * width) + 2 * c;
+    const float4 a = src[0], b = src[1];
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    *(reinterpret_cast<uint4*>(dq + t * lddq) + c) = o;
+  }
+}
+
+static int make_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S, int64_t heads, int64_t ld) {
+  uint64_t dims[4] = {128, static_cast<uint64_t>(heads), static_cast<uint64_t>(S), static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {128 * 2, static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(S) * ld * 2};
+  uint32_t box[4] = {64, 1, 128, 1};
+  return encode_tmap_bf16(tm, base, 4, dims, strides, box);
+}
+
+}  // namespace fab
+}  // namespace b200
+
+extern "C" int64_t b200_fa_bwd_workspace_bytes(int64_t B, int64_t S, int64_t num_heads, int64_t head_dim) {
+  // fp32 dQ accumulation buffer + delta
+  return B * S * num_heads * head_dim * 4 + B * num_heads * S * 4;
+}
+
+extern "C" int b200_fa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                           void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t S, int64_t num_heads,
+                           int64_t num_kv_heads, int64_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                           int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv, float softmax_scale,
+                           cudaStream_t stream) {
+  using namespace b200;
+  using namespace b200::fab;
+  B200_CHECK_ARG(q && k && v && o && dout && lse && dq && dk && dv && workspace, "fa_bwd: null pointer");
+  B200_CHECK_ARG(head_dim == 128, "fa_bwd: head_dim must be 128 (got %lld)", (long long)head_dim);
+  B200_CHECK_ARG(B > 0 && S > 0 && num_heads > 0 && num_kv_heads > 0 && num_heads % num_kv_heads == 0, "fa_bwd: bad shape");
+  B200_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 &&
+                     lddk % 8 == 0 && lddv % 8 == 0,
+                 "fa_bwd: token strides must be multiples of 8");
+  float* dq_acc = static_cast<float*>(workspace);
+  float* delta = dq_acc + B * S * num_heads * 128;
+  cudaError_t e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(B) * S * num_heads * 128 * 4, stream);
+  if (e != cudaSuccess) {
+    set_last_error("fa_bwd memset: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  {
+    const int64_t rows = B * S * num_heads;
+    const int64_t threads = rows * 16;
+    fa_bwd_delta_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(
+        static_cast<const bf16*>(o), static_cast<const bf16*>(dout), delta, (int)B, (int)S, (int)num_heads, ldo, lddo);
+    int rc = check_launch("fa_bwd(delta)");
+    if (rc) return rc;
+  }
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmdK, tmdV;
+  int rc;
+  if ((rc = make_map(&tmQ, q, B, S, num_heads, ldq)) != 0) return rc;
+  if ((rc = make_map(&tmK, k, B, S, num_kv_heads, ldk)) != 0) return rc;
+  if ((rc = make_map(&tmV, v, B, S, num_kv_heads, ldv)) != 0) return rc;
+  if ((rc = make_map(&tmdO, dout, B, S, num_heads, lddo)) != 0) return rc;
+  if ((rc = make_map(&tmdK, dk, B, S, num_kv_heads, lddk)) != 0) return rc;
+  if ((rc = make_map(&tmdV, dv, B, S, num_kv_heads, lddv)) != 0) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(fa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("fa_bwd smem attr: %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  Params p;
+  p.S = (int)S; p.B = (int)B; p.nh = (int)num_heads; p.kvh = (int)num_kv_heads;
+  p.scale = softmax_scale;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
+  dim3 grid(static_cast<unsigned>((S + 127) / 128), static_cast<unsigned>(num_kv_heads), static_cast<unsigned>(B));
+  fa_bwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmdK, tmdV, p);
+  if ((rc = check_launch("fa_bwd")) != 0) return rc;
+  {
+    const int64_t tokens = B * S;
+    const int width = static_cast<int>(num_heads * 128);
+    const int64_t total = tokens * (width / 8);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    fa_bwd_dq_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(dq_acc, static_cast<bf16*>(dq), tokens,
+                                                                              width, lddq);
+    rc = check_launch("fa_bwd(dq finish)");
+  }
+  return rc;
+}

@@ -1,0 +1,292 @@
+"""Thin torch-tensor wrappers over the C-ABI (include/b200nlp.h).
+
+PyTorch is only the device-memory carrier here: every function validates shapes/dtypes, allocates outputs with
+torch.empty and forwards raw pointers + the current CUDA stream to libb200nlp.so.  No op has a fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+BF16 = torch.bfloat16
+
+
+def _chk(t: torch.Tensor, name: str, dtype=BF16):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (the hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes: int, device, tag: str = "") -> torch.Tensor:
+    """Grow-only scratch buffer per (device, tag); kernels never allocate, the caller (this module) does."""
+    key = (device, tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GEMM
+# ----------------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, trans_a: bool = False,
+         trans_b: bool = False, accumulate: bool = False, bias: Optional[torch.Tensor] = None, cta_group: int = 2,
+         max_ctas: int = 0) -> torch.Tensor:
+    """out (+)= op(a) @ op(b) (+ bias).  a, b 2-D bf16 with unit inner stride.
+    trans_a: a is stored [K, M];  trans_b: b is stored [N, K].  Default b layout [K, N] is Paddle's nn.Linear weight."""
+    _chk(a, "a"); _chk(b, "b")
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    if trans_a:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if trans_b:
+        N, Kb = b.shape
+    else:
+        Kb, N = b.shape
+    if K != Kb:
+        raise ValueError(f"gemm: inner dimensions differ ({K} vs {Kb})")
+    if out is None:
+        if accumulate:
+            raise ValueError("gemm: accumulate=True needs an output tensor")
+        out = torch.empty(M, N, dtype=BF16, device=a.device)
+    _chk(out, "out")
+    assert out.shape == (M, N) and out.stride(1) == 1
+    if bias is not None:
+        _chk(bias, "bias", torch.float32)
+        assert bias.numel() == N
+    call("b200_gemm_bf16_ex", ptr(a), ptr(b), ptr(out), ptr(bias), M, N, K, a.stride(0), b.stride(0), out.stride(0),
+         1 if trans_a else 0, 0 if trans_b else 1, 1 if accumulate else 0, cta_group, max_ctas, stream_ptr())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# RMSNorm
+# ----------------------------------------------------------------------------------------------------------
+def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None,
+                rstd: Optional[torch.Tensor] = None):
+    _chk(x, "x"); _chk(w, "w")
+    h = x.shape[-1]
+    rows = x.numel() // h
+    assert x.is_contiguous() and w.numel() == h
+    if out is None:
+        out = torch.empty_like(x)
+    if rstd is None:
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    call("b200_rmsnorm_fwd", ptr(x), ptr(w), ptr(out), ptr(rstd), rows, h, float(eps), stream_ptr())
+    return out, rstd
+
+
+def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, rstd: torch.Tensor, dw: torch.Tensor,
+                dres: Optional[torch.Tensor] = None, accumulate_dw: bool = True, dx: Optional[torch.Tensor] = None):
+    _chk(dy, "dy"); _chk(x, "x"); _chk(w, "w"); _chk(dw, "dw"); _chk(rstd, "rstd", torch.float32)
+    h = x.shape[-1]
+    rows = x.numel() // h
+    assert dy.is_contiguous() and x.is_contiguous() and dw.numel() == h
+    if dx is None:
+        dx = torch.empty_like(x)
+    ws = _workspace(_lib.load().b200_rmsnorm_bwd_workspace_bytes(rows, h), x.device, "rmsnorm_bwd")
+    call("b200_rmsnorm_bwd", ptr(dy), ptr(x), ptr(w), ptr(rstd), ptr(dres), ptr(dx), ptr(dw), 1 if accumulate_dw else 0,
+         ptr(ws), rows, h, stream_ptr())
+    return dx
+
+
+def colsum(a: torch.Tensor, out: torch.Tensor, accumulate: bool = True):
+    """out[n] (+)= sum over rows of a[rows, n] (a may be a column slice: unit inner stride, any row stride)."""
+    _chk(a, "a"); _chk(out, "out")
+    rows, n = a.shape
+    assert a.stride(1) == 1 and out.numel() == n
+    ws = _workspace(_lib.load().b200_colsum_workspace_bytes(rows, n), a.device, "colsum")
+    call("b200_colsum_bf16", ptr(a), ptr(out), 1 if accumulate else 0, ptr(ws), rows, n, a.stride(0), stream_ptr())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# RoPE
+# ----------------------------------------------------------------------------------------------------------
+def rope_tables(head_dim: int, max_pos: int, theta: float, device):
+    """fp32 cos/sin tables [max_pos, head_dim/2], computed on the CPU exactly as the reference does
+    (llama/modeling.py:409-423) so that host and device share bits, then uploaded once."""
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    t = torch.arange(max_pos, dtype=torch.float32)
+    freqs = torch.einsum("i,j->ij", t, inv_freq)
+    return freqs.cos().contiguous().to(device), freqs.sin().contiguous().to(device)
+
+
+def rope_inplace(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seq_len: int, num_heads: int, head_dim: int,
+                 position_ids: Optional[torch.Tensor] = None, backward: bool = False):
+    """x: [tokens, ld] view whose first num_heads*head_dim columns are the heads to rotate (row stride = ld)."""
+    _chk(x, "x"); _chk(cos, "cos", torch.float32); _chk(sin, "sin", torch.float32)
+    assert x.dim() == 2 and x.stride(1) == 1
+    tokens = x.shape[0]
+    if position_ids is not None:
+        _chk(position_ids, "position_ids", torch.int32)
+        assert position_ids.numel() == tokens
+    else:
+        assert cos.shape[0] >= seq_len
+    call("b200_rope_inplace", ptr(x), ptr(cos), ptr(sin), ptr(position_ids), tokens, seq_len, x.stride(0), num_heads,
+         head_dim, 1 if backward else 0, stream_ptr())
+    return x
+
+
+# ----------------------------------------------------------------------------------------------------------
+# SwiGLU / embedding
+# ----------------------------------------------------------------------------------------------------------
+def swiglu_fwd(gate_up: torch.Tensor, out: Optional[torch.Tensor] = None):
+    _chk(gate_up, "gate_up")
+    rows, two_i = gate_up.shape
+    assert gate_up.is_contiguous() and two_i % 2 == 0
+    inter = two_i // 2
+    if out is None:
+        out = torch.empty(rows, inter, dtype=BF16, device=gate_up.device)
+    call("b200_swiglu_fwd", ptr(gate_up), ptr(out), rows, inter, stream_ptr())
+    return out
+
+
+def swiglu_bwd(gate_up: torch.Tensor, dout: torch.Tensor, dgate_up: Optional[torch.Tensor] = None):
+    _chk(gate_up, "gate_up"); _chk(dout, "dout")
+    rows, two_i = gate_up.shape
+    inter = two_i // 2
+    assert gate_up.is_contiguous() and dout.is_contiguous() and dout.shape == (rows, inter)
+    if dgate_up is None:
+        dgate_up = torch.empty_like(gate_up)
+    call("b200_swiglu_bwd", ptr(gate_up), ptr(dout), ptr(dgate_up), rows, inter, stream_ptr())
+    return dgate_up
+
+
+def embedding_fwd(ids: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor] = None):
+    _chk(ids, "ids", torch.int64); _chk(table, "table")
+    tokens = ids.numel()
+    vocab, h = table.shape
+    assert ids.is_contiguous() and table.is_contiguous()
+    if out is None:
+        out = torch.empty(tokens, h, dtype=BF16, device=table.device)
+    call("b200_embedding_fwd", ptr(ids), ptr(table), ptr(out), tokens, h, vocab, stream_ptr())
+    return out
+
+
+def embedding_bwd(ids: torch.Tensor, dout: torch.Tensor, dtable: torch.Tensor):
+    _chk(ids, "ids", torch.int64); _chk(dout, "dout"); _chk(dtable, "dtable")
+    vocab, h = dtable.shape
+    assert dout.is_contiguous() and dtable.is_contiguous()
+    call("b200_embedding_bwd", ptr(ids), ptr(dout), ptr(dtable), ids.numel(), h, vocab, stream_ptr())
+    return dtable
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Flash attention
+# ----------------------------------------------------------------------------------------------------------
+def _tok_stride(t: torch.Tensor, heads: int, d: int) -> int:
+    """t: [B, S, heads, d] view with unit stride in d, d-stride between heads and a uniform token stride."""
+    B, S, H, D = t.shape
+    assert (H, D) == (heads, d) and t.stride(3) == 1 and (H == 1 or t.stride(2) == d)
+    ld = t.stride(1)
+    assert B == 1 or t.stride(0) == S * ld, "batch stride must be S * token stride"
+    return ld
+
+
+def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: Optional[float] = None,
+                   out: Optional[torch.Tensor] = None):
+    """Causal GQA attention.  q [B,S,nh,128], k/v [B,S,kvh,128] (may be strided views of a packed QKV buffer).
+    Returns (o [B,S,nh,128] contiguous, lse [B,nh,S] fp32)."""
+    _chk(q, "q"); _chk(k, "k"); _chk(v, "v")
+    B, S, nh, d = q.shape
+    kvh = k.shape[2]
+    if softmax_scale is None:
+        softmax_scale = 1.0 / math.sqrt(d)
+    if out is None:
+        out = torch.empty(B, S, nh, d, dtype=BF16, device=q.device)
+    lse = torch.empty(B, nh, S, dtype=torch.float32, device=q.device)
+    call("b200_fa_fwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, S, nh, kvh, d, _tok_stride(q, nh, d),
+         _tok_stride(k, kvh, d), _tok_stride(v, kvh, d), _tok_stride(out, nh, d), float(softmax_scale), stream_ptr())
+    return out, lse
+
+
+def flash_attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, softmax_scale: Optional[float] = None):
+    """Gradients written into dq/dk/dv (views allowed, e.g. slices of a packed dQKV buffer)."""
+    for name, t in (("q", q), ("k", k), ("v", v), ("o", o), ("dout", dout), ("dq", dq), ("dk", dk), ("dv", dv)):
+        _chk(t, name)
+    _chk(lse, "lse", torch.float32)
+    B, S, nh, d = q.shape
+    kvh = k.shape[2]
+    if softmax_scale is None:
+        softmax_scale = 1.0 / math.sqrt(d)
+    ws = _workspace(_lib.load().b200_fa_bwd_workspace_bytes(B, S, nh, d), q.device, "fa_bwd")
+    call("b200_fa_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(dout), ptr(lse), ptr(dq), ptr(dk), ptr(dv), ptr(ws), B, S, nh,
+         kvh, d, _tok_stride(q, nh, d), _tok_stride(k, kvh, d), _tok_stride(v, kvh, d), _tok_stride(o, nh, d),
+         _tok_stride(dout, nh, d), _tok_stride(dq, nh, d), _tok_stride(dk, kvh, d), _tok_stride(dv, kvh, d),
+         float(softmax_scale), stream_ptr())
+    return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Criterion / sampling
+# ----------------------------------------------------------------------------------------------------------
+def ce_fwd(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100):
+    """Returns (loss_out [2] = (masked mean loss, count), loss_tok [T], lse [T])."""
+    _chk(logits, "logits"); _chk(labels, "labels", torch.int64)
+    T, V = logits.shape
+    assert logits.stride(1) == 1 and labels.numel() == T and labels.is_contiguous()
+    loss_tok = torch.empty(T, dtype=torch.float32, device=logits.device)
+    lse = torch.empty(T, dtype=torch.float32, device=logits.device)
+    loss_out = torch.empty(2, dtype=torch.float32, device=logits.device)
+    call("b200_ce_fwd", ptr(logits), ptr(labels), ptr(loss_tok), ptr(lse), ptr(loss_out), T, V, logits.stride(0),
+         ignore_index, stream_ptr())
+    return loss_out, loss_tok, lse
+
+
+def ce_bwd_(logits: torch.Tensor, labels: torch.Tensor, loss_tok, lse, loss_out, grad_scale: float = 1.0):
+    """Overwrites logits with dlogits."""
+    T, V = logits.shape
+    call("b200_ce_bwd", ptr(logits), ptr(labels), ptr(loss_tok), ptr(lse), ptr(loss_out), float(grad_scale), T, V,
+         logits.stride(0), stream_ptr())
+    return logits
+
+
+def argmax(logits: torch.Tensor) -> torch.Tensor:
+    _chk(logits, "logits")
+    rows, V = logits.shape
+    out = torch.empty(rows, dtype=torch.int64, device=logits.device)
+    call("b200_argmax_bf16", ptr(logits), ptr(out), rows, V, logits.stride(0), stream_ptr())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Optimizer
+# ----------------------------------------------------------------------------------------------------------
+def grad_sqnorm(grads: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None):
+    _chk(grads, "grads")
+    assert grads.is_contiguous()
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=grads.device)
+    ws = _workspace(_lib.load().b200_grad_sqnorm_workspace_bytes(), grads.device, "sqnorm")
+    call("b200_grad_sqnorm", ptr(grads), ptr(out), ptr(ws), grads.numel(), float(scale), stream_ptr())
+    return out
+
+
+def adamw_step(params, grads, master, exp_avg, exp_avg_sq, sqnorm, *, decay_end: int, lr: float, beta1: float,
+               beta2: float, eps: float, weight_decay: float, step: int, grad_scale: float = 1.0,
+               max_grad_norm: float = 1.0):
+    _chk(params, "params"); _chk(grads, "grads")
+    for n_, t in (("master", master), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        _chk(t, n_, torch.float32)
+    n = params.numel()
+    call("b200_adamw_step", ptr(params), ptr(grads), ptr(master), ptr(exp_avg), ptr(exp_avg_sq), ptr(sqnorm), n,
+         decay_end, float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
+         float(max_grad_norm), stream_ptr())
+
+
+def bf16_to_f32(src: torch.Tensor, dst: torch.Tensor):
+    _chk(src, "src"); _chk(dst, "dst", torch.float32)
+    call("b200_bf16_to_f32", ptr(src), ptr(dst), src.numel(), stream_ptr())
+    return dst

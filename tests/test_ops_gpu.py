@@ -1,0 +1,248 @@
+"""GPU parity tests of every kernel behind the C-ABI against the oracle (oracle/llama_ref.py, oracle/optim_ref.py).
+
+All calls go through paddlenlp_b200.ops -> ctypes -> libb200nlp.so.  Tolerances are written beside each check:
+bf16 outputs are compared with a normalised error  max|a-b| / max|b|  and  ||a-b|| / ||b||.
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import llama_ref as R
+from oracle import optim_ref
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+BF16 = torch.bfloat16
+
+
+def ops():
+    from paddlenlp_b200 import ops as _ops
+
+    return _ops
+
+
+def relerr(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def maxerr(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def rand_bf16(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(BF16)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_layouts(cg, ta, tb):
+    o = ops()
+    M, N, K = 520, 776, 328   # ragged against every tile dimension
+    A = rand_bf16(M, K, seed=1, scale=0.5)
+    B = rand_bf16(K, N, seed=2, scale=0.5)
+    a_d = (A.t().contiguous() if ta else A).to(DEV)
+    b_d = (B.t().contiguous() if tb else B).to(DEV)
+    out = o.gemm(a_d, b_d, trans_a=ta, trans_b=tb, cta_group=cg)
+    ref = A.float().to(DEV) @ B.float().to(DEV)
+    # one bf16 rounding of an fp32-accumulated result: <= 2^-8 relative to the largest magnitude
+    assert maxerr(out, ref) < 2 ** -7
+    assert relerr(out, ref) < 4e-3
+
+
+def test_gemm_accumulate_bias_and_views():
+    o = ops()
+    M, N, K = 384, 512, 256
+    A = rand_bf16(M, K, seed=3).to(DEV)
+    Wfull = rand_bf16(K, N + 256, seed=4).to(DEV)
+    W = Wfull[:, 128:128 + N]                      # column slice: ldb != N
+    C0 = rand_bf16(M, N, seed=5).to(DEV)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(6)).to(DEV)
+    C = C0.clone()
+    o.gemm(A, W, out=C, accumulate=True, bias=bias)
+    ref = A.float() @ W.float() + bias + C0.float()
+    assert maxerr(C, ref) < 2 ** -7
+
+
+def test_gemm_argument_errors():
+    o = ops()
+    from paddlenlp_b200._lib import B200Error
+
+    A = rand_bf16(64, 60).to(DEV)   # K = 60 is not a multiple of 8
+    B = rand_bf16(60, 64).to(DEV)
+    with pytest.raises((B200Error, AssertionError, ValueError)):
+        o.gemm(A, B)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,h", [(37, 128), (256, 4096), (64, 3584), (5, 8192)])
+def test_rmsnorm_fwd_bwd(rows, h):
+    o = ops()
+    x = rand_bf16(rows, h, seed=7)
+    w = (1.0 + 0.1 * torch.randn(h, generator=torch.Generator().manual_seed(8))).to(BF16)
+    dy = rand_bf16(rows, h, seed=9)
+    dres = rand_bf16(rows, h, seed=10)
+    eps = 1e-5
+    y, rstd = o.rmsnorm_fwd(x.to(DEV), w.to(DEV), eps)
+    ref = R.rms_norm(x.float(), w.float(), eps, "bf16")
+    assert torch.equal(y.float().cpu(), ref) or maxerr(y.cpu(), ref) < 2 ** -7   # same rounding points: ~bit-exact
+    assert (y.float().cpu() != ref).float().mean().item() < 0.01                # <1% of elements differ by 1 ulp
+    # backward against autograd of the fp32 oracle
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    R.rms_norm(xf, wf, eps, "fp32").backward(dy.float())
+    dw0 = rand_bf16(h, seed=11)
+    dw = dw0.clone().to(DEV)
+    dx = o.rmsnorm_bwd(dy.to(DEV), x.to(DEV), w.to(DEV), rstd, dw, dres=dres.to(DEV), accumulate_dw=True)
+    assert relerr(dx.cpu(), xf.grad + dres.float()) < 6e-3        # bf16 output rounding ~ 2^-9 per element
+    assert relerr(dw.cpu(), wf.grad + dw0.float()) < 6e-3
+
+
+def test_colsum():
+    o = ops()
+    a = rand_bf16(300, 1024, seed=12).to(DEV)
+    view = a[:, 256:768]
+    out0 = rand_bf16(512, seed=13).to(DEV)
+    out = out0.clone()
+    o.colsum(view, out, accumulate=True)
+    ref = view.float().sum(0) + out0.float()
+    assert relerr(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("backward", [False, True])
+def test_rope(backward):
+    o = ops()
+    B, S, nh, kvh, d = 2, 96, 4, 2, 128
+    ld = (nh + 2 * kvh) * d
+    qkv = rand_bf16(B * S, ld, seed=14)
+    cos, sin = o.rope_tables(d, 128, 500000.0, DEV)
+    x = qkv.clone().to(DEV)
+    o.rope_inplace(x, cos, sin, S, nh + kvh, d, backward=backward)
+    c, s = R.rope_tables(d, S, 500000.0)
+    qk = qkv[:, : (nh + kvh) * d].float().reshape(B, S, nh + kvh, d)
+    if backward:
+        s = -s
+    ref = R.apply_rope(qk, c, s, "bf16").reshape(B * S, -1)
+    got = x.cpu().float()
+    assert maxerr(got[:, : (nh + kvh) * d], ref) < 2 ** -7
+    assert torch.equal(got[:, (nh + kvh) * d:], qkv[:, (nh + kvh) * d:].float())   # v untouched
+    # explicit position ids
+    pos = torch.randint(0, 128, (B * S,), generator=torch.Generator().manual_seed(15)).int()
+    x2 = qkv.clone().to(DEV)
+    o.rope_inplace(x2, cos, sin, S, nh + kvh, d, position_ids=pos.to(DEV), backward=backward)
+    c2, s2 = R.rope_tables(d, 128, 500000.0)
+    if backward:
+        s2 = -s2
+    ref2 = R.apply_rope(qk, c2, s2, "bf16", position_ids=pos.long().reshape(B, S)).reshape(B * S, -1)
+    assert maxerr(x2.cpu().float()[:, : (nh + kvh) * d], ref2) < 2 ** -7
+
+
+def test_swiglu():
+    o = ops()
+    rows, inter = 130, 1192
+    gu = rand_bf16(rows, 2 * inter, seed=16, scale=2.0)
+    dm = rand_bf16(rows, inter, seed=17)
+    m = o.swiglu_fwd(gu.to(DEV))
+    g, u = gu[:, :inter].float().requires_grad_(True), gu[:, inter:].float().requires_grad_(True)
+    ref = R.swiglu(g, u, "fp32")
+    assert maxerr(m.cpu(), ref.detach()) < 2 ** -7
+    ref.backward(dm.float())
+    dgu = o.swiglu_bwd(gu.to(DEV), dm.to(DEV)).cpu()
+    assert relerr(dgu[:, :inter], g.grad) < 6e-3
+    assert relerr(dgu[:, inter:], u.grad) < 6e-3
+
+
+def test_embedding():
+    o = ops()
+    V, h, T = 1000, 256, 300
+    table = rand_bf16(V, h, seed=18)
+    ids = torch.randint(0, V, (T,), generator=torch.Generator().manual_seed(19))
+    out = o.embedding_fwd(ids.to(DEV), table.to(DEV))
+    assert torch.equal(out.cpu(), table[ids])
+    dout = rand_bf16(T, h, seed=20)
+    dtab = torch.zeros(V, h, dtype=BF16, device=DEV)
+    o.embedding_bwd(ids.to(DEV), dout.to(DEV), dtab)
+    ref = torch.zeros(V, h).index_add_(0, ids, dout.float())
+    assert relerr(dtab.cpu(), ref) < 1e-2   # bf16 atomics: each add rounds
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,S,nh,kvh", [(1, 128, 1, 1), (2, 384, 4, 1), (1, 1024, 4, 2), (1, 200, 2, 2)])
+def test_flash_attention_fwd_bwd(B, S, nh, kvh):
+    o = ops()
+    d = 128
+    ld = (nh + 2 * kvh) * d
+    qkv = rand_bf16(B, S, ld, seed=21, scale=1.0).to(DEV)
+    q = qkv[:, :, : nh * d].view(B, S, nh, d)
+    k = qkv[:, :, nh * d: (nh + kvh) * d].view(B, S, kvh, d)
+    v = qkv[:, :, (nh + kvh) * d:].view(B, S, kvh, d)
+    out, lse = o.flash_attn_fwd(q, k, v)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ref = R.attention(qf, kf, vf, "fp32")                     # [B, S, nh*d]
+    assert maxerr(out.reshape(B, S, -1), ref.detach()) < 1.5e-2   # P rounded to bf16 before PV + bf16 output
+    assert relerr(out.reshape(B, S, -1), ref.detach()) < 1e-2
+    # lse check
+    scores = torch.einsum("bqhd,bkhd->bhqk", qf, kf.repeat_interleave(nh // kvh, dim=2)) / math.sqrt(d)
+    mask = torch.full((S, S), float("-inf"), device=DEV).triu(1)
+    lse_ref = torch.logsumexp(scores + mask, dim=-1)
+    assert (lse - lse_ref).abs().max().item() < 2e-3
+    # backward
+    dout = rand_bf16(B, S, nh, d, seed=22).to(DEV)
+    ref.backward(dout.float().reshape(B, S, -1))
+    dqkv = torch.zeros_like(qkv)
+    dq = dqkv[:, :, : nh * d].view(B, S, nh, d)
+    dk = dqkv[:, :, nh * d: (nh + kvh) * d].view(B, S, kvh, d)
+    dv = dqkv[:, :, (nh + kvh) * d:].view(B, S, kvh, d)
+    o.flash_attn_bwd(q, k, v, out, dout, lse, dq, dk, dv)
+    # tolerance precedent: reference compares bf16 attention grads at 1e-2 (tests/transformers/test_ring_flash_attention.py:94-107)
+    assert relerr(dq, qf.grad) < 2e-2
+    assert relerr(dk, kf.grad) < 2e-2
+    assert relerr(dv, vf.grad) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+def test_cross_entropy():
+    o = ops()
+    T, V = 100, 5000
+    logits = rand_bf16(T, V, seed=23, scale=2.0)
+    labels = torch.randint(0, V, (T,), generator=torch.Generator().manual_seed(24))
+    labels[::7] = -100
+    lg = logits.clone().to(DEV)
+    loss_out, loss_tok, lse = o.ce_fwd(lg, labels.to(DEV))
+    lf = logits.float().requires_grad_(True)
+    ref = R.criterion(lf, labels)
+    assert abs(loss_out[0].item() - ref.item()) < 1e-4 * abs(ref.item())
+    assert loss_out[1].item() == float((labels != -100).sum())
+    ref.backward()
+    o.ce_bwd_(lg, labels.to(DEV), loss_tok, lse, loss_out, grad_scale=1.0)
+    assert relerr(lg.cpu(), lf.grad) < 6e-3
+    am = o.argmax(logits.to(DEV))
+    assert torch.equal(am.cpu(), logits.float().argmax(-1))
+
+
+def test_adamw_and_clip():
+    o = ops()
+    n, decay_end = 8 * 5000, 8 * 3000
+    g = torch.Generator().manual_seed(25)
+    p16 = (torch.randn(n, generator=g) * 0.02).to(BF16)
+    grad = (torch.randn(n, generator=g) * 0.01).to(BF16)
+    master = p16.float()
+    m = torch.randn(n, generator=g) * 1e-3
+    v = torch.rand(n, generator=g) * 1e-5
+    hp = dict(lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, step=7)
+    mask = torch.arange(n) < decay_end
+    pr, mr, vr, p16r = optim_ref.adamw_step(master, m, v, grad.float(), decay_mask=mask, grad_scale=0.5,
+                                            max_grad_norm=1.0, **hp)
+    P, G, M_, V_, MA = p16.to(DEV), grad.to(DEV), m.to(DEV), v.to(DEV), master.to(DEV)
+    sq = o.grad_sqnorm(G, scale=0.5)
+    assert abs(sq.item() - (grad.float() * 0.5).pow(2).sum().item()) < 1e-4 * sq.item()
+    o.adamw_step(P, G, MA, M_, V_, sq, decay_end=decay_end, grad_scale=0.5, max_grad_norm=1.0, **hp)
+    assert relerr(MA.cpu(), pr) < 1e-6
+    assert relerr(M_.cpu(), mr) < 1e-5
+    assert relerr(V_.cpu(), vr) < 1e-5
+    assert (P.cpu().float() != p16r.float()).float().mean().item() < 1e-3
