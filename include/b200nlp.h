@@ -49,11 +49,15 @@ int b200_device_check(void);
 int b200_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N, int64_t K,
                    int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int accumulate,
                    cudaStream_t stream);
-/* Same with tuning knobs: cta_group 1 (one CTA per 128x256 tile) or 2 (CTA pair per 256x256 tile);
- * max_ctas > 0 limits the persistent grid (used to leave SMs to a concurrent kernel). */
-int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N, int64_t K,
-                      int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int accumulate,
-                      int cta_group, int max_ctas, cudaStream_t stream);
+/* Same with a fused residual epilogue and tuning knobs.
+ *   residual (bf16 [M,N], leading dimension ldr; exclusive with accumulate):
+ *       C = bf16( bf16(acc + bias) + residual )  — the Linear-output rounding followed by the decoder layer's residual
+ *       add (llama/modeling.py:1212, 1218), i.e. the reference's two rounding points in one kernel.
+ *   cta_group 1 (one CTA per 128x256 tile) or 2 (CTA pair per 256x256 tile);
+ *   max_ctas > 0 limits the persistent grid (used to leave SMs to a concurrent kernel). */
+int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const float* bias, const void* residual, int64_t M,
+                      int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int a_mn_major,
+                      int b_mn_major, int accumulate, int cta_group, int max_ctas, cudaStream_t stream);
 
 /* ---- RMSNorm: replaces fused_ln.fused_rms_norm / fast_ln (apex-derived custom ops) --------------------------
  * fwd : y = bf16( bf16(x * rstd) * w ), rstd[row] = rsqrt(mean(x^2) + eps) in fp32 (saved for the backward).
@@ -109,11 +113,14 @@ int b200_fa_bwd(const void* q, const void* k, const void* v, const void* o, cons
 
 /* ---- Criterion: LlamaPretrainingCriterion (llama/modeling.py:1799-1825) on bf16 logits [tokens, vocab] (ld).
  * fwd : loss_tok[i] = fp32 CE (0 for ignore_index), lse[i]; loss_out[0] = sum(l_i [l_i>0]) / count, loss_out[1] = count.
- * bwd : logits are overwritten by dlogits = (softmax - onehot) * [l_i>0] * grad_scale / count (bf16). */
+ * bwd : logits are overwritten by dlogits = (softmax - onehot) * [l_i>0] * grad_scale / count (bf16);
+ *       grad_scale_dev (optional device scalar) multiplies grad_scale, so an upstream gradient that lives on the
+ *       device (loss / gradient_accumulation_steps, trainer.py:2237-2238) needs no host synchronisation. */
 int b200_ce_fwd(const void* logits, const int64_t* labels, float* loss_tok, float* lse, float* loss_out, int64_t tokens,
                 int64_t vocab, int64_t ld, int64_t ignore_index, cudaStream_t stream);
 int b200_ce_bwd(void* logits_inout, const int64_t* labels, const float* loss_tok, const float* lse,
-                const float* loss_out, float grad_scale, int64_t tokens, int64_t vocab, int64_t ld, cudaStream_t stream);
+                const float* loss_out, float grad_scale, const float* grad_scale_dev, int64_t tokens, int64_t vocab,
+                int64_t ld, cudaStream_t stream);
 /* Greedy token choice: first maximal index of each bf16 row (generation_utils.py:291-363 with top_p = 0). */
 int b200_argmax_bf16(const void* logits, int64_t* out, int64_t rows, int64_t vocab, int64_t ld, cudaStream_t stream);
 

@@ -24,7 +24,7 @@ _SIGNATURES = {
     "b200_abi_version": [],
     "b200_device_check": [],
     "b200_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, P],
-    "b200_gemm_bf16_ex": [P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, I, I, P],
+    "b200_gemm_bf16_ex": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I, I, I, I, I, P],
     "b200_rmsnorm_fwd": [P, P, P, P, I64, I64, F, P],
     "b200_rmsnorm_bwd_workspace_bytes": [I64, I64],
     "b200_rmsnorm_bwd": [P, P, P, P, P, P, P, I, P, I64, I64, P],
@@ -39,7 +39,7 @@ _SIGNATURES = {
     "b200_fa_bwd_workspace_bytes": [I64, I64, I64, I64],
     "b200_fa_bwd": [P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, I64, I64, I64, I64, I64, F, P],
     "b200_ce_fwd": [P, P, P, P, P, I64, I64, I64, I64, P],
-    "b200_ce_bwd": [P, P, P, P, P, F, I64, I64, I64, P],
+    "b200_ce_bwd": [P, P, P, P, P, F, P, I64, I64, I64, P],
     "b200_argmax_bf16": [P, P, I64, I64, I64, P],
     "b200_grad_sqnorm_workspace_bytes": [],
     "b200_grad_sqnorm": [P, P, P, I64, F, P],

@@ -10,7 +10,7 @@
 //   warp 0      TMA producer   : global -> 128B-swizzled smem ring, STAGES deep, BK = 64
 //   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (UMMA M=128*CG, N=256, K=16); tcgen05.commit
 //                                releases smem stages and publishes the finished accumulator
-//   warps 2..5  epilogue       : tcgen05.ld (TMEM -> regs), (+bias, +C_old), round to bf16, swizzled smem staging,
+//   warps 2..5  epilogue       : tcgen05.ld (TMEM -> regs), (+bias, +C_old | +residual), round to bf16, swizzled smem staging,
 //                                per-warp TMA store of 32x64 boxes
 //   TMEM        2 accumulator stages x 256 fp32 columns = all 512 columns, so the epilogue of tile i overlaps the
 //               main loop of tile i+1.
@@ -51,7 +51,7 @@ struct Cfg {
 struct Params {
   int M, N, K;
   int num_m_tiles, num_n_tiles;
-  int accumulate;          // C += result
+  int epi_mode;            // 0: C = acc ; 1: C = bf16(C_old + acc) ; 2: C = bf16(bf16(acc) + R)
   const float* bias;       // [N] fp32 or nullptr
 };
 
@@ -71,7 +71,7 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_
 template <int CG, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const Params p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const Params p) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -97,6 +97,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
+    tma_prefetch_desc(&tmR);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -211,9 +212,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
         const bool live = (row0 < p.M) && (c0 < p.N);
-        if (p.accumulate && live && lane == 0) {
+        if (p.epi_mode && live && lane == 0) {
           mbar_arrive_expect_tx(&epi_bar[q], EPI_BUF_BYTES);
-          tma_load_2d(&tmC, &epi_bar[q], my_buf + buf * EPI_BUF_BYTES, c0, row0);
+          tma_load_2d(&tmR, &epi_bar[q], my_buf + buf * EPI_BUF_BYTES, c0, row0);
         }
         uint32_t v0[32], v1[32];
         tmem_ld32(taddr + slab * EPI_BOX_COLS, v0);
@@ -226,7 +227,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
         }
         if (live) {
-          if (p.accumulate) { mbar_wait(&epi_bar[q], ephase); }
+          if (p.epi_mode) { mbar_wait(&epi_bar[q], ephase); }
           const uint32_t row_s = sbuf + lane * 128;
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
@@ -244,7 +245,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             const uint32_t addr = row_s + ((ch ^ (lane & 7)) << 4);
-            if (p.accumulate) {
+            if (p.epi_mode) {
+              if (p.epi_mode == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j]);
+              }
               const uint4 old = ld_shared_v4(addr);
               const float2 o0 = unpack_bf16x2(old.x), o1 = unpack_bf16x2(old.y), o2 = unpack_bf16x2(old.z),
                            o3 = unpack_bf16x2(old.w);
@@ -264,7 +269,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_store_2d(&tmC, my_buf + buf * EPI_BUF_BYTES, c0, row0);
             tma_store_commit();
           }
-          if (p.accumulate) ephase ^= 1u;
+          if (p.epi_mode) ephase ^= 1u;
         }
         buf ^= 1;
       }
@@ -283,8 +288,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int CG, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Params& p,
-                  int max_ctas, cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                  const Params& p, int max_ctas, cudaStream_t stream) {
   using C = Cfg<CG>;
   auto kern = gemm_bf16_kernel<CG, A_MN, B_MN>;
   static bool attr_set = false;  // per instantiation
@@ -314,7 +319,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, p);
   if (e != cudaSuccess) {
     set_last_error("gemm launch: %s", cudaGetErrorString(e));
     return static_cast<int>(e);
@@ -325,9 +330,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
 }  // namespace gemm
 }  // namespace b200
 
-extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N,
-                                 int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major,
-                                 int accumulate, int cta_group, int max_ctas, cudaStream_t stream) {
+extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const float* bias, const void* residual,
+                                 int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr,
+                                 int a_mn_major, int b_mn_major, int accumulate, int cta_group, int max_ctas,
+                                 cudaStream_t stream) {
   using namespace b200;
   using namespace b200::gemm;
   B200_CHECK_ARG(A && B && C, "gemm: null pointer");
@@ -338,9 +344,11 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const fl
                  (long long)K);
   B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "gemm: leading dimensions must be multiples of 8");
   B200_CHECK_ARG(cta_group == 1 || cta_group == 2, "gemm: cta_group must be 1 or 2");
+  B200_CHECK_ARG(!(residual && accumulate), "gemm: residual and accumulate are mutually exclusive");
+  B200_CHECK_ARG(!residual || ldr % 8 == 0, "gemm: ldr must be a multiple of 8");
   B200_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension too large");
 
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmR;
   int rc;
   {
     // A: K-major  -> stored [M, K], dims {K, M}, box {64, 128}
@@ -367,6 +375,12 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const fl
     uint64_t strides[1] = {static_cast<uint64_t>(ldc) * 2};
     uint32_t box[2] = {EPI_BOX_COLS, EPI_BOX_ROWS};
     if ((rc = encode_tmap_bf16(&tmC, C, 2, dims, strides, box)) != 0) return rc;
+    if (residual) {
+      strides[0] = static_cast<uint64_t>(ldr) * 2;
+      if ((rc = encode_tmap_bf16(&tmR, residual, 2, dims, strides, box)) != 0) return rc;
+    } else {
+      tmR = tmC;
+    }
   }
   Params p;
   p.M = static_cast<int>(M);
@@ -374,15 +388,15 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const fl
   p.K = static_cast<int>(K);
   p.num_m_tiles = static_cast<int>((M + BM * cta_group - 1) / (BM * cta_group));
   p.num_n_tiles = static_cast<int>((N + BN - 1) / BN);
-  p.accumulate = accumulate;
+  p.epi_mode = residual ? 2 : (accumulate ? 1 : 0);
   p.bias = bias;
 
 #define B200_GEMM_DISPATCH(CG)                                                                          \
   do {                                                                                                  \
-    if (a_mn_major && b_mn_major) return launch<CG, true, true>(tmA, tmB, tmC, p, max_ctas, stream);    \
-    if (a_mn_major) return launch<CG, true, false>(tmA, tmB, tmC, p, max_ctas, stream);                 \
-    if (b_mn_major) return launch<CG, false, true>(tmA, tmB, tmC, p, max_ctas, stream);                 \
-    return launch<CG, false, false>(tmA, tmB, tmC, p, max_ctas, stream);                                \
+    if (a_mn_major && b_mn_major) return launch<CG, true, true>(tmA, tmB, tmC, tmR, p, max_ctas, stream);    \
+    if (a_mn_major) return launch<CG, true, false>(tmA, tmB, tmC, tmR, p, max_ctas, stream);                 \
+    if (b_mn_major) return launch<CG, false, true>(tmA, tmB, tmC, tmR, p, max_ctas, stream);                 \
+    return launch<CG, false, false>(tmA, tmB, tmC, tmR, p, max_ctas, stream);                                \
   } while (0)
   if (cta_group == 2) B200_GEMM_DISPATCH(2);
   B200_GEMM_DISPATCH(1);
@@ -392,6 +406,6 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const fl
 extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N, int64_t K,
                               int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int accumulate,
                               cudaStream_t stream) {
-  return b200_gemm_bf16_ex(A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn_major, b_mn_major, accumulate,
+  return b200_gemm_bf16_ex(A, B, C, bias, nullptr, M, N, K, lda, ldb, ldc, 0, a_mn_major, b_mn_major, accumulate,
                            /*cta_group=*/2, /*max_ctas=*/0, stream);
 }

@@ -102,10 +102,12 @@ __global__ void ce_reduce_kernel(const float* __restrict__ loss_tok, float* __re
 __global__ void __launch_bounds__(256) ce_bwd_kernel(bf16* __restrict__ logits, const int64_t* __restrict__ labels,
                                                      const float* __restrict__ loss_tok,
                                                      const float* __restrict__ lse, const float* __restrict__ loss_out,
-                                                     float grad_scale, int vocab, int64_t ld) {
+                                                     float grad_scale, const float* __restrict__ grad_scale_ptr,
+                                                     int vocab, int64_t ld) {
   const int row = blockIdx.x;
   bf16* lr = logits + static_cast<size_t>(row) * ld;
   const float cnt = loss_out[1];
+  if (grad_scale_ptr != nullptr) grad_scale *= grad_scale_ptr[0];
   const float l = loss_tok[row];
   const float scale = (l > 0.f) ? grad_scale / fmaxf(cnt, 1.f) : 0.f;
   const float row_lse = lse[row];
@@ -284,12 +286,12 @@ extern "C" int b200_ce_fwd(const void* logits, const int64_t* labels, float* los
 }
 
 extern "C" int b200_ce_bwd(void* logits_inout, const int64_t* labels, const float* loss_tok, const float* lse,
-                           const float* loss_out, float grad_scale, int64_t tokens, int64_t vocab, int64_t ld,
-                           cudaStream_t stream) {
+                           const float* loss_out, float grad_scale, const float* grad_scale_dev, int64_t tokens,
+                           int64_t vocab, int64_t ld, cudaStream_t stream) {
   B200_CHECK_ARG(logits_inout && labels && loss_tok && lse && loss_out, "ce_bwd: null pointer");
   B200_CHECK_ARG(tokens > 0 && vocab > 0 && ld % 8 == 0, "ce_bwd: ld must be a multiple of 8");
   ce_bwd_kernel<<<static_cast<unsigned>(tokens), 256, 0, stream>>>(static_cast<bf16*>(logits_inout), labels, loss_tok, lse,
-                                                                  loss_out, grad_scale, (int)vocab, ld);
+                                                                  loss_out, grad_scale, grad_scale_dev, (int)vocab, ld);
   return check_launch("ce_bwd");
 }
 

@@ -40,9 +40,10 @@ def _workspace(nbytes: int, device, tag: str = "") -> torch.Tensor:
 # GEMM
 # ----------------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, trans_a: bool = False,
-         trans_b: bool = False, accumulate: bool = False, bias: Optional[torch.Tensor] = None, cta_group: int = 2,
-         max_ctas: int = 0) -> torch.Tensor:
-    """out (+)= op(a) @ op(b) (+ bias).  a, b 2-D bf16 with unit inner stride.
+         trans_b: bool = False, accumulate: bool = False, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, cta_group: int = 2, max_ctas: int = 0) -> torch.Tensor:
+    """out (+)= op(a) @ op(b) (+ bias)   or   out = bf16(bf16(op(a) @ op(b) + bias) + residual).
+    a, b 2-D bf16 with unit inner stride.
     trans_a: a is stored [K, M];  trans_b: b is stored [N, K].  Default b layout [K, N] is Paddle's nn.Linear weight."""
     _chk(a, "a"); _chk(b, "b")
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
@@ -65,8 +66,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     if bias is not None:
         _chk(bias, "bias", torch.float32)
         assert bias.numel() == N
-    call("b200_gemm_bf16_ex", ptr(a), ptr(b), ptr(out), ptr(bias), M, N, K, a.stride(0), b.stride(0), out.stride(0),
-         1 if trans_a else 0, 0 if trans_b else 1, 1 if accumulate else 0, cta_group, max_ctas, stream_ptr())
+    ldr = 0
+    if residual is not None:
+        _chk(residual, "residual")
+        assert residual.shape == (M, N) and residual.stride(1) == 1 and not accumulate
+        ldr = residual.stride(0)
+    call("b200_gemm_bf16_ex", ptr(a), ptr(b), ptr(out), ptr(bias), ptr(residual), M, N, K, a.stride(0), b.stride(0),
+         out.stride(0), ldr, 1 if trans_a else 0, 0 if trans_b else 1, 1 if accumulate else 0, cta_group, max_ctas,
+         stream_ptr())
     return out
 
 
@@ -245,11 +252,14 @@ def ce_fwd(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100)
     return loss_out, loss_tok, lse
 
 
-def ce_bwd_(logits: torch.Tensor, labels: torch.Tensor, loss_tok, lse, loss_out, grad_scale: float = 1.0):
-    """Overwrites logits with dlogits."""
+def ce_bwd_(logits: torch.Tensor, labels: torch.Tensor, loss_tok, lse, loss_out, grad_scale: float = 1.0,
+            grad_scale_dev: Optional[torch.Tensor] = None):
+    """Overwrites logits with dlogits.  grad_scale_dev: optional fp32 device scalar multiplied into grad_scale."""
     T, V = logits.shape
-    call("b200_ce_bwd", ptr(logits), ptr(labels), ptr(loss_tok), ptr(lse), ptr(loss_out), float(grad_scale), T, V,
-         logits.stride(0), stream_ptr())
+    if grad_scale_dev is not None:
+        _chk(grad_scale_dev, "grad_scale_dev", torch.float32)
+    call("b200_ce_bwd", ptr(logits), ptr(labels), ptr(loss_tok), ptr(lse), ptr(loss_out), float(grad_scale),
+         ptr(grad_scale_dev), T, V, logits.stride(0), stream_ptr())
     return logits
 
 

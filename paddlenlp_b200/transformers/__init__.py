@@ -1,0 +1,37 @@
+"""paddlenlp.transformers surface kept by this build (SURVEY.md §1 "public interface we keep")."""
+from .configuration_utils import LlmMetaConfig, PretrainedConfig
+from .llama.configuration import LlamaConfig
+from .llama.modeling import LlamaForCausalLM, LlamaModel, LlamaPretrainedModel, LlamaPretrainingCriterion
+from .model_outputs import CausalLMOutputWithCrossAttentions
+from .qwen2.configuration import Qwen2Config
+from .qwen2.modeling import Qwen2ForCausalLM, Qwen2Model, Qwen2PretrainedModel, Qwen2PretrainingCriterion
+
+_CONFIGS = {"llama": LlamaConfig, "qwen2": Qwen2Config}
+_CAUSAL_LM = {"llama": LlamaForCausalLM, "qwen2": Qwen2ForCausalLM}
+
+
+class AutoConfig:
+    """paddlenlp/transformers/auto/configuration.py — local config.json only."""
+
+    @staticmethod
+    def from_pretrained(path, **kwargs):
+        import json
+        import os
+
+        f = os.path.join(path, "config.json") if os.path.isdir(path) else path
+        with open(f) as fh:
+            d = json.load(fh)
+        return _CONFIGS[d.get("model_type", "llama")].from_dict(d, **kwargs)
+
+
+class AutoModelForCausalLM:
+    """paddlenlp/transformers/auto/modeling.py:71 — dispatch on config.model_type."""
+
+    @staticmethod
+    def from_config(config, dtype="bfloat16", **kwargs):
+        return _CAUSAL_LM[config.model_type].from_config(config, dtype=dtype, **kwargs)
+
+    @staticmethod
+    def from_pretrained(path, **kwargs):
+        cfg = AutoConfig.from_pretrained(path)
+        return _CAUSAL_LM[cfg.model_type].from_pretrained(path, config=cfg, **kwargs)

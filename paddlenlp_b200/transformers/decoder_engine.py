@@ -1,0 +1,322 @@
+"""DecoderEngine: the Llama/Qwen2 decoder hot path (forward, backward, flat parameter/gradient buffers).
+
+This is the host-side orchestration of the sm_100a kernels behind the C-ABI.  It replaces the per-op eager execution
+of the reference's
+    LlamaModel.forward            paddlenlp/transformers/llama/modeling.py:1588-1774
+    LlamaDecoderLayer.forward     paddlenlp/transformers/llama/modeling.py:1138-1232
+    LlamaAttention.forward        paddlenlp/transformers/llama/modeling.py:866-1119
+    LlamaMLP.forward              paddlenlp/transformers/llama/modeling.py:632-652
+    LlamaLMHead / Criterion       paddlenlp/transformers/llama/modeling.py:1894-1921, 1799-1825
+and their autograd backward with an explicit saved-tensor plan.  Per layer, forward is
+    rmsnorm -> QKV GEMM(+bias) -> RoPE (in place) -> flash attention -> O GEMM(+residual epilogue)
+            -> rmsnorm -> gate|up GEMM -> SwiGLU -> down GEMM(+residual epilogue)
+i.e. 4 tcgen05 GEMMs, 1 tcgen05 attention and 4 HBM-bound fusions; the residual adds live in GEMM epilogues.
+
+Data layout in HBM
+  * ONE flat bf16 parameter buffer and ONE flat bf16 gradient buffer (the buffer the data-parallel all-reduce and
+    the AdamW kernel operate on).  Matrices first (weight-decayed), then norm weights and biases (not decayed).
+  * q/k/v weights are stored fused as [hidden, (nh + 2*kvh) * d] (= concat of the reference's three [in,out]
+    matrices along out) and gate/up as [hidden, 2*I]; the reference names are exposed as column-slice views.
+  * activations are token-major [T, features] bf16; q/k/v are strided views of the packed QKV projection.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .. import ops
+
+BF16 = torch.bfloat16
+
+
+def _align8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class DecoderEngine:
+    def __init__(self, config, device=None, prefix: Optional[str] = None):
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("DecoderEngine needs a CUDA device: the hot path has no CPU implementation")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.cfg = config
+        self.prefix = prefix or config.model_type          # "llama" / "qwen2": top-level name in state dicts
+        self.h = config.hidden_size
+        self.nh = config.num_attention_heads
+        self.kvh = config.num_key_value_heads
+        self.d = self.h // self.nh
+        self.I = config.intermediate_size
+        self.V = config.vocab_size
+        self.L = config.num_hidden_layers
+        self.eps = config.rms_norm_eps
+        self.qkv_bias = config.model_type == "qwen2"
+        if self.d != 128:
+            raise NotImplementedError(f"head_dim {self.d}: the attention kernels are written for head_dim 128")
+        if self.h % 8 or self.I % 8 or self.V % 8:
+            raise ValueError("hidden_size, intermediate_size and vocab_size must be multiples of 8")
+        self.qkv_n = (self.nh + 2 * self.kvh) * self.d
+
+        # ---- flat layout: [matrices | vectors] ----
+        mats: List[Tuple[str, Tuple[int, ...]]] = [("embed", (self.V, self.h))]
+        vecs: List[Tuple[str, Tuple[int, ...]]] = []
+        for i in range(self.L):
+            mats += [(f"l{i}.qkv_w", (self.h, self.qkv_n)), (f"l{i}.o_w", (self.nh * self.d, self.h)),
+                     (f"l{i}.gu_w", (self.h, 2 * self.I)), (f"l{i}.down_w", (self.I, self.h))]
+            vecs += [(f"l{i}.ln1", (self.h,)), (f"l{i}.ln2", (self.h,))]
+            if self.qkv_bias:
+                vecs += [(f"l{i}.qkv_b", (self.qkv_n,))]
+        mats += [("head", (self.h, self.V))]
+        vecs += [("norm", (self.h,))]
+        self._offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+        for name, shape in mats:
+            self._offsets[name] = (off, shape)
+            off += _align8(math.prod(shape))
+        self.decay_end = off
+        for name, shape in vecs:
+            self._offsets[name] = (off, shape)
+            off += _align8(math.prod(shape))
+        self.numel = off
+        self.flat_params = torch.zeros(self.numel, dtype=BF16, device=self.device)
+        self.flat_grads = torch.zeros(self.numel, dtype=BF16, device=self.device)
+        self.p = {n: self.flat_params[o:o + math.prod(s)].view(s) for n, (o, s) in self._offsets.items()}
+        self.g = {n: self.flat_grads[o:o + math.prod(s)].view(s) for n, (o, s) in self._offsets.items()}
+        self.grads_fresh = True          # True: the next backward overwrites instead of accumulating
+        self._rope = None
+        self._saved = None
+        self._bias_f32: Dict[int, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------------
+    # parameters
+    # ------------------------------------------------------------------------------------------------
+    def num_parameters(self) -> int:
+        return sum(math.prod(s) for _, s in self._offsets.values())
+
+    def init_weights(self, seed: int = 42):
+        """Reference init (llama/modeling.py:1386-1436): N(0, initializer_range) for every Linear / Embedding /
+        lm_head weight, o_proj and down_proj scaled by 1/sqrt(2L), RMSNorm weights 1, biases 0."""
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(seed)
+        std = self.cfg.initializer_range
+        chunk = 1 << 28
+        flat = self.flat_params
+        for s in range(0, self.decay_end, chunk):
+            e = min(self.decay_end, s + chunk)
+            flat[s:e].normal_(0.0, std, generator=gen)
+        factor = 1.0 / math.sqrt(2 * self.L)
+        for i in range(self.L):
+            self.p[f"l{i}.o_w"].mul_(factor)
+            self.p[f"l{i}.down_w"].mul_(factor)
+            self.p[f"l{i}.ln1"].fill_(1.0)
+            self.p[f"l{i}.ln2"].fill_(1.0)
+            if self.qkv_bias:
+                self.p[f"l{i}.qkv_b"].zero_()
+        self.p["norm"].fill_(1.0)
+        self._bias_f32.clear()
+
+    def named_views(self, grads: bool = False) -> Dict[str, torch.Tensor]:
+        """Reference-named views (llama/modeling.py:1243-1274 name map) onto the flat buffer."""
+        src = self.g if grads else self.p
+        pre = self.prefix
+        out = {f"{pre}.embed_tokens.weight": src["embed"]}
+        qn, kn = self.nh * self.d, self.kvh * self.d
+        for i in range(self.L):
+            lp = f"{pre}.layers.{i}."
+            w = src[f"l{i}.qkv_w"]
+            out[lp + "self_attn.q_proj.weight"] = w[:, :qn]
+            out[lp + "self_attn.k_proj.weight"] = w[:, qn:qn + kn]
+            out[lp + "self_attn.v_proj.weight"] = w[:, qn + kn:]
+            if self.qkv_bias:
+                b = src[f"l{i}.qkv_b"]
+                out[lp + "self_attn.q_proj.bias"] = b[:qn]
+                out[lp + "self_attn.k_proj.bias"] = b[qn:qn + kn]
+                out[lp + "self_attn.v_proj.bias"] = b[qn + kn:]
+            out[lp + "self_attn.o_proj.weight"] = src[f"l{i}.o_w"]
+            gu = src[f"l{i}.gu_w"]
+            out[lp + "mlp.gate_proj.weight"] = gu[:, :self.I]
+            out[lp + "mlp.up_proj.weight"] = gu[:, self.I:]
+            out[lp + "mlp.down_proj.weight"] = src[f"l{i}.down_w"]
+            out[lp + "input_layernorm.weight"] = src[f"l{i}.ln1"]
+            out[lp + "post_attention_layernorm.weight"] = src[f"l{i}.ln2"]
+        out[f"{pre}.norm.weight"] = src["norm"]
+        out["lm_head.weight"] = src["head"]
+        return out
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        views = self.named_views()
+        missing = [k for k in views if k not in sd]
+        if missing:
+            raise KeyError(f"state dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
+        with torch.no_grad():
+            for k, dst in views.items():
+                src = sd[k]
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise ValueError(f"{k}: shape {tuple(src.shape)} != {tuple(dst.shape)}")
+                dst.copy_(src.to(device=self.device, dtype=BF16))
+        self._bias_f32.clear()
+
+    def _bias(self, i: int) -> Optional[torch.Tensor]:
+        if not self.qkv_bias:
+            return None
+        b = self._bias_f32.get(i)
+        if b is None:
+            b = self.p[f"l{i}.qkv_b"].float()
+            self._bias_f32[i] = b
+        return b
+
+    def params_changed(self):
+        """Call after the optimizer updated the flat buffer (fp32 bias copies are stale)."""
+        self._bias_f32.clear()
+
+    def _rope_tables(self, need_pos: int):
+        if self._rope is None or self._rope[0].shape[0] < need_pos:
+            n = max(need_pos, int(getattr(self.cfg, "max_position_embeddings", 0) or 0))
+            self._rope = ops.rope_tables(self.d, n, float(self.cfg.rope_theta), self.device)
+        return self._rope
+
+    # ------------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------------
+    def _layer_fwd(self, i: int, x: torch.Tensor, B: int, S: int, pos, save: Optional[list]):
+        T = B * S
+        p = self.p
+        n1, rstd1 = ops.rmsnorm_fwd(x, p[f"l{i}.ln1"], self.eps)
+        qkv = ops.gemm(n1, p[f"l{i}.qkv_w"], bias=self._bias(i))
+        cos, sin = self._rope
+        ops.rope_inplace(qkv, cos, sin, S, self.nh + self.kvh, self.d, position_ids=pos)
+        q4 = qkv.view(B, S, self.qkv_n)
+        qn, kn = self.nh * self.d, self.kvh * self.d
+        q = q4[:, :, :qn].unflatten(2, (self.nh, self.d))
+        k = q4[:, :, qn:qn + kn].unflatten(2, (self.kvh, self.d))
+        v = q4[:, :, qn + kn:].unflatten(2, (self.kvh, self.d))
+        attn, lse = ops.flash_attn_fwd(q, k, v)
+        attn2 = attn.view(T, qn)
+        x1 = ops.gemm(attn2, p[f"l{i}.o_w"], residual=x)
+        n2, rstd2 = ops.rmsnorm_fwd(x1, p[f"l{i}.ln2"], self.eps)
+        gu = ops.gemm(n2, p[f"l{i}.gu_w"])
+        m = ops.swiglu_fwd(gu)
+        x2 = ops.gemm(m, p[f"l{i}.down_w"], residual=x1)
+        if save is not None:
+            save.append((x, rstd1, n1, qkv, attn2, lse, x1, rstd2, n2, gu, m))
+        return x2
+
+    def _prep_inputs(self, input_ids: torch.Tensor, position_ids: Optional[torch.Tensor]):
+        if input_ids.dim() != 2:
+            raise ValueError("input_ids must be [batch, seq]")
+        B, S = input_ids.shape
+        ids = input_ids.to(device=self.device, dtype=torch.int64, non_blocking=True).contiguous().view(-1)
+        pos = None
+        need = S
+        if position_ids is not None:
+            pos = position_ids.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous().view(-1)
+            need = max(S, int(getattr(self.cfg, "max_position_embeddings", S)))
+        self._rope_tables(need)
+        return B, S, ids, pos
+
+    def hidden_states(self, input_ids, position_ids=None, save: Optional[list] = None):
+        """Embedding + decoder stack + final norm -> ([T, h] normed states, pre-norm states, rstd)."""
+        B, S, ids, pos = self._prep_inputs(input_ids, position_ids)
+        x = ops.embedding_fwd(ids, self.p["embed"])
+        for i in range(self.L):
+            x = self._layer_fwd(i, x, B, S, pos, save)
+        hf, rstd_f = ops.rmsnorm_fwd(x, self.p["norm"], self.eps)
+        return B, S, ids, pos, x, hf, rstd_f
+
+    @torch.no_grad()
+    def forward_logits(self, input_ids, position_ids=None) -> torch.Tensor:
+        """Inference forward: logits [B, S, V] (bf16).  Nothing is saved for backward."""
+        B, S, ids, pos, x, hf, _ = self.hidden_states(input_ids, position_ids, save=None)
+        logits = ops.gemm(hf, self.p["head"])
+        return logits.view(B, S, self.V)
+
+    @torch.no_grad()
+    def forward_loss(self, input_ids, labels, position_ids=None, ignore_index: int = -100, keep_for_backward=True):
+        """Training forward: returns loss_out (device [2] = masked-mean loss, token count).
+        Activations are kept for backward()."""
+        save: Optional[list] = [] if keep_for_backward else None
+        B, S, ids, pos, x, hf, rstd_f = self.hidden_states(input_ids, position_ids, save=save)
+        logits = ops.gemm(hf, self.p["head"])
+        lab = labels.to(device=self.device, dtype=torch.int64, non_blocking=True).contiguous().view(-1)
+        loss_out, loss_tok, lse = ops.ce_fwd(logits, lab, ignore_index)
+        if keep_for_backward:
+            self._saved = dict(B=B, S=S, ids=ids, pos=pos, layers=save, x_last=x, hf=hf, rstd_f=rstd_f, logits=logits,
+                               labels=lab, loss_tok=loss_tok, lse=lse, loss_out=loss_out)
+        return loss_out, logits.view(B, S, self.V)
+
+    # ------------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def backward(self, grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None):
+        """Backward of the last forward_loss(): gradients are accumulated into flat_grads (or overwrite it if
+        grads_fresh).  The logits buffer is consumed (overwritten by dlogits)."""
+        st = self._saved
+        if st is None:
+            raise RuntimeError("backward() without a preceding forward_loss()")
+        self._saved = None
+        acc = not self.grads_fresh
+        p, g = self.p, self.g
+        B, S = st["B"], st["S"]
+        dlogits = ops.ce_bwd_(st["logits"], st["labels"], st["loss_tok"], st["lse"], st["loss_out"], grad_scale,
+                              grad_scale_dev)
+        dhf = ops.gemm(dlogits, p["head"], trans_b=True)
+        ops.gemm(st["hf"], dlogits, out=g["head"], trans_a=True, accumulate=acc)
+        del dlogits
+        st["logits"] = None
+        dx = ops.rmsnorm_bwd(dhf, st["x_last"], p["norm"], st["rstd_f"], g["norm"], accumulate_dw=acc)
+        del dhf
+        layers = st["layers"]
+        for i in range(self.L - 1, -1, -1):
+            dx = self._layer_bwd(i, dx, layers[i], B, S, st["pos"], acc)
+            layers[i] = None
+        if not acc:
+            g["embed"].zero_()
+        ops.embedding_bwd(st["ids"], dx, g["embed"])
+        self.grads_fresh = False
+
+    def _layer_bwd(self, i, dx2, saved, B, S, pos, acc):
+        (x, rstd1, n1, qkv, attn2, lse, x1, rstd2, n2, gu, m) = saved
+        p, g = self.p, self.g
+        T = B * S
+        qn, kn = self.nh * self.d, self.kvh * self.d
+        # ---- MLP ----
+        dm = ops.gemm(dx2, p[f"l{i}.down_w"], trans_b=True)
+        ops.gemm(m, dx2, out=g[f"l{i}.down_w"], trans_a=True, accumulate=acc)
+        del m
+        dgu = ops.swiglu_bwd(gu, dm)
+        del dm
+        dn2 = ops.gemm(dgu, p[f"l{i}.gu_w"], trans_b=True)
+        ops.gemm(n2, dgu, out=g[f"l{i}.gu_w"], trans_a=True, accumulate=acc)
+        del dgu, gu, n2
+        dx1 = ops.rmsnorm_bwd(dn2, x1, p[f"l{i}.ln2"], rstd2, g[f"l{i}.ln2"], dres=dx2, accumulate_dw=acc)
+        del dn2, dx2, x1
+        # ---- attention ----
+        dattn = ops.gemm(dx1, p[f"l{i}.o_w"], trans_b=True)
+        ops.gemm(attn2, dx1, out=g[f"l{i}.o_w"], trans_a=True, accumulate=acc)
+        q4 = qkv.view(B, S, self.qkv_n)
+        q = q4[:, :, :qn].unflatten(2, (self.nh, self.d))
+        k = q4[:, :, qn:qn + kn].unflatten(2, (self.kvh, self.d))
+        v = q4[:, :, qn + kn:].unflatten(2, (self.kvh, self.d))
+        dqkv = torch.empty_like(qkv)
+        d4 = dqkv.view(B, S, self.qkv_n)
+        dq = d4[:, :, :qn].unflatten(2, (self.nh, self.d))
+        dk = d4[:, :, qn:qn + kn].unflatten(2, (self.kvh, self.d))
+        dv = d4[:, :, qn + kn:].unflatten(2, (self.kvh, self.d))
+        ops.flash_attn_bwd(q, k, v, attn2.view(B, S, self.nh, self.d), dattn.view(B, S, self.nh, self.d), lse, dq, dk, dv)
+        del dattn, attn2, qkv, q, k, v, q4
+        cos, sin = self._rope
+        ops.rope_inplace(dqkv, cos, sin, S, self.nh + self.kvh, self.d, position_ids=pos, backward=True)
+        if self.qkv_bias:
+            ops.colsum(dqkv, g[f"l{i}.qkv_b"], accumulate=acc)
+        dn1 = ops.gemm(dqkv, p[f"l{i}.qkv_w"], trans_b=True)
+        ops.gemm(n1, dqkv, out=g[f"l{i}.qkv_w"], trans_a=True, accumulate=acc)
+        del dqkv, n1
+        dx0 = ops.rmsnorm_bwd(dn1, x, p[f"l{i}.ln1"], rstd1, g[f"l{i}.ln1"], dres=dx1, accumulate_dw=acc)
+        return dx0
+
+    def clear_grad(self):
+        """Lazy clear: the next backward overwrites the gradient buffer instead of accumulating into it."""
+        self.grads_fresh = True

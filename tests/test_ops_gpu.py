@@ -69,6 +69,19 @@ def test_gemm_accumulate_bias_and_views():
     assert maxerr(C, ref) < 2 ** -7
 
 
+def test_gemm_residual_epilogue():
+    o = ops()
+    M, N, K = 300, 520, 192
+    A = rand_bf16(M, K, seed=30).to(DEV)
+    W = rand_bf16(K, N, seed=31).to(DEV)
+    Rs = rand_bf16(M, N, seed=32, scale=4.0).to(DEV)
+    out = o.gemm(A, W, residual=Rs)
+    lin = (A.float() @ W.float()).to(BF16).float()            # Linear output rounding ...
+    ref = (lin + Rs.float()).to(BF16).float()                  # ... then the residual-add rounding
+    mism = (out.float() != ref).float().mean().item()
+    assert mism < 0.02 and maxerr(out, ref) < 2 ** -7           # only fp32 accumulation-order ties may differ
+
+
 def test_gemm_argument_errors():
     o = ops()
     from paddlenlp_b200._lib import B200Error

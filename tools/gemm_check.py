@@ -27,8 +27,8 @@ def run_case(cg, a_mn, b_mn, big):
     res = []
 
     def gemm(A, B, C, M, N, K, acc=0, bias=None):
-        _lib.call("b200_gemm_bf16_ex", _lib.ptr(A), _lib.ptr(B), _lib.ptr(C), _lib.ptr(bias), M, N, K,
-                  A.stride(0), B.stride(0), C.stride(0), a_mn, b_mn, acc, cg, 0, _lib.stream_ptr())
+        _lib.call("b200_gemm_bf16_ex", _lib.ptr(A), _lib.ptr(B), _lib.ptr(C), _lib.ptr(bias), None, M, N, K,
+                  A.stride(0), B.stride(0), C.stride(0), 0, a_mn, b_mn, acc, cg, 0, _lib.stream_ptr())
 
     def check(M, N, K, acc=0, use_bias=False, seed=0):
         g = torch.Generator(device="cpu").manual_seed(seed)
