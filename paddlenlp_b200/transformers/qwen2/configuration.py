@@ -36,6 +36,8 @@ class Qwen2Config(PretrainedConfig):
 
     @classmethod
     def qwen2_7b(cls, **kw):
-        return cls(vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_hidden_layers=28,
-                   num_attention_heads=28, num_key_value_heads=4, rms_norm_eps=1e-6, rope_theta=1000000.0,
-                   max_position_embeddings=32768, seq_length=2048, **kw)
+        base = dict(vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_hidden_layers=28,
+                    num_attention_heads=28, num_key_value_heads=4, rms_norm_eps=1e-6, rope_theta=1000000.0,
+                    max_position_embeddings=32768, seq_length=2048)
+        base.update(kw)
+        return cls(**base)
