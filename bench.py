@@ -1,0 +1,352 @@
+"""bench.py — tokens/s of the Llama-3-8B bf16 pre-training step (BASELINE.json configs[1] / configs[2]).
+
+    python bench.py [--gpus N --steps K --warmup W]                 # N = 1 (default) runs in-process
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                      # one rank per GPU, NCCL
+    python bench.py --impl reference ...                            # the reference's math on the host CPU (oracle port)
+
+One "step" = one optimizer step over per-GPU batch 8 x seq 4096 synthetic tokens (8 micro-batches of 1 sequence with
+gradient accumulation into the flat gradient buffer — the Trainer's gradient_accumulation_steps semantics,
+trainer.py:1045-1091), including the data-parallel gradient all-reduce and the AdamW update; nothing is skipped.
+Prints ONE JSON line (rank 0).  `value` has inputs resident in HBM; `e2e` runs the same step through the public
+Trainer-facing API (model(input_ids, labels) -> loss.backward() -> optimizer.step()) with pinned-host inputs, the H2D
+copies and a D2H read of the loss inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEQ = 4096
+PER_GPU_BATCH = 8
+METRIC = "tokens/sec Llama-3-8B seq4096 bf16 pretrain step (global, all GPUs)"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"], hbm=p["hbm_gbs"],
+                    source="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port): one decoder layer fwd+bwd + lm_head/criterion fwd+bwd on a bounded token sample
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(layer_tokens: int = 512, head_tokens: int = 128, threads: int | None = None):
+    """Times the oracle (oracle/llama_ref.py, bf16-rounding mode) on the host cores and extrapolates tokens/s of the
+    full Llama-3-8B step: tokens/s = 1 / (32 * t_layer/token + t_head/token).  Attention is evaluated at
+    seq = layer_tokens (not 4096), which under-counts its ~7 % share; stated in `sample`."""
+    import torch
+
+    from oracle import llama_ref as R
+
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    cfg = R.llama3_8b()
+    g = torch.Generator().manual_seed(0)
+    h, I, d = cfg.hidden_size, cfg.intermediate_size, cfg.head_dim
+    kvd = cfg.num_key_value_heads * d
+    p = "llama.layers.0."
+    cache = cpu_reference_sample.__dict__.setdefault("_weights", {})
+    if not cache:
+        def mat(*shape):
+            return torch.empty(*shape).normal_(0.0, 0.02, generator=g)
+        cache["w"] = {p + "self_attn.q_proj.weight": mat(h, h), p + "self_attn.k_proj.weight": mat(h, kvd),
+                      p + "self_attn.v_proj.weight": mat(h, kvd), p + "self_attn.o_proj.weight": mat(h, h),
+                      p + "mlp.gate_proj.weight": mat(h, I), p + "mlp.up_proj.weight": mat(h, I),
+                      p + "mlp.down_proj.weight": mat(I, h), p + "input_layernorm.weight": torch.ones(h),
+                      p + "post_attention_layernorm.weight": torch.ones(h)}
+        cache["head"] = mat(h, cfg.vocab_size)
+    w = {k: v.detach().requires_grad_(True) for k, v in cache["w"].items()}
+    x = torch.randn(1, layer_tokens, h, generator=g).requires_grad_(True)
+    cos, sin = R.rope_tables(d, layer_tokens, cfg.rope_theta)
+    t0 = time.perf_counter()
+    y = R.decoder_layer(x, w, p, cfg, cos, sin, "bf16")
+    y.sum().backward()
+    t_layer = time.perf_counter() - t0
+    head = cache["head"].detach().requires_grad_(True)
+    hs = torch.randn(1, head_tokens, h, generator=g).requires_grad_(True)
+    labels = torch.randint(0, cfg.vocab_size, (1, head_tokens), generator=g)
+    t0 = time.perf_counter()
+    logits = R.linear(R.rms_norm(hs, torch.ones(h), cfg.rms_norm_eps, "bf16"), head, None, "bf16")
+    R.criterion(logits, labels).backward()
+    t_head = time.perf_counter() - t0
+    per_token = cfg.num_hidden_layers * t_layer / layer_tokens + t_head / head_tokens
+    return dict(value=1.0 / per_token, unit="tokens/s", cores=cores, kind="port",
+                sample=(f"oracle/llama_ref.py (torch CPU, bf16-rounding mode) fwd+bwd of ONE full-width decoder layer on "
+                        f"{layer_tokens} tokens ({t_layer:.2f} s) + final-norm/lm_head/criterion on {head_tokens} tokens "
+                        f"({t_head:.2f} s); extrapolated x32 layers; optimizer step not included"),
+                seconds=t_layer + t_head)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_sample()
+        if i >= args.warmup:
+            vals.append(r)
+    v = statistics.mean(x["value"] for x in vals)
+    secs = statistics.mean(x["seconds"] for x in vals)
+    base = dict(vals[-1]); base["value"] = v
+    base.pop("seconds", None)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "Llama-3-8B bf16 pretrain step, per-GPU batch 8 x seq 4096 (BASELINE.json configs[1])",
+                      "note": "reference arm = the reference's math on host CPU cores (PaddlePaddle is not installable "
+                              "here); each step is a bounded sample, value extrapolated to the full model"},
+           "cpu_baseline": base,
+           "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    import paddlenlp_b200.transformers as T
+    from paddlenlp_b200 import _lib
+    from paddlenlp_b200 import distributed as dist_env
+    from paddlenlp_b200.optimizer import AdamW, ClipGradByGlobalNorm, LinearAnnealingWithWarmupDecay
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    dist_env.init_parallel_env("nccl")
+    dev = torch.device("cuda", local)
+    _lib.call("b200_device_check")
+
+    cfg = T.LlamaConfig.llama3_8b(num_hidden_layers=args.layers) if args.layers else T.LlamaConfig.llama3_8b()
+    model = T.LlamaForCausalLM(cfg)
+    eng = model.engine
+    dp = dist_env.DataParallel(model) if world > 1 else None
+    sched = LinearAnnealingWithWarmupDecay(3e-5, 3e-6, warmup_step=30, decay_step=10000)   # llm/config/llama/pretrain_argument.json
+    opt = AdamW(learning_rate=sched.get_lr, beta1=0.9, beta2=0.999, epsilon=1e-8, weight_decay=0.01,
+                grad_clip=ClipGradByGlobalNorm(1.0), multi_precision=True, engine=eng)
+    opt.grad_scale = 1.0 / world
+    mb = args.micro_batch
+    accum = PER_GPU_BATCH // mb
+    tokens_per_step = PER_GPU_BATCH * SEQ * world
+
+    # synthetic data: global batch drawn on the CPU with a fixed seed; rank r owns rows r*8 .. r*8+7
+    g = torch.Generator().manual_seed(1234)
+    nbatches = 2
+    tok = torch.randint(0, cfg.vocab_size, (nbatches, PER_GPU_BATCH * world, SEQ + 1), generator=g)
+    lo, hi = dist_env.shard_rows(PER_GPU_BATCH * world, rank, world)
+    host_ids = tok[:, lo:hi, :-1].contiguous().pin_memory()
+    host_lab = tok[:, lo:hi, 1:].contiguous().pin_memory()
+    dev_ids, dev_lab = host_ids.to(dev), host_lab.to(dev)
+    l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_resident(i):
+        b = i % nbatches
+        for m in range(accum):
+            eng.forward_loss(dev_ids[b, m * mb:(m + 1) * mb], dev_lab[b, m * mb:(m + 1) * mb])
+            eng.backward(1.0 / accum)
+        if dp is not None:
+            dp.sync_gradients()
+        opt.step(); sched.step(); opt.clear_grad()
+
+    def step_e2e(i):
+        """Public API path: pinned host batch -> H2D -> model(input_ids, labels) -> loss.backward() -> all-reduce ->
+        optimizer.step(); the step's loss is read back to the host."""
+        b = i % nbatches
+        total = torch.zeros((), device=dev)
+        for m in range(accum):
+            ids = host_ids[b, m * mb:(m + 1) * mb].to(dev, non_blocking=True)
+            lab = host_lab[b, m * mb:(m + 1) * mb].to(dev, non_blocking=True)
+            loss, _ = (dp or model)(input_ids=ids, labels=lab)
+            loss = loss / accum
+            loss.backward()
+            total += loss.detach()
+        if dp is not None:
+            dp.sync_gradients()
+        opt.step(); sched.step(); opt.clear_grad()
+        return total.item()          # D2H of the step loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        """K steps bracketed by barrier + synchronize; device time by CUDA events; max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    l2_flush.zero_()
+
+    # GEMM (dominant kernel family) timed live with CUDA events on the launching stream during the timed region
+    gemm_events = []
+
+    @contextlib.contextmanager
+    def hook(name, a):
+        if name == "b200_gemm_bf16_ex":
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            yield
+            e1.record()
+            gemm_events.append((e0, e1, 2.0 * a[5] * a[6] * a[7]))
+        else:
+            yield
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    _lib.call_hook = hook if rank == 0 else None
+    ms = timed(step_resident, args.steps)
+    _lib.call_hook = None
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in gemm_events)
+    gemm_flops = sum(f for _, _, f in gemm_events)
+    n_gemm = len(gemm_events)
+
+    losses = []
+    ms_e2e = timed(lambda i: losses.append(step_e2e(i)), args.steps)
+
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    ms_per_step = ms / args.steps
+    value = tokens_per_step / (ms_per_step / 1e3)
+    e2e_value = tokens_per_step / (ms_e2e / args.steps / 1e3)
+    flops_per_token = model.get_algorithmic_flops_per_token(SEQ)
+    tf_per_gpu = value / world * flops_per_token / 1e12
+    gemm_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+    out = {
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "Llama-3-8B bf16 pretrain step, per-GPU batch 8 x seq 4096 (BASELINE.json configs[1]; "
+                               "configs[2] at 8 GPUs)",
+                   "model": "Llama-3-8B" if not args.layers else f"Llama-3-8B width, {args.layers} layers (DEBUG, not the metric)",
+                   "global_batch": PER_GPU_BATCH * world, "seq_len": SEQ, "micro_batch": mb, "grad_accum": accum,
+                   "parallelism": f"dp{world}", "optimizer": "AdamW fp32 master + global-norm clip, in the timed step",
+                   "l2": "inputs (weights 16 GB, activations) exceed the 126 MB L2; a 192 MB flush precedes the timed region"},
+        "clocks": clocks,
+        "gpu_launches": launches,
+        "model_tflops_per_gpu": tf_per_gpu,
+        "mfu": {"algorithmic_gflop_per_token": flops_per_token / 1e9, "vs_nominal_2250": tf_per_gpu / 2250.0,
+                "vs_measured_burst": tf_per_gpu / peaks["bf16_burst"], "vs_measured_sustained": tf_per_gpu / peaks["bf16_sustained"]},
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all projection/lm_head GEMMs fwd+bwd)",
+                     "achieved": gemm_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": (gemm_tf / peaks["bf16_sustained"]) if gemm_tf else None, "peak_source": peaks["source"] + ", sustained",
+                     "launches_timed": n_gemm, "avg_launch_ms": gemm_ms / max(1, n_gemm), "share_of_step": gemm_ms / ms,
+                     "traffic": None},
+        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(PER_GPU_BATCH * SEQ * 8 * 2),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": losses[-1] if losses else None},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = cpu_reference_sample()
+            cb.pop("seconds", None)
+            out["cpu_baseline"] = cb
+        except Exception as e:  # the CPU column must never take the GPU number down with it
+            out["cpu_baseline"] = {"error": str(e)[:200]}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--micro-batch", type=int, default=1, choices=[1, 2, 4, 8])
+    ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (invalidates the metric)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

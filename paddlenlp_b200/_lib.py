@@ -88,10 +88,27 @@ class B200Error(RuntimeError):
     pass
 
 
+# CUDA kernels each entry point launches (used by bench.py to report `gpu_launches`; memsets are not counted).
+KERNELS_PER_CALL = {
+    "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_rmsnorm_fwd": 1, "b200_rmsnorm_bwd": 2, "b200_colsum_bf16": 2,
+    "b200_rope_inplace": 1, "b200_swiglu_fwd": 1, "b200_swiglu_bwd": 1, "b200_embedding_fwd": 1, "b200_embedding_bwd": 1,
+    "b200_fa_fwd": 1, "b200_fa_bwd": 3, "b200_ce_fwd": 2, "b200_ce_bwd": 1, "b200_argmax_bf16": 1, "b200_grad_sqnorm": 2,
+    "b200_adamw_step": 1, "b200_bf16_to_f32": 1,
+}
+launch_count = 0       # kernels launched through this module since import
+call_hook = None       # optional callable(name, args) -> context manager, used by bench.py to time one kernel family
+
+
 def call(name, *args):
     """Call an int-returning entry point; raise B200Error with the library's message on failure."""
+    global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args)
+    launch_count += KERNELS_PER_CALL.get(name, 1)
+    if call_hook is not None:
+        with call_hook(name, args):
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.b200_last_error()
         raise B200Error(f"{name} failed (rc={rc}): {msg.decode() if msg else '?'}")

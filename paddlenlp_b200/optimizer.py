@@ -1,0 +1,174 @@
+"""AdamW + ClipGradByGlobalNorm on the engine's flat buffers, and the LR schedules the reference's scripts use.
+
+Mirrors what Trainer.create_optimizer builds (paddlenlp/trainer/trainer.py:1717-1750):
+    paddle.optimizer.AdamW(learning_rate=lr_scheduler, beta1, beta2, epsilon, parameters, weight_decay,
+                           apply_decay_param_fun=<name has no "bias"/"norm">, grad_clip=ClipGradByGlobalNorm(max_grad_norm),
+                           multi_precision=True)
+One launch pair per step (squared-norm reduction, fused clip+AdamW) over the whole model instead of per-tensor ops.
+Schedules: get_scheduler linear/cosine/constant with warm-up (trainer_utils.py) and the pre-training
+Linear/CosineAnnealingWithWarmupDecay (llm/run_pretrain.py:520-536).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class ClipGradByGlobalNorm:
+    def __init__(self, clip_norm: float = 1.0):
+        self.clip_norm = float(clip_norm)
+
+
+class LRScheduler:
+    def __init__(self, learning_rate: float):
+        self.base_lr = float(learning_rate)
+        self.last_epoch = 0
+
+    def get_lr(self) -> float:
+        raise NotImplementedError
+
+    def __call__(self) -> float:
+        return self.get_lr()
+
+    def step(self):
+        self.last_epoch += 1
+
+    def state_dict(self):
+        return {"last_epoch": self.last_epoch}
+
+    def set_state_dict(self, sd):
+        self.last_epoch = sd["last_epoch"]
+
+
+class ConstantLR(LRScheduler):
+    def get_lr(self):
+        return self.base_lr
+
+
+class LinearDecayWithWarmup(LRScheduler):
+    """get_scheduler("linear"): linear warm-up then linear decay to 0 at num_training_steps."""
+
+    def __init__(self, learning_rate, num_training_steps, num_warmup_steps):
+        super().__init__(learning_rate)
+        self.total, self.warmup = int(num_training_steps), int(num_warmup_steps)
+
+    def get_lr(self):
+        s = self.last_epoch
+        if s < self.warmup:
+            return self.base_lr * s / max(1, self.warmup)
+        return self.base_lr * max(0.0, (self.total - s) / max(1, self.total - self.warmup))
+
+
+class CosineDecayWithWarmup(LRScheduler):
+    def __init__(self, learning_rate, num_training_steps, num_warmup_steps, num_cycles: float = 0.5):
+        super().__init__(learning_rate)
+        self.total, self.warmup, self.cycles = int(num_training_steps), int(num_warmup_steps), num_cycles
+
+    def get_lr(self):
+        s = self.last_epoch
+        if s < self.warmup:
+            return self.base_lr * s / max(1, self.warmup)
+        prog = (s - self.warmup) / max(1, self.total - self.warmup)
+        return self.base_lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * self.cycles * 2.0 * prog)))
+
+
+class LinearAnnealingWithWarmupDecay(LRScheduler):
+    """llm/run_pretrain.py:520-536 schedule family: warm-up to max_lr, linear anneal to min_lr over decay_step."""
+
+    def __init__(self, max_lr, min_lr, warmup_step, decay_step):
+        super().__init__(max_lr)
+        self.max_lr, self.min_lr, self.warmup_step, self.decay_step = max_lr, min_lr, warmup_step, decay_step
+
+    def _coeff(self, ratio):
+        return 1.0 - ratio
+
+    def get_lr(self):
+        s = self.last_epoch
+        if self.warmup_step > 0 and s <= self.warmup_step:
+            return self.max_lr * s / self.warmup_step
+        if s > self.decay_step:
+            return self.min_lr
+        ratio = (s - self.warmup_step) / max(1, self.decay_step - self.warmup_step)
+        return self.min_lr + self._coeff(ratio) * (self.max_lr - self.min_lr)
+
+
+class CosineAnnealingWithWarmupDecay(LinearAnnealingWithWarmupDecay):
+    def _coeff(self, ratio):
+        return 0.5 * (math.cos(math.pi * ratio) + 1.0)
+
+
+def get_scheduler(name, learning_rate, num_warmup_steps=0, num_training_steps=None, num_cycles=0.5, **_):
+    name = str(name).lower()
+    if name == "linear":
+        return LinearDecayWithWarmup(learning_rate, num_training_steps, num_warmup_steps)
+    if name == "cosine":
+        return CosineDecayWithWarmup(learning_rate, num_training_steps, num_warmup_steps, num_cycles)
+    if name in ("constant", "constant_with_warmup"):
+        return ConstantLR(learning_rate)
+    raise ValueError(f"unknown lr_scheduler_type {name}")
+
+
+class AdamW:
+    """Flat-buffer AdamW with fp32 master weights (multi_precision) and fused global-norm clipping."""
+
+    def __init__(self, learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, parameters=None, weight_decay=0.01,
+                 apply_decay_param_fun=None, grad_clip: Optional[ClipGradByGlobalNorm] = None, multi_precision=True,
+                 engine=None):
+        if engine is None:
+            raise ValueError("AdamW needs the model's DecoderEngine (flat parameter / gradient buffers)")
+        if not multi_precision:
+            raise NotImplementedError("bf16 parameters are always updated through fp32 master weights (AMP O2)")
+        self.engine = engine
+        self._lr = learning_rate
+        self.beta1, self.beta2, self.eps, self.weight_decay = beta1, beta2, epsilon, weight_decay
+        self.grad_clip = grad_clip
+        self.step_count = 0
+        self.grad_scale = 1.0            # e.g. 1/world_size after a SUM all-reduce
+        n = engine.numel
+        dev = engine.device
+        self.master = torch.empty(n, dtype=torch.float32, device=dev)
+        ops.bf16_to_f32(engine.flat_params, self.master)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def get_lr(self) -> float:
+        return self._lr() if callable(self._lr) else float(self._lr)
+
+    def set_lr(self, lr):
+        self._lr = lr
+
+    def sync_master_from_params(self):
+        ops.bf16_to_f32(self.engine.flat_params, self.master)
+
+    def step(self):
+        eng = self.engine
+        self.step_count += 1
+        max_norm = self.grad_clip.clip_norm if self.grad_clip is not None else 0.0
+        if max_norm > 0:
+            ops.grad_sqnorm(eng.flat_grads, scale=self.grad_scale, out=self.sqnorm)
+        ops.adamw_step(eng.flat_params, eng.flat_grads, self.master, self.exp_avg, self.exp_avg_sq,
+                       self.sqnorm if max_norm > 0 else None, decay_end=eng.decay_end, lr=self.get_lr(), beta1=self.beta1,
+                       beta2=self.beta2, eps=self.eps, weight_decay=self.weight_decay, step=self.step_count,
+                       grad_scale=self.grad_scale, max_grad_norm=max_norm)
+        eng.params_changed()
+
+    def clear_grad(self, set_to_zero: bool = False):
+        self.engine.clear_grad()
+
+    def grad_norm(self) -> torch.Tensor:
+        """Global gradient norm of the last step (device scalar; reading it synchronises)."""
+        return self.sqnorm.sqrt()
+
+    def state_dict(self):
+        return {"step": self.step_count, "master": self.master, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+
+    def set_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.master.copy_(sd["master"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])

@@ -1,0 +1,340 @@
+"""Trainer — the pure data-parallel subset of paddlenlp/trainer/trainer.py on the native engine.
+
+Call pattern reproduced:
+    Trainer(model, criterion, args, data_collator, train_dataset, ..., optimizers=(None, lr_scheduler))   :273-286
+    .train()                        :687   -> _inner_training_loop :855
+       training_step                :2211  (H2D of the batch, bf16 O2 forward, loss / grad_accum, loss.backward())
+       gradient exchange            :1934-1954 / :1079-1110  -> ONE all-reduce of the flat gradient buffer
+       optimizer.step / lr_scheduler.step / optimizer.clear_grad     :1171-1185
+       _maybe_log_save_evaluate     :1388-1455 (all-gathered mean loss, speed_metrics keys of trainer_utils.py:351-380)
+Differences by design: the whole model's gradients live in one buffer, so there are no reducer buckets; gradient
+averaging (1/world) is folded into the optimizer kernel; the step is host-sync free except at logging steps.
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, List, Optional
+
+import torch
+
+from .. import distributed as dist_env
+from ..optimizer import AdamW, ClipGradByGlobalNorm, get_scheduler
+from .training_args import TrainingArguments
+
+
+@dataclass
+class TrainOutput:
+    global_step: int
+    training_loss: float
+    metrics: Dict[str, float]
+
+
+class TrainerCallback:
+    def on_train_begin(self, args, state, control, **kw): ...
+    def on_step_begin(self, args, state, control, **kw): ...
+    def on_step_end(self, args, state, control, **kw): ...
+    def on_log(self, args, state, control, logs=None, **kw): ...
+    def on_train_end(self, args, state, control, **kw): ...
+
+
+class PrinterCallback(TrainerCallback):
+    def on_log(self, args, state, control, logs=None, **kw):
+        if args.should_log and logs is not None:
+            print(", ".join(f"{k}: {v}" for k, v in logs.items()), flush=True)
+
+
+@dataclass
+class TrainerState:
+    global_step: int = 0
+    epoch: float = 0.0
+    max_steps: int = 0
+    log_history: Optional[List[Dict[str, float]]] = None
+
+
+class _PhaseTimers:
+    """CUDA-event phase timers with the reference's four phase names (plugins/timer.py: read-data,
+    forward-backward, all-reduce, optimizer-step); resolved lazily so they never block the stream."""
+
+    NAMES = ("read-data", "forward-backward", "all-reduce", "optimizer-step")
+
+    def __init__(self, enabled: bool):
+        self.enabled = enabled
+        self.pending: List = []
+        self.totals = {n: 0.0 for n in self.NAMES}
+
+    def start(self, name):
+        if not self.enabled:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return (name, e0)
+
+    def stop(self, tok):
+        if tok is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.pending.append((tok[0], tok[1], e1))
+
+    def collect(self) -> Dict[str, float]:
+        for name, e0, e1 in self.pending:
+            e1.synchronize()
+            self.totals[name] += e0.elapsed_time(e1)
+        self.pending.clear()
+        out, self.totals = self.totals, {n: 0.0 for n in self.NAMES}
+        return out
+
+
+def default_data_collator(features: List[Dict[str, Any]]) -> Dict[str, torch.Tensor]:
+    out = {}
+    for k in features[0]:
+        out[k] = torch.stack([torch.as_tensor(f[k]) for f in features])
+    return out
+
+
+class Trainer:
+    def __init__(self, model=None, criterion=None, args: Optional[TrainingArguments] = None, data_collator=None,
+                 train_dataset=None, eval_dataset=None, tokenizer=None, compute_metrics=None,
+                 callbacks: Optional[List[TrainerCallback]] = None, optimizers=(None, None)):
+        if args is None:
+            args = TrainingArguments()
+        self.args = args
+        self.model = model
+        self.criterion = criterion
+        self.data_collator = data_collator or default_data_collator
+        self.train_dataset = train_dataset
+        self.eval_dataset = eval_dataset
+        self.tokenizer = tokenizer
+        self.optimizer, self.lr_scheduler = optimizers
+        self.callbacks = list(callbacks or []) + [PrinterCallback()]
+        self.state = TrainerState(log_history=[])
+        self.control = None
+        self.model_wrapped = model
+        self.timers = _PhaseTimers(not args.skip_profile_timer)
+        torch.manual_seed(args.seed)
+
+    # ------------------------------------------------------------------------------------------------
+    def get_train_dataloader(self):
+        a = self.args
+        ds = self.train_dataset
+        if ds is None:
+            raise ValueError("Trainer: training requires a train_dataset.")
+        world, rank = a.dataset_world_size, a.dataset_rank
+        if isinstance(ds, torch.utils.data.IterableDataset):
+            return torch.utils.data.DataLoader(ds, batch_size=a.per_device_train_batch_size, collate_fn=self.data_collator,
+                                               num_workers=a.dataloader_num_workers, pin_memory=True)
+        sampler = torch.utils.data.distributed.DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=False,
+                                                                   drop_last=a.dataloader_drop_last) if world > 1 else None
+        return torch.utils.data.DataLoader(ds, batch_size=a.per_device_train_batch_size, sampler=sampler, shuffle=False,
+                                           collate_fn=self.data_collator, drop_last=a.dataloader_drop_last,
+                                           num_workers=a.dataloader_num_workers, pin_memory=True)
+
+    def create_optimizer_and_scheduler(self, num_training_steps: int):
+        self.create_scheduler(num_training_steps)
+        self.create_optimizer(self.lr_scheduler)
+
+    def create_scheduler(self, num_training_steps: int):
+        a = self.args
+        if self.lr_scheduler is None:
+            warmup = a.warmup_steps if a.warmup_steps > 0 else int(a.warmup_ratio * num_training_steps)
+            decay = a.decay_steps if a.decay_steps > 0 else num_training_steps
+            self.lr_scheduler = get_scheduler(a.lr_scheduler_type, learning_rate=a.learning_rate, num_warmup_steps=warmup,
+                                              num_training_steps=decay, num_cycles=a.num_cycles)
+        return self.lr_scheduler
+
+    def create_optimizer(self, lr_scheduler=None):
+        a = self.args
+        if self.optimizer is None:
+            # trainer.py:1730-1748: decay only parameters without "bias"/"norm" in the name == the matrices, which the
+            # engine lays out first in the flat buffer (decay_end).
+            self.optimizer = AdamW(learning_rate=(lr_scheduler.get_lr if lr_scheduler is not None else a.learning_rate),
+                                   beta1=a.adam_beta1, beta2=a.adam_beta2, epsilon=a.adam_epsilon,
+                                   weight_decay=a.weight_decay,
+                                   grad_clip=ClipGradByGlobalNorm(a.max_grad_norm) if a.max_grad_norm > 0 else None,
+                                   multi_precision=True, engine=self._engine())
+        return self.optimizer
+
+    def _engine(self):
+        m = self.model
+        return getattr(m, "engine", None) or getattr(getattr(m, "_layers", None), "engine", None)
+
+    def _wrap_model(self, model):
+        # trainer.py:1934-1954: world_size > 1 and not hybrid -> paddle.DataParallel(model)
+        if self.args.world_size > 1 and not isinstance(model, dist_env.DataParallel):
+            model = dist_env.DataParallel(model, find_unused_parameters=bool(self.args.ddp_find_unused_parameters))
+        return model
+
+    # ------------------------------------------------------------------------------------------------
+    def _prepare_inputs(self, inputs: Dict[str, Any]) -> Dict[str, Any]:
+        """Pinned host -> device (trainer.py:2099-2114)."""
+        dev = self._engine().device
+        out = {}
+        for k, v in inputs.items():
+            if isinstance(v, torch.Tensor):
+                if not v.is_cuda and not v.is_pinned():
+                    v = v.pin_memory()
+                out[k] = v.to(dev, non_blocking=True)
+            else:
+                out[k] = v
+        return out
+
+    def compute_loss(self, model, inputs, return_outputs=False):
+        """trainer.py:2157-2197: criterion(outputs, labels) when a criterion is given, else the model's own loss."""
+        if self.criterion is not None:
+            labels = inputs.pop("labels")
+            outputs = model(**inputs)
+            logits = outputs[0] if isinstance(outputs, (tuple, list)) else outputs.logits
+            loss = self.criterion(logits, labels)
+        else:
+            outputs = model(**inputs)
+            loss = outputs[0] if isinstance(outputs, (tuple, list)) else outputs.loss
+        return (loss, outputs) if return_outputs else loss
+
+    def training_step(self, model, inputs) -> torch.Tensor:
+        """trainer.py:2211-2244."""
+        inputs = self._prepare_inputs(inputs)
+        loss = self.compute_loss(model, inputs)
+        if self.args.gradient_accumulation_steps > 1:
+            loss = loss / self.args.gradient_accumulation_steps
+        loss.backward()
+        return loss.detach()
+
+    # ------------------------------------------------------------------------------------------------
+    def train(self, resume_from_checkpoint=None) -> TrainOutput:
+        a = self.args
+        if resume_from_checkpoint:
+            raise NotImplementedError("checkpoint resume is a 'next' item (SURVEY.md §8f rank 2)")
+        dl = self.get_train_dataloader()
+        accum = max(1, a.gradient_accumulation_steps)
+        try:
+            steps_per_epoch = max(len(dl) // accum, 1)
+        except TypeError:
+            steps_per_epoch = None
+        if a.max_steps > 0:
+            max_steps = a.max_steps
+            epochs = math.ceil(max_steps / steps_per_epoch) if steps_per_epoch else 10 ** 9
+        else:
+            if steps_per_epoch is None:
+                raise ValueError("max_steps must be set for iterable datasets")
+            max_steps = math.ceil(a.num_train_epochs * steps_per_epoch)
+            epochs = math.ceil(a.num_train_epochs)
+        self.state.max_steps = max_steps
+        self.create_optimizer_and_scheduler(max_steps)
+        model = self._wrap_model(self.model)
+        self.model_wrapped = model
+        engine = self._engine()
+        world = a.world_size
+        self.optimizer.grad_scale = 1.0 / world
+        self.optimizer.clear_grad()
+        for cb in self.callbacks:
+            cb.on_train_begin(a, self.state, self.control)
+
+        dev = engine.device
+        tr_loss = torch.zeros((), dtype=torch.float32, device=dev)
+        logged_loss_total = 0.0
+        logged_step = 0
+        t_log = time.time()
+        t_start = t_log
+        seq_len = a.max_seq_length or getattr(self.model.config, "seq_length", None)
+        done = False
+        for epoch in range(epochs):
+            sampler = getattr(dl, "sampler", None)
+            if hasattr(sampler, "set_epoch"):
+                sampler.set_epoch(epoch)
+            it = iter(dl)
+            step = -1
+            while True:
+                tok = self.timers.start("read-data")
+                try:
+                    inputs = next(it)
+                except StopIteration:
+                    break
+                self.timers.stop(tok)
+                step += 1
+                if step % accum == 0:
+                    for cb in self.callbacks:
+                        cb.on_step_begin(a, self.state, self.control)
+                last_micro = (step + 1) % accum == 0
+                tok = self.timers.start("forward-backward")
+                tr_loss += self.training_step(model, inputs)
+                self.timers.stop(tok)
+                if not last_micro:
+                    continue
+                tok = self.timers.start("all-reduce")
+                if world > 1:
+                    model.sync_gradients()
+                self.timers.stop(tok)
+                tok = self.timers.start("optimizer-step")
+                self.optimizer.step()
+                self.lr_scheduler.step()
+                self.optimizer.clear_grad()
+                self.timers.stop(tok)
+                self.state.global_step += 1
+                self.state.epoch = epoch + (step + 1) / max(1, (steps_per_epoch or 1) * accum)
+                for cb in self.callbacks:
+                    cb.on_step_end(a, self.state, self.control)
+                gs = self.state.global_step
+                if (a.logging_steps > 0 and gs % a.logging_steps == 0) or (a.logging_first_step and gs == 1):
+                    # trainer.py:1388-1455: mean of the all-gathered loss over the interval
+                    loss_t = tr_loss.clone()
+                    if world > 1:
+                        torch.distributed.all_reduce(loss_t)
+                        loss_t /= world
+                    loss_val = loss_t.item()
+                    tr_loss.zero_()
+                    nsteps = gs - logged_step
+                    dt = time.time() - t_log
+                    samples = nsteps * a.per_device_train_batch_size * accum * world
+                    logs = {"loss": round(loss_val / nsteps, 8), "learning_rate": float(f"{self.optimizer.get_lr():.3e}"),
+                            "global_step": gs, "interval_runtime": round(dt, 4),
+                            "interval_samples_per_second": round(samples / dt, 4),
+                            "interval_steps_per_second": round(nsteps / dt, 4)}
+                    if seq_len:
+                        tps = samples / dt * seq_len / world
+                        logs["interval_tokens_per_second_per_device"] = round(tps, 4)
+                        if hasattr(self.model, "get_model_flops"):
+                            logs["interval_hardware_tflops_per_device"] = round(
+                                tps * self.model.get_model_flops(seq_length=seq_len) / seq_len / 2 ** 40, 2)
+                            logs["interval_algorithmic_tflops_per_device"] = round(
+                                tps * self.model.get_algorithmic_flops_per_token(seq_len) / 1e12, 2)
+                    if not a.skip_profile_timer:
+                        logs.update({f"timer_{k}_ms": round(v, 2) for k, v in self.timers.collect().items()})
+                    if math.isnan(loss_val) or math.isinf(loss_val):
+                        raise ValueError(f"PaddleRecall error(102): Loss contains inf or nan values, its value is {loss_val}")
+                    logged_loss_total += loss_val
+                    logged_step = gs
+                    t_log = time.time()
+                    self.log(logs)
+                if gs >= max_steps:
+                    done = True
+                    break
+            if done:
+                break
+        torch.cuda.synchronize(dev)
+        if self.state.global_step > logged_step:
+            loss_t = tr_loss.clone()
+            if world > 1:
+                torch.distributed.all_reduce(loss_t)
+                loss_t /= world
+            logged_loss_total += loss_t.item()
+        runtime = time.time() - t_start
+        gs = max(1, self.state.global_step)
+        metrics = {"train_runtime": round(runtime, 4),
+                   "train_samples_per_second": round(gs * a.per_device_train_batch_size * accum * world / runtime, 4),
+                   "train_steps_per_second": round(gs / runtime, 4), "train_loss": logged_loss_total / gs}
+        for cb in self.callbacks:
+            cb.on_train_end(a, self.state, self.control)
+        return TrainOutput(self.state.global_step, logged_loss_total / gs, metrics)
+
+    def log(self, logs: Dict[str, float]):
+        self.state.log_history.append(dict(logs))
+        for cb in self.callbacks:
+            cb.on_log(self.args, self.state, self.control, logs=logs)
+
+    def save_model(self, output_dir: Optional[str] = None):
+        if self.args.process_index == 0:
+            m = getattr(self.model, "_layers", self.model)
+            m.save_pretrained(output_dir or self.args.output_dir)
