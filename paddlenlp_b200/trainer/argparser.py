@@ -31,16 +31,17 @@ class PdArgumentParser(argparse.ArgumentParser):
         if dataclasses.is_dataclass(dataclass_types):
             dataclass_types = [dataclass_types]
         self.dataclass_types = list(dataclass_types)
+        import typing
+
         for dt in self.dataclass_types:
+            hints = typing.get_type_hints(dt)
             for f in dataclasses.fields(dt):
-                tp = _base_type(f.type) if not isinstance(f.type, str) else str
+                tp = _base_type(hints.get(f.name, str))
                 kw = {}
-                if tp is bool or f.type in ("bool", "Optional[bool]"):
+                if tp is bool:
                     kw.update(type=_str2bool, nargs="?", const=True)
                 elif tp in (int, float, str):
                     kw.update(type=tp)
-                elif isinstance(f.type, str):
-                    kw.update(type={"int": int, "float": float}.get(f.type.replace("Optional[", "").rstrip("]"), str))
                 default = f.default if f.default is not dataclasses.MISSING else None
                 self.add_argument(f"--{f.name}", default=default, **kw)
 

@@ -1,0 +1,134 @@
+"""Host-side logic that needs no GPU: configs, schedules, argument parsing, batch sharding, and the data-parallel
+gradient exchange on 2 CPU processes (gloo)."""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_configs_match_reference_defaults_and_presets():
+    import paddlenlp_b200.transformers as T
+
+    c = T.LlamaConfig()                      # llama/configuration.py:131-161 defaults (Llama-1-7B)
+    assert (c.vocab_size, c.hidden_size, c.intermediate_size, c.num_hidden_layers, c.num_key_value_heads) == (32000, 4096, 11008, 32, 32)
+    assert c.rms_norm_eps == 1e-6 and c.rope_theta == 10000.0 and c.use_flash_attention
+    assert c.n_embd == 4096                 # attribute_map
+    c8 = T.LlamaConfig.llama3_8b()
+    assert (c8.vocab_size, c8.intermediate_size, c8.num_key_value_heads, c8.rope_theta) == (128256, 14336, 8, 500000.0)
+    q = T.Qwen2Config.qwen2_7b()
+    assert (q.hidden_size, q.num_hidden_layers, q.num_attention_heads, q.num_key_value_heads, q.vocab_size) == (3584, 28, 28, 4, 152064)
+    rt = T.LlamaConfig.from_dict(json.loads(c8.to_json_string()))
+    assert rt.to_dict() == c8.to_dict()
+    with pytest.raises(NotImplementedError):
+        T.LlamaConfig(tensor_parallel_degree=2)
+
+
+def test_flop_accounting_matches_survey():
+    import paddlenlp_b200.transformers as T
+    from paddlenlp_b200.transformers.model_utils import PretrainedModel
+
+    class Dummy(PretrainedModel):
+        def __init__(self, cfg):
+            torch.nn.Module.__init__(self)
+            self.config = cfg
+
+    m = Dummy(T.LlamaConfig.llama3_8b())
+    assert abs(m.get_algorithmic_flops_per_token(4096) / 1e9 - 48.249) < 0.01
+    assert abs(m.get_model_flops(seq_length=4096) / 4096 / 1e9 - 56.305) < 0.01     # caculate_llm_flops convention
+    mq = Dummy(T.Qwen2Config.qwen2_7b())
+    assert abs(mq.get_algorithmic_flops_per_token(2048) / 1e9 - 43.655) < 0.01
+
+
+def test_lr_schedules():
+    from paddlenlp_b200.optimizer import CosineAnnealingWithWarmupDecay, LinearAnnealingWithWarmupDecay, get_scheduler
+
+    s = get_scheduler("linear", 1e-3, num_warmup_steps=10, num_training_steps=110)
+    vals = []
+    for _ in range(111):
+        vals.append(s.get_lr()); s.step()
+    assert vals[0] == 0.0 and abs(vals[10] - 1e-3) < 1e-12 and abs(vals[60] - 5e-4) < 1e-9 and vals[110] == 0.0
+    c = CosineAnnealingWithWarmupDecay(3e-5, 3e-6, warmup_step=30, decay_step=1000)
+    c.last_epoch = 30
+    assert abs(c.get_lr() - 3e-5) < 1e-12
+    c.last_epoch = 1000
+    assert abs(c.get_lr() - 3e-6) < 1e-12
+    l = LinearAnnealingWithWarmupDecay(1.0, 0.0, warmup_step=0, decay_step=100)
+    l.last_epoch = 50
+    assert abs(l.get_lr() - 0.5) < 1e-12
+
+
+def test_argparser_json_and_cmdline(tmp_path, monkeypatch):
+    from paddlenlp_b200.trainer import PdArgumentParser, TrainingArguments
+
+    cfg = tmp_path / "a.json"
+    cfg.write_text(json.dumps({"per_device_train_batch_size": 1, "gradient_accumulation_steps": 8, "max_steps": 5,
+                               "learning_rate": 3e-5, "bf16": True}))
+    monkeypatch.setattr(sys, "argv", ["run_pretrain.py", str(cfg), "--max_steps", "7", "--weight_decay", "0.01"])
+    (args,) = PdArgumentParser(TrainingArguments).parse_json_file_and_cmd_lines()
+    assert args.max_steps == 7 and args.gradient_accumulation_steps == 8 and args.weight_decay == 0.01
+    assert args.world_size == 1 and args.data_parallel_degree == 1 and not args.use_hybrid_parallel
+    with pytest.raises(NotImplementedError):
+        TrainingArguments(sharding="stage2")
+
+
+def test_shard_rows():
+    from paddlenlp_b200.distributed import shard_rows
+
+    assert [shard_rows(64, r, 8) for r in (0, 3, 7)] == [(0, 8), (24, 32), (56, 64)]
+    with pytest.raises(ValueError):
+        shard_rows(10, 0, 4)
+
+
+WORKER = textwrap.dedent("""
+    import os, sys, torch
+    sys.path.insert(0, %r)
+    from paddlenlp_b200 import distributed as D
+    D.init_parallel_env("gloo")
+    rank, world = D.get_rank(), D.get_world_size()
+    assert world == 2
+
+    class FakeEngine:                      # the flat-buffer contract of DecoderEngine, on the CPU
+        def __init__(self):
+            self.flat_params = torch.full((1024,), float(rank + 1))
+            self.flat_grads = torch.arange(1024, dtype=torch.float32) * (rank + 1)
+
+    class FakeModel(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.engine = FakeEngine()
+
+    m = D.DataParallel(FakeModel())
+    assert torch.equal(m.engine.flat_params, torch.full((1024,), 1.0)), "rank-0 parameter broadcast at wrap time"
+    with m.no_sync():
+        assert m._sync is False
+    m.sync_gradients()                     # ONE all-reduce(SUM) of the whole gradient buffer
+    assert torch.equal(m.engine.flat_grads, torch.arange(1024, dtype=torch.float32) * 3)
+    mean = m.engine.flat_grads * (1.0 / world)      # the 1/world factor lives in the optimizer's grad_scale
+    assert torch.equal(mean, torch.arange(1024, dtype=torch.float32) * 1.5)
+    lo, hi = D.shard_rows(16)
+    assert (lo, hi) == (rank * 8, rank * 8 + 8)
+    torch.distributed.barrier()
+    print("OK", rank)
+""")
+
+
+def test_data_parallel_exchange_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    import socket
+
+    with socket.socket() as sk:             # a free port (tests/parallel_launch.py in the reference does the same)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "OK 0" in r.stdout and "OK 1" in r.stdout
