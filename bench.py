@@ -5,7 +5,7 @@
         bench.py --gpus N --steps K --warmup W                      # one rank per GPU, NCCL
     python bench.py --impl reference ...                            # the reference's math on the host CPU (oracle port)
 
-One "step" = one optimizer step over per-GPU batch 8 x seq 4096 synthetic tokens (8 micro-batches of 1 sequence with
+One "step" = one optimizer step over per-GPU batch 8 x seq 4096 synthetic tokens (4 micro-batches of 2 sequences with
 gradient accumulation into the flat gradient buffer — the Trainer's gradient_accumulation_steps semantics,
 trainer.py:1045-1091), including the data-parallel gradient all-reduce and the AdamW update; nothing is skipped.
 Prints ONE JSON line (rank 0).  `value` has inputs resident in HBM; `e2e` runs the same step through the public
@@ -307,6 +307,7 @@ def run_native(args):
                    "l2": "inputs (weights 16 GB, activations) exceed the 126 MB L2; a 192 MB flush precedes the timed region"},
         "clocks": clocks,
         "gpu_launches": launches,
+        "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
         "model_tflops_per_gpu": tf_per_gpu,
         "mfu": {"algorithmic_gflop_per_token": flops_per_token / 1e9, "vs_nominal_2250": tf_per_gpu / 2250.0,
                 "vs_measured_burst": tf_per_gpu / peaks["bf16_burst"], "vs_measured_sustained": tf_per_gpu / peaks["bf16_sustained"]},
@@ -334,7 +335,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--micro-batch", type=int, default=1, choices=[1, 2, 4, 8])
+    ap.add_argument("--micro-batch", type=int, default=2, choices=[1, 2, 4, 8])
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -71,7 +71,7 @@ def test_gemm_accumulate_bias_and_views():
 
 def test_gemm_residual_epilogue():
     o = ops()
-    M, N, K = 300, 520, 192
+    M, N, K = 304, 520, 192
     A = rand_bf16(M, K, seed=30).to(DEV)
     W = rand_bf16(K, N, seed=31).to(DEV)
     Rs = rand_bf16(M, N, seed=32, scale=4.0).to(DEV)
