@@ -7,10 +7,10 @@
 // Replaces Paddle-core flash_attn_grad (reference: fusion_ops.py:240-246 backward of scaled_dot_product_attention;
 // wrapper shape in csrc/gpu/flash_attn_bwd.cc:22-92).
 //
-// One CTA = one (batch, kv-head, 128-row kv tile); it loops over the q-heads of the GQA group and the q tiles
-// i >= j, so dK/dV are accumulated in TMEM without atomics; dQ tiles are reduced into an fp32 buffer with vector
-// red.global.add (converted to bf16 by b200_fa_bwd_dq_finish, fused with nothing else so that RoPE-backward can
-// run on the bf16 result in place).
+// One CTA = one (batch, q-head, 128-row kv tile); it loops over the q tiles i >= j, accumulating this head's dK/dV in
+// TMEM.  Work units are per q-head (not per kv-head) so that the 4096 units of a Llama-3 micro-batch balance over
+// 148 SMs (heaviest first); the GQA group's dK/dV partials and the dQ tiles are reduced into fp32 buffers by the TMA
+// unit (cp.reduce.async.bulk.tensor .add — no LSU atomics), then converted to bf16 by a finishing kernel.
 //   warp 0       TMA producer (K_j, V_j once; Q_i, dO_i per iteration)
 //   warp 1       MMA issuer   (5 UMMA GEMMs per iteration, operands K-major or MN-major straight from the same
 //                              swizzled tiles: Q and dO are consumed both ways)
@@ -26,24 +26,45 @@ namespace fab {
 constexpr int TILE_BYTES = 128 * 128 * 2;
 constexpr int HALF_BYTES = TILE_BYTES / 2;
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = 6 * TILE_BYTES + 256 + 1024;   // K, V, Q, dO, P, dS
+constexpr int STAGE_BYTES = 4 * 2 * 4096;                 // per-warp double-buffered 32x32 fp32 staging for TMA reduce
+constexpr int SMEM_BYTES = 6 * TILE_BYTES + STAGE_BYTES + 256 + 1024;   // K, V, Q, dO, P, dS, staging
 
 struct Params {
   int S, B, nh, kvh;
   float scale, scale_log2;
   const float* lse;     // [B, nh, S]  natural log
   const float* delta;   // [B, nh, S]  rowsum(dO o O)
-  float* dq_acc;        // [B, S, nh, 128] fp32
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// TMEM accumulator (this warp's 32 lanes x 128 fp32 columns) -> fp32 staging -> TMA reduce-add of 32x32 boxes.
+__device__ __forceinline__ void reduce_out_tile(uint32_t tsrc, uint8_t* stage, const CUtensorMap* tm, int lane, int head,
+                                                int row0, int batch) {
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint8_t* buf = stage + (ch & 1) * 4096;
+    if (lane == 0) tma_store_wait_read<1>();     // the reduce issued from this buffer two chunks ago has read it
+    __syncwarp();
+    uint32_t o[32];
+    tmem_ld32(tsrc + ch * 32, o);
+    tmem_ld_wait();
+    const uint32_t row_s = smem_u32(buf) + lane * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      st_shared_v4(row_s + ((c ^ (lane & 7)) << 4), make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]));
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_reduce_add_4d(tm, buf, ch * 32, head, row0, batch);
+      tma_store_commit();
+    }
+  }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-              const __grid_constant__ CUtensorMap tmdK, const __grid_constant__ CUtensorMap tmdV, const Params p) {
+              const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdK,
+              const __grid_constant__ CUtensorMap tmdV, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -52,7 +73,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint8_t* sdO = smem + 3 * TILE_BYTES;
   uint8_t* sP = smem + 4 * TILE_BYTES;
   uint8_t* sdS = smem + 5 * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * TILE_BYTES);
+  uint8_t* sStage = smem + 6 * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + STAGE_BYTES);
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;
   uint64_t* qdo_empty = bars + 2;
@@ -65,10 +87,10 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (p.S + 127) / 128;
   const int jt = static_cast<int>(blockIdx.x);     // kv tile; tile 0 has the most work and is scheduled first
-  const int kv_head = blockIdx.y, batch = blockIdx.z;
-  const int group = p.nh / p.kvh;
+  const int hq = blockIdx.y, batch = blockIdx.z;
+  const int kv_head = hq / (p.nh / p.kvh);
   const int n_q = num_tiles - jt;                  // q tiles jt .. num_tiles-1
-  const int n_iter = group * n_q;
+  const int n_iter = n_q;
   const int kv0 = jt * 128;
 
   if (warp == 0 && lane == 0) {
@@ -97,8 +119,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tma_load_4d(&tmV, kv_full, sV, 0, kv_head, kv0, batch);
       tma_load_4d(&tmV, kv_full, sV + HALF_BYTES, 64, kv_head, kv0, batch);
       for (int n = 0; n < n_iter; ++n) {
-        const int hq = kv_head * group + n / n_q;
-        const int q0 = (jt + n % n_q) * 128;
+        const int q0 = (jt + n) * 128;
         mbar_wait(qdo_empty, (n & 1) ^ 1u);
         mbar_arrive_expect_tx(qdo_full, 2 * TILE_BYTES);
         tma_load_4d(&tmQ, qdo_full, sQ, 0, hq, q0, batch);
@@ -149,9 +170,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int r = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
+    uint8_t* my_stage = sStage + quad * 8192;
     for (int n = 0; n < n_iter; ++n) {
-      const int hq = kv_head * group + n / n_q;
-      const int qt = jt + n % n_q;
+      const int qt = jt + n;
       const int q0 = qt * 128;
       const bool row_ok = (q0 + r) < p.S;
       const size_t stat_idx = (static_cast<size_t>(batch) * p.nh + hq) * p.S + q0 + r;
@@ -190,58 +211,17 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);
-      // dQ tile read-out and reduction into the fp32 buffer
+      // dQ tile read-out: TMEM -> fp32 staging -> TMA reduce-add into the fp32 dQ buffer (rows >= S are clipped)
       mbar_wait(dq_full, n & 1);
       tc_fence_after();
-      float* dq_row = p.dq_acc + ((static_cast<size_t>(batch) * p.S + q0 + r) * p.nh + hq) * 128;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t o[32];
-        tmem_ld32(tS + lane_off + ch * 32, o);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            red_add_v4(dq_row + ch * 32 + c * 4, __uint_as_float(o[4 * c]), __uint_as_float(o[4 * c + 1]),
-                       __uint_as_float(o[4 * c + 2]), __uint_as_float(o[4 * c + 3]));
-        }
-      }
+      reduce_out_tile(tS + lane_off, my_stage, &tmdQ, lane, hq, q0 + quad * 32, batch);
       tc_fence_before();
       mbar_arrive(dq_empty);
     }
-    // epilogue: dK, dV -> bf16 -> smem (reuse Q / dO tiles) -> TMA store
-    const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO);
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t tsrc = which == 0 ? tdK : tdV;
-      const uint32_t sdst = which == 0 ? aQ : adO;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t o[32];
-        tmem_ld32(tsrc + lane_off + ch * 32, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          const int c16 = ch * 4 + c8;
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[c8 * 8 + 0]), __uint_as_float(o[c8 * 8 + 1]));
-          v.y = pack_bf16x2(__uint_as_float(o[c8 * 8 + 2]), __uint_as_float(o[c8 * 8 + 3]));
-          v.z = pack_bf16x2(__uint_as_float(o[c8 * 8 + 4]), __uint_as_float(o[c8 * 8 + 5]));
-          v.w = pack_bf16x2(__uint_as_float(o[c8 * 8 + 6]), __uint_as_float(o[c8 * 8 + 7]));
-          st_shared_v4(sdst + (c16 >> 3) * HALF_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4), v);
-        }
-      }
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(1, 128);
-    if (warp == 2 && lane == 0) {
-      tma_store_4d(&tmdK, sQ, 0, kv_head, kv0, batch);
-      tma_store_4d(&tmdK, sQ + HALF_BYTES, 64, kv_head, kv0, batch);
-      tma_store_4d(&tmdV, sdO, 0, kv_head, kv0, batch);
-      tma_store_4d(&tmdV, sdO + HALF_BYTES, 64, kv_head, kv0, batch);
-      tma_store_commit();
-      tma_store_wait<0>();
-    }
+    // epilogue: this head's dK / dV partials -> fp32 reduce-add (the GQA group's heads sum in L2)
+    reduce_out_tile(tdK + lane_off, my_stage, &tmdK, lane, kv_head, kv0 + quad * 32, batch);
+    reduce_out_tile(tdV + lane_off, my_stage, &tmdV, lane, kv_head, kv0 + quad * 32, batch);
+    if (lane == 0) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -279,7 +259,7 @@ __global__ void fa_bwd_delta_kernel(const bf16* __restrict__ o, const bf16* __re
   if (row < total && sub == 0) delta[(static_cast<size_t>(b) * nh + h) * S + s] = acc;
 }
 
-// dq (bf16, token stride lddq) = bf16(dq_acc fp32 [B*S, nh*128])
+// out (bf16, token stride ld) = bf16(acc fp32 [tokens, width])
 __global__ void fa_bwd_dq_finish_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, int64_t tokens, int width,
                                         int64_t lddq) {
   const int64_t nchunk_row = width >> 3;
@@ -302,13 +282,20 @@ static int make_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S, int
   uint32_t box[4] = {64, 1, 128, 1};
   return encode_tmap_bf16(tm, base, 4, dims, strides, box);
 }
+// fp32 accumulation buffer [B, S, heads, 128] contiguous; 32x32 boxes for the per-warp TMA reduce-add.
+static int make_acc_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S, int64_t heads) {
+  uint64_t dims[4] = {128, static_cast<uint64_t>(heads), static_cast<uint64_t>(S), static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {128 * 4, static_cast<uint64_t>(heads) * 128 * 4, static_cast<uint64_t>(S) * heads * 128 * 4};
+  uint32_t box[4] = {32, 1, 32, 1};
+  return encode_tmap_f32(tm, base, 4, dims, strides, box);
+}
 
 }  // namespace fab
 }  // namespace b200
 
 extern "C" int64_t b200_fa_bwd_workspace_bytes(int64_t B, int64_t S, int64_t num_heads, int64_t head_dim) {
-  // fp32 dQ accumulation buffer + delta
-  return B * S * num_heads * head_dim * 4 + B * num_heads * S * 4;
+  // fp32 dQ accumulation buffer + fp32 dK/dV accumulation buffers (at most num_heads wide) + delta
+  return 3 * B * S * num_heads * head_dim * 4 + B * num_heads * S * 4;
 }
 
 extern "C" int b200_fa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
@@ -325,8 +312,10 @@ extern "C" int b200_fa_bwd(const void* q, const void* k, const void* v, const vo
                      lddk % 8 == 0 && lddv % 8 == 0,
                  "fa_bwd: token strides must be multiples of 8");
   float* dq_acc = static_cast<float*>(workspace);
-  float* delta = dq_acc + B * S * num_heads * 128;
-  cudaError_t e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(B) * S * num_heads * 128 * 4, stream);
+  float* dk_acc = dq_acc + B * S * num_heads * 128;
+  float* dv_acc = dk_acc + B * S * num_kv_heads * 128;
+  float* delta = dq_acc + 3 * B * S * num_heads * 128;
+  cudaError_t e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(B) * S * (num_heads + 2 * num_kv_heads) * 128 * 4, stream);
   if (e != cudaSuccess) {
     set_last_error("fa_bwd memset: %s", cudaGetErrorString(e));
     return static_cast<int>(e);
@@ -339,14 +328,15 @@ extern "C" int b200_fa_bwd(const void* q, const void* k, const void* v, const vo
     int rc = check_launch("fa_bwd(delta)");
     if (rc) return rc;
   }
-  CUtensorMap tmQ, tmK, tmV, tmdO, tmdK, tmdV;
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV;
   int rc;
   if ((rc = make_map(&tmQ, q, B, S, num_heads, ldq)) != 0) return rc;
   if ((rc = make_map(&tmK, k, B, S, num_kv_heads, ldk)) != 0) return rc;
   if ((rc = make_map(&tmV, v, B, S, num_kv_heads, ldv)) != 0) return rc;
   if ((rc = make_map(&tmdO, dout, B, S, num_heads, lddo)) != 0) return rc;
-  if ((rc = make_map(&tmdK, dk, B, S, num_kv_heads, lddk)) != 0) return rc;
-  if ((rc = make_map(&tmdV, dv, B, S, num_kv_heads, lddv)) != 0) return rc;
+  if ((rc = make_acc_map(&tmdQ, dq_acc, B, S, num_heads)) != 0) return rc;
+  if ((rc = make_acc_map(&tmdK, dk_acc, B, S, num_kv_heads)) != 0) return rc;
+  if ((rc = make_acc_map(&tmdV, dv_acc, B, S, num_kv_heads)) != 0) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     e = cudaFuncSetAttribute(fa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -360,9 +350,9 @@ extern "C" int b200_fa_bwd(const void* q, const void* k, const void* v, const vo
   p.S = (int)S; p.B = (int)B; p.nh = (int)num_heads; p.kvh = (int)num_kv_heads;
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
-  dim3 grid(static_cast<unsigned>((S + 127) / 128), static_cast<unsigned>(num_kv_heads), static_cast<unsigned>(B));
-  fa_bwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmdK, tmdV, p);
+  p.lse = lse; p.delta = delta;
+  dim3 grid(static_cast<unsigned>((S + 127) / 128), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
+  fa_bwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p);
   if ((rc = check_launch("fa_bwd")) != 0) return rc;
   {
     const int64_t tokens = B * S;
@@ -373,7 +363,16 @@ extern "C" int b200_fa_bwd(const void* q, const void* k, const void* v, const vo
     if (blocks > cap) blocks = cap;
     fa_bwd_dq_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(dq_acc, static_cast<bf16*>(dq), tokens,
                                                                               width, lddq);
-    rc = check_launch("fa_bwd(dq finish)");
+    if ((rc = check_launch("fa_bwd(dq finish)")) != 0) return rc;
+    const int kvw = static_cast<int>(num_kv_heads * 128);
+    int64_t kblocks = (tokens * (kvw / 8) + 255) / 256;
+    if (kblocks > cap) kblocks = cap;
+    fa_bwd_dq_finish_kernel<<<static_cast<unsigned>(kblocks), 256, 0, stream>>>(dk_acc, static_cast<bf16*>(dk), tokens, kvw,
+                                                                               lddk);
+    if ((rc = check_launch("fa_bwd(dk finish)")) != 0) return rc;
+    fa_bwd_dq_finish_kernel<<<static_cast<unsigned>(kblocks), 256, 0, stream>>>(dv_acc, static_cast<bf16*>(dv), tokens, kvw,
+                                                                               lddv);
+    rc = check_launch("fa_bwd(dv finish)");
   }
   return rc;
 }

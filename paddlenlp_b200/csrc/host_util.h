@@ -23,6 +23,9 @@ int sm_count();  // multiprocessors of the current device (cached per device)
 // Returns 0 on success, <0 on failure (message recorded).
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                      const uint32_t* box);
+// Same for fp32 elements (box[0] * 4 must be <= 128); used for TMA reduce-add into fp32 accumulation buffers.
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                    const uint32_t* box);
 
 }  // namespace b200
 
