@@ -17,6 +17,7 @@
 #ifndef B200NLP_H_
 #define B200NLP_H_
 
+#include <stdbool.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -44,7 +45,8 @@ int b200_device_check(void);
  *   accumulate != 0: C_new = bf16(fp32(C_old) + acc)   (gradient accumulation, cf. llm/utils/fused_layers.py:36-74)
  *   bias            : optional fp32 [N], added in fp32 before the rounding (Qwen2 q/k/v bias, qwen2/modeling.py:478-480)
  * Reference call sites: llama/modeling.py:933-935,1103 (q/k/v/o), :632-652 (gate/up/down), :1894-1921 (lm_head).
- * Requires M, N, K, lda, ldb, ldc multiples of 8 and 16-byte aligned base pointers.
+ * Requires lda, ldb, ldc multiples of 8 elements and 16-byte aligned base pointers (M, N, K themselves are free: TMA
+ * zero-fills / clips partial tiles).
  */
 int b200_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N, int64_t K,
                    int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int accumulate,
@@ -133,6 +135,80 @@ int b200_adamw_step(void* params_bf16, const void* grads_bf16, float* master, fl
                     const float* grad_sqnorm, int64_t n, int64_t decay_end, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int64_t step, float grad_scale, float max_grad_norm, cudaStream_t stream);
 int b200_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t stream);
+
+/* ======================================================================================================================
+ * Generation path (FusedMultiTransformer / paddlenlp_ops, bf16 non-quantised subset)
+ * ====================================================================================================================== */
+
+/* Fused residual add + RMSNorm: r = bf16(x + residual) (residual may be NULL), normed = RMSNorm(r) * w.
+ * normed or residual_out may be NULL (last layer: residual add only).  Replaces Paddle-core
+ * fused_rms_norm(x, w, ..., residual=) -> (out, residual_out) as called by
+ * experimental/transformers/fused_transformer_layers.py:799-805, 937-949, 976-999. */
+int b200_add_rmsnorm(const void* x, const void* residual, const void* w, void* normed, void* residual_out, int64_t rows,
+                     int64_t h, float eps, cudaStream_t stream);
+
+/* KV cache tensor: bf16 [2, B, kvh, max_len, d] (K then V), the shape the reference predictor allocates
+ * (llm/predict/predictor.py:697-706; experimental/transformers/llama/modeling.py:1768-1794).
+ * Prefill: copy rotated K and V rows of the packed [B*S, ld] QKV projection for positions s < seq_lens[b]
+ * (seq_lens may be NULL = all S).  Replaces write_cache_kv (csrc/gpu/write_cache_kv.cu:23-99). */
+int b200_write_cache_kv(const void* qkv, void* cache, const int32_t* seq_lens, int64_t B, int64_t S, int64_t num_heads,
+                        int64_t num_kv_heads, int64_t head_dim, int64_t max_len, int64_t ld, cudaStream_t stream);
+/* Decode: rotate-half RoPE of the new token's q,k at position seq_lens[b] (in place in qkv [B, ld]) and append k,v to
+ * the cache.  Replaces the RoPE + cache-write half of masked_multihead_attention
+ * (fused_transformer_layers.py:884-893) / append_attn/decoder_write_cache_with_rope_kernel.cu:47-390. */
+int b200_decode_rope_append(void* qkv, void* cache, const float* cos_table, const float* sin_table, const int32_t* seq_lens,
+                            int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len,
+                            int64_t ld, cudaStream_t stream);
+/* Decode attention of one query token per sequence over cache positions [0, seq_lens[b]] (GQA, head_dim 128);
+ * out [B, nh*d].  Replaces the attention half of masked_multihead_attention / append_attention decode
+ * (csrc/gpu/append_attn/append_attention_c16_impl.cuh:377-744). */
+int b200_decode_attention(const void* qkv, const void* cache, const int32_t* seq_lens, void* out, int64_t B,
+                          int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len, int64_t ld,
+                          float softmax_scale, cudaStream_t stream);
+
+/* Bookkeeping ops, same semantics as the reference custom ops (file:line beside each). bool = 1-byte flags. */
+/* get_padding_offset_v2 (+ remove padding): csrc/gpu/get_padding_offset_v2.cu:17-80 */
+int b200_get_padding_offset(const int64_t* input_ids, const int32_t* cum_offsets, const int32_t* seq_lens,
+                            int64_t* x_remove_padding, int32_t* padding_offset, int32_t* cum_offsets_out,
+                            int32_t* cu_seqlens_q, int32_t* cu_seqlens_k, int64_t bsz, int64_t max_seq_len,
+                            cudaStream_t stream);
+/* rebuild_padding_v2: csrc/gpu/rebuild_padding_v2.cu:18-69 (one row per sequence = its last valid token) */
+int b200_rebuild_padding(const void* tmp_out, const int32_t* cum_offsets, const int32_t* seq_lens_decoder,
+                         const int32_t* seq_lens_encoder, void* out, int64_t bsz, int64_t max_len, int64_t dim,
+                         cudaStream_t stream);
+/* set_value_by_flags_and_idx: csrc/gpu/set_value_by_flags.cu:17-35 ; _v2: csrc/gpu/set_value_by_flags_v2.cu */
+int b200_set_value_by_flags_and_idx(const bool* stop_flags, int64_t* pre_ids_all, const int64_t* pre_ids_now,
+                                    const int64_t* step_idx, int64_t bs, int64_t length, cudaStream_t stream);
+int b200_set_value_by_flags_and_idx_v2(const bool* stop_flags, int64_t* pre_ids_all, const int64_t* input_ids,
+                                       const int32_t* seq_lens_encoder, const int32_t* seq_lens_decoder,
+                                       const int64_t* step_idx, int64_t bs, int64_t length, int64_t length_input_ids,
+                                       cudaStream_t stream);
+/* get_token_penalty_multi_scores(_v2): csrc/gpu/token_penalty_multi_scores_v2.cu:19-139 (CPU twin
+ * csrc/cpu/src/token_penalty_multi_scores.cc:18-85).  In place on fp32 logits [bs, length]; temperatures / bad_tokens may
+ * be NULL (v1 op); workspace = bs*length int32. */
+int b200_token_penalty_multi_scores(const int64_t* pre_ids, float* logits, const float* penalty_scores,
+                                    const float* frequency_scores, const float* presence_scores, const float* temperatures,
+                                    const int64_t* bad_tokens, const int64_t* cur_len, const int64_t* min_len,
+                                    const int64_t* eos_token_id, int32_t* workspace, int64_t bs, int64_t length,
+                                    int64_t length_id, int64_t bad_len, int64_t eos_len, cudaStream_t stream);
+/* set_stop_value_multi_ends: v1 mode 2 csrc/gpu/stop_generation_multi_ends.cu:45-56 ; v2 …_v2.cu:35-59 */
+int b200_set_stop_value_multi_ends(bool* stop_flags, int64_t* topk_ids, int64_t* next_tokens, const int64_t* end_ids,
+                                   const int32_t* seq_lens, int64_t bs, int64_t end_length, int v2, cudaStream_t stream);
+/* update_inputs: csrc/gpu/update_inputs.cu:18-82 */
+int b200_update_inputs(bool* not_need_stop, int32_t* seq_lens_this_time, int32_t* seq_lens_encoder,
+                       int32_t* seq_lens_decoder, int64_t* input_ids, const int64_t* stop_nums, const bool* stop_flags,
+                       const bool* is_block_step, const int64_t* next_tokens, int64_t bsz, int64_t max_bsz,
+                       int64_t input_ids_stride, cudaStream_t stream);
+/* One fused state update per decode step of the dense-cache generate loop
+ * (update_model_kwargs_for_generation, experimental/transformers/generation_utils.py:185-260): step_idx, length stop,
+ * EOS stop, pre_ids history, seq_len_decoder, next/tgt ids, optional token log (column out_col, or *out_col_dev which is
+ * then incremented on the device so that the step is CUDA-graph replayable), stop_count = number of stopped rows. */
+int b200_generate_step_update(int64_t* next_tokens, bool* stop_flags, int64_t* step_idx, const int64_t* max_dec_len,
+                              int32_t* seq_len_decoder, int64_t* pre_ids, int64_t pre_len, const int64_t* eos_ids,
+                              int64_t eos_len, int64_t* out_tokens, int64_t out_stride, int64_t out_col,
+                              int64_t* out_col_dev, int32_t* stop_count, int64_t bs, cudaStream_t stream);
+int b200_argmax_f32(const float* logits, int64_t* out, int64_t rows, int64_t vocab, int64_t ld, cudaStream_t stream);
+int b200_bf16_rows_to_f32(const void* src, float* dst, int64_t rows, int64_t cols, int64_t ld, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,171 @@
+"""CPU oracle of the generation path (TEST INFRASTRUCTURE ONLY — see oracle/llama_ref.py header).
+
+  * bookkeeping ops restated in numpy from the reference's CUDA kernels (file:line beside each function); pinned
+    against the known-answer vectors of the reference's own op tests (csrc/xpu/test/python/test_*.py), committed as
+    tests/golden/bookkeeping.json by oracle/make_bookkeeping_golden.py.
+  * greedy generation restated as "run the (uncached) oracle forward on the growing sequence and take the argmax" —
+    the definition KV-cache decoding must agree with (tests/transformers/llama/test_modeling.py:171-219 cache
+    consistency, atol 1e-3).  The fused-inference numerics themselves are unpinned in the reference (every
+    dygraph-vs-fused comparison in tests/llm/test_predictor.py is @skip).
+"""
+import numpy as np
+import torch
+
+from . import llama_ref as R
+
+
+# csrc/gpu/get_padding_offset_v2.cu:17-53
+def get_padding_offset_v2(input_ids, cum_offsets, token_num, seq_lens):
+    bsz, max_len = input_ids.shape
+    seq_lens = seq_lens.reshape(-1)
+    x_remove = np.zeros(int(token_num), np.int64)
+    padding_offset = np.zeros(int(token_num), np.int32)
+    cum_out = np.zeros(bsz, np.int32)
+    cu_q = np.zeros(bsz + 1, np.int32)
+    for bi in range(bsz):
+        cum_offset = 0 if bi == 0 else int(cum_offsets[bi - 1])
+        for i in range(int(seq_lens[bi])):
+            padding_offset[bi * max_len - cum_offset + i] = cum_offset
+            x_remove[bi * max_len - cum_offset + i] = input_ids[bi, i]   # RemovePaddingV2 gets cum_offsets_out (:80-85)
+        cum_out[bi] = cum_offset
+        cu_q[bi + 1] = (bi + 1) * max_len - int(cum_offsets[bi])
+    return x_remove, cum_out, padding_offset, cu_q, cu_q.copy()
+
+
+# csrc/gpu/rebuild_padding_v2.cu:18-69
+def rebuild_padding_v2(tmp_out, cum_offsets, seq_lens_decoder, seq_lens_encoder, max_len):
+    bsz = seq_lens_encoder.reshape(-1).shape[0]
+    out = np.zeros((bsz, tmp_out.shape[1]), tmp_out.dtype)
+    for bi in range(bsz):
+        dec, enc = int(seq_lens_decoder.reshape(-1)[bi]), int(seq_lens_encoder.reshape(-1)[bi])
+        if dec == 0 and enc == 0:
+            continue
+        seq_id = enc - 1 if dec == 0 else 0
+        out[bi] = tmp_out[bi * max_len - int(cum_offsets[bi]) + seq_id]
+    return out
+
+
+# csrc/gpu/token_penalty_multi_scores_v2.cu:19-139 (order: min-length EOS mask, repeat penalty + temperature, bad words)
+def token_penalty_multi_scores_v2(pre_ids, logits, penalty, frequency, presence, temperatures, bad_tokens, cur_len, min_len,
+                                  eos_token_id):
+    logits = logits.astype(np.float32).copy()
+    bs, length = logits.shape
+    for bi in range(bs):
+        if cur_len[bi] >= 0 and cur_len[bi] < min_len[bi]:
+            for e in eos_token_id:
+                logits[bi, int(e)] = np.float32(-1e10)
+        times = np.zeros(length, np.int32)
+        if cur_len[bi] >= 0:
+            for t in pre_ids[bi]:
+                if t < 0:
+                    break
+                times[int(t)] += 1
+        a, b, g = np.float32(penalty[bi]), np.float32(frequency[bi]), np.float32(presence[bi])
+        for i in range(length):
+            v = logits[bi, i]
+            if times[i] != 0:
+                v = v * a if v < 0 else v / a
+                v = np.float32(v - np.float32(times[i]) * b - g)
+            logits[bi, i] = np.float32(v / np.float32(1.0 if temperatures is None else temperatures[bi]))
+        if bad_tokens is not None:
+            for t in bad_tokens:
+                if 0 <= t < length:
+                    logits[bi, int(t)] = np.float32(-1e10)
+    return logits
+
+
+# csrc/gpu/stop_generation_multi_ends_v2.cu:35-59
+def set_stop_value_multi_ends_v2(topk_ids, stop_flags, seq_lens, end_ids, next_tokens):
+    topk_ids, stop_flags, next_tokens = topk_ids.copy(), stop_flags.copy(), next_tokens.copy()
+    for i in range(topk_ids.shape[0]):
+        if stop_flags[i]:
+            if seq_lens[i] == 0:
+                topk_ids[i] = -1
+            else:
+                topk_ids[i] = end_ids[0]
+                next_tokens[i] = end_ids[0]
+        else:
+            next_tokens[i] = topk_ids[i]
+        if topk_ids[i] in end_ids:
+            stop_flags[i] = True
+    return topk_ids, stop_flags, next_tokens
+
+
+# csrc/gpu/stop_generation_multi_ends.cu:45-56 (mode 2)
+def set_stop_value_multi_ends(topk_ids, stop_flags, end_ids):
+    topk_ids, stop_flags = topk_ids.copy(), stop_flags.copy()
+    for i in range(topk_ids.shape[0]):
+        if stop_flags[i]:
+            topk_ids[i] = end_ids[0]
+        if topk_ids[i] in end_ids:
+            stop_flags[i] = True
+    return topk_ids, stop_flags
+
+
+# csrc/gpu/set_value_by_flags_v2.cu
+def set_value_by_flags_and_idx_v2(pre_ids_all, input_ids, seq_lens_encoder, seq_lens_decoder, step_idx, stop_flags):
+    pre = pre_ids_all.copy()
+    for i in range(pre.shape[0]):
+        if stop_flags[i]:
+            continue
+        dec, enc = int(seq_lens_decoder[i]), int(seq_lens_encoder[i])
+        if dec == 0 and enc == 0:
+            continue
+        if step_idx[i] >= 0:
+            pre[i, int(step_idx[i])] = input_ids[i, enc - 1] if dec == 0 else input_ids[i, 0]
+    return pre
+
+
+# csrc/gpu/set_value_by_flags.cu:17-25
+def set_value_by_flags_and_idx(pre_ids_all, pre_ids_now, step_idx, stop_flags):
+    pre = pre_ids_all.copy()
+    for i in range(pre.shape[0]):
+        if not stop_flags[i] and step_idx[i] >= 0:
+            pre[i, int(step_idx[i])] = pre_ids_now[i]
+    return pre
+
+
+# csrc/gpu/update_inputs.cu:18-66
+def update_inputs(stop_flags, seq_lens_this_time, seq_lens_encoder, seq_lens_decoder, input_ids, stop_nums, next_tokens,
+                  is_block_step):
+    this_time, enc, dec, ids = seq_lens_this_time.copy(), seq_lens_encoder.copy(), seq_lens_decoder.copy(), input_ids.copy()
+    bsz, max_bsz = this_time.shape[0], stop_flags.shape[0]
+    stop_sum = 0
+    for t in range(max_bsz):
+        if t < bsz:
+            stop_sum += 0 if is_block_step[t] else int(stop_flags[t])
+        else:
+            stop_sum += 1
+    for t in range(bsz):
+        stop = bool(stop_flags[t])
+        dec[t] = 0 if stop else (enc[t] if dec[t] == 0 else dec[t] + 1)
+        this_time[t] = 0 if stop else 1
+        enc[t] = 0
+        ids[t, 0] = next_tokens[t]
+    return np.array([stop_sum < int(stop_nums[0])]), this_time, enc, dec, ids
+
+
+def greedy_generate(input_ids: torch.Tensor, w, cfg: R.RefConfig, max_new: int, eos=None, mode: str = "bf16",
+                    seq_lens=None):
+    """Greedy decoding by full re-evaluation (no cache).  input_ids [B, S] right padded; returns [B, max_new] with the
+    reference's stop semantics (after EOS a sequence keeps emitting EOS)."""
+    B, S = input_ids.shape
+    lens = [S] * B if seq_lens is None else [int(x) for x in seq_lens]
+    seqs = [input_ids[b, : lens[b]].tolist() for b in range(B)]
+    out = torch.full((B, max_new), -1, dtype=torch.int64)
+    stopped = [False] * B
+    margins = torch.zeros(B, max_new)
+    for t in range(max_new):
+        for b in range(B):
+            if stopped[b]:
+                out[b, t] = eos if eos is not None else -1
+                continue
+            logits = R.model_forward(torch.tensor([seqs[b]]), w, cfg, mode=mode)[0, -1]
+            top2 = logits.topk(2).values
+            margins[b, t] = (top2[0] - top2[1]) / logits.abs().max()
+            tok = int(logits.argmax())
+            out[b, t] = tok
+            seqs[b].append(tok)
+            if eos is not None and tok == eos:
+                stopped[b] = True
+    return out, margins

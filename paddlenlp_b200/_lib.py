@@ -45,6 +45,20 @@ _SIGNATURES = {
     "b200_grad_sqnorm": [P, P, P, I64, F, P],
     "b200_adamw_step": [P, P, P, P, P, P, I64, I64, F, F, F, F, F, I64, F, F, P],
     "b200_bf16_to_f32": [P, P, I64, P],
+    "b200_add_rmsnorm": [P, P, P, P, P, I64, I64, F, P],
+    "b200_write_cache_kv": [P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
+    "b200_decode_rope_append": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, P],
+    "b200_decode_attention": [P, P, P, P, I64, I64, I64, I64, I64, I64, F, P],
+    "b200_get_padding_offset": [P, P, P, P, P, P, P, P, I64, I64, P],
+    "b200_rebuild_padding": [P, P, P, P, P, I64, I64, I64, P],
+    "b200_set_value_by_flags_and_idx": [P, P, P, P, I64, I64, P],
+    "b200_set_value_by_flags_and_idx_v2": [P, P, P, P, P, P, I64, I64, I64, P],
+    "b200_token_penalty_multi_scores": [P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, P],
+    "b200_set_stop_value_multi_ends": [P, P, P, P, P, I64, I64, I, P],
+    "b200_update_inputs": [P, P, P, P, P, P, P, P, P, I64, I64, I64, P],
+    "b200_generate_step_update": [P, P, P, P, P, P, I64, P, I64, P, I64, I64, P, P, I64, P],
+    "b200_argmax_f32": [P, P, I64, I64, I64, P],
+    "b200_bf16_rows_to_f32": [P, P, I64, I64, I64, P],
 }
 _RESTYPE = {
     "b200_last_error": c_char_p,
@@ -93,7 +107,7 @@ KERNELS_PER_CALL = {
     "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_rmsnorm_fwd": 1, "b200_rmsnorm_bwd": 2, "b200_colsum_bf16": 2,
     "b200_rope_inplace": 1, "b200_swiglu_fwd": 1, "b200_swiglu_bwd": 1, "b200_embedding_fwd": 1, "b200_embedding_bwd": 1,
     "b200_fa_fwd": 1, "b200_fa_bwd": 3, "b200_ce_fwd": 2, "b200_ce_bwd": 1, "b200_argmax_bf16": 1, "b200_grad_sqnorm": 2,
-    "b200_adamw_step": 1, "b200_bf16_to_f32": 1,
+    "b200_adamw_step": 1, "b200_bf16_to_f32": 1, "b200_token_penalty_multi_scores": 2, "b200_generate_step_update": 2,
 }
 launch_count = 0       # kernels launched through this module since import
 call_hook = None       # optional callable(name, args) -> context manager, used by bench.py to time one kernel family

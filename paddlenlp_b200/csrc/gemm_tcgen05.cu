@@ -339,9 +339,6 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const fl
   B200_CHECK_ARG(A && B && C, "gemm: null pointer");
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: non-positive dimension M=%lld N=%lld K=%lld", (long long)M,
                  (long long)N, (long long)K);
-  B200_CHECK_ARG(K % 8 == 0 && N % 8 == 0 && M % 8 == 0,
-                 "gemm: M, N, K must be multiples of 8 (got %lld, %lld, %lld)", (long long)M, (long long)N,
-                 (long long)K);
   B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "gemm: leading dimensions must be multiples of 8");
   B200_CHECK_ARG(cta_group == 1 || cta_group == 2, "gemm: cta_group must be 1 or 2");
   B200_CHECK_ARG(!(residual && accumulate), "gemm: residual and accumulate are mutually exclusive");

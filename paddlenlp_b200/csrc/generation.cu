@@ -1,0 +1,669 @@
+// Generation (KV-cache decode) hot path and per-step bookkeeping ops — the bf16, non-quantised subset of the
+// reference's `paddlenlp_ops` (csrc/gpu/*.cu) plus the Paddle-core ops FusedMultiTransformer calls
+// (paddlenlp/experimental/transformers/fused_transformer_layers.py).  All of it is HBM-/latency-bound integer and
+// elementwise work: coalesced 128-bit accesses, no tensor cores, no host synchronisation (the decode step is
+// CUDA-graph capturable: every data-dependent quantity — sequence lengths, stop flags — is read from device memory).
+#include "../../include/b200nlp.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+namespace gen {
+
+// ------------------------------------------------------------------------------------------------
+// fused residual-add + RMSNorm -> (normed, new_residual)
+// Reference: fused_rms_norm(x, norm_weight, ..., residual=residual) -> (out, residual_out)
+// (fused_transformer_layers.py:937-949 compute_ffn_layernorm, :976-999 compute_bias_residual_layernorm).
+//   r = bf16(x + residual) ; out = bf16( bf16(r * rstd) * w )   — same rounding points as the training path.
+// ------------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res,
+                                                          const bf16* __restrict__ w, bf16* __restrict__ normed,
+                                                          bf16* __restrict__ res_out, int rows, int h, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= rows) return;
+  const int nchunk = h >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * h);
+  const uint4* rr = res ? reinterpret_cast<const uint4*>(res + static_cast<size_t>(row) * h) : nullptr;
+  uint4 v[MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunk) {
+      v[i] = ld_nc_v4(xr + c);
+      uint32_t* vi = reinterpret_cast<uint32_t*>(&v[i]);
+      if (rr) {
+        const uint4 rv = ld_nc_v4(rr + c);
+        const uint32_t* ri = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = unpack_bf16x2(vi[j]), b = unpack_bf16x2(ri[j]);
+          vi[j] = pack_bf16x2(a.x + b.x, a.y + b.y);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 a = unpack_bf16x2(vi[j]); ss += a.x * a.x + a.y * a.y; }
+      if (res_out) st_na_v4(reinterpret_cast<uint4*>(res_out + static_cast<size_t>(row) * h) + c, v[i]);
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / static_cast<float>(h) + eps);
+  if (normed == nullptr) return;
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  uint4* yr = reinterpret_cast<uint4*>(normed + static_cast<size_t>(row) * h);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunk) {
+      const uint4 wv = __ldg(wr + c);
+      uint4 o;
+      const uint32_t* xi = reinterpret_cast<const uint32_t*>(&v[i]);
+      const uint32_t* wi = reinterpret_cast<const uint32_t*>(&wv);
+      uint32_t* oi = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = unpack_bf16x2(xi[j]), wf = unpack_bf16x2(wi[j]);
+        oi[j] = pack_bf16x2(bf16_round(xf.x * rstd) * wf.x, bf16_round(xf.y * rstd) * wf.y);
+      }
+      st_na_v4(yr + c, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prefill: copy the (already rotated) K and the V rows of the packed QKV projection into the cache
+// [2, B, kvh, max_len, d]  (reference: write_cache_kv, csrc/gpu/write_cache_kv.cu:23-99; here K keeps the plain
+// [max_len, d] row layout — the transposed x=8 layout there is private to Paddle's MMHA kernel).
+// ------------------------------------------------------------------------------------------------
+__global__ void write_cache_kv_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ cache, const int* __restrict__ seq_lens,
+                                      int B, int S, int nh, int kvh, int d, int max_len, int64_t ld) {
+  const int tok = blockIdx.x;          // b * S + s
+  const int b = tok / S, s = tok % S;
+  if (seq_lens != nullptr && s >= seq_lens[b]) return;
+  if (s >= max_len) return;
+  const int chunks = (kvh * d) >> 3;   // 16-byte chunks per K (or V) row group
+  const size_t half = static_cast<size_t>(B) * kvh * max_len * d;
+  for (int c = threadIdx.x; c < 2 * chunks; c += blockDim.x) {
+    const int which = c / chunks;      // 0: K, 1: V
+    const int cc = c % chunks;
+    const int head = (cc * 8) / d, off = (cc * 8) % d;
+    const uint4 v = *reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(tok) * ld + (nh + which * kvh) * d + cc * 8);
+    bf16* dst = cache + which * half + ((static_cast<size_t>(b) * kvh + head) * max_len + s) * d + off;
+    *reinterpret_cast<uint4*>(dst) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode: RoPE (rotate-half, fp32 math, one rounding) on the new token's q and k at position seq_lens[b], in place in
+// the packed [B, ld] projection, and append k, v to the cache at that position.
+// Reference: masked_multihead_attention(x=qkv, cache_kv, sequence_lengths, rotary_tensor, rotary_emb_dims=1,
+// use_neox_rotary_style=True) — neox == rotate-half in csrc (encode_rotary_qk.cu:18-56);
+// fused variant: append_attn/decoder_write_cache_with_rope_kernel.cu:47-390.
+// ------------------------------------------------------------------------------------------------
+__global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, bf16* __restrict__ cache, const float* __restrict__ cos_t,
+                                          const float* __restrict__ sin_t, const int* __restrict__ seq_lens, int B, int nh,
+                                          int kvh, int d, int max_len, int64_t ld) {
+  const int b = blockIdx.x;
+  const int pos = seq_lens[b];
+  if (pos < 0 || pos >= max_len) return;
+  const int half = d >> 1;
+  const int per_head = half >> 3;
+  const int idx = threadIdx.x;
+  const size_t cache_half = static_cast<size_t>(B) * kvh * max_len * d;
+  bf16* row = qkv + static_cast<size_t>(b) * ld;
+  if (idx < (nh + kvh) * per_head) {
+    const int head = idx / per_head;
+    const int j8 = (idx % per_head) * 8;
+    bf16* base = row + head * d;
+    uint4 a = *reinterpret_cast<const uint4*>(base + j8);
+    uint4 bb = *reinterpret_cast<const uint4*>(base + half + j8);
+    const float* cp = cos_t + static_cast<size_t>(pos) * half + j8;
+    const float* sp = sin_t + static_cast<size_t>(pos) * half + j8;
+    uint32_t* ai = reinterpret_cast<uint32_t*>(&a);
+    uint32_t* bi = reinterpret_cast<uint32_t*>(&bb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x1 = unpack_bf16x2(ai[j]), x2 = unpack_bf16x2(bi[j]);
+      const float c0 = __ldg(cp + 2 * j), c1 = __ldg(cp + 2 * j + 1), s0 = __ldg(sp + 2 * j), s1 = __ldg(sp + 2 * j + 1);
+      ai[j] = pack_bf16x2(x1.x * c0 - x2.x * s0, x1.y * c1 - x2.y * s1);
+      bi[j] = pack_bf16x2(x2.x * c0 + x1.x * s0, x2.y * c1 + x1.y * s1);
+    }
+    *reinterpret_cast<uint4*>(base + j8) = a;
+    *reinterpret_cast<uint4*>(base + half + j8) = bb;
+    if (head >= nh) {   // rotated k -> cache
+      bf16* dst = cache + ((static_cast<size_t>(b) * kvh + (head - nh)) * max_len + pos) * d;
+      *reinterpret_cast<uint4*>(dst + j8) = a;
+      *reinterpret_cast<uint4*>(dst + half + j8) = bb;
+    }
+  }
+  // v -> cache (16-byte chunks)
+  for (int c = idx; c < (kvh * d) >> 3; c += blockDim.x) {
+    const int head = (c * 8) / d, off = (c * 8) % d;
+    const uint4 v = *reinterpret_cast<const uint4*>(row + (nh + kvh) * d + c * 8);
+    bf16* dst = cache + cache_half + ((static_cast<size_t>(b) * kvh + head) * max_len + pos) * d + off;
+    *reinterpret_cast<uint4*>(dst) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode attention: one query token per sequence over the cache, GQA group shares each K/V row read.
+//   CTA = (batch, kv head); 4 warps; a half-warp (16 lanes x 16 B) reads one 256-byte K row, so a warp covers two
+//   cache rows per load; every lane keeps its 8 dims of q / o for the G q-heads of the group in registers;
+//   online softmax (exp2, fp32) per half-warp, merged across the 8 half-warps through shared memory.
+// HBM roofline: 2 * len * d * 2 bytes per (b, kv head).
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128) decode_attention_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ cache,
+                                                               const int* __restrict__ seq_lens, bf16* __restrict__ out,
+                                                               int B, int nh, int kvh, int max_len, int64_t ld,
+                                                               float scale_log2) {
+  constexpr int D = 128;
+  __shared__ float s_m[8][G], s_l[8][G];
+  __shared__ float s_o[8][G][D];
+  const int b = blockIdx.x / kvh, kh = blockIdx.x % kvh;
+  const int len = min(seq_lens[b] + 1, max_len);       // the new token was appended at index seq_lens[b]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hw = warp * 2 + (lane >> 4);               // half-warp id 0..7
+  const int sub = lane & 15;                           // which 8 dims of the row
+  float q[G][8], o[G][8], m[G], l[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const uint4 qv = *reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(b) * ld + (kh * G + g) * D + sub * 8);
+    const uint32_t* qi = reinterpret_cast<const uint32_t*>(&qv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(qi[j]);
+      q[g][2 * j] = f.x * scale_log2; q[g][2 * j + 1] = f.y * scale_log2;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[g][j] = 0.f;
+    m[g] = -INFINITY; l[g] = 0.f;
+  }
+  const size_t half = static_cast<size_t>(B) * kvh * max_len * D;
+  const bf16* kbase = cache + (static_cast<size_t>(b) * kvh + kh) * max_len * D;
+  const bf16* vbase = kbase + half;
+  for (int t = hw; t < len; t += 8) {
+    const uint4 kv = ld_nc_v4(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(t) * D) + sub);
+    const uint4 vv = ld_nc_v4(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(t) * D) + sub);
+    float kf[8], vf[8];
+    const uint32_t* ki = reinterpret_cast<const uint32_t*>(&kv);
+    const uint32_t* vi = reinterpret_cast<const uint32_t*>(&vv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16x2(ki[j]), c = unpack_bf16x2(vi[j]);
+      kf[2 * j] = a.x; kf[2 * j + 1] = a.y; vf[2 * j] = c.x; vf[2 * j + 1] = c.y;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += q[g][j] * kf[j];
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      const float mn = fmaxf(m[g], s);
+      const float corr = exp2f(m[g] - mn);
+      const float p = exp2f(s - mn);
+      l[g] = l[g] * corr + p;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[g][j] = o[g][j] * corr + p * vf[j];
+      m[g] = mn;
+    }
+  }
+  // merge the 8 half-warp partials
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    if (sub == 0) { s_m[hw][g] = m[g]; s_l[hw][g] = l[g]; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_o[hw][g][sub * 8 + j] = o[g][j];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < G * D; idx += blockDim.x) {
+    const int g = idx / D, dd = idx % D;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mm = fmaxf(mm, s_m[w][g]);
+    float acc = 0.f, lt = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float f = (s_m[w][g] == -INFINITY) ? 0.f : exp2f(s_m[w][g] - mm);
+      acc += s_o[w][g][dd] * f;
+      lt += s_l[w][g] * f;
+    }
+    out[static_cast<size_t>(b) * nh * D + (kh * G + g) * D + dd] = __float2bfloat16_rn(lt > 0.f ? acc / lt : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bookkeeping ops (integer work; semantics follow the cited kernels line by line)
+// ------------------------------------------------------------------------------------------------
+// get_padding_offset_v2 (csrc/gpu/get_padding_offset_v2.cu:17-53)
+__global__ void padding_offset_kernel(const int64_t* __restrict__ input_ids, const int* __restrict__ cum_offsets,
+                                      const int* __restrict__ seq_lens, int64_t* __restrict__ x_remove_padding,
+                                      int* __restrict__ padding_offset, int* __restrict__ cum_offsets_out,
+                                      int* __restrict__ cu_seqlens_q, int* __restrict__ cu_seqlens_k, int max_seq_len) {
+  const int bi = blockIdx.x, ti = threadIdx.x;
+  const int cum_offset = bi == 0 ? 0 : cum_offsets[bi - 1];
+  for (int i = ti; i < seq_lens[bi]; i += blockDim.x) {
+    padding_offset[bi * max_seq_len - cum_offset + i] = cum_offset;
+    x_remove_padding[bi * max_seq_len - cum_offset + i] = input_ids[bi * max_seq_len + i];   // RemovePaddingV2 (:80-85)
+  }
+  if (ti == 0) {
+    cum_offsets_out[bi] = cum_offset;
+    const int cum_seq_len = (bi + 1) * max_seq_len - cum_offsets[bi];
+    cu_seqlens_q[bi + 1] = cum_seq_len;
+    cu_seqlens_k[bi + 1] = cum_seq_len;
+    if (bi == 0) { cu_seqlens_q[0] = 0; cu_seqlens_k[0] = 0; }
+  }
+}
+
+// rebuild_padding_v2 (csrc/gpu/rebuild_padding_v2.cu:18-69): one output row per sequence = its last valid token
+// (prefill: token seq_len_encoder-1 of the sequence; decode: its single token).
+__global__ void rebuild_padding_kernel(const bf16* __restrict__ tmp_out, const int* __restrict__ cum_offsets,
+                                       const int* __restrict__ seq_lens_decoder, const int* __restrict__ seq_lens_encoder,
+                                       bf16* __restrict__ out, int max_len, int dim) {
+  const int bi = blockIdx.x;
+  int seq_id = 0;
+  if (seq_lens_decoder[bi] == 0 && seq_lens_encoder[bi] == 0) return;
+  if (seq_lens_decoder[bi] == 0) seq_id = seq_lens_encoder[bi] - 1;
+  const int ori_token_idx = bi * max_len - cum_offsets[bi] + seq_id;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x)
+    out[static_cast<size_t>(bi) * dim + i] = tmp_out[static_cast<size_t>(ori_token_idx) * dim + i];
+}
+
+// set_value_by_flags_and_idx (v1: csrc/gpu/set_value_by_flags.cu:17-25; v2: set_value_by_flags_v2.cu)
+__global__ void set_value_by_flags_kernel(const bool* __restrict__ stop_flags, int64_t* __restrict__ pre_ids_all,
+                                          const int64_t* __restrict__ pre_ids, const int64_t* __restrict__ step_idx, int bs,
+                                          int length) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < bs && !stop_flags[tid]) {
+    if (step_idx[tid] >= 0) pre_ids_all[static_cast<size_t>(tid) * length + step_idx[tid]] = pre_ids[tid];
+  }
+}
+__global__ void set_value_by_flags_v2_kernel(const bool* __restrict__ stop_flags, int64_t* __restrict__ pre_ids_all,
+                                             const int64_t* __restrict__ input_ids, const int* __restrict__ seq_lens_encoder,
+                                             const int* __restrict__ seq_lens_decoder, const int64_t* __restrict__ step_idx,
+                                             int bs, int length, int length_input_ids) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < bs && !stop_flags[tid]) {
+    int64_t* pre = pre_ids_all + static_cast<size_t>(tid) * length;
+    const int64_t* ids = input_ids + static_cast<size_t>(tid) * length_input_ids;
+    const int dec = seq_lens_decoder[tid], enc = seq_lens_encoder[tid];
+    if (dec == 0 && enc == 0) return;
+    if (step_idx[tid] >= 0) pre[step_idx[tid]] = (dec == 0) ? ids[enc - 1] : ids[0];
+  }
+}
+
+// get_token_penalty_multi_scores(_v2) (csrc/gpu/token_penalty_multi_scores_v2.cu:19-139; CPU twin
+// csrc/cpu/src/token_penalty_multi_scores.cc:18-85).  One CTA per sequence; repeat counts in a caller workspace.
+__global__ void penalty_count_kernel(const int64_t* __restrict__ pre_ids, const int64_t* __restrict__ cur_len,
+                                     int* __restrict__ repeat_times, int64_t length, int64_t length_id) {
+  const int bi = blockIdx.x;
+  if (cur_len[bi] < 0) return;
+  const int64_t* ids = pre_ids + static_cast<size_t>(bi) * length_id;
+  int* rt = repeat_times + static_cast<size_t>(bi) * length;
+  // the reference breaks at the first negative id PER THREAD stride; ids are -1 padded at the tail, so scanning
+  // until the first negative entry is equivalent.
+  for (int64_t i = threadIdx.x; i < length_id; i += blockDim.x) {
+    const int64_t id = ids[i];
+    if (id < 0) break;
+    if (id < length) atomicAdd(&rt[id], 1);
+  }
+}
+__global__ void penalty_apply_kernel(float* __restrict__ logits, const int* __restrict__ repeat_times,
+                                     const float* __restrict__ penalty, const float* __restrict__ frequency,
+                                     const float* __restrict__ presence, const float* __restrict__ temperatures,
+                                     const int64_t* __restrict__ cur_len, const int64_t* __restrict__ min_len,
+                                     const int64_t* __restrict__ eos_ids, int64_t eos_len,
+                                     const int64_t* __restrict__ bad_tokens, int64_t bad_len, int64_t length) {
+  const int bi = blockIdx.x;
+  float* lg = logits + static_cast<size_t>(bi) * length;
+  const int* rt = repeat_times + static_cast<size_t>(bi) * length;
+  const bool min_len_mask = cur_len[bi] >= 0 && cur_len[bi] < min_len[bi];
+  const float alpha = penalty[bi], beta = frequency[bi], gamma = presence[bi];
+  const float temp = temperatures ? temperatures[bi] : 1.f;
+  for (int64_t i = threadIdx.x; i < length; i += blockDim.x) {
+    float v = lg[i];
+    if (min_len_mask) {
+      for (int64_t e = 0; e < eos_len; ++e)
+        if (eos_ids[e] == i) v = -1e10f;
+    }
+    const int times = rt[i];
+    if (times != 0) {
+      v = v < 0 ? v * alpha : v / alpha;
+      v = v - times * beta - gamma;
+    }
+    v = v / temp;
+    for (int64_t k = 0; k < bad_len; ++k)
+      if (bad_tokens[k] == i) v = -1e10f;
+    lg[i] = v;
+  }
+}
+
+// set_stop_value_multi_ends: v1 mode 2 (csrc/gpu/stop_generation_multi_ends.cu:45-56), v2 (…_v2.cu:35-59)
+__device__ __forceinline__ bool in_end(int64_t id, const int64_t* end_ids, int n) {
+  for (int i = 0; i < n; ++i)
+    if (id == end_ids[i]) return true;
+  return false;
+}
+__global__ void stop_value_kernel(bool* __restrict__ stop_flags, int64_t* __restrict__ topk_ids,
+                                  int64_t* __restrict__ next_tokens, const int64_t* __restrict__ end_ids,
+                                  const int* __restrict__ seq_lens, int bs, int end_length, int v2) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= bs) return;
+  if (v2) {
+    if (stop_flags[tid]) {
+      if (seq_lens[tid] == 0) topk_ids[tid] = -1;
+      else { topk_ids[tid] = end_ids[0]; next_tokens[tid] = end_ids[0]; }
+    } else {
+      next_tokens[tid] = topk_ids[tid];
+    }
+  } else {
+    topk_ids[tid] = stop_flags[tid] ? end_ids[0] : topk_ids[tid];
+  }
+  if (in_end(topk_ids[tid], end_ids, end_length)) stop_flags[tid] = true;
+}
+
+// update_inputs (csrc/gpu/update_inputs.cu:18-66), single CTA of 1024 threads
+__global__ void update_inputs_kernel(bool* not_need_stop, int* seq_lens_this_time, int* seq_lens_encoder,
+                                     int* seq_lens_decoder, int64_t* input_ids, const int64_t* stop_nums,
+                                     const bool* stop_flags, const bool* is_block_step, const int64_t* next_tokens, int bsz,
+                                     int max_bsz, int input_ids_stride) {
+  __shared__ int red[32];
+  const int t = threadIdx.x;
+  bool stop_now = false;
+  int stop_int = 0;
+  if (t < max_bsz) {
+    if (t < bsz) {
+      stop_now = stop_flags[t];
+      stop_int = is_block_step[t] ? 0 : static_cast<int>(stop_now);
+    } else {
+      stop_int = 1;
+    }
+  }
+  if (t < bsz) {
+    const int enc = seq_lens_encoder[t], dec = seq_lens_decoder[t];
+    seq_lens_decoder[t] = stop_now ? 0 : (dec == 0 ? enc : dec + 1);
+    seq_lens_this_time[t] = stop_now ? 0 : 1;
+    seq_lens_encoder[t] = 0;
+    input_ids[static_cast<size_t>(t) * input_ids_stride] = next_tokens[t];
+  }
+  int s = stop_int;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((t & 31) == 0) red[t >> 5] = s;
+  __syncthreads();
+  if (t < 32) {
+    s = red[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (t == 0) not_need_stop[0] = static_cast<int64_t>(s) < stop_nums[0];
+  }
+}
+
+// One fused per-step state update for the dense-cache generate loop
+// (GenerationInferenceModel.update_model_kwargs_for_generation, experimental/transformers/generation_utils.py:185-260):
+//   step_idx += !stop ; stop |= step_idx >= max_dec_len ; next = stop ? eos[0] : next ; stop |= next in eos ;
+//   pre_ids[b, step_idx] = next (set_value_by_flags_and_idx of the following step) ; seq_len_decoder += !stop ;
+//   tgt_ids = next ; stop_count = sum(stop)
+__global__ void generate_step_update_kernel(int64_t* next_tokens, bool* stop_flags, int64_t* step_idx,
+                                            const int64_t* max_dec_len, int* seq_len_decoder, int64_t* pre_ids,
+                                            int64_t pre_len, const int64_t* eos_ids, int eos_len, int64_t* out_tokens,
+                                            int64_t out_stride, int64_t out_col, const int64_t* out_col_dev,
+                                            int* stop_count, int bs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (out_col_dev != nullptr) out_col = out_col_dev[0];
+  if (b < bs) {
+    bool stop = stop_flags[b];
+    int64_t step = step_idx[b];
+    if (!stop) step += 1;
+    if (step >= max_dec_len[b]) stop = true;
+    int64_t tok = stop_flags[b] ? eos_ids[0] : next_tokens[b];
+    if (in_end(tok, eos_ids, eos_len)) stop = true;
+    if (!stop_flags[b] && step >= 0 && step < pre_len) pre_ids[static_cast<size_t>(b) * pre_len + step] = tok;
+    if (!stop) seq_len_decoder[b] += 1;
+    next_tokens[b] = tok;
+    step_idx[b] = step;
+    stop_flags[b] = stop;
+    if (out_tokens != nullptr && out_col >= 0 && out_col < out_stride)
+      out_tokens[static_cast<size_t>(b) * out_stride + out_col] = tok;
+    if (stop) atomicAdd(stop_count, 1);
+  }
+}
+
+__global__ void increment_i64_kernel(int64_t* p) { p[0] += 1; }
+
+__global__ void argmax_f32_kernel(const float* __restrict__ logits, int64_t* __restrict__ out, int vocab, int64_t ld) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const float* lr = logits + static_cast<size_t>(blockIdx.x) * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+    const float f = lr[i];
+    if (f > best || (f == best && i < bi)) { best = f; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+    out[blockIdx.x] = bi;
+  }
+}
+
+__global__ void bf16_rows_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int64_t rows, int64_t cols,
+                                        int64_t ld) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = __bfloat162float(src[(i / cols) * ld + (i % cols)]);
+}
+
+}  // namespace gen
+}  // namespace b200
+
+using namespace b200;
+using namespace b200::gen;
+
+extern "C" int b200_add_rmsnorm(const void* x, const void* residual, const void* w, void* normed, void* residual_out,
+                                int64_t rows, int64_t h, float eps, cudaStream_t stream) {
+  B200_CHECK_ARG(x && (w || !normed), "add_rmsnorm: null pointer");
+  B200_CHECK_ARG(rows > 0 && h > 0 && h % 8 == 0 && h <= 8192, "add_rmsnorm: need 0 < h <= 8192, h %% 8 == 0");
+  const int nchunk = static_cast<int>(h / 8);
+  const dim3 grid(static_cast<unsigned>((rows + 3) / 4)), block(128);
+  const bf16 *xp = static_cast<const bf16*>(x), *rp = static_cast<const bf16*>(residual), *wp = static_cast<const bf16*>(w);
+  bf16 *np = static_cast<bf16*>(normed), *ro = static_cast<bf16*>(residual_out);
+  if (nchunk <= 128) add_rmsnorm_kernel<4><<<grid, block, 0, stream>>>(xp, rp, wp, np, ro, (int)rows, (int)h, eps);
+  else if (nchunk <= 512) add_rmsnorm_kernel<16><<<grid, block, 0, stream>>>(xp, rp, wp, np, ro, (int)rows, (int)h, eps);
+  else add_rmsnorm_kernel<32><<<grid, block, 0, stream>>>(xp, rp, wp, np, ro, (int)rows, (int)h, eps);
+  return check_launch("add_rmsnorm");
+}
+
+extern "C" int b200_write_cache_kv(const void* qkv, void* cache, const int32_t* seq_lens, int64_t B, int64_t S,
+                                   int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len, int64_t ld,
+                                   cudaStream_t stream) {
+  B200_CHECK_ARG(qkv && cache, "write_cache_kv: null pointer");
+  B200_CHECK_ARG(head_dim % 8 == 0 && ld % 8 == 0 && B > 0 && S > 0 && S <= max_len, "write_cache_kv: bad sizes");
+  write_cache_kv_kernel<<<static_cast<unsigned>(B * S), 128, 0, stream>>>(
+      static_cast<const bf16*>(qkv), static_cast<bf16*>(cache), seq_lens, (int)B, (int)S, (int)num_heads, (int)num_kv_heads,
+      (int)head_dim, (int)max_len, ld);
+  return check_launch("write_cache_kv");
+}
+
+extern "C" int b200_decode_rope_append(void* qkv, void* cache, const float* cos_table, const float* sin_table,
+                                       const int32_t* seq_lens, int64_t B, int64_t num_heads, int64_t num_kv_heads,
+                                       int64_t head_dim, int64_t max_len, int64_t ld, cudaStream_t stream) {
+  B200_CHECK_ARG(qkv && cache && cos_table && sin_table && seq_lens, "decode_rope_append: null pointer");
+  B200_CHECK_ARG(head_dim % 16 == 0 && ld % 8 == 0, "decode_rope_append: head_dim %% 16, ld %% 8");
+  const int threads_needed = static_cast<int>((num_heads + num_kv_heads) * (head_dim / 16));
+  B200_CHECK_ARG(threads_needed <= 1024, "decode_rope_append: too many heads");
+  const int threads = (threads_needed + 31) / 32 * 32;
+  decode_rope_append_kernel<<<static_cast<unsigned>(B), threads, 0, stream>>>(
+      static_cast<bf16*>(qkv), static_cast<bf16*>(cache), cos_table, sin_table, seq_lens, (int)B, (int)num_heads,
+      (int)num_kv_heads, (int)head_dim, (int)max_len, ld);
+  return check_launch("decode_rope_append");
+}
+
+extern "C" int b200_decode_attention(const void* qkv, const void* cache, const int32_t* seq_lens, void* out, int64_t B,
+                                     int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len, int64_t ld,
+                                     float softmax_scale, cudaStream_t stream) {
+  B200_CHECK_ARG(qkv && cache && seq_lens && out, "decode_attention: null pointer");
+  B200_CHECK_ARG(head_dim == 128, "decode_attention: head_dim must be 128 (got %lld)", (long long)head_dim);
+  B200_CHECK_ARG(num_heads % num_kv_heads == 0, "decode_attention: num_heads %% num_kv_heads != 0");
+  const int G = static_cast<int>(num_heads / num_kv_heads);
+  const float sl2 = softmax_scale * 1.4426950408889634f;
+  const dim3 grid(static_cast<unsigned>(B * num_kv_heads)), block(128);
+  const bf16* q = static_cast<const bf16*>(qkv);
+  const bf16* c = static_cast<const bf16*>(cache);
+  bf16* o = static_cast<bf16*>(out);
+#define B200_DA(GG)                                                                                                  \
+  case GG:                                                                                                           \
+    decode_attention_kernel<GG><<<grid, block, 0, stream>>>(q, c, seq_lens, o, (int)B, (int)num_heads, (int)num_kv_heads, \
+                                                            (int)max_len, ld, sl2);                                 \
+    break;
+  switch (G) {
+    B200_DA(1) B200_DA(2) B200_DA(4) B200_DA(7) B200_DA(8)
+    default:
+      return fail_arg("decode_attention: GQA group size %d not instantiated (1, 2, 4, 7, 8)", G);
+  }
+#undef B200_DA
+  return check_launch("decode_attention");
+}
+
+extern "C" int b200_get_padding_offset(const int64_t* input_ids, const int32_t* cum_offsets, const int32_t* seq_lens,
+                                       int64_t* x_remove_padding, int32_t* padding_offset, int32_t* cum_offsets_out,
+                                       int32_t* cu_seqlens_q, int32_t* cu_seqlens_k, int64_t bsz, int64_t max_seq_len,
+                                       cudaStream_t stream) {
+  B200_CHECK_ARG(input_ids && cum_offsets && seq_lens && x_remove_padding && padding_offset && cum_offsets_out &&
+                     cu_seqlens_q && cu_seqlens_k && bsz > 0,
+                 "get_padding_offset: bad arguments");
+  padding_offset_kernel<<<static_cast<unsigned>(bsz), 128, 0, stream>>>(input_ids, cum_offsets, seq_lens, x_remove_padding,
+                                                                       padding_offset, cum_offsets_out, cu_seqlens_q,
+                                                                       cu_seqlens_k, (int)max_seq_len);
+  return check_launch("get_padding_offset");
+}
+
+extern "C" int b200_rebuild_padding(const void* tmp_out, const int32_t* cum_offsets, const int32_t* seq_lens_decoder,
+                                    const int32_t* seq_lens_encoder, void* out, int64_t bsz, int64_t max_len, int64_t dim,
+                                    cudaStream_t stream) {
+  B200_CHECK_ARG(tmp_out && cum_offsets && seq_lens_decoder && seq_lens_encoder && out && bsz > 0, "rebuild_padding: bad arguments");
+  rebuild_padding_kernel<<<static_cast<unsigned>(bsz), 256, 0, stream>>>(static_cast<const bf16*>(tmp_out), cum_offsets,
+                                                                        seq_lens_decoder, seq_lens_encoder,
+                                                                        static_cast<bf16*>(out), (int)max_len, (int)dim);
+  return check_launch("rebuild_padding");
+}
+
+extern "C" int b200_set_value_by_flags_and_idx(const bool* stop_flags, int64_t* pre_ids_all, const int64_t* pre_ids_now,
+                                               const int64_t* step_idx, int64_t bs, int64_t length, cudaStream_t stream) {
+  B200_CHECK_ARG(stop_flags && pre_ids_all && pre_ids_now && step_idx && bs > 0, "set_value_by_flags_and_idx: bad arguments");
+  set_value_by_flags_kernel<<<static_cast<unsigned>((bs + 127) / 128), 128, 0, stream>>>(stop_flags, pre_ids_all, pre_ids_now,
+                                                                                        step_idx, (int)bs, (int)length);
+  return check_launch("set_value_by_flags_and_idx");
+}
+
+extern "C" int b200_set_value_by_flags_and_idx_v2(const bool* stop_flags, int64_t* pre_ids_all, const int64_t* input_ids,
+                                                  const int32_t* seq_lens_encoder, const int32_t* seq_lens_decoder,
+                                                  const int64_t* step_idx, int64_t bs, int64_t length,
+                                                  int64_t length_input_ids, cudaStream_t stream) {
+  B200_CHECK_ARG(stop_flags && pre_ids_all && input_ids && seq_lens_encoder && seq_lens_decoder && step_idx && bs > 0,
+                 "set_value_by_flags_and_idx_v2: bad arguments");
+  set_value_by_flags_v2_kernel<<<static_cast<unsigned>((bs + 127) / 128), 128, 0, stream>>>(
+      stop_flags, pre_ids_all, input_ids, seq_lens_encoder, seq_lens_decoder, step_idx, (int)bs, (int)length,
+      (int)length_input_ids);
+  return check_launch("set_value_by_flags_and_idx_v2");
+}
+
+extern "C" int b200_token_penalty_multi_scores(const int64_t* pre_ids, float* logits, const float* penalty_scores,
+                                               const float* frequency_scores, const float* presence_scores,
+                                               const float* temperatures, const int64_t* bad_tokens, const int64_t* cur_len,
+                                               const int64_t* min_len, const int64_t* eos_token_id, int32_t* workspace,
+                                               int64_t bs, int64_t length, int64_t length_id, int64_t bad_len,
+                                               int64_t eos_len, cudaStream_t stream) {
+  B200_CHECK_ARG(pre_ids && logits && penalty_scores && frequency_scores && presence_scores && cur_len && min_len &&
+                     eos_token_id && workspace && bs > 0 && length > 0,
+                 "token_penalty_multi_scores: bad arguments");
+  cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(bs) * length * sizeof(int32_t), stream);
+  if (e != cudaSuccess) {
+    set_last_error("token_penalty memset: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  penalty_count_kernel<<<static_cast<unsigned>(bs), 1, 0, stream>>>(pre_ids, cur_len, workspace, length, length_id);
+  int rc = check_launch("token_penalty(count)");
+  if (rc) return rc;
+  penalty_apply_kernel<<<static_cast<unsigned>(bs), 512, 0, stream>>>(logits, workspace, penalty_scores, frequency_scores,
+                                                                     presence_scores, temperatures, cur_len, min_len,
+                                                                     eos_token_id, eos_len, bad_tokens, bad_len, length);
+  return check_launch("token_penalty(apply)");
+}
+
+extern "C" int b200_set_stop_value_multi_ends(bool* stop_flags, int64_t* topk_ids, int64_t* next_tokens,
+                                              const int64_t* end_ids, const int32_t* seq_lens, int64_t bs, int64_t end_length,
+                                              int v2, cudaStream_t stream) {
+  B200_CHECK_ARG(stop_flags && topk_ids && end_ids && bs > 0 && end_length > 0, "set_stop_value_multi_ends: bad arguments");
+  B200_CHECK_ARG(!v2 || (next_tokens && seq_lens), "set_stop_value_multi_ends(v2): next_tokens and seq_lens required");
+  stop_value_kernel<<<static_cast<unsigned>((bs + 127) / 128), 128, 0, stream>>>(stop_flags, topk_ids, next_tokens, end_ids,
+                                                                                seq_lens, (int)bs, (int)end_length, v2);
+  return check_launch("set_stop_value_multi_ends");
+}
+
+extern "C" int b200_update_inputs(bool* not_need_stop, int32_t* seq_lens_this_time, int32_t* seq_lens_encoder,
+                                  int32_t* seq_lens_decoder, int64_t* input_ids, const int64_t* stop_nums,
+                                  const bool* stop_flags, const bool* is_block_step, const int64_t* next_tokens, int64_t bsz,
+                                  int64_t max_bsz, int64_t input_ids_stride, cudaStream_t stream) {
+  B200_CHECK_ARG(not_need_stop && seq_lens_this_time && seq_lens_encoder && seq_lens_decoder && input_ids && stop_nums &&
+                     stop_flags && is_block_step && next_tokens,
+                 "update_inputs: null pointer");
+  B200_CHECK_ARG(bsz > 0 && bsz <= max_bsz && max_bsz <= 1024, "update_inputs: need 0 < bsz <= max_bsz <= 1024");
+  update_inputs_kernel<<<1, 1024, 0, stream>>>(not_need_stop, seq_lens_this_time, seq_lens_encoder, seq_lens_decoder,
+                                              input_ids, stop_nums, stop_flags, is_block_step, next_tokens, (int)bsz,
+                                              (int)max_bsz, (int)input_ids_stride);
+  return check_launch("update_inputs");
+}
+
+extern "C" int b200_generate_step_update(int64_t* next_tokens, bool* stop_flags, int64_t* step_idx, const int64_t* max_dec_len,
+                                         int32_t* seq_len_decoder, int64_t* pre_ids, int64_t pre_len, const int64_t* eos_ids,
+                                         int64_t eos_len, int64_t* out_tokens, int64_t out_stride, int64_t out_col,
+                                         int64_t* out_col_dev, int32_t* stop_count, int64_t bs, cudaStream_t stream) {
+  B200_CHECK_ARG(next_tokens && stop_flags && step_idx && max_dec_len && seq_len_decoder && pre_ids && eos_ids && stop_count &&
+                     bs > 0 && eos_len > 0,
+                 "generate_step_update: bad arguments");
+  cudaError_t e = cudaMemsetAsync(stop_count, 0, sizeof(int32_t), stream);
+  if (e != cudaSuccess) {
+    set_last_error("generate_step_update memset: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  generate_step_update_kernel<<<static_cast<unsigned>((bs + 127) / 128), 128, 0, stream>>>(
+      next_tokens, stop_flags, step_idx, max_dec_len, seq_len_decoder, pre_ids, pre_len, eos_ids, (int)eos_len, out_tokens,
+      out_stride, out_col, out_col_dev, stop_count, (int)bs);
+  int rc = check_launch("generate_step_update");
+  if (rc) return rc;
+  if (out_col_dev != nullptr) {
+    increment_i64_kernel<<<1, 1, 0, stream>>>(out_col_dev);
+    rc = check_launch("generate_step_update(counter)");
+  }
+  return rc;
+}
+
+extern "C" int b200_argmax_f32(const float* logits, int64_t* out, int64_t rows, int64_t vocab, int64_t ld,
+                               cudaStream_t stream) {
+  B200_CHECK_ARG(logits && out && rows > 0 && vocab > 0, "argmax_f32: bad arguments");
+  argmax_f32_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(logits, out, (int)vocab, ld);
+  return check_launch("argmax_f32");
+}
+
+extern "C" int b200_bf16_rows_to_f32(const void* src, float* dst, int64_t rows, int64_t cols, int64_t ld,
+                                     cudaStream_t stream) {
+  B200_CHECK_ARG(src && dst && rows > 0 && cols > 0, "bf16_rows_to_f32: bad arguments");
+  bf16_rows_to_f32_kernel<<<sm_count() * 4, 256, 0, stream>>>(static_cast<const bf16*>(src), dst, rows, cols, ld);
+  return check_launch("bf16_rows_to_f32");
+}

@@ -1,0 +1,138 @@
+"""FusedMultiTransformer — the stacked-layer inference block of
+paddlenlp/experimental/transformers/fused_transformer_layers.py (:205-345 config, :348-792 weights, :1027-1182 forward)
+for the bf16, non-quantised, rmsnorm + swiglu + rotate-half-RoPE case, on the native sm_100a kernels.
+
+Weight layouts are the reference's:
+    qkv_weight    [(nh + 2*kvh) * d, h]   (transposed, trans_qkvw=True)      -> GEMM with B stored [N, K]
+    linear_weight [nh * d, h]             ffn1_weight [h, 2*I] (gate | up)    ffn2_weight [I, h]
+    ln_scale / ffn_ln_scale [h]
+KV cache per layer: bf16 [2, B, kvh, max_len, d].
+Layer loop (:1126-1174): the output norm of layer i is fused with the residual add and is layer i+1's input norm.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from ... import ops
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class FusedMultiTransformerConfig:
+    embed_dim: int
+    num_heads: int
+    dim_feedforward: int
+    kv_num_heads: int = -1
+    num_layers: int = -1
+    epsilon: float = 1e-5
+    norm_type: str = "rmsnorm"
+    activation: str = "swiglu"
+    use_neox_rotary_style: bool = True       # csrc naming: neox == rotate-half (encode_rotary_qk.cu:18-56)
+    rope_theta: float = 10000.0
+    max_position_embeddings: int = 4096
+    qkv_bias: bool = False
+    nranks: int = 1
+    trans_qkvw: bool = True
+
+    def __post_init__(self):
+        if self.kv_num_heads <= 0:
+            self.kv_num_heads = self.num_heads
+        if self.norm_type != "rmsnorm" or self.activation != "swiglu":
+            raise NotImplementedError("only the rmsnorm + swiglu (Llama / Qwen2) block is implemented")
+        if not self.use_neox_rotary_style:
+            raise NotImplementedError("interleaved-pair RoPE is not used by Llama/Qwen2 (SURVEY.md §8 naming trap)")
+        if self.nranks != 1:
+            raise NotImplementedError("tensor-parallel generation is out of scope (config 5 is single-GPU)")
+        if not self.trans_qkvw:
+            raise NotImplementedError("trans_qkvw=False")
+        if self.embed_dim // self.num_heads != 128:
+            raise NotImplementedError("head_dim must be 128")
+
+
+class FusedMultiTransformerBase:
+    def __init__(self, config: FusedMultiTransformerConfig, device=None):
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("FusedMultiTransformer needs a CUDA device: there is no CPU implementation")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.config = config
+        self.device = torch.device(device)
+        c = config
+        self.h, self.nh, self.kvh, self.I, self.L = c.embed_dim, c.num_heads, c.kv_num_heads, c.dim_feedforward, c.num_layers
+        self.d = self.h // self.nh
+        self.qkv_n = (self.nh + 2 * self.kvh) * self.d
+
+        def z(*shape):
+            return torch.zeros(*shape, dtype=BF16, device=self.device)
+
+        self.ln_scales = [torch.ones(self.h, dtype=BF16, device=self.device) for _ in range(self.L)]
+        self.qkv_weights = [z(self.qkv_n, self.h) for _ in range(self.L)]
+        self.qkv_biases: List[Optional[torch.Tensor]] = [z(self.qkv_n) if c.qkv_bias else None for _ in range(self.L)]
+        self.linear_weights = [z(self.nh * self.d, self.h) for _ in range(self.L)]
+        self.ffn_ln_scales = [torch.ones(self.h, dtype=BF16, device=self.device) for _ in range(self.L)]
+        self.ffn1_weights = [z(self.h, 2 * self.I) for _ in range(self.L)]
+        self.ffn2_weights = [z(self.I, self.h) for _ in range(self.L)]
+        self._bias_f32 = [None] * self.L
+        self.rope = ops.rope_tables(self.d, c.max_position_embeddings, float(c.rope_theta), self.device)
+
+    def _bias(self, i):
+        if self.qkv_biases[i] is None:
+            return None
+        if self._bias_f32[i] is None:
+            self._bias_f32[i] = self.qkv_biases[i].float()
+        return self._bias_f32[i]
+
+    # compute_qkv (:817-820): linear(ln_out, qkv_weight, transpose_weight=True)
+    def compute_qkv(self, ln_out, i):
+        return ops.gemm(ln_out, self.qkv_weights[i], trans_b=True, bias=self._bias(i))
+
+    # compute_fmha (:829-882): qkv_transpose_split -> encode_rotary_qk -> write_cache_kv -> var-len attention
+    def compute_fmha(self, qkv, cache, B, S, seq_lens_encoder):
+        cos, sin = self.rope
+        ops.rope_inplace(qkv, cos, sin, S, self.nh + self.kvh, self.d)
+        ops.write_cache_kv(qkv, cache, seq_lens_encoder, B, S, self.nh, self.kvh, self.d)
+        q4 = qkv.view(B, S, self.qkv_n)
+        qn, kn = self.nh * self.d, self.kvh * self.d
+        q = q4[:, :, :qn].unflatten(2, (self.nh, self.d))
+        k = q4[:, :, qn:qn + kn].unflatten(2, (self.kvh, self.d))
+        v = q4[:, :, qn + kn:].unflatten(2, (self.kvh, self.d))
+        attn, _ = ops.flash_attn_fwd(q, k, v)           # right-padded prompts are exact under the causal mask
+        return attn.view(B * S, qn)
+
+    # compute_mmha (:884-893): masked_multihead_attention over the cache
+    def compute_mmha(self, qkv, cache, seq_lens_decoder):
+        cos, sin = self.rope
+        ops.decode_rope_append(qkv, cache, cos, sin, seq_lens_decoder, self.nh, self.kvh, self.d)
+        return ops.decode_attention(qkv, cache, seq_lens_decoder, self.nh, self.kvh, self.d)
+
+    def forward(self, src: torch.Tensor, caches: List[torch.Tensor], *, B: int, S: int, seq_lens_encoder=None,
+                seq_lens_decoder=None, time_step=None) -> torch.Tensor:
+        """src [B*S, h] embeddings.  time_step None = prefill (S prompt positions per sequence, right padded);
+        otherwise decode (S == 1, seq_lens_decoder[b] = number of cached tokens).  Returns hidden states [B*S, h]."""
+        eps = self.config.epsilon
+        decode = time_step is not None
+        residual = src
+        ln_out, _ = ops.add_rmsnorm(src, None, self.ln_scales[0], eps, want_residual=False)   # compute_layernorm_before_qkv
+        for i in range(self.L):
+            qkv = self.compute_qkv(ln_out, i)
+            if decode:
+                attn = self.compute_mmha(qkv, caches[i], seq_lens_decoder)
+            else:
+                attn = self.compute_fmha(qkv, caches[i], B, S, seq_lens_encoder)
+            out = ops.gemm(attn, self.linear_weights[i])                                      # compute_out_linear (:895-896)
+            ln_out, residual = ops.add_rmsnorm(out, residual, self.ffn_ln_scales[i], eps)     # compute_ffn_layernorm (:937-949)
+            ffn1 = ops.gemm(ln_out, self.ffn1_weights[i])
+            act = ops.swiglu_fwd(ffn1)                                                        # fused_bias_act("swiglu") (:100-168)
+            ffn2 = ops.gemm(act, self.ffn2_weights[i])
+            if i != self.L - 1:                                                               # compute_bias_residual_layernorm (:976-999)
+                ln_out, residual = ops.add_rmsnorm(ffn2, residual, self.ln_scales[i + 1], eps)
+            else:
+                _, residual = ops.add_rmsnorm(ffn2, residual, None, eps, want_normed=False)
+        return residual
+
+    __call__ = forward

@@ -300,3 +300,131 @@ def bf16_to_f32(src: torch.Tensor, dst: torch.Tensor):
     _chk(src, "src"); _chk(dst, "dst", torch.float32)
     call("b200_bf16_to_f32", ptr(src), ptr(dst), src.numel(), stream_ptr())
     return dst
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Generation path
+# ----------------------------------------------------------------------------------------------------------
+def add_rmsnorm(x, residual, w, eps, want_normed=True, want_residual=True):
+    """(normed, residual_out) = fused_rms_norm(x, w, residual=residual); either output may be skipped."""
+    _chk(x, "x")
+    h = x.shape[-1]
+    rows = x.numel() // h
+    normed = torch.empty_like(x) if want_normed else None
+    res_out = torch.empty_like(x) if want_residual else None
+    call("b200_add_rmsnorm", ptr(x), ptr(residual), ptr(w), ptr(normed), ptr(res_out), rows, h, float(eps), stream_ptr())
+    return normed, res_out
+
+
+def write_cache_kv(qkv, cache, seq_lens, B, S, nh, kvh, d):
+    """qkv [B*S, ld] (post-RoPE) -> cache [2, B, kvh, max_len, d] for s < seq_lens[b]."""
+    _chk(qkv, "qkv"); _chk(cache, "cache")
+    assert cache.is_contiguous() and cache.shape[0] == 2 and cache.shape[1] == B and cache.shape[2] == kvh
+    max_len = cache.shape[3]
+    call("b200_write_cache_kv", ptr(qkv), ptr(cache), ptr(seq_lens), B, S, nh, kvh, d, max_len, qkv.stride(0), stream_ptr())
+
+
+def decode_rope_append(qkv, cache, cos, sin, seq_lens, nh, kvh, d):
+    _chk(qkv, "qkv"); _chk(cache, "cache"); _chk(seq_lens, "seq_lens", torch.int32)
+    B = qkv.shape[0]
+    call("b200_decode_rope_append", ptr(qkv), ptr(cache), ptr(cos), ptr(sin), ptr(seq_lens), B, nh, kvh, d, cache.shape[3],
+         qkv.stride(0), stream_ptr())
+
+
+def decode_attention(qkv, cache, seq_lens, nh, kvh, d, softmax_scale=None, out=None):
+    _chk(qkv, "qkv"); _chk(cache, "cache"); _chk(seq_lens, "seq_lens", torch.int32)
+    B = qkv.shape[0]
+    if out is None:
+        out = torch.empty(B, nh * d, dtype=BF16, device=qkv.device)
+    if softmax_scale is None:
+        softmax_scale = 1.0 / math.sqrt(d)
+    call("b200_decode_attention", ptr(qkv), ptr(cache), ptr(seq_lens), ptr(out), B, nh, kvh, d, cache.shape[3],
+         qkv.stride(0), float(softmax_scale), stream_ptr())
+    return out
+
+
+def get_padding_offset(input_ids, cum_offsets, token_num, seq_lens):
+    """get_padding_offset_v2: returns (x_remove_padding, cum_offsets_out, padding_offset, cu_seqlens_q, cu_seqlens_k)."""
+    bsz, max_len = input_ids.shape
+    dev = input_ids.device
+    xr = torch.zeros(int(token_num), dtype=torch.int64, device=dev)
+    po = torch.zeros(int(token_num), dtype=torch.int32, device=dev)
+    co = torch.zeros(bsz, dtype=torch.int32, device=dev)
+    cq = torch.zeros(bsz + 1, dtype=torch.int32, device=dev)
+    ck = torch.zeros(bsz + 1, dtype=torch.int32, device=dev)
+    call("b200_get_padding_offset", ptr(input_ids), ptr(cum_offsets), ptr(seq_lens), ptr(xr), ptr(po), ptr(co), ptr(cq), ptr(ck),
+         bsz, max_len, stream_ptr())
+    return xr, co, po, cq, ck
+
+
+def rebuild_padding(tmp_out, cum_offsets, seq_lens_decoder, seq_lens_encoder, max_len):
+    _chk(tmp_out, "tmp_out")
+    bsz, dim = seq_lens_encoder.numel(), tmp_out.shape[1]
+    out = torch.zeros(bsz, dim, dtype=BF16, device=tmp_out.device)
+    call("b200_rebuild_padding", ptr(tmp_out), ptr(cum_offsets), ptr(seq_lens_decoder), ptr(seq_lens_encoder), ptr(out), bsz,
+         max_len, dim, stream_ptr())
+    return out
+
+
+def set_value_by_flags_and_idx(pre_ids_all, pre_ids_now, step_idx, stop_flags):
+    bs, length = pre_ids_all.shape
+    call("b200_set_value_by_flags_and_idx", ptr(stop_flags), ptr(pre_ids_all), ptr(pre_ids_now), ptr(step_idx), bs, length,
+         stream_ptr())
+
+
+def set_value_by_flags_and_idx_v2(pre_ids_all, input_ids, seq_lens_this_time, seq_lens_encoder, seq_lens_decoder, step_idx,
+                                  stop_flags):
+    bs, length = pre_ids_all.shape
+    call("b200_set_value_by_flags_and_idx_v2", ptr(stop_flags), ptr(pre_ids_all), ptr(input_ids), ptr(seq_lens_encoder),
+         ptr(seq_lens_decoder), ptr(step_idx), bs, length, input_ids.shape[1], stream_ptr())
+
+
+def token_penalty_multi_scores(pre_ids, logits, penalty_scores, frequency_scores, presence_scores, temperatures, bad_tokens,
+                               cur_len, min_len, eos_token_id):
+    """In place on fp32 logits (get_token_penalty_multi_scores_v2; pass temperatures/bad_tokens=None for the v1 op)."""
+    _chk(logits, "logits", torch.float32)
+    bs, length = logits.shape
+    ws = _workspace(bs * length * 4, logits.device, "penalty")
+    call("b200_token_penalty_multi_scores", ptr(pre_ids), ptr(logits), ptr(penalty_scores), ptr(frequency_scores),
+         ptr(presence_scores), ptr(temperatures), ptr(bad_tokens), ptr(cur_len), ptr(min_len), ptr(eos_token_id), ptr(ws), bs,
+         length, pre_ids.shape[1], 0 if bad_tokens is None else bad_tokens.numel(), eos_token_id.numel(), stream_ptr())
+    return logits
+
+
+def set_stop_value_multi_ends(topk_ids, stop_flags, end_ids, seq_lens=None, next_tokens=None):
+    """v2 when seq_lens / next_tokens are given, else the v1 op in mode 2.  In place."""
+    v2 = seq_lens is not None
+    call("b200_set_stop_value_multi_ends", ptr(stop_flags), ptr(topk_ids), ptr(next_tokens), ptr(end_ids), ptr(seq_lens),
+         topk_ids.numel(), end_ids.numel(), 1 if v2 else 0, stream_ptr())
+
+
+def update_inputs(stop_flags, not_need_stop, seq_lens_this_time, seq_lens_encoder, seq_lens_decoder, input_ids, stop_nums,
+                  next_tokens, is_block_step):
+    call("b200_update_inputs", ptr(not_need_stop), ptr(seq_lens_this_time), ptr(seq_lens_encoder), ptr(seq_lens_decoder),
+         ptr(input_ids), ptr(stop_nums), ptr(stop_flags), ptr(is_block_step), ptr(next_tokens), seq_lens_this_time.numel(),
+         stop_flags.numel(), input_ids.shape[1], stream_ptr())
+
+
+def generate_step_update(next_tokens, stop_flags, step_idx, max_dec_len, seq_len_decoder, pre_ids, eos_ids, out_tokens,
+                         stop_count, out_col=0, out_col_dev=None):
+    bs = next_tokens.numel()
+    call("b200_generate_step_update", ptr(next_tokens), ptr(stop_flags), ptr(step_idx), ptr(max_dec_len), ptr(seq_len_decoder),
+         ptr(pre_ids), pre_ids.shape[1], ptr(eos_ids), eos_ids.numel(), ptr(out_tokens),
+         0 if out_tokens is None else out_tokens.shape[1], int(out_col), ptr(out_col_dev), ptr(stop_count), bs, stream_ptr())
+
+
+def argmax_f32(logits):
+    _chk(logits, "logits", torch.float32)
+    rows, V = logits.shape
+    out = torch.empty(rows, dtype=torch.int64, device=logits.device)
+    call("b200_argmax_f32", ptr(logits), ptr(out), rows, V, logits.stride(0), stream_ptr())
+    return out
+
+
+def bf16_rows_to_f32(src, out=None):
+    _chk(src, "src")
+    rows, cols = src.shape
+    if out is None:
+        out = torch.empty(rows, cols, dtype=torch.float32, device=src.device)
+    call("b200_bf16_rows_to_f32", ptr(src), ptr(out), rows, cols, src.stride(0), stream_ptr())
+    return out

@@ -1,0 +1,66 @@
+"""Pin the numpy restatements of the generation bookkeeping ops (oracle/generation_ref.py) against the known-answer
+vectors of the reference's own op tests (tests/golden/bookkeeping.json <- csrc/xpu/test/python/test_*.py)."""
+import json
+import os
+
+import numpy as np
+
+from oracle import generation_ref as G
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bookkeeping.json")))
+
+
+def test_get_padding_offset_v2_known_answer():
+    g = GOLD["get_padding_offset_v2"]
+    xr, co, po, cq, ck = G.get_padding_offset_v2(np.array(g["input_ids"], np.int64), np.array(g["cum_offsets"], np.int32),
+                                                 g["token_num"], np.array(g["seq_lens"], np.int32))
+    assert xr.tolist() == g["ref_x_remove_padding"]
+    assert co.tolist() == g["ref_cum_offsets_out"] == [0, 6, 13]
+    assert po.tolist() == g["ref_padding_offset"]
+    assert cq.tolist() == g["ref_cu_seqlens_q"] == [0, 4, 7, 13] and ck.tolist() == g["ref_cu_seqlens_k"]
+
+
+def test_token_penalty_v2_known_answer():
+    g = GOLD["token_penalty_v2"]
+    for case in g["cases"]:
+        out = G.token_penalty_multi_scores_v2(
+            np.array(case["pre_ids"], np.int64), np.array(case["logits"], np.float32), g["penalty_scores"],
+            g["frequency_scores"], g["presence_scores"], g["temperatures"], g["bad_tokens"], g["cur_len"], g["min_len"],
+            g["eos_token_id"])
+        ref = np.array(case["ref_logits"], np.float32)
+        assert np.sum(np.abs(out - ref)) < 1e-6     # the reference's own assertion (test_get_token_penalty_multi_scores_v2.py:86-88)
+
+
+def test_set_stop_value_multi_ends_v2_known_answer():
+    g = GOLD["set_stop_value_multi_ends_v2"]
+    topk, stop, nxt = G.set_stop_value_multi_ends_v2(np.array(g["topk_ids"], np.int64), np.array(g["stop_flags"], bool),
+                                                     np.array(g["seq_lens"], np.int32), g["end_ids"],
+                                                     np.array(g["next_tokens"], np.int64))
+    assert topk.tolist() == g["ref_topk_ids"] and nxt.tolist() == g["ref_next_tokens"] and stop.tolist() == g["ref_stop_flags"]
+
+
+def test_set_value_by_flags_and_idx_v2_known_answer():
+    g = GOLD["set_value_by_flags_and_idx_v2"]
+    out = G.set_value_by_flags_and_idx_v2(np.array(g["pre_ids_all"], np.int64), np.array(g["input_ids"], np.int64),
+                                          g["seq_lens_encoder"], g["seq_lens_decoder"], g["step_idx"], g["stop_flags"])
+    assert out.tolist() == g["ref_pre_ids_all"]
+
+
+def _update_inputs_case():
+    g = GOLD["update_inputs"]
+    max_bs = len(g["stop_flags"])
+    ids = np.zeros((max_bs, 4), np.int64)       # only column 0 is touched by the op
+    ids[:, 0] = g["input_ids_col0_before"]
+    return g, ids
+
+
+def test_update_inputs_known_answer():
+    g, ids = _update_inputs_case()
+    nns, tt, enc, dec, ids2 = G.update_inputs(np.array(g["stop_flags"], bool), np.array(g["seq_lens_this_time"], np.int32),
+                                              np.array(g["seq_lens_encoder"], np.int32), np.array(g["seq_lens_decoder"], np.int32),
+                                              ids, g["stop_nums"], np.array(g["next_tokens"], np.int64),
+                                              np.array(g["is_block_step"], bool))
+    assert bool(nns[0]) == g["ref_not_need_stop"]
+    assert tt.tolist() == g["ref_seq_lens_this_time"]
+    assert enc.tolist() == g["ref_seq_lens_encoder"] and dec.tolist() == g["ref_seq_lens_decoder"]
+    assert ids2[:, 0].tolist() == g["ref_input_ids_col0"]
