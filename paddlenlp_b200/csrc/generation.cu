@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const bf16* __res
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hw = warp * 2 + (lane >> 4);               // half-warp id 0..7
   const int sub = lane & 15;                           // which 8 dims of the row
+  const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
   float q[G][8], o[G][8], m[G], l[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
@@ -200,10 +201,11 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const bf16* __res
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += q[g][j] * kf[j];
-      s += __shfl_xor_sync(0xffffffffu, s, 8);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      // the two half-warps of a warp can have different trip counts: shuffle within the half-warp only
+      s += __shfl_xor_sync(hmask, s, 8);
+      s += __shfl_xor_sync(hmask, s, 4);
+      s += __shfl_xor_sync(hmask, s, 2);
+      s += __shfl_xor_sync(hmask, s, 1);
       const float mn = fmaxf(m[g], s);
       const float corr = exp2f(m[g] - mn);
       const float p = exp2f(s - mn);

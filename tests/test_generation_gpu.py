@@ -207,13 +207,16 @@ def test_greedy_generation_matches_uncached_oracle(use_graph):
     out = out.cpu()
     # token-id argmax must match wherever the oracle's top-1/top-2 margin is above bf16 noise; after a legitimate
     # near-tie divergence the sequences differ, so compare up to the first non-decisive position of each row.
+    compared = 0
     for b in range(B):
         for tpos in range(new):
             if margins[b, tpos] < 2e-2:
                 break
             assert int(out[b, tpos]) == int(ref[b, tpos]), (b, tpos, out[b].tolist(), ref[b].tolist())
-    assert (out == ref).float().mean().item() > 0.8
-    assert dec.cpu().tolist() == (lens + new - 1).tolist()            # cache slots used = prompt + generated - 1
+            compared += 1
+    assert compared >= 12, f"only {compared} decisive positions were compared"
+    # the last generated token is never fed back: the last appended cache index is prompt + generated - 2
+    assert dec.cpu().tolist() == (lens + new - 2).tolist()
 
 
 def test_generation_stops_on_eos_and_penalty_path_runs():
