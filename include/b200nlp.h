@@ -61,6 +61,15 @@ int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const float* bias, 
                       int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int a_mn_major,
                       int b_mn_major, int accumulate, int cta_group, int max_ctas, cudaStream_t stream);
 
+/* Weight-streaming GEMM for the decode step (M <= ~128 tokens): same math as b200_gemm_bf16 (C = op(A) op(B) + bias, one
+ * rounding), but K is split over CTAs (split_k, 0 = auto) so that every SM streams part of the weight matrix; fp32 partial
+ * tiles are summed in L2 by TMA reduce-add into `workspace` (b200_gemm_splitk_workspace_bytes) and rounded once.
+ * Replaces the cuBLASLt calls of FusedMultiTransformer's decode step (fused_transformer_layers.py:817-820, 895-896, 967-974). */
+int64_t b200_gemm_splitk_workspace_bytes(int64_t M, int64_t N);
+int b200_gemm_bf16_splitk(const void* A, const void* B, void* C, const float* bias, void* workspace, int64_t M, int64_t N,
+                          int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int split_k,
+                          cudaStream_t stream);
+
 /* ---- RMSNorm: replaces fused_ln.fused_rms_norm / fast_ln (apex-derived custom ops) --------------------------
  * fwd : y = bf16( bf16(x * rstd) * w ), rstd[row] = rsqrt(mean(x^2) + eps) in fp32 (saved for the backward).
  * bwd : dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) (+ dres, the gradient arriving through the residual branch);

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "b200_device_check": [],
     "b200_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, P],
     "b200_gemm_bf16_ex": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I, I, I, I, I, P],
+    "b200_gemm_splitk_workspace_bytes": [I64, I64],
+    "b200_gemm_bf16_splitk": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, P],
     "b200_rmsnorm_fwd": [P, P, P, P, I64, I64, F, P],
     "b200_rmsnorm_bwd_workspace_bytes": [I64, I64],
     "b200_rmsnorm_bwd": [P, P, P, P, P, P, P, I, P, I64, I64, P],
@@ -63,6 +65,7 @@ _SIGNATURES = {
 _RESTYPE = {
     "b200_last_error": c_char_p,
     "b200_rmsnorm_bwd_workspace_bytes": c_int64,
+    "b200_gemm_splitk_workspace_bytes": c_int64,
     "b200_colsum_workspace_bytes": c_int64,
     "b200_fa_bwd_workspace_bytes": c_int64,
     "b200_grad_sqnorm_workspace_bytes": c_int64,
@@ -104,7 +107,7 @@ class B200Error(RuntimeError):
 
 # CUDA kernels each entry point launches (used by bench.py to report `gpu_launches`; memsets are not counted).
 KERNELS_PER_CALL = {
-    "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_rmsnorm_fwd": 1, "b200_rmsnorm_bwd": 2, "b200_colsum_bf16": 2,
+    "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_gemm_bf16_splitk": 2, "b200_rmsnorm_fwd": 1, "b200_rmsnorm_bwd": 2, "b200_colsum_bf16": 2,
     "b200_rope_inplace": 1, "b200_swiglu_fwd": 1, "b200_swiglu_bwd": 1, "b200_embedding_fwd": 1, "b200_embedding_bwd": 1,
     "b200_fa_fwd": 1, "b200_fa_bwd": 3, "b200_ce_fwd": 2, "b200_ce_bwd": 1, "b200_argmax_bf16": 1, "b200_grad_sqnorm": 2,
     "b200_adamw_step": 1, "b200_bf16_to_f32": 1, "b200_token_penalty_multi_scores": 2, "b200_generate_step_update": 2,

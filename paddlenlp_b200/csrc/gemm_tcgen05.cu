@@ -51,7 +51,9 @@ struct Cfg {
 struct Params {
   int M, N, K;
   int num_m_tiles, num_n_tiles;
-  int epi_mode;            // 0: C = acc ; 1: C = bf16(C_old + acc) ; 2: C = bf16(bf16(acc) + R)
+  int epi_mode;            // 0: C = acc ; 1: C = bf16(C_old + acc) ; 2: C = bf16(bf16(acc) + R) ; 3: F32ws += acc (split-K)
+  int split_k;             // work items per output tile (K is cut into split_k ranges of kb_per_split k-blocks)
+  int kb_per_split;
   const float* bias;       // [N] fp32 or nullptr
 };
 
@@ -90,8 +92,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool is_leader = cta_rank == 0;
   const int pair_id = blockIdx.x / CG;
   const int num_pairs = gridDim.x / CG;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;   // work items
+  const int num_kb_total = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -122,10 +124,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int t = pair_id; t < num_tiles; t += num_pairs) {
         int m_blk, n_blk;
-        tile_coords(t, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
+        tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
+        const int kb0 = (t % p.split_k) * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         const int m0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM;   // this CTA's A rows
         const int n0 = n_blk * BN + static_cast<int>(cta_rank) * C::B_COLS;   // this CTA's B columns
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
@@ -169,7 +172,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tmem_empty[as], aphase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = (t % p.split_k) * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -178,7 +182,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t da = umma_desc_sw128(sa + k * a_adv, a_lbo, 1024);
             const uint64_t db = umma_desc_sw128(sb + k * b_adv, b_lbo, 1024);
-            umma_ss<CG>(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_ss<CG>(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -198,7 +202,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int buf = 0;
     for (int t = pair_id; t < num_tiles; t += num_pairs) {
       int m_blk, n_blk;
-      tile_coords(t, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
+      tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
       const int row0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM + q * 32;
       const int col0 = n_blk * BN;
       mbar_wait(&tmem_full[as], aphase);
@@ -212,7 +216,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
         const bool live = (row0 < p.M) && (c0 < p.N);
-        if (p.epi_mode && live && lane == 0) {
+        if (p.epi_mode && p.epi_mode != 3 && live && lane == 0) {
           mbar_arrive_expect_tx(&epi_bar[q], EPI_BUF_BYTES);
           tma_load_2d(&tmR, &epi_bar[q], my_buf + buf * EPI_BUF_BYTES, c0, row0);
         }
@@ -226,7 +230,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
         }
-        if (live) {
+        if (live && p.epi_mode == 3) {
+          // split-K: fp32 partial tile -> swizzled staging -> TMA reduce-add into the fp32 workspace (two 32-col boxes)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int hb = buf ^ half;
+            if (half == 1) {
+              if (lane == 0) tma_store_wait_read<1>();
+              __syncwarp();
+            }
+            const uint32_t row_s = my_buf_s + hb * EPI_BUF_BYTES + lane * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint32_t* v = half ? v1 : v0;
+              st_shared_v4(row_s + ((c ^ (lane & 7)) << 4), make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && c0 + half * 32 < p.N) {
+              tma_reduce_add_2d(&tmR, my_buf + hb * EPI_BUF_BYTES, c0 + half * 32, row0);
+              tma_store_commit();
+            }
+          }
+        } else if (live) {
           if (p.epi_mode) { mbar_wait(&epi_bar[q], ephase); }
           const uint32_t row_s = sbuf + lane * 128;
 #pragma unroll
@@ -271,7 +297,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (p.epi_mode) ephase ^= 1u;
         }
-        buf ^= 1;
+        if (p.epi_mode != 3) buf ^= 1;
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
@@ -301,7 +327,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     }
     attr_set = true;
   }
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   int sms = sm_count();
   if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
   int pairs = sms / CG;
@@ -386,6 +412,8 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const fl
   p.num_m_tiles = static_cast<int>((M + BM * cta_group - 1) / (BM * cta_group));
   p.num_n_tiles = static_cast<int>((N + BN - 1) / BN);
   p.epi_mode = residual ? 2 : (accumulate ? 1 : 0);
+  p.split_k = 1;
+  p.kb_per_split = static_cast<int>((K + BK - 1) / BK);
   p.bias = bias;
 
 #define B200_GEMM_DISPATCH(CG)                                                                          \
@@ -398,6 +426,107 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const fl
   if (cta_group == 2) B200_GEMM_DISPATCH(2);
   B200_GEMM_DISPATCH(1);
 #undef B200_GEMM_DISPATCH
+}
+
+namespace b200 {
+namespace gemm {
+// out[m, n] = bf16(ws[m, n] + bias[n])
+__global__ void splitk_finish_kernel(const float* __restrict__ ws, const float* __restrict__ bias, bf16* __restrict__ out,
+                                     int64_t M, int64_t N, int64_t ldc) {
+  const int64_t nch = N >> 3;
+  const int64_t total = M * nch;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / nch, c = i % nch;
+    const float4* src = reinterpret_cast<const float4*>(ws + r * N) + 2 * c;
+    float4 a = src[0], b = src[1];
+    if (bias != nullptr) {
+      const float4* bp = reinterpret_cast<const float4*>(bias) + 2 * c;
+      const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+      a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w;
+      b.x += b1.x; b.y += b1.y; b.z += b1.z; b.w += b1.w;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    *(reinterpret_cast<uint4*>(out + r * ldc) + c) = o;
+  }
+}
+}  // namespace gemm
+}  // namespace b200
+
+extern "C" int64_t b200_gemm_splitk_workspace_bytes(int64_t M, int64_t N) { return M * N * 4; }
+
+// Weight-streaming ("skinny") GEMM for the decode step: M <= 128 tokens, the weight matrix dominates the traffic, so K is
+// split across CTAs until the persistent grid covers every SM; fp32 partial tiles are reduced in L2 by the TMA unit.
+extern "C" int b200_gemm_bf16_splitk(const void* A, const void* B, void* C, const float* bias, void* workspace, int64_t M,
+                                     int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major,
+                                     int b_mn_major, int split_k, cudaStream_t stream) {
+  using namespace b200;
+  using namespace b200::gemm;
+  B200_CHECK_ARG(A && B && C && workspace, "gemm_splitk: null pointer");
+  B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && N % 8 == 0, "gemm_splitk: bad dimensions (N must be a multiple of 8)");
+  B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "gemm_splitk: leading dimensions must be multiples of 8");
+  CUtensorMap tmA, tmB, tmC, tmF;
+  int rc;
+  {
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (a_mn_major) { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = BK; }
+    else            { dims[0] = K; dims[1] = M; box[0] = BK; box[1] = 128; }
+    strides[0] = static_cast<uint64_t>(lda) * 2;
+    if ((rc = encode_tmap_bf16(&tmA, A, 2, dims, strides, box)) != 0) return rc;
+  }
+  {
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (b_mn_major) { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
+    else            { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = 128; }
+    strides[0] = static_cast<uint64_t>(ldb) * 2;
+    if ((rc = encode_tmap_bf16(&tmB, B, 2, dims, strides, box)) != 0) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldc) * 2};
+    uint32_t box[2] = {EPI_BOX_COLS, EPI_BOX_ROWS};
+    if ((rc = encode_tmap_bf16(&tmC, C, 2, dims, strides, box)) != 0) return rc;   // unused by mode 3, kept valid
+    uint64_t fstrides[1] = {static_cast<uint64_t>(N) * 4};
+    uint32_t fbox[2] = {32, 32};
+    if ((rc = encode_tmap_f32(&tmF, workspace, 2, dims, fstrides, fbox)) != 0) return rc;
+  }
+  Params p;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.num_m_tiles = static_cast<int>((M + BM - 1) / BM);
+  p.num_n_tiles = static_cast<int>((N + BN - 1) / BN);
+  const int num_kb = static_cast<int>((K + BK - 1) / BK);
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  if (split_k <= 0) {
+    // smallest split that gives every SM at least one work item, capped so each item keeps >= 4 k-blocks
+    const int sms = sm_count();
+    split_k = (sms + tiles - 1) / tiles;
+    if (split_k > num_kb / 4) split_k = num_kb / 4;
+    if (split_k < 1) split_k = 1;
+  }
+  p.kb_per_split = (num_kb + split_k - 1) / split_k;
+  p.split_k = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty ranges
+  p.epi_mode = 3;
+  p.bias = nullptr;
+  cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(M) * N * 4, stream);
+  if (e != cudaSuccess) {
+    set_last_error("gemm_splitk memset: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  if (a_mn_major && b_mn_major) rc = launch<1, true, true>(tmA, tmB, tmC, tmF, p, 0, stream);
+  else if (a_mn_major) rc = launch<1, true, false>(tmA, tmB, tmC, tmF, p, 0, stream);
+  else if (b_mn_major) rc = launch<1, false, true>(tmA, tmB, tmC, tmF, p, 0, stream);
+  else rc = launch<1, false, false>(tmA, tmB, tmC, tmF, p, 0, stream);
+  if (rc) return rc;
+  const int64_t total = M * (N / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  splitk_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const float*>(workspace), bias,
+                                                                         static_cast<bf16*>(C), M, N, ldc);
+  return check_launch("gemm_splitk(finish)");
 }
 
 extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N, int64_t K,

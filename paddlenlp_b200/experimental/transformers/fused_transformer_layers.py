@@ -87,9 +87,16 @@ class FusedMultiTransformerBase:
             self._bias_f32[i] = self.qkv_biases[i].float()
         return self._bias_f32[i]
 
+    SKINNY_M = 128     # at or below this many token rows the GEMMs are weight-streaming bound: split-K kernel
+
+    def _mm(self, a, w, trans_b=False, bias=None):
+        if a.shape[0] <= self.SKINNY_M:
+            return ops.gemm_skinny(a, w, trans_b=trans_b, bias=bias)
+        return ops.gemm(a, w, trans_b=trans_b, bias=bias)
+
     # compute_qkv (:817-820): linear(ln_out, qkv_weight, transpose_weight=True)
     def compute_qkv(self, ln_out, i):
-        return ops.gemm(ln_out, self.qkv_weights[i], trans_b=True, bias=self._bias(i))
+        return self._mm(ln_out, self.qkv_weights[i], trans_b=True, bias=self._bias(i))
 
     # compute_fmha (:829-882): qkv_transpose_split -> encode_rotary_qk -> write_cache_kv -> var-len attention
     def compute_fmha(self, qkv, cache, B, S, seq_lens_encoder):
@@ -124,11 +131,11 @@ class FusedMultiTransformerBase:
                 attn = self.compute_mmha(qkv, caches[i], seq_lens_decoder)
             else:
                 attn = self.compute_fmha(qkv, caches[i], B, S, seq_lens_encoder)
-            out = ops.gemm(attn, self.linear_weights[i])                                      # compute_out_linear (:895-896)
+            out = self._mm(attn, self.linear_weights[i])                                      # compute_out_linear (:895-896)
             ln_out, residual = ops.add_rmsnorm(out, residual, self.ffn_ln_scales[i], eps)     # compute_ffn_layernorm (:937-949)
-            ffn1 = ops.gemm(ln_out, self.ffn1_weights[i])
+            ffn1 = self._mm(ln_out, self.ffn1_weights[i])
             act = ops.swiglu_fwd(ffn1)                                                        # fused_bias_act("swiglu") (:100-168)
-            ffn2 = ops.gemm(act, self.ffn2_weights[i])
+            ffn2 = self._mm(act, self.ffn2_weights[i])
             if i != self.L - 1:                                                               # compute_bias_residual_layernorm (:976-999)
                 ln_out, residual = ops.add_rmsnorm(ffn2, residual, self.ln_scales[i + 1], eps)
             else:

@@ -76,7 +76,7 @@ class LlamaForCausalLMInferenceModel(GenerationInferenceModel):
     # ---- forward ----
     def _head(self, hidden):
         hn, _ = ops.add_rmsnorm(hidden, None, self.norm_weight, self.config.rms_norm_eps, want_residual=False)
-        return ops.gemm(hn, self.lm_head_weight)
+        return self.transformer_block._mm(hn, self.lm_head_weight)
 
     def _prefill(self, input_ids, seq_lens_encoder, caches):
         B, S = input_ids.shape

@@ -77,6 +77,25 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     return out
 
 
+def gemm_skinny(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, trans_b: bool = False,
+                bias: Optional[torch.Tensor] = None, split_k: int = 0) -> torch.Tensor:
+    """Decode-step GEMM (few token rows, weight-streaming bound): split-K over all SMs, fp32 TMA reduce, one rounding."""
+    _chk(a, "a"); _chk(b, "b")
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N, Kb = (b.shape if trans_b else (b.shape[1], b.shape[0]))
+    if K != Kb:
+        raise ValueError(f"gemm_skinny: inner dimensions differ ({K} vs {Kb})")
+    if out is None:
+        out = torch.empty(M, N, dtype=BF16, device=a.device)
+    if bias is not None:
+        _chk(bias, "bias", torch.float32)
+    ws = _workspace(M * N * 4, a.device, "splitk")
+    call("b200_gemm_bf16_splitk", ptr(a), ptr(b), ptr(out), ptr(bias), ptr(ws), M, N, K, a.stride(0), b.stride(0),
+         out.stride(0), 0, 0 if trans_b else 1, split_k, stream_ptr())
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------
 # RMSNorm
 # ----------------------------------------------------------------------------------------------------------

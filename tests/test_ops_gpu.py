@@ -82,6 +82,19 @@ def test_gemm_residual_epilogue():
     assert mism < 0.02 and maxerr(out, ref) < 2 ** -7           # only fp32 accumulation-order ties may differ
 
 
+@pytest.mark.parametrize("tb", [False, True])
+@pytest.mark.parametrize("M,N,K,split", [(64, 6144, 4096, 0), (64, 4096, 14336, 0), (8, 520, 328, 3), (100, 1024, 640, 0)])
+def test_gemm_skinny_splitk(M, N, K, split, tb):
+    o = ops()
+    A = rand_bf16(M, K, seed=40, scale=0.5)
+    B = rand_bf16(K, N, seed=41, scale=0.5)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(42))
+    b_d = (B.t().contiguous() if tb else B).to(DEV)
+    out = o.gemm_skinny(A.to(DEV), b_d, trans_b=tb, bias=bias.to(DEV), split_k=split)
+    ref = A.float().to(DEV) @ B.float().to(DEV) + bias.to(DEV)
+    assert maxerr(out, ref) < 2 ** -7 and relerr(out, ref) < 4e-3
+
+
 def test_gemm_argument_errors():
     o = ops()
     from paddlenlp_b200._lib import B200Error
