@@ -94,9 +94,8 @@ class GenerationInferenceModel:
             step(); done += 1                                    # warm-up (sets kernel attributes, allocator pools)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph):                        # capture only records: no step is executed here
                 step()
-            done += 1
         while done < n_steps:
             if graph is not None:
                 graph.replay()
