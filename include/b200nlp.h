@@ -63,7 +63,8 @@ int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const float* bias, 
 
 /* Weight-streaming GEMM for the decode step (M <= ~128 tokens): same math as b200_gemm_bf16 (C = op(A) op(B) + bias, one
  * rounding), but K is split over CTAs (split_k, 0 = auto) so that every SM streams part of the weight matrix; fp32 partial
- * tiles are summed in L2 by TMA reduce-add into `workspace` (b200_gemm_splitk_workspace_bytes) and rounded once.
+ * tiles are summed in L2 by TMA reduce-add into `workspace` (b200_gemm_splitk_workspace_bytes; must be ZERO on entry,
+ * is returned zeroed) and rounded once.
  * Replaces the cuBLASLt calls of FusedMultiTransformer's decode step (fused_transformer_layers.py:817-820, 895-896, 967-974). */
 int64_t b200_gemm_splitk_workspace_bytes(int64_t M, int64_t N);
 int b200_gemm_bf16_splitk(const void* A, const void* B, void* C, const float* bias, void* workspace, int64_t M, int64_t N,

@@ -430,16 +430,18 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const fl
 
 namespace b200 {
 namespace gemm {
-// out[m, n] = bf16(ws[m, n] + bias[n])
-__global__ void splitk_finish_kernel(const float* __restrict__ ws, const float* __restrict__ bias, bf16* __restrict__ out,
+// out[m, n] = bf16(ws[m, n] + bias[n]) ; ws is re-zeroed for the next split-K GEMM that uses it
+__global__ void splitk_finish_kernel(float* __restrict__ ws, const float* __restrict__ bias, bf16* __restrict__ out,
                                      int64_t M, int64_t N, int64_t ldc) {
   const int64_t nch = N >> 3;
   const int64_t total = M * nch;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = i / nch, c = i % nch;
-    const float4* src = reinterpret_cast<const float4*>(ws + r * N) + 2 * c;
+    float4* src = reinterpret_cast<float4*>(ws + r * N) + 2 * c;
     float4 a = src[0], b = src[1];
+    src[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias != nullptr) {
       const float4* bp = reinterpret_cast<const float4*>(bias) + 2 * c;
       const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
@@ -511,11 +513,7 @@ extern "C" int b200_gemm_bf16_splitk(const void* A, const void* B, void* C, cons
   p.split_k = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty ranges
   p.epi_mode = 3;
   p.bias = nullptr;
-  cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(M) * N * 4, stream);
-  if (e != cudaSuccess) {
-    set_last_error("gemm_splitk memset: %s", cudaGetErrorString(e));
-    return static_cast<int>(e);
-  }
+  // `workspace` must be all-zero on entry; the finish kernel leaves it zeroed again (no memset per GEMM).
   if (a_mn_major && b_mn_major) rc = launch<1, true, true>(tmA, tmB, tmC, tmF, p, 0, stream);
   else if (a_mn_major) rc = launch<1, true, false>(tmA, tmB, tmC, tmF, p, 0, stream);
   else if (b_mn_major) rc = launch<1, false, true>(tmA, tmB, tmC, tmF, p, 0, stream);
@@ -524,7 +522,7 @@ extern "C" int b200_gemm_bf16_splitk(const void* A, const void* B, void* C, cons
   const int64_t total = M * (N / 8);
   int64_t blocks = (total + 255) / 256;
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  splitk_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const float*>(workspace), bias,
+  splitk_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<float*>(workspace), bias,
                                                                          static_cast<bf16*>(C), M, N, ldc);
   return check_launch("gemm_splitk(finish)");
 }

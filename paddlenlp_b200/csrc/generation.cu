@@ -185,34 +185,47 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const bf16* __res
   const size_t half = static_cast<size_t>(B) * kvh * max_len * D;
   const bf16* kbase = cache + (static_cast<size_t>(b) * kvh + kh) * max_len * D;
   const bf16* vbase = kbase + half;
-  for (int t = hw; t < len; t += 8) {
-    const uint4 kv = ld_nc_v4(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(t) * D) + sub);
-    const uint4 vv = ld_nc_v4(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(t) * D) + sub);
-    float kf[8], vf[8];
-    const uint32_t* ki = reinterpret_cast<const uint32_t*>(&kv);
-    const uint32_t* vi = reinterpret_cast<const uint32_t*>(&vv);
+  constexpr int U = 4;      // rows in flight per half-warp: 8 x 16-byte loads issued before any math (memory-level parallelism)
+  for (int t0 = hw; t0 < len; t0 += 8 * U) {
+    uint4 kv[U], vv[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 a = unpack_bf16x2(ki[j]), c = unpack_bf16x2(vi[j]);
-      kf[2 * j] = a.x; kf[2 * j + 1] = a.y; vf[2 * j] = c.x; vf[2 * j + 1] = c.y;
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + 8 * u;
+      if (t < len) {
+        kv[u] = ld_nc_v4(reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(t) * D) + sub);
+        vv[u] = ld_nc_v4(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(t) * D) + sub);
+      }
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float s = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + 8 * u;
+      if (t >= len) break;                 // uniform within the half-warp
+      float kf[8], vf[8];
+      const uint32_t* ki = reinterpret_cast<const uint32_t*>(&kv[u]);
+      const uint32_t* vi = reinterpret_cast<const uint32_t*>(&vv[u]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += q[g][j] * kf[j];
-      // the two half-warps of a warp can have different trip counts: shuffle within the half-warp only
-      s += __shfl_xor_sync(hmask, s, 8);
-      s += __shfl_xor_sync(hmask, s, 4);
-      s += __shfl_xor_sync(hmask, s, 2);
-      s += __shfl_xor_sync(hmask, s, 1);
-      const float mn = fmaxf(m[g], s);
-      const float corr = exp2f(m[g] - mn);
-      const float p = exp2f(s - mn);
-      l[g] = l[g] * corr + p;
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(ki[j]), c = unpack_bf16x2(vi[j]);
+        kf[2 * j] = a.x; kf[2 * j + 1] = a.y; vf[2 * j] = c.x; vf[2 * j + 1] = c.y;
+      }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[g][j] = o[g][j] * corr + p * vf[j];
-      m[g] = mn;
+      for (int g = 0; g < G; ++g) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += q[g][j] * kf[j];
+        // the two half-warps of a warp can have different trip counts: shuffle within the half-warp only
+        s += __shfl_xor_sync(hmask, s, 8);
+        s += __shfl_xor_sync(hmask, s, 4);
+        s += __shfl_xor_sync(hmask, s, 2);
+        s += __shfl_xor_sync(hmask, s, 1);
+        const float mn = fmaxf(m[g], s);
+        const float corr = exp2f(m[g] - mn);
+        const float p = exp2f(s - mn);
+        l[g] = l[g] * corr + p;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[g][j] = o[g][j] * corr + p * vf[j];
+        m[g] = mn;
+      }
     }
   }
   // merge the 8 half-warp partials

@@ -36,6 +36,16 @@ def _workspace(nbytes: int, device, tag: str = "") -> torch.Tensor:
     return buf
 
 
+def _zero_workspace(nbytes: int, device, tag: str) -> torch.Tensor:
+    """Scratch buffer that is zero-filled when (re)allocated; its users must hand it back zeroed."""
+    key = (device, tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
 # ----------------------------------------------------------------------------------------------------------
 # GEMM
 # ----------------------------------------------------------------------------------------------------------
@@ -90,7 +100,7 @@ def gemm_skinny(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = 
         out = torch.empty(M, N, dtype=BF16, device=a.device)
     if bias is not None:
         _chk(bias, "bias", torch.float32)
-    ws = _workspace(M * N * 4, a.device, "splitk")
+    ws = _zero_workspace(M * N * 4, a.device, "splitk")
     call("b200_gemm_bf16_splitk", ptr(a), ptr(b), ptr(out), ptr(bias), ptr(ws), M, N, K, a.stride(0), b.stride(0),
          out.stride(0), 0, 0 if trans_b else 1, split_k, stream_ptr())
     return out
