@@ -170,11 +170,14 @@ int b200_decode_rope_append(void* qkv, void* cache, const float* cos_table, cons
                             int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len,
                             int64_t ld, cudaStream_t stream);
 /* Decode attention of one query token per sequence over cache positions [0, seq_lens[b]] (GQA, head_dim 128);
- * out [B, nh*d].  Replaces the attention half of masked_multihead_attention / append_attention decode
+ * out [B, nh*d].  num_splits > 1 splits each sequence's cache range over that many CTAs (split-KV, merged by a second
+ * kernel through `workspace`), as the reference's append_attention does (append_attention_c16_impl.cuh:826-1000).
+ * Replaces the attention half of masked_multihead_attention / append_attention decode
  * (csrc/gpu/append_attn/append_attention_c16_impl.cuh:377-744). */
-int b200_decode_attention(const void* qkv, const void* cache, const int32_t* seq_lens, void* out, int64_t B,
+int64_t b200_decode_attention_workspace_bytes(int64_t B, int64_t num_heads, int64_t num_splits);
+int b200_decode_attention(const void* qkv, const void* cache, const int32_t* seq_lens, void* out, void* workspace, int64_t B,
                           int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len, int64_t ld,
-                          float softmax_scale, cudaStream_t stream);
+                          float softmax_scale, int64_t num_splits, cudaStream_t stream);
 
 /* Bookkeeping ops, same semantics as the reference custom ops (file:line beside each). bool = 1-byte flags. */
 /* get_padding_offset_v2 (+ remove padding): csrc/gpu/get_padding_offset_v2.cu:17-80 */

@@ -157,13 +157,18 @@ __global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, bf16* __restri
 template <int G>
 __global__ void __launch_bounds__(128) decode_attention_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ cache,
                                                                const int* __restrict__ seq_lens, bf16* __restrict__ out,
-                                                               int B, int nh, int kvh, int max_len, int64_t ld,
-                                                               float scale_log2) {
+                                                               float* __restrict__ partial, int B, int nh, int kvh,
+                                                               int max_len, int64_t ld, float scale_log2) {
   constexpr int D = 128;
   __shared__ float s_m[8][G], s_l[8][G];
   __shared__ float s_o[8][G][D];
   const int b = blockIdx.x / kvh, kh = blockIdx.x % kvh;
-  const int len = min(seq_lens[b] + 1, max_len);       // the new token was appended at index seq_lens[b]
+  const int total_len = min(seq_lens[b] + 1, max_len);  // the new token was appended at index seq_lens[b]
+  // split-KV: gridDim.y CTAs share one (b, kv head); each takes a contiguous range of the cache
+  const int nsplit = gridDim.y, split = blockIdx.y;
+  const int chunk = (total_len + nsplit - 1) / nsplit;
+  const int t_begin = split * chunk;
+  const int len = min(total_len, t_begin + chunk);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hw = warp * 2 + (lane >> 4);               // half-warp id 0..7
   const int sub = lane & 15;                           // which 8 dims of the row
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const bf16* __res
   const bf16* kbase = cache + (static_cast<size_t>(b) * kvh + kh) * max_len * D;
   const bf16* vbase = kbase + half;
   constexpr int U = 4;      // rows in flight per half-warp: 8 x 16-byte loads issued before any math (memory-level parallelism)
-  for (int t0 = hw; t0 < len; t0 += 8 * U) {
+  for (int t0 = t_begin + hw; t0 < len; t0 += 8 * U) {
     uint4 kv[U], vv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -248,8 +253,39 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const bf16* __res
       acc += s_o[w][g][dd] * f;
       lt += s_l[w][g] * f;
     }
-    out[static_cast<size_t>(b) * nh * D + (kh * G + g) * D + dd] = __float2bfloat16_rn(lt > 0.f ? acc / lt : 0.f);
+    if (nsplit == 1) {
+      out[static_cast<size_t>(b) * nh * D + (kh * G + g) * D + dd] = __float2bfloat16_rn(lt > 0.f ? acc / lt : 0.f);
+    } else {
+      // partial[b, head, split, 0:128] = unnormalised o ; [.., 128] = running max (log2 units) ; [.., 129] = sum
+      float* dst = partial + ((static_cast<size_t>(b) * nh + kh * G + g) * nsplit + split) * (D + 2);
+      dst[dd] = acc;
+      if (dd == 0) { dst[D] = mm; dst[D + 1] = lt; }
+    }
   }
+}
+
+// merge the split-KV partials: one warp per (b, head)
+__global__ void decode_attention_merge_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int rows, int nsplit) {
+  constexpr int D = 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* base = partial + static_cast<size_t>(row) * nsplit * (D + 2);
+  float mm = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, base[s * (D + 2) + D]);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, lt = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float ms = base[s * (D + 2) + D];
+    const float f = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
+    lt += base[s * (D + 2) + D + 1] * f;
+    const float4 o = *reinterpret_cast<const float4*>(base + s * (D + 2) + lane * 4);
+    acc[0] += o.x * f; acc[1] += o.y * f; acc[2] += o.z * f; acc[3] += o.w * f;
+  }
+  const float inv = lt > 0.f ? 1.f / lt : 0.f;
+  uint2 o2;
+  o2.x = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+  o2.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+  *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * D + lane * 4) = o2;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -529,22 +565,28 @@ extern "C" int b200_decode_rope_append(void* qkv, void* cache, const float* cos_
   return check_launch("decode_rope_append");
 }
 
-extern "C" int b200_decode_attention(const void* qkv, const void* cache, const int32_t* seq_lens, void* out, int64_t B,
-                                     int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len, int64_t ld,
-                                     float softmax_scale, cudaStream_t stream) {
+extern "C" int64_t b200_decode_attention_workspace_bytes(int64_t B, int64_t num_heads, int64_t num_splits) {
+  return num_splits > 1 ? B * num_heads * num_splits * (128 + 2) * 4 : 0;
+}
+
+extern "C" int b200_decode_attention(const void* qkv, const void* cache, const int32_t* seq_lens, void* out, void* workspace,
+                                     int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len,
+                                     int64_t ld, float softmax_scale, int64_t num_splits, cudaStream_t stream) {
   B200_CHECK_ARG(qkv && cache && seq_lens && out, "decode_attention: null pointer");
+  B200_CHECK_ARG(num_splits >= 1 && num_splits <= 64 && (num_splits == 1 || workspace), "decode_attention: bad num_splits / workspace");
   B200_CHECK_ARG(head_dim == 128, "decode_attention: head_dim must be 128 (got %lld)", (long long)head_dim);
   B200_CHECK_ARG(num_heads % num_kv_heads == 0, "decode_attention: num_heads %% num_kv_heads != 0");
   const int G = static_cast<int>(num_heads / num_kv_heads);
   const float sl2 = softmax_scale * 1.4426950408889634f;
-  const dim3 grid(static_cast<unsigned>(B * num_kv_heads)), block(128);
+  const dim3 grid(static_cast<unsigned>(B * num_kv_heads), static_cast<unsigned>(num_splits)), block(128);
   const bf16* q = static_cast<const bf16*>(qkv);
   const bf16* c = static_cast<const bf16*>(cache);
   bf16* o = static_cast<bf16*>(out);
+  float* part = static_cast<float*>(workspace);
 #define B200_DA(GG)                                                                                                  \
   case GG:                                                                                                           \
-    decode_attention_kernel<GG><<<grid, block, 0, stream>>>(q, c, seq_lens, o, (int)B, (int)num_heads, (int)num_kv_heads, \
-                                                            (int)max_len, ld, sl2);                                 \
+    decode_attention_kernel<GG><<<grid, block, 0, stream>>>(q, c, seq_lens, o, part, (int)B, (int)num_heads,         \
+                                                            (int)num_kv_heads, (int)max_len, ld, sl2);              \
     break;
   switch (G) {
     B200_DA(1) B200_DA(2) B200_DA(4) B200_DA(7) B200_DA(8)
@@ -552,7 +594,11 @@ extern "C" int b200_decode_attention(const void* qkv, const void* cache, const i
       return fail_arg("decode_attention: GQA group size %d not instantiated (1, 2, 4, 7, 8)", G);
   }
 #undef B200_DA
-  return check_launch("decode_attention");
+  int rc = check_launch("decode_attention");
+  if (rc || num_splits == 1) return rc;
+  const int rows = static_cast<int>(B * num_heads);
+  decode_attention_merge_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(part, o, rows, (int)num_splits);
+  return check_launch("decode_attention(merge)");
 }
 
 extern "C" int b200_get_padding_offset(const int64_t* input_ids, const int32_t* cum_offsets, const int32_t* seq_lens,

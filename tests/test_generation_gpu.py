@@ -132,6 +132,9 @@ def test_decode_rope_append_and_attention(nh, kvh):
     qkv_d, cache_d = qkv.clone().to(DEV), cache.clone().to(DEV)
     o.decode_rope_append(qkv_d, cache_d, cos, sin, lens.to(DEV), nh, kvh, d)
     out = o.decode_attention(qkv_d, cache_d, lens.to(DEV), nh, kvh, d).float().cpu()
+    out1 = o.decode_attention(qkv_d, cache_d, lens.to(DEV), nh, kvh, d, num_splits=1).float().cpu()
+    out3 = o.decode_attention(qkv_d, cache_d, lens.to(DEV), nh, kvh, d, num_splits=3).float().cpu()
+    assert (out1 - out3).abs().max() < 1e-2 * out1.abs().max()
     c, s = R.rope_tables(d, max_len, 10000.0)
     for b in range(B):
         p = int(lens[b])

@@ -32,7 +32,7 @@ def main():
     max_len = a.prompt + a.gen
     caches = m.allocate_caches(a.batch, max_len)
     # warm-up (kernel attributes, allocator)
-    m.generate(ids, max_length=8, eos_token_id=-1, cache_kvs=caches, use_cuda_graph=not a.no_graph)
+    m.generate(ids, max_length=min(8, a.gen), eos_token_id=-1, cache_kvs=caches, use_cuda_graph=not a.no_graph)
     torch.cuda.synchronize()
     # prefill alone
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
