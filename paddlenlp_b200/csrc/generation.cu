@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const bf16* __res
       out[static_cast<size_t>(b) * nh * D + (kh * G + g) * D + dd] = __float2bfloat16_rn(lt > 0.f ? acc / lt : 0.f);
     } else {
       // partial[b, head, split, 0:128] = unnormalised o ; [.., 128] = running max (log2 units) ; [.., 129] = sum
-      float* dst = partial + ((static_cast<size_t>(b) * nh + kh * G + g) * nsplit + split) * (D + 2);
+      // (row stride 132 floats keeps the float4 reads of the merge kernel 16-byte aligned)
+      float* dst = partial + ((static_cast<size_t>(b) * nh + kh * G + g) * nsplit + split) * (D + 4);
       dst[dd] = acc;
       if (dd == 0) { dst[D] = mm; dst[D + 1] = lt; }
     }
@@ -270,15 +271,15 @@ __global__ void decode_attention_merge_kernel(const float* __restrict__ partial,
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* base = partial + static_cast<size_t>(row) * nsplit * (D + 2);
+  const float* base = partial + static_cast<size_t>(row) * nsplit * (D + 4);
   float mm = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, base[s * (D + 2) + D]);
+  for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, base[s * (D + 4) + D]);
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, lt = 0.f;
   for (int s = 0; s < nsplit; ++s) {
-    const float ms = base[s * (D + 2) + D];
+    const float ms = base[s * (D + 4) + D];
     const float f = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
-    lt += base[s * (D + 2) + D + 1] * f;
-    const float4 o = *reinterpret_cast<const float4*>(base + s * (D + 2) + lane * 4);
+    lt += base[s * (D + 4) + D + 1] * f;
+    const float4 o = *reinterpret_cast<const float4*>(base + s * (D + 4) + lane * 4);
     acc[0] += o.x * f; acc[1] += o.y * f; acc[2] += o.z * f; acc[3] += o.w * f;
   }
   const float inv = lt > 0.f ? 1.f / lt : 0.f;
@@ -566,7 +567,7 @@ extern "C" int b200_decode_rope_append(void* qkv, void* cache, const float* cos_
 }
 
 extern "C" int64_t b200_decode_attention_workspace_bytes(int64_t B, int64_t num_heads, int64_t num_splits) {
-  return num_splits > 1 ? B * num_heads * num_splits * (128 + 2) * 4 : 0;
+  return num_splits > 1 ? B * num_heads * num_splits * (128 + 4) * 4 : 0;
 }
 
 extern "C" int b200_decode_attention(const void* qkv, const void* cache, const int32_t* seq_lens, void* out, void* workspace,
