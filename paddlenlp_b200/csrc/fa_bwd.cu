@@ -14,8 +14,10 @@
 //   warp 0       TMA producer (K_j, V_j once; Q_i, dO_i per iteration)
 //   warp 1       MMA issuer   (5 UMMA GEMMs per iteration, operands K-major or MN-major straight from the same
 //                              swizzled tiles: Q and dO are consumed both ways)
-//   warps 2..5   one thread per q row: P and dS from TMEM S / dP, written as bf16 to swizzled smem; dQ read-out
-//   TMEM: S|dQ [0,128)  dP [128,256)  dV [256,384)  dK [384,512)
+//   warps 2..9   two threads per q row (64 columns each; the backward needs no row reduction): P and dS from TMEM
+//                S / dP, written as bf16 to swizzled smem; dQ / dK / dV read-out
+//   TMEM: S [0,128)  dP|dQ [128,256)  dV [256,384)  dK [384,512).  dQ reuses the dP columns, so S_{i+1} = Q_{i+1} K^T is
+//   issued while the dQ_i tile is still being read out, and the Q/dO stage is released before the dQ GEMM is issued.
 #include "../../include/b200nlp.h"
 #include "common.cuh"
 #include "host_util.h"
@@ -25,8 +27,8 @@ namespace fab {
 
 constexpr int TILE_BYTES = 128 * 128 * 2;
 constexpr int HALF_BYTES = TILE_BYTES / 2;
-constexpr int NUM_THREADS = 192;
-constexpr int STAGE_BYTES = 4 * 2 * 4096;                 // per-warp double-buffered 32x32 fp32 staging for TMA reduce
+constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 compute warps
+constexpr int STAGE_BYTES = 8 * 4096;                     // per-warp 32x32 fp32 staging for TMA reduce
 constexpr int SMEM_BYTES = 6 * TILE_BYTES + STAGE_BYTES + 256 + 1024;   // K, V, Q, dO, P, dS, staging
 
 struct Params {
@@ -36,17 +38,16 @@ struct Params {
   const float* delta;   // [B, nh, S]  rowsum(dO o O)
 };
 
-// TMEM accumulator (this warp's 32 lanes x 128 fp32 columns) -> fp32 staging -> TMA reduce-add of 32x32 boxes.
-__device__ __forceinline__ void reduce_out_tile(uint32_t tsrc, uint8_t* stage, const CUtensorMap* tm, int lane, int head,
-                                                int row0, int batch) {
-#pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    uint8_t* buf = stage + (ch & 1) * 4096;
-    if (lane == 0) tma_store_wait_read<1>();     // the reduce issued from this buffer two chunks ago has read it
-    __syncwarp();
+// TMEM accumulator (this warp's 32 lanes, fp32 columns [32*ch0, 32*(ch0+nch))) -> fp32 staging -> TMA reduce-add of
+// 32x32 boxes.  One 4 KB staging buffer per warp: the previous reduce must have finished reading it.
+__device__ __forceinline__ void reduce_out_tile(uint32_t tsrc, uint8_t* buf, const CUtensorMap* tm, int lane, int head,
+                                                int row0, int batch, int ch0, int nch) {
+  for (int ch = ch0; ch < ch0 + nch; ++ch) {
     uint32_t o[32];
     tmem_ld32(tsrc + ch * 32, o);
     tmem_ld_wait();
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
     const uint32_t row_s = smem_u32(buf) + lane * 128;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
@@ -99,9 +100,9 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     mbar_init(qdo_full, 1);
     mbar_init(qdo_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, 256);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 128);
+    mbar_init(dq_empty, 256);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_ptr_smem, 512);
@@ -144,10 +145,11 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_wait(kv_full, 0);
       for (int n = 0; n < n_iter; ++n) {
         mbar_wait(qdo_full, n & 1);
-        mbar_wait(dq_empty, (n & 1) ^ 1u);     // S/dQ columns drained by the previous iteration's read-out
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tS, kmaj(aQ, kk), kmaj(aK, kk), id_kk, kk > 0);      // S = Q K^T
+        mbar_wait(dq_empty, (n & 1) ^ 1u);     // dP|dQ columns drained by the previous iteration's dQ read-out
+        tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tdP, kmaj(adO, kk), kmaj(aV, kk), id_kk, kk > 0);    // dP = dO V^T
         umma_commit(s_full);
@@ -159,18 +161,19 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)                                                                  // dK += dS^T Q
           umma_ss<1>(tdK, mnmaj(adS, kk), mnmaj(aQ, kk), id_mm, (n > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(qdo_empty);                // Q / dO are not read by the dQ GEMM: the next tiles can be loaded now
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tS, kmaj(adS, kk), mnmaj(aK, kk), id_km, kk > 0);     // dQ = dS K
-        umma_commit(qdo_empty);
+        for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tdP, kmaj(adS, kk), mnmaj(aK, kk), id_km, kk > 0);    // dQ = dS K
         umma_commit(dq_full);
       }
     }
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3;                 // TMEM lane quadrant (warps w and w+4 share the rows of a quadrant)
+    const int chalf = (warp - 2) >> 2;         // which 64 of the 128 tile columns this thread handles
     const int r = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
-    uint8_t* my_stage = sStage + quad * 8192;
+    uint8_t* my_stage = sStage + (warp - 2) * 4096;
     for (int n = 0; n < n_iter; ++n) {
       const int qt = jt + n;
       const int q0 = qt * 128;
@@ -182,7 +185,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_wait(s_full, n & 1);
       tc_fence_after();
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = chalf * 2; ch < chalf * 2 + 2; ++ch) {
         uint32_t sv[32], dv[32];
         tmem_ld32(tS + lane_off + ch * 32, sv);
         tmem_ld32(tdP + lane_off + ch * 32, dv);
@@ -214,13 +217,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       // dQ tile read-out: TMEM -> fp32 staging -> TMA reduce-add into the fp32 dQ buffer (rows >= S are clipped)
       mbar_wait(dq_full, n & 1);
       tc_fence_after();
-      reduce_out_tile(tS + lane_off, my_stage, &tmdQ, lane, hq, q0 + quad * 32, batch);
+      reduce_out_tile(tdP + lane_off, my_stage, &tmdQ, lane, hq, q0 + quad * 32, batch, chalf * 2, 2);
       tc_fence_before();
       mbar_arrive(dq_empty);
     }
     // epilogue: this head's dK / dV partials -> fp32 reduce-add (the GQA group's heads sum in L2)
-    reduce_out_tile(tdK + lane_off, my_stage, &tmdK, lane, kv_head, kv0 + quad * 32, batch);
-    reduce_out_tile(tdV + lane_off, my_stage, &tmdV, lane, kv_head, kv0 + quad * 32, batch);
+    reduce_out_tile(tdK + lane_off, my_stage, &tmdK, lane, kv_head, kv0 + quad * 32, batch, chalf * 2, 2);
+    reduce_out_tile(tdV + lane_off, my_stage, &tmdV, lane, kv_head, kv0 + quad * 32, batch, chalf * 2, 2);
     if (lane == 0) tma_store_wait<0>();
   }
   tc_fence_before();

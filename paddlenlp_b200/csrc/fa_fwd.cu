@@ -11,8 +11,9 @@
 // One CTA = one (batch, q-head, 128-row q tile); kv tiles 0..i (square 128x128 causal tiles).
 //   warp 0        TMA producer: Q once, K and V through 2-stage rings (128B swizzle)
 //   warp 1        MMA issuer:   S[j&1] = Q K_j^T (UMMA 128x128x16 x8) ; O += P_j V_j (V consumed MN-major)
-//   warps 2..5    softmax:      one thread per q row (TMEM lane); S read with tcgen05.ld, online softmax with lazy
-//                               rescaling of the TMEM-resident O accumulator, P written to swizzled smem as bf16
+//   warps 2..9    softmax:      two threads per q row (TMEM lane), 64 score columns each (row max exchanged through
+//                               smem); S read with tcgen05.ld, online softmax with lazy rescaling of the TMEM-resident
+//                               O accumulator, P written to swizzled smem as bf16
 //   TMEM: S0 [0,128) S1 [128,256) O [256,384).  QK_{j+1} is issued before P_j V_j so the tensor pipe works on the
 //   next scores while the softmax warps exponentiate the current ones.
 #include "../../include/b200nlp.h"
@@ -27,8 +28,8 @@ constexpr int BQ = 128;      // q rows per CTA
 constexpr int BKV = 128;     // kv rows per tile
 constexpr int TILE_BYTES = 128 * 128 * 2;   // 32 KB (two 64-column halves of 16 KB)
 constexpr int HALF_BYTES = TILE_BYTES / 2;
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = 6 * TILE_BYTES + 256 + 1024;   // Q, K0, K1, V0, V1, P + barriers + align slack
+constexpr int NUM_THREADS = 320;   // TMA warp, MMA warp, 8 softmax warps
+constexpr int SMEM_BYTES = 6 * TILE_BYTES + 256 + 3 * 1024 + 1024;   // Q, K0, K1, V0, V1, P + barriers + row-stat exchange + align slack
 constexpr float RESCALE_THRESHOLD = 8.f;                  // log2 units
 
 struct Params {
@@ -57,6 +58,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint64_t* p_full = bars + 13;     // [1]
   uint64_t* pv_done = bars + 14;    // [1]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
+  float* s_stat = reinterpret_cast<float*>(smem + 6 * TILE_BYTES + 256);   // [3][2][128]: two max buffers + row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_q_tiles = (p.S + BQ - 1) / BQ;
@@ -72,9 +74,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
     }
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
@@ -154,53 +156,57 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
   } else {
     // ------------------------------- softmax / epilogue -------------------------------
-    const int quad = warp & 3;
+    const int quad = warp & 3;                            // TMEM lane quadrant (warps w and w+4 share its rows)
+    const int chalf = (warp - 2) >> 2;                    // score / output columns [64*chalf, 64*chalf + 64)
     const int r = quad * 32 + lane;                       // q row within the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    float m_used = -INFINITY, l = 0.f;
+    float m_used = -INFINITY, l = 0.f;                    // l: partial row sum over this thread's columns
     const uint32_t sP_a = smem_u32(sP);
     for (int j = 0; j < n_kv; ++j) {
       const int sb = j & 1;
       mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t sv[128];
+      uint32_t sv[64];
       {
         uint32_t(*c)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
-        const uint32_t ta = tS0 + lane_off + static_cast<uint32_t>(sb * 128);
-        tmem_ld32(ta, c[0]); tmem_ld32(ta + 32, c[1]); tmem_ld32(ta + 64, c[2]); tmem_ld32(ta + 96, c[3]);
+        const uint32_t ta = tS0 + lane_off + static_cast<uint32_t>(sb * 128 + chalf * 64);
+        tmem_ld32(ta, c[0]); tmem_ld32(ta + 32, c[1]);
         tmem_ld_wait();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
-      // scale to log2 units, causal mask on the diagonal tile, row max
+      // scale to log2 units, causal mask on the diagonal tile, row max over this thread's 64 columns
       float rowmax = -INFINITY;
       const bool diag = (j == qt);
 #pragma unroll
-      for (int c = 0; c < 128; ++c) {
+      for (int c = 0; c < 64; ++c) {
         float s = __uint_as_float(sv[c]) * p.scale_log2;
-        if (diag && c > r) s = -INFINITY;
+        if (diag && (chalf * 64 + c) > r) s = -INFINITY;
         sv[c] = __float_as_uint(s);
         rowmax = fmaxf(rowmax, s);
       }
+      // exchange with the thread that owns the other 64 columns of this row
+      s_stat[(sb * 2 + chalf) * 128 + r] = rowmax;
+      named_bar_sync(2, 256);
+      rowmax = fmaxf(rowmax, s_stat[(sb * 2 + (chalf ^ 1)) * 128 + r]);
       bool rescale = false;
       float factor = 1.f;
       if (j == 0) {
         m_used = rowmax;
       } else {
         const bool need = rowmax > m_used + RESCALE_THRESHOLD;
-        rescale = __any_sync(0xffffffffu, need);
+        rescale = __any_sync(0xffffffffu, need);          // identical in both warps of the row pair
         if (need) {
           factor = exp2f(m_used - rowmax);
           l *= factor;
           m_used = rowmax;
         }
       }
-      // exponentiate; accumulate the row sum in fp32; pack to bf16
-      uint32_t pk[64];
+      uint32_t pk[32];
       float rs = 0.f;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
+      for (int c = 0; c < 32; ++c) {
         const float p0 = exp2f(__uint_as_float(sv[2 * c]) - m_used);
         const float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) - m_used);
         rs += p0 + p1;
@@ -210,55 +216,57 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);   // P buffer free, O accumulator quiescent
         tc_fence_after();
-        if (rescale) {
+        if (rescale) {                     // each thread rescales its 64 output columns
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int ch = 0; ch < 2; ++ch) {
             uint32_t o[32];
-            tmem_ld32(tO + lane_off + ch * 32, o);
+            tmem_ld32(tO + lane_off + chalf * 64 + ch * 32, o);
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
-            tmem_st32(tO + lane_off + ch * 32, o);
+            tmem_st32(tO + lane_off + chalf * 64 + ch * 32, o);
           }
           tmem_st_wait();
         }
       }
-      // P -> swizzled smem (A operand, K-major along kv)
+      // P -> swizzled smem (A operand, K-major along kv); this thread's 64 columns are exactly half `chalf`
 #pragma unroll
-      for (int c16 = 0; c16 < 16; ++c16) {
-        const uint32_t addr = sP_a + (c16 >> 3) * HALF_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4);
-        st_shared_v4(addr, make_uint4(pk[4 * c16], pk[4 * c16 + 1], pk[4 * c16 + 2], pk[4 * c16 + 3]));
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t addr = sP_a + chalf * HALF_BYTES + r * 128 + ((k ^ (r & 7)) << 4);
+        st_shared_v4(addr, make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
     // epilogue: O / l -> bf16 -> smem (reuse Q tile) -> TMA store ; LSE
+    s_stat[(4 + chalf) * 128 + r] = l;
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
+    named_bar_sync(2, 256);
+    l += s_stat[(4 + (chalf ^ 1)) * 128 + r];
     const float inv_l = 1.f / l;
     const uint32_t sO_a = smem_u32(sQ);
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int ch = 0; ch < 2; ++ch) {
       uint32_t o[32];
-      tmem_ld32(tO + lane_off + ch * 32, o);
+      tmem_ld32(tO + lane_off + chalf * 64 + ch * 32, o);
       tmem_ld_wait();
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
-        const int c16 = ch * 4 + c8;   // 16-byte chunk index within the 256-byte row
+        const int k = ch * 4 + c8;     // 16-byte chunk within this thread's 128-byte half row
         uint4 v;
         v.x = pack_bf16x2(__uint_as_float(o[c8 * 8 + 0]) * inv_l, __uint_as_float(o[c8 * 8 + 1]) * inv_l);
         v.y = pack_bf16x2(__uint_as_float(o[c8 * 8 + 2]) * inv_l, __uint_as_float(o[c8 * 8 + 3]) * inv_l);
         v.z = pack_bf16x2(__uint_as_float(o[c8 * 8 + 4]) * inv_l, __uint_as_float(o[c8 * 8 + 5]) * inv_l);
         v.w = pack_bf16x2(__uint_as_float(o[c8 * 8 + 6]) * inv_l, __uint_as_float(o[c8 * 8 + 7]) * inv_l);
-        const uint32_t addr = sO_a + (c16 >> 3) * HALF_BYTES + r * 128 + (((c16 & 7) ^ (r & 7)) << 4);
-        st_shared_v4(addr, v);
+        st_shared_v4(sO_a + chalf * HALF_BYTES + r * 128 + ((k ^ (r & 7)) << 4), v);
       }
     }
-    if (q0 + r < p.S)
+    if (chalf == 0 && q0 + r < p.S)
       p.lse[(static_cast<size_t>(batch) * p.nh + head) * p.S + q0 + r] = (m_used + log2f(l)) * 0.6931471805599453f;
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, 256);
     if (warp == 2 && lane == 0) {
       tma_store_4d(&tmO, sQ, 0, head, q0, batch);
       tma_store_4d(&tmO, sQ + HALF_BYTES, 64, head, q0, batch);
