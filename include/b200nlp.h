@@ -64,7 +64,8 @@ int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const float* bias, 
 /* Weight-streaming GEMM for the decode step (M <= ~128 tokens): same math as b200_gemm_bf16 (C = op(A) op(B) + bias, one
  * rounding), but K is split over CTAs (split_k, 0 = auto) so that every SM streams part of the weight matrix; fp32 partial
  * tiles are summed in L2 by TMA reduce-add into `workspace` (b200_gemm_splitk_workspace_bytes; must be ZERO on entry,
- * is returned zeroed) and rounded once.
+ * is returned zeroed) and rounded once.  C == NULL skips the rounding pass: the consumer (b200_add_rmsnorm_f32,
+ * b200_decode_rope_append_f32) reads the fp32 sums, rounds them once to bf16 and re-zeroes the workspace.
  * Replaces the cuBLASLt calls of FusedMultiTransformer's decode step (fused_transformer_layers.py:817-820, 895-896, 967-974). */
 int64_t b200_gemm_splitk_workspace_bytes(int64_t M, int64_t N);
 int b200_gemm_bf16_splitk(const void* A, const void* B, void* C, const float* bias, void* workspace, int64_t M, int64_t N,
@@ -156,6 +157,9 @@ int b200_bf16_to_f32(const void* src, float* dst, int64_t n, cudaStream_t stream
  * experimental/transformers/fused_transformer_layers.py:799-805, 937-949, 976-999. */
 int b200_add_rmsnorm(const void* x, const void* residual, const void* w, void* normed, void* residual_out, int64_t rows,
                      int64_t h, float eps, cudaStream_t stream);
+/* Same, x given as the fp32 split-K workspace [rows, h] of the producing GEMM (rounded to bf16 here, workspace re-zeroed). */
+int b200_add_rmsnorm_f32(float* x_f32_ws, const void* residual, const void* w, void* normed, void* residual_out,
+                         int64_t rows, int64_t h, float eps, cudaStream_t stream);
 
 /* KV cache tensor: bf16 [2, B, kvh, max_len, d] (K then V), the shape the reference predictor allocates
  * (llm/predict/predictor.py:697-706; experimental/transformers/llama/modeling.py:1768-1794).
@@ -169,6 +173,11 @@ int b200_write_cache_kv(const void* qkv, void* cache, const int32_t* seq_lens, i
 int b200_decode_rope_append(void* qkv, void* cache, const float* cos_table, const float* sin_table, const int32_t* seq_lens,
                             int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len,
                             int64_t ld, cudaStream_t stream);
+/* Same, the QKV projection given as the fp32 split-K workspace [B, (nh+2kvh)*d] (+ optional fp32 bias): rounded to bf16
+ * into qkv first, workspace re-zeroed. */
+int b200_decode_rope_append_f32(void* qkv, float* acc_f32_ws, const float* bias, void* cache, const float* cos_table,
+                                const float* sin_table, const int32_t* seq_lens, int64_t B, int64_t num_heads,
+                                int64_t num_kv_heads, int64_t head_dim, int64_t max_len, int64_t ld, cudaStream_t stream);
 /* Decode attention of one query token per sequence over cache positions [0, seq_lens[b]] (GQA, head_dim 128);
  * out [B, nh*d].  num_splits > 1 splits each sequence's cache range over that many CTAs (split-KV, merged by a second
  * kernel through `workspace`), as the reference's append_attention does (append_attention_c16_impl.cuh:826-1000).

@@ -48,6 +48,8 @@ _SIGNATURES = {
     "b200_adamw_step": [P, P, P, P, P, P, I64, I64, F, F, F, F, F, I64, F, F, P],
     "b200_bf16_to_f32": [P, P, I64, P],
     "b200_add_rmsnorm": [P, P, P, P, P, I64, I64, F, P],
+    "b200_add_rmsnorm_f32": [P, P, P, P, P, I64, I64, F, P],
+    "b200_decode_rope_append_f32": [P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, P],
     "b200_write_cache_kv": [P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
     "b200_decode_rope_append": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, P],
     "b200_decode_attention_workspace_bytes": [I64, I64, I64],

@@ -343,6 +343,14 @@ __device__ __forceinline__ void st_shared_v4(uint32_t saddr, const uint4& v) {
                : "memory");
 }
 
+// 2^x on the SFU (MUFU.EX2), flush-to-zero, no denormal fix-up code around it (exp2f() without fast-math expands to
+// several instructions per call, which matters in the attention inner loops: 128x128 of them per tile).
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -194,8 +194,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const int col = ch * 32 + 2 * c;
-          float p0 = exp2f(__uint_as_float(sv[2 * c]) * p.scale_log2 - lse2);
-          float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) * p.scale_log2 - lse2);
+          float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * c]), p.scale_log2, -lse2));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * c + 1]), p.scale_log2, -lse2));
           if (!row_ok || (diag && col > r)) p0 = 0.f;
           if (!row_ok || (diag && col + 1 > r)) p1 = 0.f;
           const float d0 = p0 * (__uint_as_float(dv[2 * c]) - drow) * p.scale;

@@ -176,16 +176,18 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
-      // scale to log2 units, causal mask on the diagonal tile, row max over this thread's 64 columns
+      // causal mask on the diagonal tile, row max over this thread's 64 columns (raw scores; the positive softmax
+      // scale is folded into the exponent below as one FFMA per element)
       float rowmax = -INFINITY;
       const bool diag = (j == qt);
+      if (diag) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float s = __uint_as_float(sv[c]) * p.scale_log2;
-        if (diag && (chalf * 64 + c) > r) s = -INFINITY;
-        sv[c] = __float_as_uint(s);
-        rowmax = fmaxf(rowmax, s);
+        for (int c = 0; c < 64; ++c)
+          if ((chalf * 64 + c) > r) sv[c] = 0xff800000u;   // -inf
       }
+#pragma unroll
+      for (int c = 0; c < 64; ++c) rowmax = fmaxf(rowmax, __uint_as_float(sv[c]));
+      rowmax *= p.scale_log2;
       // exchange with the thread that owns the other 64 columns of this row
       s_stat[(sb * 2 + chalf) * 128 + r] = rowmax;
       named_bar_sync(2, 256);
@@ -198,17 +200,18 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const bool need = rowmax > m_used + RESCALE_THRESHOLD;
         rescale = __any_sync(0xffffffffu, need);          // identical in both warps of the row pair
         if (need) {
-          factor = exp2f(m_used - rowmax);
+          factor = fast_exp2(m_used - rowmax);
           l *= factor;
           m_used = rowmax;
         }
       }
       uint32_t pk[32];
       float rs = 0.f;
+      const float neg_m = -m_used;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const float p0 = exp2f(__uint_as_float(sv[2 * c]) - m_used);
-        const float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) - m_used);
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * c]), p.scale_log2, neg_m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * c + 1]), p.scale_log2, neg_m));
         rs += p0 + p1;
         pk[c] = pack_bf16x2(p0, p1);
       }

@@ -16,8 +16,11 @@ namespace gen {
 // (fused_transformer_layers.py:937-949 compute_ffn_layernorm, :976-999 compute_bias_residual_layernorm).
 //   r = bf16(x + residual) ; out = bf16( bf16(r * rstd) * w )   — same rounding points as the training path.
 // ------------------------------------------------------------------------------------------------
+// x_f32 != nullptr: x is the fp32 split-K accumulation of the producing GEMM; it is rounded to bf16 here (the Linear
+// output rounding) and the workspace is handed back zeroed — this fuses the split-K "finish" pass into the norm.
 template <int MAXV>
-__global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res,
+__global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict__ x, float* __restrict__ x_f32,
+                                                          const bf16* __restrict__ res,
                                                           const bf16* __restrict__ w, bf16* __restrict__ normed,
                                                           bf16* __restrict__ res_out, int rows, int h, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -25,6 +28,7 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict
   if (row >= rows) return;
   const int nchunk = h >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * h);
+  float4* xf = x_f32 ? reinterpret_cast<float4*>(x_f32 + static_cast<size_t>(row) * h) : nullptr;
   const uint4* rr = res ? reinterpret_cast<const uint4*>(res + static_cast<size_t>(row) * h) : nullptr;
   uint4 v[MAXV];
   float ss = 0.f;
@@ -32,7 +36,14 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict
   for (int i = 0; i < MAXV; ++i) {
     const int c = lane + 32 * i;
     if (c < nchunk) {
-      v[i] = ld_nc_v4(xr + c);
+      if (xf) {
+        const float4 a = xf[2 * c], b = xf[2 * c + 1];
+        xf[2 * c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xf[2 * c + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+      } else {
+        v[i] = ld_nc_v4(xr + c);
+      }
       uint32_t* vi = reinterpret_cast<uint32_t*>(&v[i]);
       if (rr) {
         const uint4 rv = ld_nc_v4(rr + c);
@@ -102,17 +113,39 @@ __global__ void write_cache_kv_kernel(const bf16* __restrict__ qkv, bf16* __rest
 // use_neox_rotary_style=True) — neox == rotate-half in csrc (encode_rotary_qk.cu:18-56);
 // fused variant: append_attn/decoder_write_cache_with_rope_kernel.cu:47-390.
 // ------------------------------------------------------------------------------------------------
-__global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, bf16* __restrict__ cache, const float* __restrict__ cos_t,
+// acc_f32 != nullptr: the packed projection arrives as the fp32 split-K accumulation (+ optional fp32 bias); it is rounded
+// to bf16 here (the Linear output rounding), written to qkv, and the workspace is handed back zeroed.
+__device__ __forceinline__ uint4 take_f32_chunk(float* acc, const float* bias, int col) {
+  float4* p = reinterpret_cast<float4*>(acc + col);
+  float4 a = p[0], b = p[1];
+  p[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  p[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias != nullptr) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col) + 1);
+    a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w; b.x += b1.x; b.y += b1.y; b.z += b1.z; b.w += b1.w;
+  }
+  return make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+}
+
+__global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, float* __restrict__ acc_f32, const float* __restrict__ bias,
+                                          bf16* __restrict__ cache, const float* __restrict__ cos_t,
                                           const float* __restrict__ sin_t, const int* __restrict__ seq_lens, int B, int nh,
                                           int kvh, int d, int max_len, int64_t ld) {
   const int b = blockIdx.x;
   const int pos = seq_lens[b];
-  if (pos < 0 || pos >= max_len) return;
   const int half = d >> 1;
   const int per_head = half >> 3;
   const int idx = threadIdx.x;
   const size_t cache_half = static_cast<size_t>(B) * kvh * max_len * d;
   bf16* row = qkv + static_cast<size_t>(b) * ld;
+  float* arow = acc_f32 ? acc_f32 + static_cast<size_t>(b) * (nh + 2 * kvh) * d : nullptr;
+  if (arow != nullptr) {
+    // materialise the bf16 projection first (all columns), then rotate in place exactly like the bf16 path
+    for (int c = idx; c < ((nh + 2 * kvh) * d) >> 3; c += blockDim.x)
+      *reinterpret_cast<uint4*>(row + c * 8) = take_f32_chunk(arow, bias, c * 8);
+    __syncthreads();
+  }
+  if (pos < 0 || pos >= max_len) return;
   if (idx < (nh + kvh) * per_head) {
     const int head = idx / per_head;
     const int j8 = (idx % per_head) * 8;
@@ -155,7 +188,7 @@ __global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, bf16* __restri
 // HBM roofline: 2 * len * d * 2 bytes per (b, kv head).
 // ------------------------------------------------------------------------------------------------
 template <int G>
-__global__ void __launch_bounds__(128) decode_attention_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ cache,
+__global__ void __launch_bounds__(128, (G <= 4 ? 4 : 2)) decode_attention_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ cache,
                                                                const int* __restrict__ seq_lens, bf16* __restrict__ out,
                                                                float* __restrict__ partial, int B, int nh, int kvh,
                                                                int max_len, int64_t ld, float scale_log2) {
@@ -527,17 +560,32 @@ __global__ void bf16_rows_to_f32_kernel(const bf16* __restrict__ src, float* __r
 using namespace b200;
 using namespace b200::gen;
 
+static int add_rmsnorm_launch(const void* x, float* x_f32, const void* residual, const void* w, void* normed,
+                              void* residual_out, int64_t rows, int64_t h, float eps, cudaStream_t stream);
+
 extern "C" int b200_add_rmsnorm(const void* x, const void* residual, const void* w, void* normed, void* residual_out,
                                 int64_t rows, int64_t h, float eps, cudaStream_t stream) {
-  B200_CHECK_ARG(x && (w || !normed), "add_rmsnorm: null pointer");
+  B200_CHECK_ARG(x, "add_rmsnorm: null pointer");
+  return add_rmsnorm_launch(x, nullptr, residual, w, normed, residual_out, rows, h, eps, stream);
+}
+
+extern "C" int b200_add_rmsnorm_f32(float* x_f32_ws, const void* residual, const void* w, void* normed, void* residual_out,
+                                    int64_t rows, int64_t h, float eps, cudaStream_t stream) {
+  B200_CHECK_ARG(x_f32_ws, "add_rmsnorm_f32: null pointer");
+  return add_rmsnorm_launch(nullptr, x_f32_ws, residual, w, normed, residual_out, rows, h, eps, stream);
+}
+
+static int add_rmsnorm_launch(const void* x, float* x_f32, const void* residual, const void* w, void* normed,
+                              void* residual_out, int64_t rows, int64_t h, float eps, cudaStream_t stream) {
+  B200_CHECK_ARG((w || !normed), "add_rmsnorm: null pointer");
   B200_CHECK_ARG(rows > 0 && h > 0 && h % 8 == 0 && h <= 8192, "add_rmsnorm: need 0 < h <= 8192, h %% 8 == 0");
   const int nchunk = static_cast<int>(h / 8);
   const dim3 grid(static_cast<unsigned>((rows + 3) / 4)), block(128);
   const bf16 *xp = static_cast<const bf16*>(x), *rp = static_cast<const bf16*>(residual), *wp = static_cast<const bf16*>(w);
   bf16 *np = static_cast<bf16*>(normed), *ro = static_cast<bf16*>(residual_out);
-  if (nchunk <= 128) add_rmsnorm_kernel<4><<<grid, block, 0, stream>>>(xp, rp, wp, np, ro, (int)rows, (int)h, eps);
-  else if (nchunk <= 512) add_rmsnorm_kernel<16><<<grid, block, 0, stream>>>(xp, rp, wp, np, ro, (int)rows, (int)h, eps);
-  else add_rmsnorm_kernel<32><<<grid, block, 0, stream>>>(xp, rp, wp, np, ro, (int)rows, (int)h, eps);
+  if (nchunk <= 128) add_rmsnorm_kernel<4><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+  else if (nchunk <= 512) add_rmsnorm_kernel<16><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+  else add_rmsnorm_kernel<32><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
   return check_launch("add_rmsnorm");
 }
 
@@ -552,17 +600,30 @@ extern "C" int b200_write_cache_kv(const void* qkv, void* cache, const int32_t* 
   return check_launch("write_cache_kv");
 }
 
+extern "C" int b200_decode_rope_append_f32(void* qkv, float* acc_f32_ws, const float* bias, void* cache,
+                                           const float* cos_table, const float* sin_table, const int32_t* seq_lens,
+                                           int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim,
+                                           int64_t max_len, int64_t ld, cudaStream_t stream);
+
 extern "C" int b200_decode_rope_append(void* qkv, void* cache, const float* cos_table, const float* sin_table,
                                        const int32_t* seq_lens, int64_t B, int64_t num_heads, int64_t num_kv_heads,
                                        int64_t head_dim, int64_t max_len, int64_t ld, cudaStream_t stream) {
+  return b200_decode_rope_append_f32(qkv, nullptr, nullptr, cache, cos_table, sin_table, seq_lens, B, num_heads,
+                                     num_kv_heads, head_dim, max_len, ld, stream);
+}
+
+extern "C" int b200_decode_rope_append_f32(void* qkv, float* acc_f32_ws, const float* bias, void* cache,
+                                           const float* cos_table, const float* sin_table, const int32_t* seq_lens,
+                                           int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim,
+                                           int64_t max_len, int64_t ld, cudaStream_t stream) {
   B200_CHECK_ARG(qkv && cache && cos_table && sin_table && seq_lens, "decode_rope_append: null pointer");
   B200_CHECK_ARG(head_dim % 16 == 0 && ld % 8 == 0, "decode_rope_append: head_dim %% 16, ld %% 8");
   const int threads_needed = static_cast<int>((num_heads + num_kv_heads) * (head_dim / 16));
   B200_CHECK_ARG(threads_needed <= 1024, "decode_rope_append: too many heads");
   const int threads = (threads_needed + 31) / 32 * 32;
   decode_rope_append_kernel<<<static_cast<unsigned>(B), threads, 0, stream>>>(
-      static_cast<bf16*>(qkv), static_cast<bf16*>(cache), cos_table, sin_table, seq_lens, (int)B, (int)num_heads,
-      (int)num_kv_heads, (int)head_dim, (int)max_len, ld);
+      static_cast<bf16*>(qkv), acc_f32_ws, bias, static_cast<bf16*>(cache), cos_table, sin_table, seq_lens, (int)B,
+      (int)num_heads, (int)num_kv_heads, (int)head_dim, (int)max_len, ld);
   return check_launch("decode_rope_append");
 }
 

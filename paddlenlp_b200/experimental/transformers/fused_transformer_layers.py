@@ -128,7 +128,26 @@ class FusedMultiTransformerBase:
         decode = time_step is not None
         residual = src
         ln_out, _ = ops.add_rmsnorm(src, None, self.ln_scales[0], eps, want_residual=False)   # compute_layernorm_before_qkv
+        fused = decode and src.shape[0] <= self.SKINNY_M
         for i in range(self.L):
+            if fused:
+                # decode step: the split-K GEMMs leave fp32 sums that the next kernel rounds once (same rounding points,
+                # three launches fewer per layer)
+                cos, sin = self.rope
+                acc = ops.gemm_skinny_f32(ln_out, self.qkv_weights[i], trans_b=True, tag="splitk_qkv")
+                qkv = ops.decode_rope_append_f32(acc, self._bias(i), caches[i], cos, sin, seq_lens_decoder, self.nh, self.kvh,
+                                                 self.d)
+                attn = ops.decode_attention(qkv, caches[i], seq_lens_decoder, self.nh, self.kvh, self.d)
+                acc = ops.gemm_skinny_f32(attn, self.linear_weights[i], tag="splitk_h")
+                ln_out, residual = ops.add_rmsnorm_f32(acc, residual, self.ffn_ln_scales[i], eps)
+                ffn1 = self._mm(ln_out, self.ffn1_weights[i])
+                act = ops.swiglu_fwd(ffn1)
+                acc = ops.gemm_skinny_f32(act, self.ffn2_weights[i], tag="splitk_h")
+                if i != self.L - 1:
+                    ln_out, residual = ops.add_rmsnorm_f32(acc, residual, self.ln_scales[i + 1], eps)
+                else:
+                    _, residual = ops.add_rmsnorm_f32(acc, residual, None, eps, want_normed=False)
+                continue
             qkv = self.compute_qkv(ln_out, i)
             if decode:
                 attn = self.compute_mmha(qkv, caches[i], seq_lens_decoder)

@@ -106,6 +106,18 @@ def gemm_skinny(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = 
     return out
 
 
+def gemm_skinny_f32(a: torch.Tensor, b: torch.Tensor, *, trans_b: bool = False, split_k: int = 0, tag: str = "splitk_f32"):
+    """Split-K GEMM that leaves its result as fp32 sums in a (zero-on-entry) workspace [M, N]; the consumer kernel
+    (add_rmsnorm_f32 / decode_rope_append_f32) rounds once and re-zeroes it.  Returns the fp32 workspace view."""
+    _chk(a, "a"); _chk(b, "b")
+    M, K = a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    ws = _zero_workspace(M * N * 4, a.device, tag)
+    call("b200_gemm_bf16_splitk", ptr(a), ptr(b), None, None, ptr(ws), M, N, K, a.stride(0), b.stride(0), N, 0,
+         0 if trans_b else 1, split_k, stream_ptr())
+    return ws[: M * N * 4].view(torch.float32).view(M, N)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # RMSNorm
 # ----------------------------------------------------------------------------------------------------------
@@ -343,6 +355,26 @@ def add_rmsnorm(x, residual, w, eps, want_normed=True, want_residual=True):
     res_out = torch.empty_like(x) if want_residual else None
     call("b200_add_rmsnorm", ptr(x), ptr(residual), ptr(w), ptr(normed), ptr(res_out), rows, h, float(eps), stream_ptr())
     return normed, res_out
+
+
+def add_rmsnorm_f32(x_f32, residual, w, eps, want_normed=True, want_residual=True):
+    """add_rmsnorm whose x is the fp32 split-K workspace of the producing GEMM (consumed and re-zeroed)."""
+    _chk(x_f32, "x_f32", torch.float32)
+    rows, h = x_f32.shape
+    normed = torch.empty(rows, h, dtype=BF16, device=x_f32.device) if want_normed else None
+    res_out = torch.empty(rows, h, dtype=BF16, device=x_f32.device) if want_residual else None
+    call("b200_add_rmsnorm_f32", ptr(x_f32), ptr(residual), ptr(w), ptr(normed), ptr(res_out), rows, h, float(eps), stream_ptr())
+    return normed, res_out
+
+
+def decode_rope_append_f32(acc_f32, bias, cache, cos, sin, seq_lens, nh, kvh, d):
+    """RoPE + cache append on the fp32 split-K QKV accumulation; returns the bf16 packed projection [B, (nh+2kvh)*d]."""
+    _chk(acc_f32, "acc_f32", torch.float32); _chk(cache, "cache"); _chk(seq_lens, "seq_lens", torch.int32)
+    B, n = acc_f32.shape
+    qkv = torch.empty(B, n, dtype=BF16, device=acc_f32.device)
+    call("b200_decode_rope_append_f32", ptr(qkv), ptr(acc_f32), ptr(bias), ptr(cache), ptr(cos), ptr(sin), ptr(seq_lens), B,
+         nh, kvh, d, cache.shape[3], n, stream_ptr())
+    return qkv
 
 
 def write_cache_kv(qkv, cache, seq_lens, B, S, nh, kvh, d):
