@@ -92,7 +92,7 @@ class FusedMultiTransformerBase:
     def _mm(self, a, w, trans_b=False, bias=None):
         n = w.shape[0] if trans_b else w.shape[1]
         if a.shape[0] <= self.SKINNY_M:
-            if n >= 148 * 256:        # enough 256-wide column tiles to cover every SM: no split-K needed
+            if n >= 100 * 256:        # enough 256-wide column tiles to keep most SMs streaming: no split-K needed
                 return ops.gemm(a, w, trans_b=trans_b, bias=bias, cta_group=1)
             return ops.gemm_skinny(a, w, trans_b=trans_b, bias=bias)
         return ops.gemm(a, w, trans_b=trans_b, bias=bias)
