@@ -23,17 +23,17 @@ __global__ void __launch_bounds__(128) rmsnorm_fwd_kernel(const bf16* __restrict
   if (row >= rows) return;
   const int nchunk = h >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * h);
+  // branch-free load phase: every 16-byte load of the row is in flight before the first use
   uint4 v[MAXV];
+  const int last = nchunk - 1;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) v[i] = ld_nc_v4(xr + min(lane + 32 * i, last));
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nchunk) {
-      v[i] = ld_nc_v4(xr + c);
-      const float2 a = unpack_bf16x2(v[i].x), b = unpack_bf16x2(v[i].y), cc = unpack_bf16x2(v[i].z),
-                   d = unpack_bf16x2(v[i].w);
-      ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
-    }
+    const float2 a = unpack_bf16x2(v[i].x), b = unpack_bf16x2(v[i].y), cc = unpack_bf16x2(v[i].z), d = unpack_bf16x2(v[i].w);
+    const float part = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
+    ss += ((lane + 32 * i) < nchunk) ? part : 0.f;
   }
   ss = warp_sum(ss);
   const float rstd = rsqrtf(ss / static_cast<float>(h) + eps);

@@ -30,32 +30,45 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * h);
   float4* xf = x_f32 ? reinterpret_cast<float4*>(x_f32 + static_cast<size_t>(row) * h) : nullptr;
   const uint4* rr = res ? reinterpret_cast<const uint4*>(res + static_cast<size_t>(row) * h) : nullptr;
-  uint4 v[MAXV];
+  // Phase 1: issue every load of the row before anything else (branch-free: out-of-range chunks re-read the last valid
+  // chunk and are masked later), so the whole row is one memory round trip instead of one per chunk.
+  uint4 v[MAXV], rv[MAXV];
+  float4 fa[MAXV], fb[MAXV];
+  const int last = nchunk - 1;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = min(lane + 32 * i, last);
+    if (xf) { fa[i] = xf[2 * c]; fb[i] = xf[2 * c + 1]; }
+    else v[i] = ld_nc_v4(xr + c);
+    if (rr) rv[i] = ld_nc_v4(rr + c);
+  }
+  // Phase 2: round the fp32 input (if any), add the residual, accumulate the sum of squares
   float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const bool ok = (lane + 32 * i) < nchunk;
+    if (xf) v[i] = make_uint4(pack_bf16x2(fa[i].x, fa[i].y), pack_bf16x2(fa[i].z, fa[i].w), pack_bf16x2(fb[i].x, fb[i].y),
+                              pack_bf16x2(fb[i].z, fb[i].w));
+    uint32_t* vi = reinterpret_cast<uint32_t*>(&v[i]);
+    if (rr) {
+      const uint32_t* ri = reinterpret_cast<const uint32_t*>(&rv[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(vi[j]), b = unpack_bf16x2(ri[j]);
+        vi[j] = pack_bf16x2(a.x + b.x, a.y + b.y);
+      }
+    }
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 a = unpack_bf16x2(vi[j]); part += a.x * a.x + a.y * a.y; }
+    ss += ok ? part : 0.f;
+  }
+  // Phase 3: hand the fp32 workspace back zeroed, write the new residual
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = lane + 32 * i;
     if (c < nchunk) {
-      if (xf) {
-        const float4 a = xf[2 * c], b = xf[2 * c + 1];
-        xf[2 * c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        xf[2 * c + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
-      } else {
-        v[i] = ld_nc_v4(xr + c);
-      }
-      uint32_t* vi = reinterpret_cast<uint32_t*>(&v[i]);
-      if (rr) {
-        const uint4 rv = ld_nc_v4(rr + c);
-        const uint32_t* ri = reinterpret_cast<const uint32_t*>(&rv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 a = unpack_bf16x2(vi[j]), b = unpack_bf16x2(ri[j]);
-          vi[j] = pack_bf16x2(a.x + b.x, a.y + b.y);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { const float2 a = unpack_bf16x2(vi[j]); ss += a.x * a.x + a.y * a.y; }
+      if (xf) { xf[2 * c] = make_float4(0.f, 0.f, 0.f, 0.f); xf[2 * c + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
       if (res_out) st_na_v4(reinterpret_cast<uint4*>(res_out + static_cast<size_t>(row) * h) + c, v[i]);
     }
   }

@@ -135,15 +135,27 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(bf16* __restrict__ logits, 
 }
 
 // argmax over a bf16 row (first maximal index, like paddle.argmax / torch.argmax on ties -> lowest index).
-__global__ void __launch_bounds__(256) argmax_kernel(const bf16* __restrict__ logits, int64_t* __restrict__ out,
-                                                     int vocab, int64_t ld) {
-  __shared__ float sv[8];
-  __shared__ int si[8];
+__global__ void __launch_bounds__(1024) argmax_kernel(const bf16* __restrict__ logits, int64_t* __restrict__ out,
+                                                      int vocab, int64_t ld) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
   const int row = blockIdx.x;
   const bf16* lr = logits + static_cast<size_t>(row) * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+  const int nchunk = ((reinterpret_cast<uintptr_t>(lr) & 15) == 0) ? (vocab >> 3) : 0;   // 128-bit loads when aligned
+  for (int c = threadIdx.x; c < nchunk; c += blockDim.x) {
+    const uint4 v = ld_nc_v4(reinterpret_cast<const uint4*>(lr) + c);
+    const uint32_t* vi = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(vi[j]);
+      const int i0 = c * 8 + 2 * j;
+      if (f.x > best || (f.x == best && i0 < bi)) { best = f.x; bi = i0; }
+      if (f.y > best || (f.y == best && i0 + 1 < bi)) { best = f.y; bi = i0 + 1; }
+    }
+  }
+  for (int i = (nchunk << 3) + threadIdx.x; i < vocab; i += blockDim.x) {
     const float f = __bfloat162float(lr[i]);
     if (f > best || (f == best && i < bi)) { best = f; bi = i; }
   }
@@ -298,7 +310,7 @@ extern "C" int b200_ce_bwd(void* logits_inout, const int64_t* labels, const floa
 extern "C" int b200_argmax_bf16(const void* logits, int64_t* out, int64_t rows, int64_t vocab, int64_t ld,
                                 cudaStream_t stream) {
   B200_CHECK_ARG(logits && out && rows > 0 && vocab > 0, "argmax: bad arguments");
-  argmax_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(static_cast<const bf16*>(logits), out, (int)vocab, ld);
+  argmax_kernel<<<static_cast<unsigned>(rows), 1024, 0, stream>>>(static_cast<const bf16*>(logits), out, (int)vocab, ld);
   return check_launch("argmax");
 }
 
