@@ -58,8 +58,35 @@ def make(model_type: str, path: str):
     print(path, os.path.getsize(path), "bytes; loss", float(loss))
 
 
+def make_gpt2(path: str):
+    """Tiny random HF GPT2LMHeadModel -> reference-named weights, ids, fp32 logits, reference-criterion loss."""
+    import transformers
+
+    from oracle import gpt_ref
+
+    torch.manual_seed(11)
+    cfg = transformers.GPT2Config(vocab_size=160, n_positions=64, n_embd=64, n_layer=2, n_head=4, resid_pdrop=0.0,
+                                  embd_pdrop=0.0, attn_pdrop=0.0, activation_function="gelu_new")
+    m = transformers.GPT2LMHeadModel(cfg).float().eval()
+    with torch.no_grad():
+        for p_ in m.parameters():
+            p_.add_(torch.randn_like(p_) * 0.05)
+    g = torch.Generator().manual_seed(3)
+    tok = torch.randint(1, 160, (2, 33), generator=g)
+    ids, labels = tok[:, :-1].contiguous(), tok[:, 1:].contiguous()
+    labels[0, :4] = 0                                               # ignore_index = 0
+    with torch.no_grad():
+        logits = m(input_ids=ids).logits
+    w = gpt_ref.from_hf_state_dict(m.state_dict(), 2)
+    torch.save({"weights": w, "input_ids": ids, "labels": labels, "hf_logits_fp32": logits,
+                "loss_fp32": gpt_ref.criterion(logits, labels), "n_layer": 2, "n_head": 4,
+                "generator": f"oracle/make_golden.py, transformers {transformers.__version__}"}, path)
+    print(path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
+    make_gpt2(os.path.join(out, "gpt2_tiny.pt"))
     make("llama", os.path.join(out, "llama_tiny.pt"))
     make("qwen2", os.path.join(out, "qwen2_tiny.pt"))

@@ -1,13 +1,15 @@
 """paddlenlp.transformers surface kept by this build (SURVEY.md §1 "public interface we keep")."""
 from .configuration_utils import LlmMetaConfig, PretrainedConfig
+from .gpt.configuration import GPTConfig
+from .gpt.modeling import GPTForCausalLM, GPTLMHeadModel, GPTModel, GPTPretrainingCriterion
 from .llama.configuration import LlamaConfig
 from .llama.modeling import LlamaForCausalLM, LlamaModel, LlamaPretrainedModel, LlamaPretrainingCriterion
 from .model_outputs import CausalLMOutputWithCrossAttentions
 from .qwen2.configuration import Qwen2Config
 from .qwen2.modeling import Qwen2ForCausalLM, Qwen2Model, Qwen2PretrainedModel, Qwen2PretrainingCriterion
 
-_CONFIGS = {"llama": LlamaConfig, "qwen2": Qwen2Config}
-_CAUSAL_LM = {"llama": LlamaForCausalLM, "qwen2": Qwen2ForCausalLM}
+_CONFIGS = {"llama": LlamaConfig, "qwen2": Qwen2Config, "gpt": GPTConfig}
+_CAUSAL_LM = {"llama": LlamaForCausalLM, "qwen2": Qwen2ForCausalLM, "gpt": GPTForCausalLM}
 
 
 class AutoConfig:
