@@ -117,9 +117,13 @@ class DecoderEngine:
         self.p["norm"].fill_(1.0)
         self._bias_f32.clear()
 
-    def named_views(self, grads: bool = False) -> Dict[str, torch.Tensor]:
-        """Reference-named views (llama/modeling.py:1243-1274 name map) onto the flat buffer."""
-        src = self.g if grads else self.p
+    def named_views(self, grads: bool = False, flat: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """Reference-named views (llama/modeling.py:1243-1274 name map) onto the flat parameter buffer, the flat gradient
+        buffer, or any other flat buffer with the same layout (e.g. the optimizer's fp32 master weights)."""
+        if flat is not None:
+            src = {n: flat[o:o + math.prod(s)].view(s) for n, (o, s) in self._offsets.items()}
+        else:
+            src = self.g if grads else self.p
         pre = self.prefix
         out = {f"{pre}.embed_tokens.weight": src["embed"]}
         qn, kn = self.nh * self.d, self.kvh * self.d

@@ -76,16 +76,19 @@ def test_one_optimizer_step_matches_oracle():
     # oracle: clip by the global norm of ALL gradients, then AdamW per tensor (decay only on matrices)
     flat = torch.cat([grads_ref[k].reshape(-1) for k in grads_ref])
     coef = float(optim_ref.clip_coef(flat, 1.0))
-    new = dict(model.named_parameters())
+    new = model.engine.named_views(flat=opt.master)        # fp32 master weights (bf16 params = round(master))
     worst = 0.0
     for k, g_ in grads_ref.items():
         decay = torch.full_like(w[k], ("norm" not in k and "bias" not in k), dtype=torch.bool)
         p, _, _, _ = optim_ref.adamw_step(w[k], torch.zeros_like(w[k]), torch.zeros_like(w[k]), g_ * coef, lr=1e-3, beta1=0.9,
                                           beta2=0.999, eps=1e-8, weight_decay=0.1, step=1, decay_mask=decay, max_grad_norm=0.0)
         upd_ref, upd = p - w[k], new[k].detach().float().cpu() - w[k]
-        # first Adam step moves every weight by ~lr * sign(g): compare the update direction/magnitude
+        # the first Adam step moves every weight with a gradient by ~lr * sign(g) (+ decay): a sign flip can only come
+        # from a gradient whose sign differs, i.e. |g| below the bf16 gradient noise
         agree = (torch.sign(upd_ref) == torch.sign(upd)).float().mean().item()
         worst = max(worst, 1 - agree)
-        assert agree > 0.97, (k, agree)
+        assert agree > 0.95, (k, agree)
+        rel = ((upd - upd_ref).norm() / (upd_ref.norm() + 1e-30)).item()
+        assert rel < 0.35, (k, rel)
     gn = float(opt.grad_norm())
     assert abs(gn - float(flat.norm())) < 0.03 * float(flat.norm())
