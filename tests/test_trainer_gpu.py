@@ -14,7 +14,7 @@ def tiny(model_type="llama"):
     import paddlenlp_b200.transformers as T
 
     kw = dict(vocab_size=512, hidden_size=256, intermediate_size=688, num_hidden_layers=2, num_attention_heads=2,
-              num_key_value_heads=1, max_position_embeddings=256, seq_length=128)
+              num_key_value_heads=1, max_position_embeddings=256, seq_length=128, rope_theta=500000.0, rms_norm_eps=1e-5)
     return (T.Qwen2ForCausalLM(T.Qwen2Config(**kw)) if model_type == "qwen2" else T.LlamaForCausalLM(T.LlamaConfig(**kw)))
 
 
