@@ -1,0 +1,79 @@
+"""Config 4: Qwen2-7B full-parameter SFT, bf16, seq 2048, through the Trainer API with synthetic instruction pairs.
+
+    python tools/sft_bench.py [--steps 4 --micro-batch 4 --accum 2]           # 1 GPU
+    python -m torch.distributed.run --nproc-per-node N tools/sft_bench.py     # pure data parallel
+
+Synthetic data: src_len ~ U{64..1024}, tgt_len ~ U{16..2048-src_len}, labels = [-100]*src + tgt shifted
+by one (llm/utils/data.py:196-199), right-padded to 2048 with pad id / -100 (DataCollatorForSeq2Seq semantics).
+tokens/s counts all 2048 positions (the reference's speed_metrics convention) and, separately, non-pad tokens."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import paddlenlp_b200.transformers as T  # noqa: E402
+from paddlenlp_b200.trainer import Trainer, TrainingArguments  # noqa: E402
+
+S = 2048
+
+
+class SyntheticSFT(torch.utils.data.Dataset):
+    def __init__(self, n, vocab, seed=1234):
+        g = torch.Generator().manual_seed(seed)
+        self.items = []
+        for _ in range(n):
+            src = int(torch.randint(64, 1025, (1,), generator=g))
+            tgt = int(torch.randint(16, S - src + 1, (1,), generator=g))
+            toks = torch.randint(1, vocab, (src + tgt,), generator=g)
+            labels = torch.cat([torch.full((src,), -100), toks[src:]])
+            ids, lab = toks[:-1], labels[1:]                       # shift by one
+            pad = S - ids.numel()
+            self.items.append((torch.cat([ids, torch.zeros(pad, dtype=torch.int64)]),
+                               torch.cat([lab, torch.full((pad,), -100)]), src + tgt - 1))
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        return {"input_ids": self.items[i][0], "labels": self.items[i][1]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--micro-batch", type=int, default=4)
+    ap.add_argument("--accum", type=int, default=2)
+    ap.add_argument("--layers", type=int, default=0)
+    a = ap.parse_args()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    args = TrainingArguments(output_dir="/tmp/sft_out", per_device_train_batch_size=a.micro_batch,
+                             gradient_accumulation_steps=a.accum, max_steps=a.steps + a.warmup, learning_rate=3e-5,
+                             weight_decay=0.01, warmup_steps=1, logging_steps=1, max_seq_length=S, lr_scheduler_type="linear")
+    cfg = T.Qwen2Config.qwen2_7b(num_hidden_layers=a.layers) if a.layers else T.Qwen2Config.qwen2_7b()
+    model = T.AutoModelForCausalLM.from_config(cfg, dtype="bfloat16")
+    n = (a.steps + a.warmup) * a.micro_batch * a.accum * args.world_size
+    ds = SyntheticSFT(n, cfg.vocab_size)
+    trainer = Trainer(model=model, args=args, train_dataset=ds)
+    t0 = time.time()
+    trainer.train()
+    hist = trainer.state.log_history[a.warmup:]
+    if args.process_index == 0:
+        sps = sum(h["interval_samples_per_second"] for h in hist) / len(hist)
+        nonpad = sum(it[2] for it in ds.items) / len(ds.items)
+        rec = dict(model="Qwen2-7B" if not a.layers else f"Qwen2-7B width, {a.layers} layers", n_gpus=args.world_size,
+                   seq_len=S, micro_batch=a.micro_batch, grad_accum=a.accum, steps=a.steps,
+                   tokens_per_s=sps * S, nonpad_tokens_per_s=sps * nonpad, loss_first=hist[0]["loss"], loss_last=hist[-1]["loss"],
+                   tflops_per_gpu=sps * S / args.world_size * model.get_algorithmic_flops_per_token(S) / 1e12,
+                   mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
+        print(json.dumps(rec), flush=True)
+
+
+if __name__ == "__main__":
+    main()
