@@ -35,6 +35,10 @@ const char* b200_last_error(void);
 int b200_abi_version(void);
 /* 0 if the current device is compute capability 10.x (B200); error otherwise. */
 int b200_device_check(void);
+/* Programmatic dependent launch for the GEMM kernels (returns the previous setting; NOT an error code): when enabled, a GEMM
+ * may start while the previous kernel of the stream is still draining — it prefetches its weight tiles and sets up TMEM /
+ * barriers, and only waits (griddepcontrol.wait) before touching activations or outputs.  Used for the decode-step chain. */
+int b200_set_pdl(int enable);
 
 /* ---- GEMM: replaces paddle.matmul / nn.Linear (cuBLASLt) --------------------------------------------------
  * C[M,N] (+)= op(A)[M,K] * op(B)[K,N] (+ bias[N]);  bf16 operands, fp32 accumulation in TMEM, ONE rounding to bf16.

@@ -33,6 +33,9 @@ int check_launch(const char* what) {
   return 0;
 }
 
+static int g_pdl = 0;
+bool pdl_enabled() { return g_pdl != 0; }
+
 int sm_count() {
   static int cached[64];
   int dev = 0;
@@ -108,6 +111,12 @@ extern "C" {
 const char* b200_last_error(void) { return b200::tls_err; }
 
 int b200_abi_version(void) { return B200NLP_ABI_VERSION; }
+
+int b200_set_pdl(int enable) {
+  int old = b200::g_pdl;
+  b200::g_pdl = enable ? 1 : 0;
+  return old;
+}
 
 int b200_device_check(void) {
   int dev = 0;

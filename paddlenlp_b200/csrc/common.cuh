@@ -41,6 +41,13 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor is still running: it must execute pdl_wait() before its first access to data the predecessor
+// produces (or overwrites).  pdl_launch_dependents() lets the NEXT kernel in the stream begin launching early; it is
+// harmless when that kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Mask that clears the "peer CTA" bit of a shared::cluster address, so that the address refers to the
 // even (leader) CTA of a CTA pair.
 static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;

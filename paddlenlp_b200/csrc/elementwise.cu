@@ -236,6 +236,7 @@ __global__ void rope_kernel(bf16* __restrict__ x, const float* __restrict__ cos_
 // backward: dg = dm * u * silu'(g), du = dm * silu(g), written packed as [dg | du].
 // ------------------------------------------------------------------------------------------------
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ m, int64_t rows, int inter) {
+  pdl_launch_dependents();
   const int64_t nchunk_row = inter >> 3;
   const int64_t total = rows * nchunk_row;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;

@@ -54,6 +54,7 @@ struct Params {
   int epi_mode;            // 0: C = acc ; 1: C = bf16(C_old + acc) ; 2: C = bf16(bf16(acc) + R) ; 3: F32ws += acc (split-K)
   int split_k;             // work items per output tile (K is cut into split_k ranges of kb_per_split k-blocks)
   int kb_per_split;
+  int b_prefetch;          // PDL: issue the first stages' B (weight) loads before griddepcontrol.wait
   const float* bias;       // [N] fp32 or nullptr
 };
 
@@ -94,6 +95,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_pairs = gridDim.x / CG;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;   // work items
   const int num_kb_total = (p.K + BK - 1) / BK;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -122,6 +124,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // With PDL (p.b_prefetch): the B operand (weights) of the first stages does not depend on the previous kernel, so
+      // its TMA loads are issued before griddepcontrol.wait; the A loads (activations) follow after the wait.
+      int prefetched = 0;
+      if (p.b_prefetch && pair_id < num_tiles) {
+        int m_blk, n_blk;
+        tile_coords(pair_id / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
+        const int kb0 = (pair_id % p.split_k) * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        const int n0 = n_blk * BN + static_cast<int>(cta_rank) * C::B_COLS;
+        prefetched = min(C::STAGES, kb1 - kb0);
+        for (int s = 0; s < prefetched; ++s) {
+          uint8_t* sb = smem + s * C::STAGE_BYTES + C::A_BYTES;
+          const int k0 = (kb0 + s) * BK;
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES * CG);
+          auto load = [&](const CUtensorMap* tm, void* dst, int c0, int c1) {
+            if constexpr (CG == 2) tma_load_2d_pair(tm, &full_bar[s], dst, c0, c1);
+            else tma_load_2d(tm, &full_bar[s], dst, c0, c1);
+          };
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int c = 0; c < C::B_COLS / 64; ++c) load(&tmB, sb + c * (64 * BK * 2), n0 + c * 64, k0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < C::B_COLS / 128; ++c) load(&tmB, sb + c * (128 * BK * 2), k0, n0 + c * 128);
+          }
+        }
+      }
+      pdl_wait();
       for (int t = pair_id; t < num_tiles; t += num_pairs) {
         int m_blk, n_blk;
         tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
@@ -129,11 +158,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM;   // this CTA's A rows
         const int n0 = n_blk * BN + static_cast<int>(cta_rank) * C::B_COLS;   // this CTA's B columns
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const bool b_done = (t == pair_id) && (kb - kb0 < prefetched);     // B tile (and expect_tx) already issued
+          if (!b_done) mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           const int k0 = kb * BK;
-          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * CG);
+          if (is_leader && !b_done) mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * CG);
           auto load = [&](const CUtensorMap* tm, void* dst, int c0, int c1) {
             if constexpr (CG == 2) tma_load_2d_pair(tm, &full_bar[stage], dst, c0, c1);
             else tma_load_2d(tm, &full_bar[stage], dst, c0, c1);
@@ -145,12 +175,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else {
             load(&tmA, sa, k0, m0);  // A stored [M, K] row-major: one 64 (K) x 128 (M) box
           }
-          if constexpr (B_MN) {
+          if (!b_done) {
+            if constexpr (B_MN) {
 #pragma unroll
-            for (int c = 0; c < C::B_COLS / 64; ++c) load(&tmB, sb + c * (64 * BK * 2), n0 + c * 64, k0);
-          } else {
+              for (int c = 0; c < C::B_COLS / 64; ++c) load(&tmB, sb + c * (64 * BK * 2), n0 + c * 64, k0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < C::B_COLS / 128; ++c) load(&tmB, sb + c * (128 * BK * 2), k0, n0 + c * 128);
+              for (int c = 0; c < C::B_COLS / 128; ++c) load(&tmB, sb + c * (128 * BK * 2), k0, n0 + c * 128);
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -193,6 +225,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ===================================== epilogue =====================================
+    pdl_wait();                                    // outputs / residual / workspace belong to the previous kernel until now
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
     uint8_t* my_buf = epi_smem + q * 2 * EPI_BUF_BYTES;
     const uint32_t my_buf_s = smem_u32(my_buf);
@@ -338,14 +371,22 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, p);
+  Params pp = p;
+  pp.b_prefetch = 0;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+    pp.b_prefetch = 1;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, pp);
   if (e != cudaSuccess) {
     set_last_error("gemm launch: %s", cudaGetErrorString(e));
     return static_cast<int>(e);

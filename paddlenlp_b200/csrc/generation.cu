@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ res,
                                                           const bf16* __restrict__ w, bf16* __restrict__ normed,
                                                           bf16* __restrict__ res_out, int rows, int h, float eps) {
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
   if (row >= rows) return;
@@ -144,6 +145,7 @@ __global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, float* __restr
                                           bf16* __restrict__ cache, const float* __restrict__ cos_t,
                                           const float* __restrict__ sin_t, const int* __restrict__ seq_lens, int B, int nh,
                                           int kvh, int d, int max_len, int64_t ld) {
+  pdl_launch_dependents();
   const int b = blockIdx.x;
   const int pos = seq_lens[b];
   const int half = d >> 1;
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(128, (G <= 4 ? 4 : 2)) decode_attention_kernel
   constexpr int D = 128;
   __shared__ float s_m[8][G], s_l[8][G];
   __shared__ float s_o[8][G][D];
+  pdl_launch_dependents();
   const int b = blockIdx.x / kvh, kh = blockIdx.x % kvh;
   const int total_len = min(seq_lens[b] + 1, max_len);  // the new token was appended at index seq_lens[b]
   // split-KV: gridDim.y CTAs share one (b, kv head); each takes a contiguous range of the cache
@@ -314,6 +317,7 @@ __global__ void __launch_bounds__(128, (G <= 4 ? 4 : 2)) decode_attention_kernel
 // merge the split-KV partials: one warp per (b, head)
 __global__ void decode_attention_merge_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int rows, int nsplit) {
   constexpr int D = 128;
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;

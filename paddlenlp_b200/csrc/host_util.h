@@ -15,6 +15,7 @@ int fail_arg(const char* fmt, ...);   // records message, returns -1
 int check_launch(const char* what);  // cudaGetLastError() -> return code
 
 int sm_count();  // multiprocessors of the current device (cached per device)
+bool pdl_enabled();   // b200_set_pdl(): launch GEMMs with programmatic dependent launch (decode-step kernel chains)
 
 // Encode a 2-D or 3-D bf16 (2-byte element) tiled tensor map with 128-byte swizzle.
 //   dims[i]    extent of dimension i in elements (dimension 0 is contiguous)

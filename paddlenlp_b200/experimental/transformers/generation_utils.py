@@ -36,7 +36,7 @@ class GenerationInferenceModel:
     def generate(self, input_ids: torch.Tensor, seq_len_encoder: Optional[torch.Tensor] = None, max_length: int = 64,
                  eos_token_id=None, cache_kvs: Optional[List[torch.Tensor]] = None, temperature: float = 1.0,
                  top_p: float = 0.0, penalty_score: float = 1.0, frequency_score: float = 0.0, presence_score: float = 0.0,
-                 min_length: int = 0, use_cuda_graph: bool = True, sync_interval: int = 16, **kwargs):
+                 min_length: int = 0, use_cuda_graph: bool = True, sync_interval: int = 16, use_pdl: bool = True, **kwargs):
         """input_ids [B, S] (right padded); returns (ids [B, max_length], stop_flags, seq_len_decoder)."""
         if top_p not in (0, 0.0, None):
             raise NotImplementedError("top-p sampling: only greedy (top_p = 0) is implemented")
@@ -87,22 +87,30 @@ class GenerationInferenceModel:
             tgt.copy_(nxt)
             update(tgt)
 
+        from ... import _lib
+
         graph = None
         n_steps = max_length - 1
         done = 0
-        if use_cuda_graph and n_steps > 2:
-            step(); done += 1                                    # warm-up (sets kernel attributes, allocator pools)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):                        # capture only records: no step is executed here
-                step()
-        while done < n_steps:
-            if graph is not None:
-                graph.replay()
-            else:
-                step()
-            done += 1
-            if sync_interval > 0 and done % sync_interval == 0 and int(st["stop_count"].item()) >= B:
-                break
+        # programmatic dependent launch: every GEMM of the decode step prefetches its weight tiles while the previous
+        # kernel drains (b200_set_pdl); restored on exit
+        old_pdl = _lib.load().b200_set_pdl(1 if use_pdl else 0)
+        try:
+            if use_cuda_graph and n_steps > 2:
+                step(); done += 1                                # warm-up (sets kernel attributes, allocator pools)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):                    # capture only records: no step is executed here
+                    step()
+            while done < n_steps:
+                if graph is not None:
+                    graph.replay()
+                else:
+                    step()
+                done += 1
+                if sync_interval > 0 and done % sync_interval == 0 and int(st["stop_count"].item()) >= B:
+                    break
+        finally:
+            _lib.load().b200_set_pdl(old_pdl)
         self.last_generate_steps = done + 1
         return st["out"], st["stop_flags"].to(torch.int32), st["seq_len_decoder"]

@@ -192,8 +192,8 @@ def test_prefill_logits_equal_training_path(model_type):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_greedy_generation_matches_uncached_oracle(use_graph):
+@pytest.mark.parametrize("use_graph,use_pdl", [(False, False), (True, False), (True, True), (False, True)])
+def test_greedy_generation_matches_uncached_oracle(use_graph, use_pdl):
     cfg = _tiny()
     w = R.init_weights(cfg, seed=9)
     w = {k: (v * 4).to(BF16).float() if k.endswith("weight") and "norm" not in k else v for k, v in w.items()}
@@ -205,7 +205,7 @@ def test_greedy_generation_matches_uncached_oracle(use_graph):
     for b in range(B):
         ids[b, lens[b]:] = 0                                         # right padding
     out, stop, dec = m.generate(ids.to(DEV), seq_len_encoder=lens.to(DEV), max_length=new, eos_token_id=-7,
-                                use_cuda_graph=use_graph, sync_interval=4)
+                                use_cuda_graph=use_graph, sync_interval=4, use_pdl=use_pdl)
     ref, margins = G.greedy_generate(ids, w, cfg, new, eos=None, mode="bf16", seq_lens=lens)
     out = out.cpu()
     # token-id argmax must match wherever the oracle's top-1/top-2 margin is above bf16 noise; after a legitimate

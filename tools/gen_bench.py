@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--gen", type=int, default=1920)
     ap.add_argument("--layers", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true")
     a = ap.parse_args()
     cfg = T.LlamaConfig.llama3_8b(num_hidden_layers=a.layers) if a.layers else T.LlamaConfig.llama3_8b()
     m = LlamaForCausalLMInferenceModel(cfg)
@@ -32,7 +33,7 @@ def main():
     max_len = a.prompt + a.gen
     caches = m.allocate_caches(a.batch, max_len)
     # warm-up (kernel attributes, allocator)
-    m.generate(ids, max_length=min(8, a.gen), eos_token_id=-1, cache_kvs=caches, use_cuda_graph=not a.no_graph)
+    m.generate(ids, max_length=min(8, a.gen), eos_token_id=-1, cache_kvs=caches, use_cuda_graph=not a.no_graph, use_pdl=not a.no_pdl)
     torch.cuda.synchronize()
     # prefill alone
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -44,7 +45,7 @@ def main():
     prefill_ms = e0.elapsed_time(e1)
     e0.record()
     out, stop, dec = m.generate(ids, max_length=a.gen, eos_token_id=-1, cache_kvs=caches, use_cuda_graph=not a.no_graph,
-                                sync_interval=0)
+                                sync_interval=0, use_pdl=not a.no_pdl)
     e1.record()
     torch.cuda.synchronize()
     total_ms = e0.elapsed_time(e1)
@@ -63,7 +64,7 @@ def main():
     rec = dict(batch=a.batch, prompt=a.prompt, gen=a.gen, layers=L, prefill_ms=prefill_ms, decode_ms=decode_ms, ms_per_step=ms_step,
                decode_tokens_per_s=a.batch * steps / (decode_ms / 1e3), bytes_per_step_gb=bytes_per_step / 1e9,
                achieved_gbs=achieved, hbm_peak_gbs=peaks["hbm_gbs"], roofline_frac=achieved / peaks["hbm_gbs"],
-               graph=not a.no_graph, mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, last_tokens=out[0, -4:].tolist())
+               graph=not a.no_graph, pdl=not a.no_pdl, mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, last_tokens=out[0, -4:].tolist())
     print(json.dumps(rec), flush=True)
 
 
