@@ -250,35 +250,58 @@ __global__ void __launch_bounds__(128, (G <= 4 ? 4 : 2)) decode_attention_kernel
         vv[u] = ld_nc_v4(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(t) * D) + sub);
       }
     }
+    // Blockwise online softmax over the U rows of this iteration: all U*G dot products and their half-warp reductions are
+    // independent (instruction-level parallelism instead of one dependent chain per row), then one max / one rescale per
+    // head and iteration.
+    float sc[U][G];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int t = t0 + 8 * u;
-      if (t >= len) break;                 // uniform within the half-warp
-      float kf[8], vf[8];
       const uint32_t* ki = reinterpret_cast<const uint32_t*>(&kv[u]);
-      const uint32_t* vi = reinterpret_cast<const uint32_t*>(&vv[u]);
+      float kf[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = unpack_bf16x2(ki[j]), c = unpack_bf16x2(vi[j]);
-        kf[2 * j] = a.x; kf[2 * j + 1] = a.y; vf[2 * j] = c.x; vf[2 * j + 1] = c.y;
-      }
+      for (int j = 0; j < 4; ++j) { const float2 a = unpack_bf16x2(ki[j]); kf[2 * j] = a.x; kf[2 * j + 1] = a.y; }
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += q[g][j] * kf[j];
-        // the two half-warps of a warp can have different trip counts: shuffle within the half-warp only
-        s += __shfl_xor_sync(hmask, s, 8);
-        s += __shfl_xor_sync(hmask, s, 4);
-        s += __shfl_xor_sync(hmask, s, 2);
-        s += __shfl_xor_sync(hmask, s, 1);
-        const float mn = fmaxf(m[g], s);
-        const float corr = exp2f(m[g] - mn);
-        const float p = exp2f(s - mn);
-        l[g] = l[g] * corr + p;
+        sc[u][g] = s;
+      }
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[g][j] = o[g][j] * corr + p * vf[j];
-        m[g] = mn;
+    for (int off = 8; off > 0; off >>= 1) {
+      // the two half-warps of a warp can have different trip counts: shuffle within the half-warp only
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int g = 0; g < G; ++g) sc[u][g] += __shfl_xor_sync(hmask, sc[u][g], off);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float mn = m[g];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (t0 + 8 * u < len) mn = fmaxf(mn, sc[u][g]);
+      const float corr = fast_exp2(m[g] - mn);      // m = -inf on the first block -> corr = 0, o and l are still 0
+      m[g] = mn;
+      l[g] *= corr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[g][j] *= corr;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (t0 + 8 * u < len) {                      // uniform within the half-warp
+        const uint32_t* vi = reinterpret_cast<const uint32_t*>(&vv[u]);
+        float vf[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 c = unpack_bf16x2(vi[j]); vf[2 * j] = c.x; vf[2 * j + 1] = c.y; }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float p = fast_exp2(sc[u][g] - m[g]);
+          l[g] += p;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[g][j] += p * vf[j];
+        }
       }
     }
   }
