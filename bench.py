@@ -32,6 +32,28 @@ PER_GPU_BATCH = 8
 METRIC = "tokens/sec Llama-3-8B seq4096 bf16 pretrain step (global, all GPUs)"
 
 
+def gemm_traffic_from_profile():
+    """Average DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
+    capture of the same kernel family at the bench shapes (profiles/r01_ncu_summary.md); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_summary.md")
+    try:
+        tot, n, section = 0.0, 0, ""
+        for line in open(path):
+            if line.startswith("| **"):
+                section = line
+            if "prof_top" not in section or "gemm_bf16_kernel" not in line:
+                continue
+            cells = [c.strip() for c in line.strip().strip("|").split("|")]
+            vals = []
+            for c in cells[2:4]:                       # dram rd, dram wr
+                num, unit = c.split()[0], c.split()[1]
+                vals.append(float(num) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit])
+            tot += sum(vals); n += 1
+        return (tot / n) if n else None
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -315,7 +337,8 @@ def run_native(args):
                      "achieved": gemm_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": (gemm_tf / peaks["bf16_sustained"]) if gemm_tf else None, "peak_source": peaks["source"] + ", sustained",
                      "launches_timed": n_gemm, "avg_launch_ms": gemm_ms / max(1, n_gemm), "share_of_step": gemm_ms / ms,
-                     "traffic": None},
+                     "algorithmic_flops_per_launch": gemm_flops / max(1, n_gemm),
+                     "traffic": gemm_traffic_from_profile(), "traffic_unit": "bytes/launch (ncu --set full, profiles/r01_ncu_summary.md)"},
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(PER_GPU_BATCH * SEQ * 8 * 2),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": losses[-1] if losses else None},
     }
