@@ -11,7 +11,7 @@ Linear/CosineAnnealingWithWarmupDecay (llm/run_pretrain.py:520-536).
 from __future__ import annotations
 
 import math
-from typing import Optional
+from typing import Dict, Optional
 
 import torch
 
@@ -172,3 +172,62 @@ class AdamW:
         self.master.copy_(sd["master"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+
+    # -- per-parameter (reference-named) state: the unified-checkpoint layout -----------------------------------
+    # trainer/plugins/unified_checkpoint.py:95-103,437-452: optimizer tensors are keyed "<param name>/moment1_0",
+    # "<param name>/moment2_0", "<param name>/beta1_pow_acc_0", "<param name>/beta2_pow_acc_0"; fp32 master weights are
+    # keyed by the bare parameter name.
+    def named_optimizer_state(self) -> Dict[str, torch.Tensor]:
+        eng = self.engine
+        m1 = eng.named_views(flat=self.exp_avg)
+        m2 = eng.named_views(flat=self.exp_avg_sq)
+        b1 = torch.tensor([self.beta1 ** self.step_count], dtype=torch.float32)
+        b2 = torch.tensor([self.beta2 ** self.step_count], dtype=torch.float32)
+        out: Dict[str, torch.Tensor] = {}
+        for k in m1:
+            out[k + "/moment1_0"] = m1[k]
+            out[k + "/moment2_0"] = m2[k]
+            out[k + "/beta1_pow_acc_0"] = b1.clone()      # safetensors refuses aliased tensors
+            out[k + "/beta2_pow_acc_0"] = b2.clone()
+        return out
+
+    def named_master_weights(self) -> Dict[str, torch.Tensor]:
+        return self.engine.named_views(flat=self.master)
+
+    def load_named_state(self, optim_items, master_items, step: Optional[int] = None):
+        """`optim_items` / `master_items`: iterables of (key, host tensor) in the layout above.  The step count comes from
+        `step` when given, else from beta1_pow_acc (beta1 ** step)."""
+        eng = self.engine
+        m1 = eng.named_views(flat=self.exp_avg)
+        m2 = eng.named_views(flat=self.exp_avg_sq)
+        mw = eng.named_views(flat=self.master)
+        seen = set()
+        pow_step = None
+        with torch.no_grad():
+            for key, t in optim_items:
+                name, _, kind = key.rpartition("/")
+                if kind == "moment1_0":
+                    m1[name].copy_(t.to(m1[name].device))
+                elif kind == "moment2_0":
+                    m2[name].copy_(t.to(m2[name].device))
+                elif kind == "beta1_pow_acc_0":
+                    v = float(t.reshape(-1)[0])
+                    if 0.0 < v < 1.0:
+                        pow_step = round(math.log(v) / math.log(self.beta1))
+                    elif v == 1.0:
+                        pow_step = 0
+                    continue
+                elif kind == "beta2_pow_acc_0":
+                    continue
+                else:
+                    raise KeyError(f"unknown optimizer state entry {key}")
+                seen.add(key)
+            for name, t in master_items:
+                mw[name].copy_(t.to(mw[name].device))
+                seen.add(name)
+        missing = [k for k in m1 if (k + "/moment1_0") not in seen or (k + "/moment2_0") not in seen or k not in seen]
+        if missing:
+            raise KeyError(f"optimizer checkpoint is missing state for {len(missing)} parameters, e.g. {missing[:3]}")
+        if step is not None and pow_step is not None and abs(step - pow_step) > 1 and self.beta1 ** step > 1e-30:
+            raise ValueError(f"optimizer step {step} disagrees with beta1_pow_acc ({pow_step} steps)")
+        self.step_count = int(step if step is not None else (pow_step or 0))

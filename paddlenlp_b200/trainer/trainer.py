@@ -12,8 +12,13 @@ averaging (1/world) is folded into the optimizer kernel; the step is host-sync f
 """
 from __future__ import annotations
 
+import dataclasses
+import json
 import math
 import os
+import random
+import re
+import shutil
 import time
 from dataclasses import dataclass
 from typing import Any, Callable, Dict, List, Optional
@@ -46,12 +51,52 @@ class PrinterCallback(TrainerCallback):
             print(", ".join(f"{k}: {v}" for k, v in logs.items()), flush=True)
 
 
+PREFIX_CHECKPOINT_DIR = "checkpoint"              # trainer_utils.py
+TRAINER_STATE_NAME = "trainer_state.json"         # trainer.py:168
+SCHEDULER_NAME = "scheduler.pdparams"             # trainer.py:171
+TRAINING_ARGS_NAME = "training_args.json"
+
+
 @dataclass
 class TrainerState:
+    """trainer_callback.py:47-118 (the fields the data-parallel loop maintains) with the same JSON round trip."""
+    epoch: Optional[float] = 0.0
     global_step: int = 0
-    epoch: float = 0.0
     max_steps: int = 0
+    num_train_epochs: int = 0
+    total_flos: float = 0
     log_history: Optional[List[Dict[str, float]]] = None
+    best_metric: Optional[float] = None
+    best_model_checkpoint: Optional[str] = None
+    is_local_process_zero: bool = True
+    is_world_process_zero: bool = True
+    trial_name: Optional[str] = None
+    trial_params: Optional[Dict[str, Any]] = None
+
+    def __post_init__(self):
+        if self.log_history is None:
+            self.log_history = []
+
+    def save_to_json(self, json_path: str):
+        with open(json_path, "w", encoding="utf-8") as f:
+            f.write(json.dumps(dataclasses.asdict(self), indent=2, sort_keys=True) + "\n")
+
+    @classmethod
+    def load_from_json(cls, json_path: str):
+        with open(json_path, encoding="utf-8") as f:
+            return cls(**json.load(f))
+
+
+def get_last_checkpoint(folder: str) -> Optional[str]:
+    """trainer_utils.py get_last_checkpoint: the `checkpoint-N` sub-directory with the largest N, or None."""
+    if not os.path.isdir(folder):
+        return None
+    best = None
+    for name in os.listdir(folder):
+        m = re.fullmatch(PREFIX_CHECKPOINT_DIR + r"-(\d+)", name)
+        if m and os.path.isdir(os.path.join(folder, name)) and (best is None or int(m.group(1)) > best[0]):
+            best = (int(m.group(1)), name)
+    return os.path.join(folder, best[1]) if best else None
 
 
 class _PhaseTimers:
@@ -205,8 +250,14 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------
     def train(self, resume_from_checkpoint=None) -> TrainOutput:
         a = self.args
+        if resume_from_checkpoint is None:
+            resume_from_checkpoint = a.resume_from_checkpoint
+        if resume_from_checkpoint is True:                       # trainer.py:569-580: newest checkpoint-N in output_dir
+            resume_from_checkpoint = get_last_checkpoint(a.output_dir)
+            if resume_from_checkpoint is None:
+                raise ValueError(f"No valid checkpoint found in output directory ({a.output_dir})")
         if resume_from_checkpoint:
-            raise NotImplementedError("checkpoint resume is a 'next' item (SURVEY.md §8f rank 2)")
+            self._load_from_checkpoint(resume_from_checkpoint)
         dl = self.get_train_dataloader()
         accum = max(1, a.gradient_accumulation_steps)
         try:
@@ -229,6 +280,18 @@ class Trainer:
         world = a.world_size
         self.optimizer.grad_scale = 1.0 / world
         self.optimizer.clear_grad()
+        # trainer.py:872-905: restore state, then skip the epochs / batches already consumed
+        epochs_trained, skip_batches = 0, 0
+        if resume_from_checkpoint:
+            self._load_optimizer_and_scheduler(resume_from_checkpoint)
+            self.state = TrainerState.load_from_json(os.path.join(resume_from_checkpoint, TRAINER_STATE_NAME))
+            self.state.max_steps = max_steps
+            self._load_rng_state(resume_from_checkpoint)
+            if not a.ignore_data_skip and steps_per_epoch:
+                epochs_trained = self.state.global_step // steps_per_epoch
+                skip_batches = (self.state.global_step % steps_per_epoch) * accum
+        self.state.num_train_epochs = epochs
+        self.state.is_world_process_zero = a.process_index == 0
         for cb in self.callbacks:
             cb.on_train_begin(a, self.state, self.control)
 
@@ -240,12 +303,17 @@ class Trainer:
         t_start = t_log
         seq_len = a.max_seq_length or getattr(self.model.config, "seq_length", None)
         done = False
-        for epoch in range(epochs):
+        logged_step = self.state.global_step
+        for epoch in range(epochs_trained, epochs):
             sampler = getattr(dl, "sampler", None)
             if hasattr(sampler, "set_epoch"):
                 sampler.set_epoch(epoch)
             it = iter(dl)
             step = -1
+            if epoch == epochs_trained and skip_batches:
+                for _ in range(skip_batches):                    # trainer.py:1005-1020 (skip_first_batches)
+                    next(it)
+                step = skip_batches - 1
             while True:
                 tok = self.timers.start("read-data")
                 try:
@@ -308,6 +376,8 @@ class Trainer:
                     logged_step = gs
                     t_log = time.time()
                     self.log(logs)
+                if a.save_strategy == "steps" and a.save_steps > 0 and gs % a.save_steps == 0:
+                    self._save_checkpoint(model)
                 if gs >= max_steps:
                     done = True
                     break
@@ -335,6 +405,110 @@ class Trainer:
             cb.on_log(self.args, self.state, self.control, logs=logs)
 
     def save_model(self, output_dir: Optional[str] = None):
+        """trainer.py:2294-2330: rank 0 writes config + safetensors shards + training args."""
+        output_dir = output_dir or self.args.output_dir
         if self.args.process_index == 0:
             m = getattr(self.model, "_layers", self.model)
-            m.save_pretrained(output_dir or self.args.output_dir)
+            m.save_pretrained(output_dir)
+            with open(os.path.join(output_dir, TRAINING_ARGS_NAME), "w", encoding="utf-8") as f:
+                f.write(self.args.to_json_string() + "\n")
+
+    # ------------------------------------------------------------------------------------------------
+    # checkpoint save / resume  (trainer.py:2363-2525 _save_checkpoint, :569-640 _load_from_checkpoint,
+    # :2595-2680 _load_optimizer_and_scheduler, :1752-1814 _load_rng_state; unified_checkpoint.py:301-540)
+    # ------------------------------------------------------------------------------------------------
+    def _rng_states(self):
+        dev = self._engine().device
+        return {"python": random.getstate(), "numpy": __import__("numpy").random.get_state(),
+                "cpu": torch.get_rng_state(), "cuda": torch.cuda.get_rng_state(dev) if dev.type == "cuda" else None}
+
+    def _save_checkpoint(self, model=None, metrics=None):
+        from ..transformers import conversion_utils as cu
+
+        a = self.args
+        out = os.path.join(a.output_dir, f"{PREFIX_CHECKPOINT_DIR}-{self.state.global_step}")
+        world = a.world_size
+        rng = self._rng_states()
+        if world > 1:                                            # trainer.py:2495-2500: one list entry per rank
+            rng_list = [None] * world
+            torch.distributed.all_gather_object(rng_list, rng)
+        if a.process_index == 0:
+            tmp = out + ".tmp"
+            shutil.rmtree(tmp, ignore_errors=True)
+            os.makedirs(tmp)
+            if self._engine().device.type == "cuda":
+                torch.cuda.synchronize(self._engine().device)
+            m = getattr(self.model, "_layers", self.model)
+            m.save_pretrained(tmp)
+            if not a.save_only_model:
+                cu.save_sharded(self.optimizer.named_optimizer_state(), tmp, cu.SAFE_OPTIMIZER_NAME,
+                                cu.SAFE_OPTIMIZER_INDEX_NAME)
+                cu.save_sharded(self.optimizer.named_master_weights(), tmp, cu.SAFE_MASTER_WEIGHTS_NAME,
+                                cu.SAFE_MASTER_WEIGHTS_INDEX_NAME)
+                torch.save(self.lr_scheduler.state_dict(), os.path.join(tmp, SCHEDULER_NAME))
+            self.state.save_to_json(os.path.join(tmp, TRAINER_STATE_NAME))
+            with open(os.path.join(tmp, TRAINING_ARGS_NAME), "w", encoding="utf-8") as f:
+                f.write(a.to_json_string() + "\n")
+            if world > 1:
+                torch.save(rng_list, os.path.join(tmp, f"rng_state_{world}.pth"))
+            else:
+                torch.save(rng, os.path.join(tmp, "rng_state.pth"))
+            shutil.rmtree(out, ignore_errors=True)
+            os.replace(tmp, out)                                 # a crash mid-save never leaves a half checkpoint-N
+            self._rotate_checkpoints()
+        if world > 1:
+            torch.distributed.barrier()
+        return out
+
+    def _rotate_checkpoints(self):
+        """trainer.py:2549-2576: keep the newest `save_total_limit` checkpoint-N directories."""
+        limit = self.args.save_total_limit
+        if not limit or limit <= 0:
+            return
+        found = []
+        for name in os.listdir(self.args.output_dir):
+            m = re.fullmatch(PREFIX_CHECKPOINT_DIR + r"-(\d+)", name)
+            if m:
+                found.append((int(m.group(1)), name))
+        for _, name in sorted(found)[:-limit]:
+            shutil.rmtree(os.path.join(self.args.output_dir, name), ignore_errors=True)
+
+    def _load_from_checkpoint(self, checkpoint: str):
+        from ..transformers import conversion_utils as cu
+
+        if not os.path.isdir(checkpoint) or not cu.has_safetensors(checkpoint):
+            raise ValueError(f"Can't find a valid checkpoint at {checkpoint}")
+        m = getattr(self.model, "_layers", self.model)
+        m._load_streaming(cu.iter_sharded(checkpoint), convert_from_hf=False)
+
+    def _load_optimizer_and_scheduler(self, checkpoint: str):
+        from ..transformers import conversion_utils as cu
+
+        if not cu.has_safetensors(checkpoint, cu.SAFE_OPTIMIZER_NAME, cu.SAFE_OPTIMIZER_INDEX_NAME):
+            # save_only_model checkpoints: fresh moments, master weights re-derived from the bf16 parameters
+            self.optimizer.sync_master_from_params()
+            return
+        state = TrainerState.load_from_json(os.path.join(checkpoint, TRAINER_STATE_NAME))
+        self.optimizer.load_named_state(
+            cu.iter_sharded(checkpoint, cu.SAFE_OPTIMIZER_NAME, cu.SAFE_OPTIMIZER_INDEX_NAME),
+            cu.iter_sharded(checkpoint, cu.SAFE_MASTER_WEIGHTS_NAME, cu.SAFE_MASTER_WEIGHTS_INDEX_NAME),
+            step=state.global_step)
+        sched = os.path.join(checkpoint, SCHEDULER_NAME)
+        if os.path.isfile(sched):
+            self.lr_scheduler.set_state_dict(torch.load(sched))
+
+    def _load_rng_state(self, checkpoint: str):
+        a = self.args
+        world = a.world_size
+        path = os.path.join(checkpoint, f"rng_state_{world}.pth" if world > 1 else "rng_state.pth")
+        if not os.path.isfile(path):
+            return                                               # trainer.py:1777-1783: warn-and-continue
+        st = torch.load(path, weights_only=False)
+        if world > 1:
+            st = st[a.process_index]
+        random.setstate(st["python"])
+        __import__("numpy").random.set_state(st["numpy"])
+        torch.set_rng_state(st["cpu"])
+        dev = self._engine().device
+        if st.get("cuda") is not None and dev.type == "cuda":
+            torch.cuda.set_rng_state(st["cuda"], dev)

@@ -37,6 +37,10 @@ class TrainingArguments:
     logging_steps: int = 500
     logging_first_step: bool = False
     save_steps: int = 0
+    save_strategy: str = "steps"
+    save_total_limit: Optional[int] = None
+    resume_from_checkpoint: Optional[str] = None
+    save_only_model: bool = False
     seed: int = 42
     bf16: bool = True
     fp16: bool = False

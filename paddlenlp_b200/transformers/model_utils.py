@@ -60,21 +60,76 @@ class PretrainedModel(nn.Module):
     _from_config = from_config
 
     @classmethod
-    def from_pretrained(cls, path, config=None, dtype="bfloat16", **kwargs):
-        """Local directory with config.json (+ optional model_state.pt).  Hub download is out of scope."""
+    def from_pretrained(cls, path, config=None, dtype="bfloat16", convert_from_hf=None, **kwargs):
+        """Local directory with config.json and weights: `model.safetensors` / sharded `model-0000i-of-0000N.safetensors`
+        + `model.safetensors.index.json` (the reference's unified on-disk layout, utils/env.py:97-98), or the legacy
+        single `model_state.pt`.  Weights in HuggingFace naming/layout are detected (or forced with
+        `convert_from_hf=True`) and converted on the fly (llama/modeling.py:1243-1274).  Hub download is out of scope."""
+        from . import conversion_utils as cu
+
         if config is None:
             config = cls.config_class.from_pretrained(path)
         model = cls(config, **kwargs)
-        wfile = os.path.join(path, "model_state.pt") if os.path.isdir(path) else None
-        if wfile and os.path.exists(wfile):
-            model.set_state_dict(torch.load(wfile, map_location="cpu"))
+        if not os.path.isdir(path):
+            return model
+        legacy = os.path.join(path, "model_state.pt")
+        if cu.has_safetensors(path):
+            if convert_from_hf is None:
+                convert_from_hf = cu.looks_like_hf(cu.list_keys(path))
+            model._load_streaming(cu.iter_sharded(path), convert_from_hf)
+        elif os.path.exists(legacy):
+            model.set_state_dict(torch.load(legacy, map_location="cpu"))
         return model
 
-    def save_pretrained(self, save_directory: str):
+    def _load_streaming(self, items, convert_from_hf: bool = False):
+        """Copies (name, host tensor) pairs into the flat parameter buffer one tensor at a time."""
+        from . import conversion_utils as cu
+
+        views = self.engine.named_views()
+        mt = self.engine.prefix
+        seen = set()
+        embed = None
+        with torch.no_grad():
+            for k, v in items:
+                if convert_from_hf:
+                    conv = cu.hf_to_paddle_state_dict({k: v}, mt)
+                    if k != "lm_head.weight":
+                        conv.pop("lm_head.weight", None)      # tied-head fallback is resolved after the loop
+                else:
+                    conv = {k: v}
+                for nk, nv in conv.items():
+                    if nk not in views:
+                        continue                      # e.g. rotary inv_freq buffers (llama/modeling.py:1240)
+                    if tuple(nv.shape) != tuple(views[nk].shape):
+                        raise ValueError(f"{nk}: shape {tuple(nv.shape)} != {tuple(views[nk].shape)}")
+                    views[nk].copy_(nv.to(device=self.engine.device, dtype=torch.bfloat16))
+                    seen.add(nk)
+                    if nk.endswith("embed_tokens.weight"):
+                        embed = nk
+        if "lm_head.weight" not in seen and embed is not None and getattr(self.config, "tie_word_embeddings", False):
+            with torch.no_grad():
+                views["lm_head.weight"].copy_(views[embed].t())
+            seen.add("lm_head.weight")
+        missing = [k for k in views if k not in seen]
+        if missing:
+            raise KeyError(f"checkpoint is missing {len(missing)} tensors, e.g. {missing[:3]}")
+        self.engine.params_changed()
+
+    def save_pretrained(self, save_directory: str, max_shard_size="5GB", safe_serialization: bool = True,
+                        hf_format: bool = False):
+        """config.json + safetensors shards + index (model_utils.py save_pretrained / shard_checkpoint :562-640).
+        `hf_format=True` writes HuggingFace names and `[out, in]` Linear layouts instead of the Paddle ones."""
+        from . import conversion_utils as cu
+
         os.makedirs(save_directory, exist_ok=True)
         self.config.save_pretrained(save_directory)
-        torch.save({k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()},
-                   os.path.join(save_directory, "model_state.pt"))
+        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        if not safe_serialization:
+            torch.save({k: v.cpu().contiguous() for k, v in sd.items()}, os.path.join(save_directory, "model_state.pt"))
+            return
+        if hf_format:
+            sd = cu.paddle_to_hf_state_dict(sd, self.engine.prefix)
+        cu.save_sharded(sd, save_directory, max_shard_size=max_shard_size)
 
     # -- parameters ---------------------------------------------------------------------------------
     def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):

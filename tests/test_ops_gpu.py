@@ -272,3 +272,62 @@ def test_adamw_and_clip():
     assert relerr(M_.cpu(), mr) < 1e-5
     assert relerr(V_.cpu(), vr) < 1e-5
     assert (P.cpu().float() != p16r.float()).float().mean().item() < 1e-3
+
+
+# ----------------------------------------------------------------------------------------------------------
+# The reference's per-op plug-in seam (llama/fusion_ops.py) with autograd: forward and gradients vs the oracle
+# ----------------------------------------------------------------------------------------------------------
+def test_fusion_ops_seam_autograd():
+    from paddlenlp_b200.transformers.llama import fusion_ops as F
+    from paddlenlp_b200.transformers.llama.configuration import LlamaConfig
+
+    b, s, nh, kvh, d, h, inter = 2, 256, 4, 2, 128, 512, 384
+    g = torch.Generator().manual_seed(5)
+    leaf = lambda *shape, sc=1.0: (torch.randn(*shape, generator=g) * sc).to(BF16)
+
+    # --- rms norm
+    x, w, dy = leaf(b, s, h), (1 + 0.1 * torch.randn(h, generator=g)).to(BF16), leaf(b, s, h)
+    xd, wd = x.to(DEV).requires_grad_(), w.to(DEV).requires_grad_()
+    y = F.fusion_rms_norm(xd, wd, 1e-5)
+    y.backward(dy.to(DEV))
+    xo, wo = x.float().requires_grad_(), w.float().requires_grad_()
+    yo = R.rms_norm(xo, wo, 1e-5, "fp32")
+    yo.backward(dy.float())
+    assert maxerr(y.cpu(), yo) < 1e-2 and relerr(xd.grad.cpu(), xo.grad) < 1e-2 and relerr(wd.grad.cpu(), wo.grad) < 1e-2
+
+    # --- rope (with and without position_ids) + flash attention + reshape
+    q, k, v, do = leaf(b, s, nh, d), leaf(b, s, kvh, d), leaf(b, s, kvh, d), leaf(b, s, nh * d)
+    rot = F.LlamaRotaryEmbedding(d, max_position_embeddings=512, base=500000.0, device=DEV)
+    cos, sin = R.rope_tables(d, 512, 500000.0)
+    for pos in (None, torch.arange(s).flip(0)[None, :].expand(b, s).contiguous()):
+        qd, kd, vd = (t.to(DEV).requires_grad_() for t in (q, k, v))
+        q2, k2 = F.fusion_rope(qd, kd, vd, None, None if pos is None else pos.to(DEV), None, rot)
+        if pos is not None:          # permuted positions only exercise RoPE (causality needs ordered positions)
+            qo = R.apply_rope(q.float(), cos, sin, "fp32", pos)
+            assert maxerr(q2.cpu(), qo) < 1e-2
+            continue
+        out = F.fusion_flash_attention(q2, LlamaConfig(), k2, vd, None, False)
+        assert out.shape == (b, s, nh * d)
+        out.backward(do.to(DEV))
+        qo, ko, vo = (t.float().requires_grad_() for t in (q, k, v))
+        oo = R.attention(R.apply_rope(qo, cos, sin, "fp32"), R.apply_rope(ko, cos, sin, "fp32"), vo, "fp32")
+        oo.backward(do.float())
+        assert maxerr(out.cpu(), oo) < 2e-2
+        for name, a, r in (("dq", qd.grad, qo.grad), ("dk", kd.grad, ko.grad), ("dv", vd.grad, vo.grad)):
+            assert relerr(a.cpu(), r) < 2e-2, (name, relerr(a.cpu(), r))
+    with pytest.raises(NotImplementedError):
+        F.fusion_flash_attention(q2, LlamaConfig(), k2, vd, torch.ones(1, device=DEV), False)
+    with pytest.raises(AssertionError):
+        F.fusion_rope(qd, kd, vd, None, None, (kd, vd), rot)
+
+    # --- swiglu: both call forms of llama/modeling.py:38-45
+    gt, up, dz = leaf(b, s, inter), leaf(b, s, inter), leaf(b, s, inter)
+    gd, ud = gt.to(DEV).requires_grad_(), up.to(DEV).requires_grad_()
+    z = F.swiglu(gd, ud)
+    z.backward(dz.to(DEV))
+    go, uo = gt.float().requires_grad_(), up.float().requires_grad_()
+    zo = R.swiglu(go, uo, "fp32")
+    zo.backward(dz.float())
+    assert maxerr(z.cpu(), zo) < 1e-2 and relerr(gd.grad.cpu(), go.grad) < 1e-2 and relerr(ud.grad.cpu(), uo.grad) < 1e-2
+    z2 = F.swiglu(torch.cat([gt, up], -1).to(DEV))
+    assert torch.equal(z2, z.detach())

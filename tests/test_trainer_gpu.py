@@ -92,3 +92,41 @@ def test_one_optimizer_step_matches_oracle():
         assert rel < 0.35, (k, rel)
     gn = float(opt.grad_norm())
     assert abs(gn - float(flat.norm())) < 0.03 * float(flat.norm())
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """save at step 3 (model shards + optimizer.safetensors + master_weights.safetensors + scheduler +
+    trainer_state.json + rng), resume in a fresh Trainer, finish at step 6 -> the same bits as the uninterrupted run."""
+    import json
+    import os
+
+    from paddlenlp_b200.trainer import Trainer, TrainingArguments
+    from paddlenlp_b200.trainer.trainer import get_last_checkpoint
+
+    def run(out_dir, max_steps, resume=None, save_steps=0):
+        model = tiny("qwen2")
+        args = TrainingArguments(output_dir=str(out_dir), per_device_train_batch_size=2, gradient_accumulation_steps=2,
+                                 max_steps=max_steps, learning_rate=1e-3, weight_decay=0.01, warmup_steps=2, logging_steps=1,
+                                 max_seq_length=128, lr_scheduler_type="cosine", save_steps=save_steps, save_total_limit=1)
+        tr = Trainer(model=model, args=args, train_dataset=ToyDataset(16, 128, 512, True))
+        tr.train(resume_from_checkpoint=resume)
+        return tr
+
+    full = run(tmp_path / "full", 6)
+    run(tmp_path / "part", 3, save_steps=1)                       # saves at 1, 2, 3; save_total_limit keeps only the last
+    ck = get_last_checkpoint(str(tmp_path / "part"))
+    assert ck.endswith("checkpoint-3") and sorted(os.listdir(tmp_path / "part")) == ["checkpoint-3"]
+    files = set(os.listdir(ck))
+    assert {"config.json", "model.safetensors", "optimizer.safetensors", "master_weights.safetensors", "scheduler.pdparams",
+            "trainer_state.json", "rng_state.pth", "training_args.json"} <= files
+    assert json.load(open(os.path.join(ck, "trainer_state.json")))["global_step"] == 3
+    # resume: max_steps 6 with the same schedule; the data loader skips the 3*2 consumed batches
+    import shutil
+    shutil.copytree(ck, tmp_path / "resumed" / "checkpoint-3")
+    res = run(tmp_path / "resumed", 6, resume=True)
+    assert res.state.global_step == 6
+    assert torch.equal(res.model.engine.flat_params, full.model.engine.flat_params)
+    assert torch.equal(res.optimizer.master, full.optimizer.master)
+    assert torch.equal(res.optimizer.exp_avg_sq, full.optimizer.exp_avg_sq)
+    assert [h["loss"] for h in res.state.log_history][-3:] == [h["loss"] for h in full.state.log_history][-3:]
+    assert res.optimizer.get_lr() == full.optimizer.get_lr()
