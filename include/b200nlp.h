@@ -191,6 +191,12 @@ int64_t b200_decode_attention_workspace_bytes(int64_t B, int64_t num_heads, int6
 int b200_decode_attention(const void* qkv, const void* cache, const int32_t* seq_lens, void* out, void* workspace, int64_t B,
                           int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len, int64_t ld,
                           float softmax_scale, int64_t num_splits, cudaStream_t stream);
+/* Same contract on the tensor cores: a persistent tcgen05 kernel streams the cache with TMA through a 192 KB ring per SM
+ * (S^T = K_tile Q^T and O^T += V_tile^T P^T, the G query heads of a group padded to N=16); GQA group size 1, 2, 4, 7 or 8.
+ * Cache rows past the sequence length must hold finite values (zero-filled allocation, as the reference's paddle.zeros). */
+int b200_decode_attention_tc(const void* qkv, const void* cache, const int32_t* seq_lens, void* out, void* workspace, int64_t B,
+                             int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len, int64_t ld,
+                             float softmax_scale, int64_t num_splits, cudaStream_t stream);
 
 /* Bookkeeping ops, same semantics as the reference custom ops (file:line beside each). bool = 1-byte flags. */
 /* get_padding_offset_v2 (+ remove padding): csrc/gpu/get_padding_offset_v2.cu:17-80 */

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "b200_decode_rope_append": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, P],
     "b200_decode_attention_workspace_bytes": [I64, I64, I64],
     "b200_decode_attention": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, F, I64, P],
+    "b200_decode_attention_tc": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, F, I64, P],
     "b200_get_padding_offset": [P, P, P, P, P, P, P, P, I64, I64, P],
     "b200_rebuild_padding": [P, P, P, P, P, I64, I64, I64, P],
     "b200_set_value_by_flags_and_idx": [P, P, P, P, I64, I64, P],
@@ -115,7 +116,7 @@ KERNELS_PER_CALL = {
     "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_gemm_bf16_splitk": 2, "b200_rmsnorm_fwd": 1, "b200_rmsnorm_bwd": 2, "b200_colsum_bf16": 2,
     "b200_rope_inplace": 1, "b200_swiglu_fwd": 1, "b200_swiglu_bwd": 1, "b200_embedding_fwd": 1, "b200_embedding_bwd": 1,
     "b200_fa_fwd": 1, "b200_fa_bwd": 3, "b200_ce_fwd": 2, "b200_ce_bwd": 1, "b200_argmax_bf16": 1, "b200_grad_sqnorm": 2,
-    "b200_adamw_step": 1, "b200_bf16_to_f32": 1, "b200_token_penalty_multi_scores": 2, "b200_generate_step_update": 2, "b200_decode_attention": 2,
+    "b200_adamw_step": 1, "b200_bf16_to_f32": 1, "b200_token_penalty_multi_scores": 2, "b200_generate_step_update": 2, "b200_decode_attention": 2, "b200_decode_attention_tc": 2,
 }
 launch_count = 0       # kernels launched through this module since import
 call_hook = None       # optional callable(name, args) -> context manager, used by bench.py to time one kernel family

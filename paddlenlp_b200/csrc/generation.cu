@@ -667,6 +667,14 @@ extern "C" int b200_decode_rope_append_f32(void* qkv, float* acc_f32_ws, const f
   return check_launch("decode_rope_append");
 }
 
+namespace b200 {
+// shared with decode_attn_tc.cu
+int launch_decode_attention_merge(const float* partial, void* out, int rows, int nsplit, cudaStream_t stream) {
+  gen::decode_attention_merge_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(partial, static_cast<bf16*>(out), rows, nsplit);
+  return check_launch("decode_attention(merge)");
+}
+}  // namespace b200
+
 extern "C" int64_t b200_decode_attention_workspace_bytes(int64_t B, int64_t num_heads, int64_t num_splits) {
   return num_splits > 1 ? B * num_heads * num_splits * (128 + 4) * 4 : 0;
 }

@@ -392,20 +392,32 @@ def decode_rope_append(qkv, cache, cos, sin, seq_lens, nh, kvh, d):
          qkv.stride(0), stream_ptr())
 
 
-def decode_attention(qkv, cache, seq_lens, nh, kvh, d, softmax_scale=None, out=None, num_splits: int = 0):
+def decode_attention(qkv, cache, seq_lens, nh, kvh, d, softmax_scale=None, out=None, num_splits: int = 0, impl: str = "tc"):
+    """impl "tc": persistent tcgen05 kernel (TMA-streamed cache); "simt": the CUDA-core kernel (half-warp per cache row)."""
     _chk(qkv, "qkv"); _chk(cache, "cache"); _chk(seq_lens, "seq_lens", torch.int32)
     B = qkv.shape[0]
     if out is None:
         out = torch.empty(B, nh * d, dtype=BF16, device=qkv.device)
     if softmax_scale is None:
         softmax_scale = 1.0 / math.sqrt(d)
-    if num_splits <= 0:
-        # enough CTAs for ~8 per SM without making the ranges shorter than ~64 cache rows at full length
-        num_splits = max(1, min(cache.shape[3] // 64, (8 * 148 + B * kvh - 1) // (B * kvh)))
+    max_len = cache.shape[3]
+    if impl == "tc":
+        if num_splits <= 0:
+            # persistent CTAs walk (split, b, kv head) items round-robin; split only when there are too few (b, kv head)
+            # pairs to give every SM ~3 items (a split costs partial traffic, a merge launch and an item boundary)
+            num_splits = max(1, min((max_len + 127) // 128, (3 * 148 + B * kvh - 1) // (B * kvh)))
+        fn = "b200_decode_attention_tc"
+    elif impl == "simt":
+        if num_splits <= 0:
+            # enough CTAs for ~8 per SM without making the ranges shorter than ~64 cache rows at full length
+            num_splits = max(1, min(max_len // 64, (8 * 148 + B * kvh - 1) // (B * kvh)))
+        fn = "b200_decode_attention"
+    else:
+        raise ValueError(f"decode_attention impl {impl!r}")
     ws = None
     if num_splits > 1:
         ws = _workspace(_lib.load().b200_decode_attention_workspace_bytes(B, nh, num_splits), qkv.device, "decode_attn")
-    call("b200_decode_attention", ptr(qkv), ptr(cache), ptr(seq_lens), ptr(out), ptr(ws), B, nh, kvh, d, cache.shape[3],
+    call(fn, ptr(qkv), ptr(cache), ptr(seq_lens), ptr(out), ptr(ws), B, nh, kvh, d, max_len,
          qkv.stride(0), float(softmax_scale), num_splits, stream_ptr())
     return out
 

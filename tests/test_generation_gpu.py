@@ -120,8 +120,9 @@ def test_add_rmsnorm():
     assert (n.float().cpu() != ref).float().mean().item() < 0.01
 
 
+@pytest.mark.parametrize("impl", ["tc", "simt"])
 @pytest.mark.parametrize("nh,kvh", [(4, 1), (8, 2), (7, 1)])
-def test_decode_rope_append_and_attention(nh, kvh):
+def test_decode_rope_append_and_attention(nh, kvh, impl):
     o = ops()
     B, d, max_len = 3, 128, 96
     g = torch.Generator().manual_seed(2)
@@ -131,9 +132,9 @@ def test_decode_rope_append_and_attention(nh, kvh):
     cos, sin = o.rope_tables(d, max_len, 10000.0, DEV)
     qkv_d, cache_d = qkv.clone().to(DEV), cache.clone().to(DEV)
     o.decode_rope_append(qkv_d, cache_d, cos, sin, lens.to(DEV), nh, kvh, d)
-    out = o.decode_attention(qkv_d, cache_d, lens.to(DEV), nh, kvh, d).float().cpu()
-    out1 = o.decode_attention(qkv_d, cache_d, lens.to(DEV), nh, kvh, d, num_splits=1).float().cpu()
-    out3 = o.decode_attention(qkv_d, cache_d, lens.to(DEV), nh, kvh, d, num_splits=3).float().cpu()
+    out = o.decode_attention(qkv_d, cache_d, lens.to(DEV), nh, kvh, d, impl=impl).float().cpu()
+    out1 = o.decode_attention(qkv_d, cache_d, lens.to(DEV), nh, kvh, d, num_splits=1, impl=impl).float().cpu()
+    out3 = o.decode_attention(qkv_d, cache_d, lens.to(DEV), nh, kvh, d, num_splits=3, impl=impl).float().cpu()
     assert (out1 - out3).abs().max() < 1e-2 * out1.abs().max()
     c, s = R.rope_tables(d, max_len, 10000.0)
     for b in range(B):
@@ -152,6 +153,34 @@ def test_decode_rope_append_and_attention(nh, kvh):
         ref = torch.einsum("ht,htd->hd", torch.softmax(sc, -1), Vr).reshape(-1)
         err = (out[b] - ref).abs().max() / ref.abs().max()
         assert err < 1.5e-2, (b, err)
+
+
+@pytest.mark.parametrize("nh,kvh,B,max_len,splits", [(32, 8, 24, 700, 0), (8, 1, 200, 300, 1), (28, 4, 5, 1100, 4), (2, 2, 3, 130, 2)])
+def test_decode_attention_tc_long(nh, kvh, B, max_len, splits):
+    """The persistent tcgen05 kernel over many work items per CTA, several 128-row tiles per item, ragged lengths (incl. 0
+    cached tokens and a full cache), vs an fp32 reference and vs the CUDA-core kernel."""
+    o = ops()
+    d = 128
+    g = torch.Generator().manual_seed(B + nh)
+    lens = torch.randint(0, max_len - 1, (B,), generator=g).to(torch.int32)
+    lens[0], lens[-1] = 0, max_len - 1                                   # shortest case; cache already full (clamped)
+    cache = torch.randn(2, B, kvh, max_len, d, generator=g).to(BF16)
+    qkv = torch.randn(B, (nh + 2 * kvh) * d, generator=g).to(BF16)
+    qkv_d, cache_d, lens_d = qkv.to(DEV), cache.to(DEV), lens.to(DEV)
+    out = o.decode_attention(qkv_d, cache_d, lens_d, nh, kvh, d, num_splits=splits, impl="tc").float().cpu()
+    alt = o.decode_attention(qkv_d, cache_d, lens_d, nh, kvh, d, impl="simt").float().cpu()
+    rep = nh // kvh
+    q = qkv[:, : nh * d].float().view(B, kvh, rep, d)
+    K, V = cache[0].float(), cache[1].float()                            # [B, kvh, max_len, d]
+    sc = torch.einsum("bkrd,bktd->bkrt", q, K) / d ** 0.5
+    total = torch.clamp(lens.long() + 1, max=max_len)
+    mask = torch.arange(max_len)[None, :] >= total[:, None]
+    sc = sc.masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = torch.einsum("bkrt,bktd->bkrd", torch.softmax(sc, -1), V).reshape(B, nh * d)
+    scale = ref.abs().max()
+    assert (out - ref).abs().max() / scale < 1.5e-2
+    assert (out - alt).abs().max() / scale < 1.5e-2
+    assert torch.isfinite(out).all()
 
 
 def _tiny(model_type="llama"):

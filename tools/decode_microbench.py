@@ -50,8 +50,10 @@ def main():
     qkv = torch.randn(B, (nh + 2 * kvh) * d, device=dev).to(torch.bfloat16)
     for t in (128, 512, 1024, 2047):
         lens = torch.full((B,), t, dtype=torch.int32, device=dev)
-        us = timeit(lambda: ops.decode_attention(qkv, cache, lens, nh, kvh, d))
-        print(json.dumps(dict(op=f"decode_attention[t={t}]", us=us, gbs=2 * B * kvh * (t + 1) * d * 2 / us / 1e3)))
+        for impl, splits in (("simt", 0), ("tc", 0), ("tc", 1), ("tc", 2), ("tc", 4)):
+            us = timeit(lambda: ops.decode_attention(qkv, cache, lens, nh, kvh, d, impl=impl, num_splits=splits))
+            print(json.dumps(dict(op=f"decode_attention[{impl} splits={splits} t={t}]", us=us,
+                                  gbs=2 * B * kvh * (t + 1) * d * 2 / us / 1e3)))
     cos, sin = ops.rope_tables(d, max_len, 500000.0, dev)
     lens = torch.full((B,), 100, dtype=torch.int32, device=dev)
     print(json.dumps(dict(op="decode_rope_append", us=timeit(lambda: ops.decode_rope_append(qkv, cache, cos, sin, lens, nh, kvh, d)))))
