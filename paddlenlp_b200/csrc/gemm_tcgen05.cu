@@ -55,6 +55,7 @@ struct Params {
   int split_k;             // work items per output tile (K is cut into split_k ranges of kb_per_split k-blocks)
   int kb_per_split;
   int b_prefetch;          // PDL: issue the first stages' B (weight) loads before griddepcontrol.wait
+  int l2_prefetch_kb;      // PDL: ... and L2-prefetch this many further B k-blocks of the CTA's first work item
   const float* bias;       // [N] fp32 or nullptr
 };
 
@@ -147,6 +148,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else {
 #pragma unroll
             for (int c = 0; c < C::B_COLS / 128; ++c) load(&tmB, sb + c * (128 * BK * 2), k0, n0 + c * 128);
+          }
+        }
+        // Beyond the smem ring: warm L2 with the next B k-blocks while the predecessor kernel is still running, so the
+        // weight stream does not idle during the (activation-only) kernels between two GEMMs of the decode step.
+        const int l2_end = min(kb1 - kb0, prefetched + p.l2_prefetch_kb);
+        for (int s = prefetched; s < l2_end; ++s) {
+          const int k0 = (kb0 + s) * BK;
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int c = 0; c < C::B_COLS / 64; ++c) tma_prefetch_l2_2d(&tmB, n0 + c * 64, k0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < C::B_COLS / 128; ++c) tma_prefetch_l2_2d(&tmB, k0, n0 + c * 128);
           }
         }
       }
@@ -380,11 +394,16 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   cfg.numAttrs = 1;
   Params pp = p;
   pp.b_prefetch = 0;
+  pp.l2_prefetch_kb = 0;
   if (pdl_enabled()) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
     pp.b_prefetch = 1;
+    // at most ~64 MB of weights resident in L2 ahead of the loads (the L2 is 126 MB and also holds the activations)
+    const long long per_kb = static_cast<long long>(C::B_COLS) * BK * 2 * pairs * CG;
+    long long kbs = (64ll << 20) / per_kb;
+    pp.l2_prefetch_kb = static_cast<int>(kbs > 64 ? 64 : kbs);
   }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, pp);
   if (e != cudaSuccess) {

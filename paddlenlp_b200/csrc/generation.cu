@@ -18,14 +18,19 @@ namespace gen {
 // ------------------------------------------------------------------------------------------------
 // x_f32 != nullptr: x is the fp32 split-K accumulation of the producing GEMM; it is rounded to bf16 here (the Linear
 // output rounding) and the workspace is handed back zeroed — this fuses the split-K "finish" pass into the norm.
-template <int MAXV>
+// WPR = warps per row: 1 -> four rows per CTA (many rows, prefill); 4 -> one row per CTA (the 64-row decode step, where one
+// warp per row leaves the op latency-bound on 16 SMs).
+template <int MAXV, int WPR>
 __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict__ x, float* __restrict__ x_f32,
                                                           const bf16* __restrict__ res,
                                                           const bf16* __restrict__ w, bf16* __restrict__ normed,
                                                           bf16* __restrict__ res_out, int rows, int h, float eps) {
   pdl_launch_dependents();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 4 + warp;
+  constexpr int TPR = 32 * WPR;                     // threads per row
+  __shared__ float s_part[4];
+  const int warp = threadIdx.x >> 5;
+  const int lane = (WPR == 1) ? (threadIdx.x & 31) : static_cast<int>(threadIdx.x);   // position within the row
+  const int row = (WPR == 1) ? blockIdx.x * 4 + warp : static_cast<int>(blockIdx.x);
   if (row >= rows) return;
   const int nchunk = h >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * h);
@@ -38,16 +43,24 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict
   const int last = nchunk - 1;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int c = min(lane + 32 * i, last);
+    const int c = min(lane + TPR * i, last);
     if (xf) { fa[i] = xf[2 * c]; fb[i] = xf[2 * c + 1]; }
     else v[i] = ld_nc_v4(xr + c);
     if (rr) rv[i] = ld_nc_v4(rr + c);
+  }
+  // (one row per CTA: also fetch the norm weight now, so that the row costs one memory round trip, not two)
+  uint4 wv_pre[WPR > 1 ? MAXV : 1];
+  if constexpr (WPR > 1) {
+    if (normed != nullptr) {
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) wv_pre[i] = __ldg(reinterpret_cast<const uint4*>(w) + min(lane + TPR * i, last));
+    }
   }
   // Phase 2: round the fp32 input (if any), add the residual, accumulate the sum of squares
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const bool ok = (lane + 32 * i) < nchunk;
+    const bool ok = (lane + TPR * i) < nchunk;
     if (xf) v[i] = make_uint4(pack_bf16x2(fa[i].x, fa[i].y), pack_bf16x2(fa[i].z, fa[i].w), pack_bf16x2(fb[i].x, fb[i].y),
                               pack_bf16x2(fb[i].z, fb[i].w));
     uint32_t* vi = reinterpret_cast<uint32_t*>(&v[i]);
@@ -67,22 +80,28 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict
   // Phase 3: hand the fp32 workspace back zeroed, write the new residual
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int c = lane + 32 * i;
+    const int c = lane + TPR * i;
     if (c < nchunk) {
       if (xf) { xf[2 * c] = make_float4(0.f, 0.f, 0.f, 0.f); xf[2 * c + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
       if (res_out) st_na_v4(reinterpret_cast<uint4*>(res_out + static_cast<size_t>(row) * h) + c, v[i]);
     }
   }
   ss = warp_sum(ss);
+  if constexpr (WPR > 1) {
+    if ((threadIdx.x & 31) == 0) s_part[warp] = ss;
+    __syncthreads();
+    ss = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+  }
   const float rstd = rsqrtf(ss / static_cast<float>(h) + eps);
   if (normed == nullptr) return;
   const uint4* wr = reinterpret_cast<const uint4*>(w);
   uint4* yr = reinterpret_cast<uint4*>(normed + static_cast<size_t>(row) * h);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int c = lane + 32 * i;
+    const int c = lane + TPR * i;
     if (c < nchunk) {
-      const uint4 wv = __ldg(wr + c);
+      uint4 wv;
+      if constexpr (WPR > 1) wv = wv_pre[i]; else wv = __ldg(wr + c);
       uint4 o;
       const uint32_t* xi = reinterpret_cast<const uint32_t*>(&v[i]);
       const uint32_t* wi = reinterpret_cast<const uint32_t*>(&wv);
@@ -620,12 +639,20 @@ static int add_rmsnorm_launch(const void* x, float* x_f32, const void* residual,
   B200_CHECK_ARG((w || !normed), "add_rmsnorm: null pointer");
   B200_CHECK_ARG(rows > 0 && h > 0 && h % 8 == 0 && h <= 8192, "add_rmsnorm: need 0 < h <= 8192, h %% 8 == 0");
   const int nchunk = static_cast<int>(h / 8);
-  const dim3 grid(static_cast<unsigned>((rows + 3) / 4)), block(128);
+  const dim3 block(128);
   const bf16 *xp = static_cast<const bf16*>(x), *rp = static_cast<const bf16*>(residual), *wp = static_cast<const bf16*>(w);
   bf16 *np = static_cast<bf16*>(normed), *ro = static_cast<bf16*>(residual_out);
-  if (nchunk <= 128) add_rmsnorm_kernel<4><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
-  else if (nchunk <= 512) add_rmsnorm_kernel<16><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
-  else add_rmsnorm_kernel<32><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+  if (rows <= 1024) {            // few rows (decode step): one CTA per row
+    const dim3 grid(static_cast<unsigned>(rows));
+    if (nchunk <= 256) add_rmsnorm_kernel<2, 4><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+    else if (nchunk <= 512) add_rmsnorm_kernel<4, 4><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+    else add_rmsnorm_kernel<8, 4><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+  } else {
+    const dim3 grid(static_cast<unsigned>((rows + 3) / 4));
+    if (nchunk <= 128) add_rmsnorm_kernel<4, 1><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+    else if (nchunk <= 512) add_rmsnorm_kernel<16, 1><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+    else add_rmsnorm_kernel<32, 1><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+  }
   return check_launch("add_rmsnorm");
 }
 
