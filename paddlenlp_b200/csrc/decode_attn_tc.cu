@@ -8,8 +8,8 @@
 //
 // The op is a pure stream of the cache through the SM (2*len*d*2 bytes per (b, kv head), ~4 flop/byte), so the design
 // goal is bytes in flight, not math:
-//   * persistent kernel, one CTA per SM; work items (split, b, kv head) are walked round-robin, and the TMA producer runs
-//     ahead ACROSS items, so the 6 x 32 KB K/V ring (192 KB in flight per SM) never drains between items;
+//   * persistent kernel, two CTAs per SM; work items (split, b, kv head) are walked round-robin, and the TMA producer runs
+//     ahead ACROSS items, so the 3 x 32 KB K/V ring per CTA (192 KB in flight per SM) never drains between items;
 //   * "swapped" orientation so the cache tile is the 128-row M operand and the G query heads of the group are the
 //     (padded to 16) N operand:  S^T[kv, h] = K_tile Q^T  (UMMA 128x16x16 x8),  O^T[d, h] += V_tile^T P^T  (V consumed
 //     MN-major straight from the row-major cache tile); no CUDA-core instruction ever touches a K/V byte;
@@ -32,7 +32,7 @@ constexpr int TILE_BYTES = BKV * D * 2;        // 32 KB, two 64-column halves of
 constexpr int HALF_BYTES = TILE_BYTES / 2;
 constexpr int QP_BYTES = NPAD * D * 2;         // 4 KB: [16 rows x 128] in two 2 KB halves (Q tile and P^T tile)
 constexpr int QP_HALF = QP_BYTES / 2;
-constexpr int NSLOT = 6;
+constexpr int NSLOT = 3;                       // x 2 CTAs per SM = 192 KB of cache tiles in flight per SM
 constexpr int NUM_THREADS = 192;               // TMA warp, MMA warp, 4 softmax warps
 constexpr int OFF_Q = NSLOT * TILE_BYTES;
 constexpr int OFF_P = OFF_Q + 2 * QP_BYTES;
@@ -81,7 +81,7 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 }
 
 template <int G>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 decode_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, const Params p) {
   static_assert(G >= 1 && G <= 8, "group size");
@@ -90,8 +90,8 @@ decode_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   uint8_t* sQ = smem + OFF_Q;               // 2 buffers
   uint8_t* sP = smem + OFF_P;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* full = bars;                    // [6]
-  uint64_t* empty = bars + 6;               // [6]
+  uint64_t* full = bars;                    // [NSLOT <= 6]
+  uint64_t* empty = bars + 6;               // [NSLOT <= 6]
   uint64_t* q_full = bars + 12;             // [2]
   uint64_t* q_empty = bars + 14;            // [2]
   uint64_t* s_full = bars + 16;             // [2]
@@ -395,7 +395,8 @@ extern "C" int b200_decode_attention_tc(const void* qkv, const void* cache, cons
   p.max_len = static_cast<int>(max_len); p.nsplit = static_cast<int>(num_splits);
   p.items = static_cast<int>(B * num_kv_heads * num_splits);
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  const unsigned grid = static_cast<unsigned>(p.items < sm_count() ? p.items : sm_count());
+  const int max_ctas = 2 * sm_count();      // two co-resident CTAs per SM: item prologues/epilogues of one overlap the other's stream
+  const unsigned grid = static_cast<unsigned>(p.items < max_ctas ? p.items : max_ctas);
 #define B200_DTC(GG)                                                                                                 \
   case GG: {                                                                                                         \
     static bool attr_set = false;                                                                                    \
