@@ -126,6 +126,7 @@ decode_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                                // q / cache / seq_lens belong to the predecessor kernels until now
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tS0 = tmem_base, tO = tmem_base + 32;
 
@@ -409,7 +410,7 @@ extern "C" int b200_decode_attention_tc(const void* qkv, const void* cache, cons
       }                                                                                                              \
       attr_set = true;                                                                                               \
     }                                                                                                                \
-    decode_attention_tc_kernel<GG><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);                    \
+    launch_pdl(decode_attention_tc_kernel<GG>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmQ, tmK, tmV, p); \
   } break;
   switch (G) {
     B200_DTC(1) B200_DTC(2) B200_DTC(4) B200_DTC(7) B200_DTC(8)

@@ -237,6 +237,7 @@ __global__ void rope_kernel(bf16* __restrict__ x, const float* __restrict__ cos_
 // ------------------------------------------------------------------------------------------------
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ m, int64_t rows, int inter) {
   pdl_launch_dependents();
+  pdl_wait();
   const int64_t nchunk_row = inter >> 3;
   const int64_t total = rows * nchunk_row;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -409,8 +410,8 @@ extern "C" int b200_swiglu_fwd(const void* gate_up, void* out, int64_t rows, int
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  swiglu_fwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<const bf16*>(gate_up),
-                                                                      static_cast<bf16*>(out), rows, (int)inter);
+  launch_pdl(swiglu_fwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, static_cast<const bf16*>(gate_up),
+             static_cast<bf16*>(out), rows, (int)inter);
   return check_launch("swiglu_fwd");
 }
 

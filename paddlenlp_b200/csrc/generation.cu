@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ w, bf16* __restrict__ normed,
                                                           bf16* __restrict__ res_out, int rows, int h, float eps) {
   pdl_launch_dependents();
+  pdl_wait();
   constexpr int TPR = 32 * WPR;                     // threads per row
   __shared__ float s_part[4];
   const int warp = threadIdx.x >> 5;
@@ -165,6 +166,7 @@ __global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, float* __restr
                                           const float* __restrict__ sin_t, const int* __restrict__ seq_lens, int B, int nh,
                                           int kvh, int d, int max_len, int64_t ld) {
   pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int pos = seq_lens[b];
   const int half = d >> 1;
@@ -360,6 +362,7 @@ __global__ void __launch_bounds__(128, (G <= 4 ? 4 : 2)) decode_attention_kernel
 __global__ void decode_attention_merge_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int rows, int nsplit) {
   constexpr int D = 128;
   pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -644,14 +647,14 @@ static int add_rmsnorm_launch(const void* x, float* x_f32, const void* residual,
   bf16 *np = static_cast<bf16*>(normed), *ro = static_cast<bf16*>(residual_out);
   if (rows <= 1024) {            // few rows (decode step): one CTA per row
     const dim3 grid(static_cast<unsigned>(rows));
-    if (nchunk <= 256) add_rmsnorm_kernel<2, 4><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
-    else if (nchunk <= 512) add_rmsnorm_kernel<4, 4><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
-    else add_rmsnorm_kernel<8, 4><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+    if (nchunk <= 256) launch_pdl(add_rmsnorm_kernel<2, 4>, grid, block, 0, stream, xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+    else if (nchunk <= 512) launch_pdl(add_rmsnorm_kernel<4, 4>, grid, block, 0, stream, xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+    else launch_pdl(add_rmsnorm_kernel<8, 4>, grid, block, 0, stream, xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
   } else {
     const dim3 grid(static_cast<unsigned>((rows + 3) / 4));
-    if (nchunk <= 128) add_rmsnorm_kernel<4, 1><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
-    else if (nchunk <= 512) add_rmsnorm_kernel<16, 1><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
-    else add_rmsnorm_kernel<32, 1><<<grid, block, 0, stream>>>(xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+    if (nchunk <= 128) launch_pdl(add_rmsnorm_kernel<4, 1>, grid, block, 0, stream, xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+    else if (nchunk <= 512) launch_pdl(add_rmsnorm_kernel<16, 1>, grid, block, 0, stream, xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
+    else launch_pdl(add_rmsnorm_kernel<32, 1>, grid, block, 0, stream, xp, x_f32, rp, wp, np, ro, (int)rows, (int)h, eps);
   }
   return check_launch("add_rmsnorm");
 }
@@ -688,16 +691,17 @@ extern "C" int b200_decode_rope_append_f32(void* qkv, float* acc_f32_ws, const f
   const int threads_needed = static_cast<int>((num_heads + num_kv_heads) * (head_dim / 16));
   B200_CHECK_ARG(threads_needed <= 1024, "decode_rope_append: too many heads");
   const int threads = (threads_needed + 31) / 32 * 32;
-  decode_rope_append_kernel<<<static_cast<unsigned>(B), threads, 0, stream>>>(
-      static_cast<bf16*>(qkv), acc_f32_ws, bias, static_cast<bf16*>(cache), cos_table, sin_table, seq_lens, (int)B,
-      (int)num_heads, (int)num_kv_heads, (int)head_dim, (int)max_len, ld);
+  launch_pdl(decode_rope_append_kernel, dim3(static_cast<unsigned>(B)), dim3(threads), 0, stream, static_cast<bf16*>(qkv),
+             acc_f32_ws, bias, static_cast<bf16*>(cache), cos_table, sin_table, seq_lens, (int)B, (int)num_heads,
+             (int)num_kv_heads, (int)head_dim, (int)max_len, ld);
   return check_launch("decode_rope_append");
 }
 
 namespace b200 {
 // shared with decode_attn_tc.cu
 int launch_decode_attention_merge(const float* partial, void* out, int rows, int nsplit, cudaStream_t stream) {
-  gen::decode_attention_merge_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(partial, static_cast<bf16*>(out), rows, nsplit);
+  launch_pdl(gen::decode_attention_merge_kernel, dim3((rows + 3) / 4), dim3(128), 0, stream, partial, static_cast<bf16*>(out), rows,
+             nsplit);
   return check_launch("decode_attention(merge)");
 }
 }  // namespace b200
@@ -734,7 +738,7 @@ extern "C" int b200_decode_attention(const void* qkv, const void* cache, const i
   int rc = check_launch("decode_attention");
   if (rc || num_splits == 1) return rc;
   const int rows = static_cast<int>(B * num_heads);
-  decode_attention_merge_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(part, o, rows, (int)num_splits);
+  launch_pdl(decode_attention_merge_kernel, dim3((rows + 3) / 4), dim3(128), 0, stream, part, o, rows, (int)num_splits);
   return check_launch("decode_attention(merge)");
 }
 

@@ -17,6 +17,24 @@ int check_launch(const char* what);  // cudaGetLastError() -> return code
 int sm_count();  // multiprocessors of the current device (cached per device)
 bool pdl_enabled();   // b200_set_pdl(): launch GEMMs with programmatic dependent launch (decode-step kernel chains)
 
+// Launch `kern` on `stream`; when PDL is enabled the launch carries the programmatic-stream-serialization attribute, so the
+// grid may become resident while its predecessor is still running.  Such kernels MUST call pdl_wait() (common.cuh) before
+// touching memory the predecessor writes.  Returns the cudaLaunchKernelEx status (recorded by check_launch()).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Encode a 2-D or 3-D bf16 (2-byte element) tiled tensor map with 128-byte swizzle.
 //   dims[i]    extent of dimension i in elements (dimension 0 is contiguous)
 //   strides[i] byte stride of dimension i+1 (i < rank-1); must be multiples of 16
