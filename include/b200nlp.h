@@ -241,6 +241,15 @@ int b200_generate_step_update(int64_t* next_tokens, bool* stop_flags, int64_t* s
                               int64_t* out_col_dev, int32_t* stop_count, int64_t bs, cudaStream_t stream);
 int b200_argmax_f32(const float* logits, int64_t* out, int64_t rows, int64_t vocab, int64_t ld, cudaStream_t stream);
 int b200_bf16_rows_to_f32(const void* src, float* dst, int64_t rows, int64_t cols, int64_t ld, cudaStream_t stream);
+/* In-place fp32 softmax over each row of logits [rows, vocab] (row stride ld): `probs = F.softmax(logits)`,
+ * experimental/transformers/generation_utils.py:327. */
+int b200_softmax_f32(float* logits, int64_t rows, int64_t vocab, int64_t ld, cudaStream_t stream);
+/* top_p_sampling_reject (csrc/gpu/sample_kernels/top_p_sampling_reject.cu:18-60, sampling.cuh:197-376): rejection sampling
+ * of one token per row from probs [bs, vocab] restricted to the top-p nucleus; top_p [bs]; uniform [max_rounds, bs] are
+ * the U(0,1) draws (the reference draws max_rounds = 32 per row from its generator inside the op); out [bs] int64.
+ * top_p == 0 selects the arg max. */
+int b200_top_p_sampling_reject(const float* probs, const float* top_p, const float* uniform, int64_t* out, int64_t bs,
+                               int64_t vocab, int64_t ld, int64_t max_rounds, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -145,6 +145,32 @@ def update_inputs(stop_flags, seq_lens_this_time, seq_lens_encoder, seq_lens_dec
     return np.array([stop_sum < int(stop_nums[0])]), this_time, enc, dec, ids
 
 
+def top_p_sampling_reject(probs, top_p, uniform, max_rounds=32):
+    """csrc/gpu/sample_kernels/sampling.cuh:286-376 (kernel) and :197-280 (inverse-CDF step), sequential fp32.
+    probs [bs, d] fp32, top_p [bs], uniform [max_rounds, bs] -> ids [bs]."""
+    probs = np.asarray(probs, np.float32)
+    bs, d = probs.shape
+    out = np.zeros(bs, np.int64)
+    for b in range(bs):
+        p = probs[b]
+        q, pivot, sid = np.float32(1.0), np.float32(0.0), d - 1
+        for r in range(max_rounds):
+            u = np.float32(uniform[r, b]) * q
+            valid = p > pivot
+            cdf = np.cumsum(np.where(valid, p, np.float32(0)), dtype=np.float32)
+            hit = np.nonzero((cdf > u) & valid)[0]
+            sid = int(hit[0]) if hit.size else d - 1            # :313 default sampled_id = d - 1
+            pivot = max(pivot, p[sid])
+            above = p > pivot
+            q = np.float32(p[above].sum(dtype=np.float32))
+            if 0 < q < np.float32(top_p[b]):                    # :362
+                break
+            if above.sum() < 1:                                  # :367 (top_p == 0 -> top-1)
+                break
+        out[b] = sid
+    return out
+
+
 def greedy_generate(input_ids: torch.Tensor, w, cfg: R.RefConfig, max_new: int, eos=None, mode: str = "bf16",
                     seq_lens=None):
     """Greedy decoding by full re-evaluation (no cache).  input_ids [B, S] right padded; returns [B, max_new] with the

@@ -55,6 +55,8 @@ _SIGNATURES = {
     "b200_decode_rope_append": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, P],
     "b200_decode_attention_workspace_bytes": [I64, I64, I64],
     "b200_decode_attention": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, F, I64, P],
+    "b200_softmax_f32": [P, I64, I64, I64, P],
+    "b200_top_p_sampling_reject": [P, P, P, P, I64, I64, I64, I64, P],
     "b200_decode_attention_tc": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, F, I64, P],
     "b200_get_padding_offset": [P, P, P, P, P, P, P, P, I64, I64, P],
     "b200_rebuild_padding": [P, P, P, P, P, I64, I64, I64, P],

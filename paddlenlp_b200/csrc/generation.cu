@@ -616,6 +616,146 @@ __global__ void bf16_rows_to_f32_kernel(const bf16* __restrict__ src, float* __r
     dst[i] = __bfloat162float(src[(i / cols) * ld + (i % cols)]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sampling: softmax over fp32 logits and rejection top-p sampling.
+// Reference: `probs = F.softmax(logits)` then top_p_sampling_reject(probs, top_p, seed)
+// (experimental/transformers/generation_utils.py:326-336; csrc/gpu/sample_kernels/top_p_sampling_reject.cu:18-60,
+//  kernel sample_kernels/sampling.cuh:286-376, inverse-CDF step :197-280).  The uniform draws are an INPUT here (the
+// reference draws [32, bs] of them from Paddle's generator), so the op is a deterministic function of its arguments.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_reduce_1024(float v, float* s_w, bool is_max) {
+  // all 1024 threads call; s_w has 32 floats; result broadcast to every thread
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  __syncthreads();                       // s_w free from the previous use
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = s_w[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, r, o);
+    r = is_max ? fmaxf(r, t) : r + t;
+  }
+  return r;
+}
+
+// in place: logits[row, :] -> softmax probabilities (fp32)
+__global__ void __launch_bounds__(1024) softmax_f32_kernel(float* __restrict__ x, int vocab, int64_t ld) {
+  __shared__ float s_w[32];
+  float* row = x + static_cast<size_t>(blockIdx.x) * ld;
+  const int n4 = vocab >> 2;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n4; i += 1024) {
+    const float4 v = reinterpret_cast<const float4*>(row)[i];
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  m = block_reduce_1024(m, s_w, true);
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n4; i += 1024) {
+    const float4 v = reinterpret_cast<const float4*>(row)[i];
+    sum += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+  }
+  sum = block_reduce_1024(sum, s_w, false);
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x; i < n4; i += 1024) {
+    float4 v = reinterpret_cast<float4*>(row)[i];
+    v.x = expf(v.x - m) * inv; v.y = expf(v.y - m) * inv; v.z = expf(v.z - m) * inv; v.w = expf(v.w - m) * inv;
+    reinterpret_cast<float4*>(row)[i] = v;
+  }
+}
+
+// One CTA (1024 threads) per row.  Round r: u = uniform[r, b] * q; sampled = first index whose inclusive CDF over
+// {p_j > pivot} exceeds u (vocab-1 if none); pivot = max(pivot, p[sampled]); (q, count) = mass / number of {p_j > pivot};
+// stop when 0 < q < top_p, or when count == 0 (covers top_p == 0 -> arg max).
+__global__ void __launch_bounds__(1024) top_p_sampling_reject_kernel(const float* __restrict__ probs, const float* __restrict__ top_p,
+                                                                     const float* __restrict__ uniform, int64_t* __restrict__ out,
+                                                                     int vocab, int64_t ld, int bs, int max_rounds) {
+  __shared__ float s_w[32];
+  __shared__ int s_sampled;
+  __shared__ int s_cnt[32];
+  const int b = blockIdx.x, tx = threadIdx.x, lane = tx & 31, warp = tx >> 5;
+  const float* row = probs + static_cast<size_t>(b) * ld;
+  const float tp = top_p[b];
+  const int n4 = vocab >> 2;
+  const int iters = (n4 + 1023) / 1024;
+  float q = 1.f, pivot = 0.f;
+  int sampled = vocab - 1;
+  for (int round = 0; round < max_rounds; ++round) {
+    if (tx == 0) s_sampled = vocab - 1;
+    const float u = uniform[static_cast<size_t>(round) * bs + b] * q;
+    float aggregate = 0.f;
+    for (int it = 0; it < iters; ++it) {
+      const int i4 = it * 1024 + tx;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i4 < n4) v = reinterpret_cast<const float4*>(row)[i4];
+      const float f0 = v.x > pivot ? v.x : 0.f, f1 = v.y > pivot ? v.y : 0.f, f2 = v.z > pivot ? v.z : 0.f,
+                  f3 = v.w > pivot ? v.w : 0.f;
+      const float c0 = f0, c1 = c0 + f1, c2 = c1 + f2, c3 = c2 + f3;     // thread-local inclusive sums
+      // block-wide exclusive prefix of the thread totals
+      float incl = c3;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      __syncthreads();                               // s_w / s_sampled settled from the previous iteration
+      if (lane == 31) s_w[warp] = incl;
+      __syncthreads();
+      float wsum = s_w[lane];
+      float wincl = wsum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += t;
+      }
+      const float total = __shfl_sync(0xffffffffu, wincl, 31);
+      const float warp_excl = __shfl_sync(0xffffffffu, wincl - wsum, warp);
+      const float base = aggregate + warp_excl + (incl - c3);              // mass strictly before this thread's 4 elements
+      if (aggregate + total > u) {
+        // first (lowest-index) valid element whose inclusive CDF exceeds u; the block scan is only monotone up to fp32
+        // rounding, so every candidate thread votes and the minimum wins (sampling.cuh:267-270)
+        if (base + c3 > u) {
+          int j = -1;
+          if (base + c0 > u && f0 > 0.f) j = 0;
+          else if (base + c1 > u && f1 > 0.f) j = 1;
+          else if (base + c2 > u && f2 > 0.f) j = 2;
+          else if (f3 > 0.f) j = 3;
+          if (j >= 0) atomicMin(&s_sampled, i4 * 4 + j);
+        }
+        aggregate += total;
+        break;
+      }
+      aggregate += total;
+    }
+    __syncthreads();
+    sampled = s_sampled;
+    pivot = fmaxf(pivot, row[sampled]);
+    float mass = 0.f;
+    int cnt = 0;
+    for (int i4 = tx; i4 < n4; i4 += 1024) {
+      const float4 v = reinterpret_cast<const float4*>(row)[i4];
+      if (v.x > pivot) { mass += v.x; ++cnt; }
+      if (v.y > pivot) { mass += v.y; ++cnt; }
+      if (v.z > pivot) { mass += v.z; ++cnt; }
+      if (v.w > pivot) { mass += v.w; ++cnt; }
+    }
+    q = block_reduce_1024(mass, s_w, false);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    int total_cnt = s_cnt[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total_cnt += __shfl_xor_sync(0xffffffffu, total_cnt, o);
+    if (q > 0.f && q < tp) break;
+    if (total_cnt < 1) break;
+  }
+  if (tx == 0) out[b] = sampled;
+}
+
 }  // namespace gen
 }  // namespace b200
 
@@ -868,4 +1008,20 @@ extern "C" int b200_bf16_rows_to_f32(const void* src, float* dst, int64_t rows, 
   B200_CHECK_ARG(src && dst && rows > 0 && cols > 0, "bf16_rows_to_f32: bad arguments");
   bf16_rows_to_f32_kernel<<<sm_count() * 4, 256, 0, stream>>>(static_cast<const bf16*>(src), dst, rows, cols, ld);
   return check_launch("bf16_rows_to_f32");
+}
+
+extern "C" int b200_softmax_f32(float* logits, int64_t rows, int64_t vocab, int64_t ld, cudaStream_t stream) {
+  B200_CHECK_ARG(logits && rows > 0 && vocab > 0 && vocab % 4 == 0 && ld % 4 == 0, "softmax_f32: vocab and ld must be multiples of 4");
+  softmax_f32_kernel<<<static_cast<unsigned>(rows), 1024, 0, stream>>>(logits, (int)vocab, ld);
+  return check_launch("softmax_f32");
+}
+
+extern "C" int b200_top_p_sampling_reject(const float* probs, const float* top_p, const float* uniform, int64_t* out,
+                                          int64_t bs, int64_t vocab, int64_t ld, int64_t max_rounds, cudaStream_t stream) {
+  B200_CHECK_ARG(probs && top_p && uniform && out, "top_p_sampling_reject: null pointer");
+  B200_CHECK_ARG(bs > 0 && vocab > 0 && vocab % 4 == 0 && ld % 4 == 0 && max_rounds > 0,
+                 "top_p_sampling_reject: vocab and ld must be multiples of 4");
+  top_p_sampling_reject_kernel<<<static_cast<unsigned>(bs), 1024, 0, stream>>>(probs, top_p, uniform, out, (int)vocab, ld,
+                                                                               (int)bs, (int)max_rounds);
+  return check_launch("top_p_sampling_reject");
 }

@@ -5,7 +5,8 @@ Per step the reference runs: set_value_by_flags_and_idx -> cast fp32 -> get_toke
 -> softmax -> top_p_sampling_reject -> set_stop_value_multi_ends -> save_with_output, with one host sync in the `while`
 condition.  Here the whole decode step (embedding .. lm_head .. token choice .. state update) is device-resident and
 replayed as a CUDA graph; the stop condition is polled every `sync_interval` steps.  Greedy decoding (top_p == 0, the
-benchmark setting: predictor.py:1196-1199) is implemented; rejection top-p sampling is a "next" item.
+benchmark setting: predictor.py:1196-1199) takes the arg-max directly; top_p > 0 runs softmax + rejection top-p sampling
+(`top_p_sampling_reject`) with uniforms from a torch CUDA generator (graph-safe).
 """
 from __future__ import annotations
 
@@ -24,22 +25,29 @@ class GenerationInferenceModel:
         raise NotImplementedError
 
     def _choose(self, logits, st):
-        """fp32 cast -> penalties -> temperature -> argmax (== softmax + top-p 0)."""
-        if st["plain"]:
+        """fp32 cast -> penalties -> temperature -> softmax -> top-p sampling; with top_p == 0 the arg-max is taken
+        directly (identical result: the sampler degenerates to top-1)."""
+        greedy = st["top_p"] is None
+        if greedy and st["plain"]:
             return ops.argmax(logits)
         lf = ops.bf16_rows_to_f32(logits)
         ops.token_penalty_multi_scores(st["pre_ids"], lf, st["penalty"], st["frequency"], st["presence"], st["temperature"],
                                        None, st["step_idx"], st["min_dec_len"], st["eos"])
-        return ops.argmax_f32(lf)
+        if greedy:
+            return ops.argmax_f32(lf)
+        ops.softmax_f32_(lf)
+        return ops.top_p_sampling_reject(lf, st["top_p"], generator=st["generator"])
 
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, seq_len_encoder: Optional[torch.Tensor] = None, max_length: int = 64,
                  eos_token_id=None, cache_kvs: Optional[List[torch.Tensor]] = None, temperature: float = 1.0,
                  top_p: float = 0.0, penalty_score: float = 1.0, frequency_score: float = 0.0, presence_score: float = 0.0,
-                 min_length: int = 0, use_cuda_graph: bool = True, sync_interval: int = 16, use_pdl: bool = True, **kwargs):
-        """input_ids [B, S] (right padded); returns (ids [B, max_length], stop_flags, seq_len_decoder)."""
-        if top_p not in (0, 0.0, None):
-            raise NotImplementedError("top-p sampling: only greedy (top_p = 0) is implemented")
+                 min_length: int = 0, use_cuda_graph: bool = True, sync_interval: int = 16, use_pdl: bool = True, seed: int = 0,
+                 **kwargs):
+        """input_ids [B, S] (right padded); returns (ids [B, max_length], stop_flags, seq_len_decoder).
+        top_p in (0, 1]: sample from the top-p nucleus (seed != 0 makes the draw reproducible); top_p 0: greedy."""
+        if top_p is not None and not (0.0 <= float(top_p) <= 1.0):
+            raise ValueError(f"top_p must be in [0, 1], got {top_p}")
         dev = self.device
         B, S = input_ids.shape
         ids = input_ids.to(dev, torch.int64).contiguous()
@@ -63,8 +71,15 @@ class GenerationInferenceModel:
             frequency=torch.full((B,), frequency_score, dtype=torch.float32, device=dev),
             presence=torch.full((B,), presence_score, dtype=torch.float32, device=dev),
             temperature=torch.full((B,), temperature, dtype=torch.float32, device=dev),
-            plain=(penalty_score == 1.0 and frequency_score == 0.0 and presence_score == 0.0 and min_length <= 0),
+            plain=(penalty_score == 1.0 and frequency_score == 0.0 and presence_score == 0.0 and min_length <= 0
+                   and temperature == 1.0),
+            top_p=None, generator=None,
         )
+        if top_p:
+            st["top_p"] = torch.full((B,), float(top_p), dtype=torch.float32, device=dev)
+            if seed:
+                st["generator"] = torch.Generator(device=dev)
+                st["generator"].manual_seed(int(seed))
 
         def update(next_tokens):
             # step_idx / stop flags / pre_ids / seq_len_decoder / token log — one kernel, no host sync.
@@ -100,6 +115,8 @@ class GenerationInferenceModel:
                 step(); done += 1                                # warm-up (sets kernel attributes, allocator pools)
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
+                if st["generator"] is not None:                  # philox offsets of a private generator advance per replay
+                    graph.register_generator_state(st["generator"])
                 with torch.cuda.graph(graph):                    # capture only records: no step is executed here
                     step()
             while done < n_steps:

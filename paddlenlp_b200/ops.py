@@ -492,6 +492,35 @@ def generate_step_update(next_tokens, stop_flags, step_idx, max_dec_len, seq_len
          0 if out_tokens is None else out_tokens.shape[1], int(out_col), ptr(out_col_dev), ptr(stop_count), bs, stream_ptr())
 
 
+def softmax_f32_(logits):
+    """In-place fp32 row softmax (generation_utils.py:327)."""
+    _chk(logits, "logits", torch.float32)
+    rows, V = logits.shape
+    assert logits.stride(1) == 1
+    call("b200_softmax_f32", ptr(logits), rows, V, logits.stride(0), stream_ptr())
+    return logits
+
+
+def top_p_sampling_reject(probs, top_p, uniform=None, seed: int = 0, max_rounds: int = 32, generator=None):
+    """top_p_sampling_reject(probs, top_p, seed) of the reference (csrc/gpu/sample_kernels/top_p_sampling_reject.cu).
+    probs [bs, V] fp32, top_p [bs] fp32 -> ids [bs] int64.  `uniform` [max_rounds, bs] may be supplied (tests); otherwise it
+    is drawn from `generator` (or a fresh generator seeded with `seed` when seed != 0, else torch's default CUDA generator)."""
+    _chk(probs, "probs", torch.float32); _chk(top_p, "top_p", torch.float32)
+    bs, V = probs.shape
+    assert probs.stride(1) == 1 and top_p.numel() == bs
+    if uniform is None:
+        if generator is None and seed:
+            generator = torch.Generator(device=probs.device)
+            generator.manual_seed(int(seed))
+        uniform = torch.rand(max_rounds, bs, dtype=torch.float32, device=probs.device, generator=generator)
+    _chk(uniform, "uniform", torch.float32)
+    assert uniform.is_contiguous() and uniform.shape == (max_rounds, bs)
+    out = torch.empty(bs, dtype=torch.int64, device=probs.device)
+    call("b200_top_p_sampling_reject", ptr(probs), ptr(top_p), ptr(uniform), ptr(out), bs, V, probs.stride(0), max_rounds,
+         stream_ptr())
+    return out
+
+
 def argmax_f32(logits):
     _chk(logits, "logits", torch.float32)
     rows, V = logits.shape

@@ -267,3 +267,65 @@ def test_generation_stops_on_eos_and_penalty_path_runs():
     out2, _, _ = m.generate(ids, max_length=6, eos_token_id=-7, use_cuda_graph=False, penalty_score=1.2, frequency_score=0.1,
                             presence_score=0.1, temperature=0.8, min_length=2)
     assert out2.shape == (2, 6) and int(out2.min()) >= 0
+
+
+def test_softmax_and_top_p_sampling_reject():
+    o = ops()
+    rng = np.random.default_rng(7)
+    # (1) softmax vs torch
+    lg = torch.tensor(rng.standard_normal((5, 40080)).astype(np.float32) * 5)
+    pr = o.softmax_f32_(lg.clone().to(DEV)).cpu()
+    ref = torch.softmax(lg, -1)
+    assert ((pr - ref).abs() <= 1e-5 * ref + 1e-12).all() and abs(float(pr.sum(-1).min()) - 1) < 1e-5   # few-ulp agreement
+    # (2) dyadic probabilities (every partial sum exact in fp32, whatever the summation order): bit-exact vs the oracle
+    bs, V = 6, 8192
+    w = rng.integers(0, 64, size=(bs, V)).astype(np.float64)
+    w[:, :7] = 0                                                      # zero-probability tokens are never sampled
+    w[0, 100] = 5000; w[1, V - 1] = 9000                              # a dominant token; one at the very end
+    tot = 2.0 ** 20
+    w[:, 500] += tot - w.sum(-1)                                       # rows sum to exactly 2^20
+    p = (w / tot).astype(np.float32)
+    assert np.all(p.sum(-1, dtype=np.float64) == 1.0) and (p >= 0).all()
+    u = ((rng.integers(0, 2 ** 16, size=(32, bs)) + 0.5) / 2 ** 16).astype(np.float32)   # never equal to a partial sum
+    for tp in (0.0, 0.25, 0.6, 1.0):
+        tpv = np.full(bs, tp, np.float32)
+        got = o.top_p_sampling_reject(t(p, torch.float32), t(tpv, torch.float32), uniform=t(u, torch.float32)).cpu().numpy()
+        assert np.array_equal(got, G.top_p_sampling_reject(p, tpv, u)), tp
+    # (3) realistic softmax rows on the reference test's shape: sample inside the nucleus, top_p 0 == arg max, reproducible
+    probs = torch.softmax(torch.tensor(rng.standard_normal((3, 40080)).astype(np.float32) * 3), -1)
+    pd = probs.to(DEV)
+    ids0 = o.top_p_sampling_reject(pd, t(np.zeros(3, np.float32), torch.float32), seed=11).cpu()
+    assert torch.equal(ids0, probs.argmax(-1))
+    tpv = np.array([0.2, 0.7, 0.95], np.float32)
+    a = o.top_p_sampling_reject(pd, t(tpv, torch.float32), seed=11).cpu()
+    b = o.top_p_sampling_reject(pd, t(tpv, torch.float32), seed=11).cpu()
+    assert torch.equal(a, b)
+    for i in range(3):
+        assert float(probs[i][probs[i] > probs[i, a[i]]].sum()) < tpv[i] + 1e-6
+    # (4) frequencies follow the renormalised nucleus (top_p 1 == plain sampling): 4 tokens, 20000 draws
+    small = torch.tensor([[0.5, 0.25, 0.125, 0.125]], dtype=torch.float32).repeat(20000, 1).to(DEV)
+    ids = o.top_p_sampling_reject(small, torch.ones(20000, dtype=torch.float32, device=DEV), seed=3).cpu()
+    freq = torch.bincount(ids, minlength=4).float() / 20000
+    assert (freq - torch.tensor([0.5, 0.25, 0.125, 0.125])).abs().max() < 0.015
+    ids = o.top_p_sampling_reject(small, torch.full((20000,), 0.6, dtype=torch.float32, device=DEV), seed=3).cpu()
+    freq = torch.bincount(ids, minlength=4).float() / 20000                 # nucleus {0, 1}: mass above token 1 is 0.5 < 0.6
+    assert freq[2] == 0 and freq[3] == 0 and abs(float(freq[0]) - 2 / 3) < 0.02
+
+
+def test_generate_with_top_p_sampling():
+    """generate(top_p > 0): reproducible for a fixed seed, CUDA-graph and eager agree, tiny top_p reproduces greedy."""
+    cfg = _tiny()
+    w = R.init_weights(cfg, seed=5)
+    m, _ = _infer_model(cfg, w)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(1, cfg.vocab_size, (3, 12), generator=g)
+    greedy, _, _ = m.generate(ids, max_length=10, top_p=0.0)
+    tiny_p, _, _ = m.generate(ids, max_length=10, top_p=1e-6, seed=5)
+    assert torch.equal(greedy, tiny_p)
+    a, _, _ = m.generate(ids, max_length=10, top_p=0.9, temperature=1.3, seed=42)
+    b, _, _ = m.generate(ids, max_length=10, top_p=0.9, temperature=1.3, seed=42)
+    c, _, _ = m.generate(ids, max_length=10, top_p=0.9, temperature=1.3, seed=42, use_cuda_graph=False)
+    assert torch.equal(a, b) and a.shape == (3, 10) and int(a.min()) >= 0 and int(a.max()) < cfg.vocab_size
+    assert torch.equal(a, c)
+    d, _, _ = m.generate(ids, max_length=10, top_p=0.9, temperature=1.3, seed=43)
+    assert not torch.equal(a, d)

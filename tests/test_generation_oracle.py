@@ -64,3 +64,27 @@ def test_update_inputs_known_answer():
     assert tt.tolist() == g["ref_seq_lens_this_time"]
     assert enc.tolist() == g["ref_seq_lens_encoder"] and dec.tolist() == g["ref_seq_lens_decoder"]
     assert ids2[:, 0].tolist() == g["ref_input_ids_col0"]
+
+
+def test_top_p_sampling_reject_oracle_properties():
+    """The reference's own test for this op only prints (csrc/gpu/test/python/test_top_p_sampling_reject.py: no asserts), so
+    the restatement is pinned by the properties the algorithm guarantees, on the reference test's shapes (3 x 40080)."""
+    rng = np.random.default_rng(2023)
+    bs, V = 3, 40080
+    p = rng.random((bs, V), dtype=np.float32)
+    p /= p.sum(-1, keepdims=True)
+    u = rng.random((32, bs), dtype=np.float32)
+    # top_p = 0 -> arg max (sampling.cuh:365-369)
+    assert np.array_equal(G.top_p_sampling_reject(p, np.zeros(bs, np.float32), u), p.argmax(-1))
+    # the sample always lies inside the top-p nucleus: the mass strictly above it is < top_p
+    peaked = np.exp(rng.standard_normal((bs, V)).astype(np.float32) * 4)
+    peaked /= peaked.sum(-1, keepdims=True)
+    for tp in (0.3, 0.8, 1.0):
+        ids = G.top_p_sampling_reject(peaked, np.full(bs, tp, np.float32), u)
+        for b in range(bs):
+            assert peaked[b][peaked[b] > peaked[b, ids[b]]].sum() < tp
+    # top_p = 1: plain inverse-CDF sampling in index order, accepted in the first round
+    ids = G.top_p_sampling_reject(p, np.ones(bs, np.float32), u)
+    for b in range(bs):
+        cdf = np.cumsum(p[b], dtype=np.float32)
+        assert ids[b] == int(np.nonzero(cdf > u[0, b])[0][0])
