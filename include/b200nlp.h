@@ -198,6 +198,24 @@ int b200_decode_attention_tc(const void* qkv, const void* cache, const int32_t* 
                              int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len, int64_t ld,
                              float softmax_scale, int64_t num_splits, cudaStream_t stream);
 
+/* Paged ("block") KV cache of FusedBlockMultiTransformer / append_attention (fused_transformer_layers.py:2192-2354,
+ * csrc/gpu/append_attention.cu:428-851): key_cache / value_cache [num_blocks, kvh, block_size, head_dim] bf16,
+ * block_tables [B, max_blocks_per_seq] int32 (logical block -> physical block).  Same math as the dense entry points above:
+ * prefill cache fill, decode RoPE + append (acc_f32_ws / bias optional as in b200_decode_rope_append_f32), decode attention
+ * (tcgen05 kernel; each 128-row tile is gathered page by page with TMA; block_size 32, 64 or 128). */
+int b200_write_cache_kv_paged(const void* qkv, void* key_cache, void* value_cache, const int32_t* block_tables,
+                              const int32_t* seq_lens, int64_t B, int64_t S, int64_t num_heads, int64_t num_kv_heads,
+                              int64_t head_dim, int64_t block_size, int64_t max_blocks_per_seq, int64_t ld, cudaStream_t stream);
+int b200_decode_rope_append_paged(void* qkv, float* acc_f32_ws, const float* bias, void* key_cache, void* value_cache,
+                                  const int32_t* block_tables, const float* cos_table, const float* sin_table,
+                                  const int32_t* seq_lens, int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim,
+                                  int64_t block_size, int64_t max_blocks_per_seq, int64_t ld, cudaStream_t stream);
+int b200_decode_attention_paged(const void* qkv, const void* key_cache, const void* value_cache, const int32_t* block_tables,
+                                const int32_t* seq_lens, void* out, void* workspace, int64_t B, int64_t num_heads,
+                                int64_t num_kv_heads, int64_t head_dim, int64_t num_blocks, int64_t block_size,
+                                int64_t max_blocks_per_seq, int64_t ld, float softmax_scale, int64_t num_splits,
+                                cudaStream_t stream);
+
 /* Bookkeeping ops, same semantics as the reference custom ops (file:line beside each). bool = 1-byte flags. */
 /* get_padding_offset_v2 (+ remove padding): csrc/gpu/get_padding_offset_v2.cu:17-80 */
 int b200_get_padding_offset(const int64_t* input_ids, const int32_t* cum_offsets, const int32_t* seq_lens,

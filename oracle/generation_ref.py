@@ -195,3 +195,26 @@ def greedy_generate(input_ids: torch.Tensor, w, cfg: R.RefConfig, max_new: int, 
             if eos is not None and tok == eos:
                 stopped[b] = True
     return out, margins
+
+
+def paged_decode_attention(q, key_cache, value_cache, block_tables, seq_lens, scale=None):
+    """Decode attention over a block (paged) KV cache, the layout of FusedBlockMultiTransformer / append_attention
+    (fused_transformer_layers.py:2192-2354): key/value_cache [num_blocks, kvh, block_size, d], block_tables [B, max_blocks],
+    sequence b attends to positions 0..seq_lens[b] (the new token already appended).  q [B, nh, d] -> [B, nh*d], fp32."""
+    q = np.asarray(q, np.float32)
+    B, nh, d = q.shape
+    nb, kvh, bs, _ = key_cache.shape
+    rep = nh // kvh
+    scale = scale or 1.0 / np.sqrt(d)
+    out = np.zeros((B, nh, d), np.float32)
+    for b in range(B):
+        total = min(int(seq_lens[b]) + 1, block_tables.shape[1] * bs)
+        pos = np.arange(total)
+        phys = np.asarray(block_tables[b])[pos // bs]
+        K = np.asarray(key_cache, np.float32)[phys, :, pos % bs]          # [total, kvh, d]
+        V = np.asarray(value_cache, np.float32)[phys, :, pos % bs]
+        for h in range(nh):
+            s = K[:, h // rep] @ q[b, h] * scale
+            p = np.exp(s - s.max())
+            out[b, h] = (p / p.sum()) @ V[:, h // rep]
+    return out.reshape(B, nh * d)

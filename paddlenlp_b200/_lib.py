@@ -55,6 +55,9 @@ _SIGNATURES = {
     "b200_decode_rope_append": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, P],
     "b200_decode_attention_workspace_bytes": [I64, I64, I64],
     "b200_decode_attention": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, F, I64, P],
+    "b200_write_cache_kv_paged": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, P],
+    "b200_decode_rope_append_paged": [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P],
+    "b200_decode_attention_paged": [P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, F, I64, P],
     "b200_softmax_f32": [P, I64, I64, I64, P],
     "b200_top_p_sampling_reject": [P, P, P, P, I64, I64, I64, I64, P],
     "b200_decode_attention_tc": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, F, I64, P],
@@ -118,7 +121,7 @@ KERNELS_PER_CALL = {
     "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_gemm_bf16_splitk": 2, "b200_rmsnorm_fwd": 1, "b200_rmsnorm_bwd": 2, "b200_colsum_bf16": 2,
     "b200_rope_inplace": 1, "b200_swiglu_fwd": 1, "b200_swiglu_bwd": 1, "b200_embedding_fwd": 1, "b200_embedding_bwd": 1,
     "b200_fa_fwd": 1, "b200_fa_bwd": 3, "b200_ce_fwd": 2, "b200_ce_bwd": 1, "b200_argmax_bf16": 1, "b200_grad_sqnorm": 2,
-    "b200_adamw_step": 1, "b200_bf16_to_f32": 1, "b200_token_penalty_multi_scores": 2, "b200_generate_step_update": 2, "b200_decode_attention": 2, "b200_decode_attention_tc": 2,
+    "b200_adamw_step": 1, "b200_bf16_to_f32": 1, "b200_token_penalty_multi_scores": 2, "b200_generate_step_update": 2, "b200_decode_attention": 2, "b200_decode_attention_tc": 2, "b200_decode_attention_paged": 2,
 }
 launch_count = 0       # kernels launched through this module since import
 call_hook = None       # optional callable(name, args) -> context manager, used by bench.py to time one kernel family

@@ -47,6 +47,10 @@ struct Params {
   float* partial;     // [B*nh, nsplit, 132] or null
   int B, nh, kvh, max_len, nsplit, items;
   float scale_log2;
+  // paged cache (block_tables != nullptr): key/value caches are [num_blocks, kvh, block_size, 128] and sequence b's logical
+  // block i lives in physical block block_tables[b * max_blocks + i]  (FusedBlockMultiTransformer / append_attention)
+  const int* block_tables;
+  int max_blocks, block_size;
 };
 
 struct Item {
@@ -80,7 +84,7 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                : "memory");
 }
 
-template <int G>
+template <int G, bool PAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 decode_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, const Params p) {
@@ -121,6 +125,10 @@ decode_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const int t = threadIdx.x - 64;
     *reinterpret_cast<uint4*>(sP + t * 32) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(sP + t * 32 + 16) = make_uint4(0, 0, 0, 0);
+    if constexpr (PAGED) {
+      // pages past the end of a sequence are not fetched: their smem rows must still be finite (P = 0 there, 0 * NaN = NaN)
+      for (int i = t; i < NSLOT * TILE_BYTES / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    }
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -147,14 +155,38 @@ decode_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         const int plane = it.b * p.kvh + it.kh;
         for (int j = 0; j < it.ntiles; ++j) {
           const int t0 = it.t_begin + j * BKV;
+          if constexpr (PAGED) {
+            // a 128-row tile = 128 / block_size pages looked up in the block table; pages at or past t_end are skipped
+            const int ppt = BKV / p.block_size;
+            int phys[4];
+            int npages = 0;
+            for (int pg = 0; pg < ppt; ++pg) {
+              const int tpos = t0 + pg * p.block_size;
+              if (tpos < it.t_end) phys[npages++] = __ldg(p.block_tables + static_cast<size_t>(it.b) * p.max_blocks + tpos / p.block_size);
+            }
+            const uint32_t page_bytes = static_cast<uint32_t>(p.block_size) * D * 2;
 #pragma unroll
-          for (int kv = 0; kv < 2; ++kv, ++c) {
-            const uint32_t slot = c % NSLOT;
-            mbar_wait(&empty[slot], ((c / NSLOT) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&full[slot], TILE_BYTES);
-            const CUtensorMap* tm = kv ? &tmV : &tmK;
-            tma_load_3d(tm, &full[slot], smem + slot * TILE_BYTES, 0, t0, plane);
-            tma_load_3d(tm, &full[slot], smem + slot * TILE_BYTES + HALF_BYTES, 64, t0, plane);
+            for (int kv = 0; kv < 2; ++kv, ++c) {
+              const uint32_t slot = c % NSLOT;
+              mbar_wait(&empty[slot], ((c / NSLOT) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&full[slot], page_bytes * npages);
+              const CUtensorMap* tm = kv ? &tmV : &tmK;
+              for (int pg = 0; pg < npages; ++pg) {
+                uint8_t* dst = smem + slot * TILE_BYTES + pg * (page_bytes / 2);
+                tma_load_4d(tm, &full[slot], dst, 0, 0, it.kh, phys[pg]);
+                tma_load_4d(tm, &full[slot], dst + HALF_BYTES, 64, 0, it.kh, phys[pg]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int kv = 0; kv < 2; ++kv, ++c) {
+              const uint32_t slot = c % NSLOT;
+              mbar_wait(&empty[slot], ((c / NSLOT) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&full[slot], TILE_BYTES);
+              const CUtensorMap* tm = kv ? &tmV : &tmK;
+              tma_load_3d(tm, &full[slot], smem + slot * TILE_BYTES, 0, t0, plane);
+              tma_load_3d(tm, &full[slot], smem + slot * TILE_BYTES + HALF_BYTES, 64, t0, plane);
+            }
           }
         }
       }
@@ -359,6 +391,49 @@ int launch_decode_attention_merge(const float* partial, void* out, int rows, int
 
 }  // namespace b200
 
+namespace b200 {
+namespace dtc {
+
+template <bool PAGED>
+static int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const Params& p, int G, void* out,
+                  int64_t B, int64_t num_heads, int64_t num_splits, cudaStream_t stream) {
+  const int max_ctas = 2 * sm_count();      // two co-resident CTAs per SM: item prologues/epilogues of one overlap the other's stream
+  const unsigned grid = static_cast<unsigned>(p.items < max_ctas ? p.items : max_ctas);
+#define B200_DTC(GG)                                                                                                 \
+  case GG: {                                                                                                         \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      cudaError_t e = cudaFuncSetAttribute(decode_attention_tc_kernel<GG, PAGED>,                                    \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);                \
+      if (e != cudaSuccess) {                                                                                        \
+        set_last_error("decode_attention_tc smem attr: %s", cudaGetErrorString(e));                                  \
+        return static_cast<int>(e);                                                                                  \
+      }                                                                                                              \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    launch_pdl(decode_attention_tc_kernel<GG, PAGED>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmQ, tmK, tmV, p); \
+  } break;
+  switch (G) {
+    B200_DTC(1) B200_DTC(2) B200_DTC(4) B200_DTC(7) B200_DTC(8)
+    default:
+      return fail_arg("decode_attention_tc: GQA group size %d not instantiated (1, 2, 4, 7, 8)", G);
+  }
+#undef B200_DTC
+  int rc = check_launch("decode_attention_tc");
+  if (rc || num_splits == 1) return rc;
+  return launch_decode_attention_merge(p.partial, out, static_cast<int>(B * num_heads), static_cast<int>(num_splits), stream);
+}
+
+static int make_q_map(CUtensorMap* tm, const void* qkv, int64_t B, int64_t num_heads, int64_t ld) {
+  uint64_t dims[3] = {128, static_cast<uint64_t>(num_heads), static_cast<uint64_t>(B)};
+  uint64_t strides[2] = {128 * 2, static_cast<uint64_t>(ld) * 2};
+  uint32_t box[3] = {64, NPAD, 1};
+  return encode_tmap_bf16(tm, qkv, 3, dims, strides, box);
+}
+
+}  // namespace dtc
+}  // namespace b200
+
 extern "C" int b200_decode_attention_tc(const void* qkv, const void* cache, const int32_t* seq_lens, void* out, void* workspace,
                                         int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t max_len,
                                         int64_t ld, float softmax_scale, int64_t num_splits, cudaStream_t stream) {
@@ -370,15 +445,9 @@ extern "C" int b200_decode_attention_tc(const void* qkv, const void* cache, cons
   B200_CHECK_ARG(head_dim == 128, "decode_attention_tc: head_dim must be 128 (got %lld)", (long long)head_dim);
   B200_CHECK_ARG(B > 0 && num_kv_heads > 0 && num_heads % num_kv_heads == 0 && max_len > 0 && ld % 8 == 0,
                  "decode_attention_tc: bad shape");
-  const int G = static_cast<int>(num_heads / num_kv_heads);
   CUtensorMap tmQ, tmK, tmV;
   int rc;
-  {
-    uint64_t dims[3] = {128, static_cast<uint64_t>(num_heads), static_cast<uint64_t>(B)};
-    uint64_t strides[2] = {128 * 2, static_cast<uint64_t>(ld) * 2};
-    uint32_t box[3] = {64, NPAD, 1};
-    if ((rc = encode_tmap_bf16(&tmQ, qkv, 3, dims, strides, box)) != 0) return rc;
-  }
+  if ((rc = make_q_map(&tmQ, qkv, B, num_heads, ld)) != 0) return rc;
   {
     uint64_t dims[3] = {128, static_cast<uint64_t>(max_len), static_cast<uint64_t>(B * num_kv_heads)};
     uint64_t strides[2] = {128 * 2, static_cast<uint64_t>(max_len) * 128 * 2};
@@ -388,7 +457,7 @@ extern "C" int b200_decode_attention_tc(const void* qkv, const void* cache, cons
     if ((rc = encode_tmap_bf16(&tmV, kbase + static_cast<size_t>(B) * num_kv_heads * max_len * 128, 3, dims, strides, box)) != 0)
       return rc;
   }
-  Params p;
+  Params p = {};
   p.seq_lens = seq_lens;
   p.out = static_cast<bf16*>(out);
   p.partial = num_splits > 1 ? static_cast<float*>(workspace) : nullptr;
@@ -396,29 +465,47 @@ extern "C" int b200_decode_attention_tc(const void* qkv, const void* cache, cons
   p.max_len = static_cast<int>(max_len); p.nsplit = static_cast<int>(num_splits);
   p.items = static_cast<int>(B * num_kv_heads * num_splits);
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  const int max_ctas = 2 * sm_count();      // two co-resident CTAs per SM: item prologues/epilogues of one overlap the other's stream
-  const unsigned grid = static_cast<unsigned>(p.items < max_ctas ? p.items : max_ctas);
-#define B200_DTC(GG)                                                                                                 \
-  case GG: {                                                                                                         \
-    static bool attr_set = false;                                                                                    \
-    if (!attr_set) {                                                                                                 \
-      cudaError_t e = cudaFuncSetAttribute(decode_attention_tc_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           SMEM_BYTES);                                                             \
-      if (e != cudaSuccess) {                                                                                        \
-        set_last_error("decode_attention_tc smem attr: %s", cudaGetErrorString(e));                                  \
-        return static_cast<int>(e);                                                                                  \
-      }                                                                                                              \
-      attr_set = true;                                                                                               \
-    }                                                                                                                \
-    launch_pdl(decode_attention_tc_kernel<GG>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmQ, tmK, tmV, p); \
-  } break;
-  switch (G) {
-    B200_DTC(1) B200_DTC(2) B200_DTC(4) B200_DTC(7) B200_DTC(8)
-    default:
-      return fail_arg("decode_attention_tc: GQA group size %d not instantiated (1, 2, 4, 7, 8)", G);
+  return launch<false>(tmQ, tmK, tmV, p, static_cast<int>(num_heads / num_kv_heads), out, B, num_heads, num_splits, stream);
+}
+
+extern "C" int b200_decode_attention_paged(const void* qkv, const void* key_cache, const void* value_cache,
+                                           const int32_t* block_tables, const int32_t* seq_lens, void* out, void* workspace,
+                                           int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim,
+                                           int64_t num_blocks, int64_t block_size, int64_t max_blocks_per_seq, int64_t ld,
+                                           float softmax_scale, int64_t num_splits, cudaStream_t stream) {
+  using namespace b200;
+  using namespace b200::dtc;
+  B200_CHECK_ARG(qkv && key_cache && value_cache && block_tables && seq_lens && out, "decode_attention_paged: null pointer");
+  B200_CHECK_ARG(num_splits >= 1 && num_splits <= 64 && (num_splits == 1 || workspace),
+                 "decode_attention_paged: bad num_splits / workspace");
+  B200_CHECK_ARG(head_dim == 128, "decode_attention_paged: head_dim must be 128 (got %lld)", (long long)head_dim);
+  B200_CHECK_ARG(block_size == 32 || block_size == 64 || block_size == 128,
+                 "decode_attention_paged: block_size must be 32, 64 or 128 (got %lld)", (long long)block_size);
+  B200_CHECK_ARG(B > 0 && num_kv_heads > 0 && num_heads % num_kv_heads == 0 && num_blocks > 0 && max_blocks_per_seq > 0 &&
+                     ld % 8 == 0,
+                 "decode_attention_paged: bad shape");
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_q_map(&tmQ, qkv, B, num_heads, ld)) != 0) return rc;
+  {
+    uint64_t dims[4] = {128, static_cast<uint64_t>(block_size), static_cast<uint64_t>(num_kv_heads),
+                        static_cast<uint64_t>(num_blocks)};
+    uint64_t strides[3] = {128 * 2, static_cast<uint64_t>(block_size) * 128 * 2,
+                           static_cast<uint64_t>(num_kv_heads) * block_size * 128 * 2};
+    uint32_t box[4] = {64, static_cast<uint32_t>(block_size), 1, 1};
+    if ((rc = encode_tmap_bf16(&tmK, key_cache, 4, dims, strides, box)) != 0) return rc;
+    if ((rc = encode_tmap_bf16(&tmV, value_cache, 4, dims, strides, box)) != 0) return rc;
   }
-#undef B200_DTC
-  rc = check_launch("decode_attention_tc");
-  if (rc || num_splits == 1) return rc;
-  return launch_decode_attention_merge(p.partial, out, static_cast<int>(B * num_heads), static_cast<int>(num_splits), stream);
+  Params p = {};
+  p.seq_lens = seq_lens;
+  p.out = static_cast<bf16*>(out);
+  p.partial = num_splits > 1 ? static_cast<float*>(workspace) : nullptr;
+  p.B = static_cast<int>(B); p.nh = static_cast<int>(num_heads); p.kvh = static_cast<int>(num_kv_heads);
+  p.max_len = static_cast<int>(max_blocks_per_seq * block_size); p.nsplit = static_cast<int>(num_splits);
+  p.items = static_cast<int>(B * num_kv_heads * num_splits);
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.block_tables = block_tables;
+  p.max_blocks = static_cast<int>(max_blocks_per_seq);
+  p.block_size = static_cast<int>(block_size);
+  return launch<true>(tmQ, tmK, tmV, p, static_cast<int>(num_heads / num_kv_heads), out, B, num_heads, num_splits, stream);
 }

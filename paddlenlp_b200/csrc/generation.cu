@@ -122,21 +122,39 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(const bf16* __restrict
 // [2, B, kvh, max_len, d]  (reference: write_cache_kv, csrc/gpu/write_cache_kv.cu:23-99; here K keeps the plain
 // [max_len, d] row layout — the transposed x=8 layout there is private to Paddle's MMHA kernel).
 // ------------------------------------------------------------------------------------------------
-__global__ void write_cache_kv_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ cache, const int* __restrict__ seq_lens,
-                                      int B, int S, int nh, int kvh, int d, int max_len, int64_t ld) {
+// Where a (sequence, kv head, position) row of the cache lives.  Dense: k/v = the two halves of [2, B, kvh, max_len, d].
+// Paged (block_tables != nullptr): k/v = [num_blocks, kvh, block_size, d] and logical block pos / block_size of sequence b is
+// physical block block_tables[b * max_blocks + pos / block_size] (FusedBlockMultiTransformer, fused_transformer_layers.py:2192;
+// cache write: csrc/gpu/append_attn/decoder_write_cache_with_rope_kernel.cu, encoder_write_cache_with_rope_kernel.cu).
+struct CacheView {
+  bf16* k;
+  bf16* v;
+  const int* block_tables;
+  int max_blocks, block_size, kvh, max_len, d;
+  __device__ __forceinline__ bf16* row(bool is_v, int b, int head, int pos) const {
+    bf16* base = is_v ? v : k;
+    if (block_tables != nullptr) {
+      const int phys = __ldg(block_tables + static_cast<size_t>(b) * max_blocks + pos / block_size);
+      return base + ((static_cast<size_t>(phys) * kvh + head) * block_size + pos % block_size) * d;
+    }
+    return base + ((static_cast<size_t>(b) * kvh + head) * max_len + pos) * d;
+  }
+};
+
+__global__ void write_cache_kv_kernel(const bf16* __restrict__ qkv, const CacheView cv, const int* __restrict__ seq_lens,
+                                      int S, int nh, int64_t ld) {
   const int tok = blockIdx.x;          // b * S + s
   const int b = tok / S, s = tok % S;
+  const int kvh = cv.kvh, d = cv.d;
   if (seq_lens != nullptr && s >= seq_lens[b]) return;
-  if (s >= max_len) return;
+  if (s >= cv.max_len) return;
   const int chunks = (kvh * d) >> 3;   // 16-byte chunks per K (or V) row group
-  const size_t half = static_cast<size_t>(B) * kvh * max_len * d;
   for (int c = threadIdx.x; c < 2 * chunks; c += blockDim.x) {
     const int which = c / chunks;      // 0: K, 1: V
     const int cc = c % chunks;
     const int head = (cc * 8) / d, off = (cc * 8) % d;
     const uint4 v = *reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(tok) * ld + (nh + which * kvh) * d + cc * 8);
-    bf16* dst = cache + which * half + ((static_cast<size_t>(b) * kvh + head) * max_len + s) * d + off;
-    *reinterpret_cast<uint4*>(dst) = v;
+    *reinterpret_cast<uint4*>(cv.row(which != 0, b, head, s) + off) = v;
   }
 }
 
@@ -162,9 +180,10 @@ __device__ __forceinline__ uint4 take_f32_chunk(float* acc, const float* bias, i
 }
 
 __global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, float* __restrict__ acc_f32, const float* __restrict__ bias,
-                                          bf16* __restrict__ cache, const float* __restrict__ cos_t,
-                                          const float* __restrict__ sin_t, const int* __restrict__ seq_lens, int B, int nh,
-                                          int kvh, int d, int max_len, int64_t ld) {
+                                          const CacheView cv, const float* __restrict__ cos_t,
+                                          const float* __restrict__ sin_t, const int* __restrict__ seq_lens, int nh,
+                                          int64_t ld) {
+  const int kvh = cv.kvh, d = cv.d, max_len = cv.max_len;
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x;
@@ -172,7 +191,6 @@ __global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, float* __restr
   const int half = d >> 1;
   const int per_head = half >> 3;
   const int idx = threadIdx.x;
-  const size_t cache_half = static_cast<size_t>(B) * kvh * max_len * d;
   bf16* row = qkv + static_cast<size_t>(b) * ld;
   float* arow = acc_f32 ? acc_f32 + static_cast<size_t>(b) * (nh + 2 * kvh) * d : nullptr;
   if (arow != nullptr) {
@@ -202,7 +220,7 @@ __global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, float* __restr
     *reinterpret_cast<uint4*>(base + j8) = a;
     *reinterpret_cast<uint4*>(base + half + j8) = bb;
     if (head >= nh) {   // rotated k -> cache
-      bf16* dst = cache + ((static_cast<size_t>(b) * kvh + (head - nh)) * max_len + pos) * d;
+      bf16* dst = cv.row(false, b, head - nh, pos);
       *reinterpret_cast<uint4*>(dst + j8) = a;
       *reinterpret_cast<uint4*>(dst + half + j8) = bb;
     }
@@ -211,8 +229,7 @@ __global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, float* __restr
   for (int c = idx; c < (kvh * d) >> 3; c += blockDim.x) {
     const int head = (c * 8) / d, off = (c * 8) % d;
     const uint4 v = *reinterpret_cast<const uint4*>(row + (nh + kvh) * d + c * 8);
-    bf16* dst = cache + cache_half + ((static_cast<size_t>(b) * kvh + head) * max_len + pos) * d + off;
-    *reinterpret_cast<uint4*>(dst) = v;
+    *reinterpret_cast<uint4*>(cv.row(true, b, head, pos) + off) = v;
   }
 }
 
@@ -764,6 +781,9 @@ using namespace b200::gen;
 
 static int add_rmsnorm_launch(const void* x, float* x_f32, const void* residual, const void* w, void* normed,
                               void* residual_out, int64_t rows, int64_t h, float eps, cudaStream_t stream);
+static int rope_append_launch(void* qkv, float* acc_f32_ws, const float* bias, const CacheView& cv, const float* cos_table,
+                              const float* sin_table, const int32_t* seq_lens, int64_t B, int64_t num_heads, int64_t ld,
+                              cudaStream_t stream);
 
 extern "C" int b200_add_rmsnorm(const void* x, const void* residual, const void* w, void* normed, void* residual_out,
                                 int64_t rows, int64_t h, float eps, cudaStream_t stream) {
@@ -804,10 +824,40 @@ extern "C" int b200_write_cache_kv(const void* qkv, void* cache, const int32_t* 
                                    cudaStream_t stream) {
   B200_CHECK_ARG(qkv && cache, "write_cache_kv: null pointer");
   B200_CHECK_ARG(head_dim % 8 == 0 && ld % 8 == 0 && B > 0 && S > 0 && S <= max_len, "write_cache_kv: bad sizes");
-  write_cache_kv_kernel<<<static_cast<unsigned>(B * S), 128, 0, stream>>>(
-      static_cast<const bf16*>(qkv), static_cast<bf16*>(cache), seq_lens, (int)B, (int)S, (int)num_heads, (int)num_kv_heads,
-      (int)head_dim, (int)max_len, ld);
+  CacheView cv = {};
+  cv.k = static_cast<bf16*>(cache);
+  cv.v = cv.k + static_cast<size_t>(B) * num_kv_heads * max_len * head_dim;
+  cv.kvh = (int)num_kv_heads; cv.max_len = (int)max_len; cv.d = (int)head_dim;
+  write_cache_kv_kernel<<<static_cast<unsigned>(B * S), 128, 0, stream>>>(static_cast<const bf16*>(qkv), cv, seq_lens, (int)S,
+                                                                          (int)num_heads, ld);
   return check_launch("write_cache_kv");
+}
+
+static int paged_view(CacheView* cv, void* key_cache, void* value_cache, const int32_t* block_tables, int64_t num_kv_heads,
+                      int64_t head_dim, int64_t block_size, int64_t max_blocks_per_seq, const char* what) {
+  if (!(key_cache && value_cache && block_tables)) return fail_arg("%s: null pointer", what);
+  if (!(block_size > 0 && max_blocks_per_seq > 0 && head_dim % 8 == 0)) return fail_arg("%s: bad block geometry", what);
+  *cv = {};
+  cv->k = static_cast<bf16*>(key_cache);
+  cv->v = static_cast<bf16*>(value_cache);
+  cv->block_tables = block_tables;
+  cv->max_blocks = (int)max_blocks_per_seq; cv->block_size = (int)block_size; cv->kvh = (int)num_kv_heads;
+  cv->max_len = (int)(max_blocks_per_seq * block_size); cv->d = (int)head_dim;
+  return 0;
+}
+
+extern "C" int b200_write_cache_kv_paged(const void* qkv, void* key_cache, void* value_cache, const int32_t* block_tables,
+                                         const int32_t* seq_lens, int64_t B, int64_t S, int64_t num_heads,
+                                         int64_t num_kv_heads, int64_t head_dim, int64_t block_size,
+                                         int64_t max_blocks_per_seq, int64_t ld, cudaStream_t stream) {
+  CacheView cv;
+  int rc = paged_view(&cv, key_cache, value_cache, block_tables, num_kv_heads, head_dim, block_size, max_blocks_per_seq,
+                      "write_cache_kv_paged");
+  if (rc) return rc;
+  B200_CHECK_ARG(qkv && ld % 8 == 0 && B > 0 && S > 0 && S <= cv.max_len, "write_cache_kv_paged: bad sizes");
+  write_cache_kv_kernel<<<static_cast<unsigned>(B * S), 128, 0, stream>>>(static_cast<const bf16*>(qkv), cv, seq_lens, (int)S,
+                                                                          (int)num_heads, ld);
+  return check_launch("write_cache_kv_paged");
 }
 
 extern "C" int b200_decode_rope_append_f32(void* qkv, float* acc_f32_ws, const float* bias, void* cache,
@@ -827,14 +877,36 @@ extern "C" int b200_decode_rope_append_f32(void* qkv, float* acc_f32_ws, const f
                                            int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim,
                                            int64_t max_len, int64_t ld, cudaStream_t stream) {
   B200_CHECK_ARG(qkv && cache && cos_table && sin_table && seq_lens, "decode_rope_append: null pointer");
-  B200_CHECK_ARG(head_dim % 16 == 0 && ld % 8 == 0, "decode_rope_append: head_dim %% 16, ld %% 8");
-  const int threads_needed = static_cast<int>((num_heads + num_kv_heads) * (head_dim / 16));
+  CacheView cv = {};
+  cv.k = static_cast<bf16*>(cache);
+  cv.v = cv.k + static_cast<size_t>(B) * num_kv_heads * max_len * head_dim;
+  cv.kvh = (int)num_kv_heads; cv.max_len = (int)max_len; cv.d = (int)head_dim;
+  return rope_append_launch(qkv, acc_f32_ws, bias, cv, cos_table, sin_table, seq_lens, B, num_heads, ld, stream);
+}
+
+static int rope_append_launch(void* qkv, float* acc_f32_ws, const float* bias, const CacheView& cv, const float* cos_table,
+                              const float* sin_table, const int32_t* seq_lens, int64_t B, int64_t num_heads, int64_t ld,
+                              cudaStream_t stream) {
+  B200_CHECK_ARG(cv.d % 16 == 0 && ld % 8 == 0, "decode_rope_append: head_dim %% 16, ld %% 8");
+  const int threads_needed = static_cast<int>((num_heads + cv.kvh) * (cv.d / 16));
   B200_CHECK_ARG(threads_needed <= 1024, "decode_rope_append: too many heads");
   const int threads = (threads_needed + 31) / 32 * 32;
   launch_pdl(decode_rope_append_kernel, dim3(static_cast<unsigned>(B)), dim3(threads), 0, stream, static_cast<bf16*>(qkv),
-             acc_f32_ws, bias, static_cast<bf16*>(cache), cos_table, sin_table, seq_lens, (int)B, (int)num_heads,
-             (int)num_kv_heads, (int)head_dim, (int)max_len, ld);
+             acc_f32_ws, bias, cv, cos_table, sin_table, seq_lens, (int)num_heads, ld);
   return check_launch("decode_rope_append");
+}
+
+extern "C" int b200_decode_rope_append_paged(void* qkv, float* acc_f32_ws, const float* bias, void* key_cache, void* value_cache,
+                                             const int32_t* block_tables, const float* cos_table, const float* sin_table,
+                                             const int32_t* seq_lens, int64_t B, int64_t num_heads, int64_t num_kv_heads,
+                                             int64_t head_dim, int64_t block_size, int64_t max_blocks_per_seq, int64_t ld,
+                                             cudaStream_t stream) {
+  CacheView cv;
+  int rc = paged_view(&cv, key_cache, value_cache, block_tables, num_kv_heads, head_dim, block_size, max_blocks_per_seq,
+                      "decode_rope_append_paged");
+  if (rc) return rc;
+  B200_CHECK_ARG(qkv && cos_table && sin_table && seq_lens, "decode_rope_append_paged: null pointer");
+  return rope_append_launch(qkv, acc_f32_ws, bias, cv, cos_table, sin_table, seq_lens, B, num_heads, ld, stream);
 }
 
 namespace b200 {

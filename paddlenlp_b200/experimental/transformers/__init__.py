@@ -1,6 +1,5 @@
 """paddlenlp.experimental.transformers surface kept by this build (fused_transformer_layers.py:67-78)."""
-from .fused_transformer_layers import FusedMultiTransformerBase, FusedMultiTransformerConfig
+from .fused_transformer_layers import FusedBlockMultiTransformer, FusedMultiTransformerBase, FusedMultiTransformerConfig
 from .generation_utils import GenerationInferenceModel
 from .llama.modeling import LlamaForCausalLMInferenceModel
 
-FusedBlockMultiTransformer = None      # paged (block) KV cache: "next" item, SURVEY.md §8f rank 1

@@ -101,11 +101,25 @@ class FusedMultiTransformerBase:
     def compute_qkv(self, ln_out, i):
         return self._mm(ln_out, self.qkv_weights[i], trans_b=True, bias=self._bias(i))
 
+    # ---- the three places that touch the KV cache (overridden by FusedBlockMultiTransformer) ----
+    def _write_cache(self, qkv, caches, i, B, S, seq_lens_encoder, kw):
+        ops.write_cache_kv(qkv, caches[i], seq_lens_encoder, B, S, self.nh, self.kvh, self.d)
+
+    def _rope_append(self, qkv, acc, caches, i, seq_lens_decoder, kw):
+        cos, sin = self.rope
+        if acc is not None:
+            return ops.decode_rope_append_f32(acc, self._bias(i), caches[i], cos, sin, seq_lens_decoder, self.nh, self.kvh, self.d)
+        ops.decode_rope_append(qkv, caches[i], cos, sin, seq_lens_decoder, self.nh, self.kvh, self.d)
+        return qkv
+
+    def _attend(self, qkv, caches, i, seq_lens_decoder, kw):
+        return ops.decode_attention(qkv, caches[i], seq_lens_decoder, self.nh, self.kvh, self.d)
+
     # compute_fmha (:829-882): qkv_transpose_split -> encode_rotary_qk -> write_cache_kv -> var-len attention
-    def compute_fmha(self, qkv, cache, B, S, seq_lens_encoder):
+    def compute_fmha(self, qkv, caches, i, B, S, seq_lens_encoder, kw):
         cos, sin = self.rope
         ops.rope_inplace(qkv, cos, sin, S, self.nh + self.kvh, self.d)
-        ops.write_cache_kv(qkv, cache, seq_lens_encoder, B, S, self.nh, self.kvh, self.d)
+        self._write_cache(qkv, caches, i, B, S, seq_lens_encoder, kw)
         q4 = qkv.view(B, S, self.qkv_n)
         qn, kn = self.nh * self.d, self.kvh * self.d
         q = q4[:, :, :qn].unflatten(2, (self.nh, self.d))
@@ -115,13 +129,12 @@ class FusedMultiTransformerBase:
         return attn.view(B * S, qn)
 
     # compute_mmha (:884-893): masked_multihead_attention over the cache
-    def compute_mmha(self, qkv, cache, seq_lens_decoder):
-        cos, sin = self.rope
-        ops.decode_rope_append(qkv, cache, cos, sin, seq_lens_decoder, self.nh, self.kvh, self.d)
-        return ops.decode_attention(qkv, cache, seq_lens_decoder, self.nh, self.kvh, self.d)
+    def compute_mmha(self, qkv, caches, i, seq_lens_decoder, kw):
+        qkv = self._rope_append(qkv, None, caches, i, seq_lens_decoder, kw)
+        return self._attend(qkv, caches, i, seq_lens_decoder, kw)
 
     def forward(self, src: torch.Tensor, caches: List[torch.Tensor], *, B: int, S: int, seq_lens_encoder=None,
-                seq_lens_decoder=None, time_step=None) -> torch.Tensor:
+                seq_lens_decoder=None, time_step=None, **kw) -> torch.Tensor:
         """src [B*S, h] embeddings.  time_step None = prefill (S prompt positions per sequence, right padded);
         otherwise decode (S == 1, seq_lens_decoder[b] = number of cached tokens).  Returns hidden states [B*S, h]."""
         eps = self.config.epsilon
@@ -133,11 +146,9 @@ class FusedMultiTransformerBase:
             if fused:
                 # decode step: the split-K GEMMs leave fp32 sums that the next kernel rounds once (same rounding points,
                 # three launches fewer per layer)
-                cos, sin = self.rope
                 acc = ops.gemm_skinny_f32(ln_out, self.qkv_weights[i], trans_b=True, tag="splitk_qkv")
-                qkv = ops.decode_rope_append_f32(acc, self._bias(i), caches[i], cos, sin, seq_lens_decoder, self.nh, self.kvh,
-                                                 self.d)
-                attn = ops.decode_attention(qkv, caches[i], seq_lens_decoder, self.nh, self.kvh, self.d)
+                qkv = self._rope_append(None, acc, caches, i, seq_lens_decoder, kw)
+                attn = self._attend(qkv, caches, i, seq_lens_decoder, kw)
                 acc = ops.gemm_skinny_f32(attn, self.linear_weights[i], tag="splitk_h")
                 ln_out, residual = ops.add_rmsnorm_f32(acc, residual, self.ffn_ln_scales[i], eps)
                 ffn1 = self._mm(ln_out, self.ffn1_weights[i])
@@ -150,9 +161,9 @@ class FusedMultiTransformerBase:
                 continue
             qkv = self.compute_qkv(ln_out, i)
             if decode:
-                attn = self.compute_mmha(qkv, caches[i], seq_lens_decoder)
+                attn = self.compute_mmha(qkv, caches, i, seq_lens_decoder, kw)
             else:
-                attn = self.compute_fmha(qkv, caches[i], B, S, seq_lens_encoder)
+                attn = self.compute_fmha(qkv, caches, i, B, S, seq_lens_encoder, kw)
             out = self._mm(attn, self.linear_weights[i])                                      # compute_out_linear (:895-896)
             ln_out, residual = ops.add_rmsnorm(out, residual, self.ffn_ln_scales[i], eps)     # compute_ffn_layernorm (:937-949)
             ffn1 = self._mm(ln_out, self.ffn1_weights[i])
@@ -165,3 +176,28 @@ class FusedMultiTransformerBase:
         return residual
 
     __call__ = forward
+
+
+class FusedBlockMultiTransformer(FusedMultiTransformerBase):
+    """Paged ("block") KV cache variant (fused_transformer_layers.py:2192-2354, `compute_attn` -> append_attention /
+    block_multihead_attention).  `caches` is the reference's list of 2*L tensors [key_cache_0, value_cache_0, key_cache_1, ...],
+    each [max_block_nums, kv_num_heads, block_size, head_dim]; `block_tables` [B, max_blocks_per_seq] int32 (-1 = unused)
+    arrives as a keyword argument, as in the reference.  The math is the dense path's: only cache addressing changes."""
+
+    @staticmethod
+    def _tables(kw):
+        bt = kw.get("block_tables")
+        if bt is None:
+            raise ValueError("FusedBlockMultiTransformer needs block_tables=[B, max_blocks_per_seq] int32")
+        return bt
+
+    def _write_cache(self, qkv, caches, i, B, S, seq_lens_encoder, kw):
+        ops.write_cache_kv_paged(qkv, caches[2 * i], caches[2 * i + 1], self._tables(kw), seq_lens_encoder, B, S, self.nh)
+
+    def _rope_append(self, qkv, acc, caches, i, seq_lens_decoder, kw):
+        cos, sin = self.rope
+        return ops.decode_rope_append_paged(qkv, caches[2 * i], caches[2 * i + 1], self._tables(kw), cos, sin, seq_lens_decoder,
+                                            self.nh, acc_f32=acc, bias=self._bias(i) if acc is not None else None)
+
+    def _attend(self, qkv, caches, i, seq_lens_decoder, kw):
+        return ops.decode_attention_paged(qkv, caches[2 * i], caches[2 * i + 1], self._tables(kw), seq_lens_decoder, self.nh)

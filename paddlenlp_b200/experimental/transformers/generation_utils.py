@@ -55,7 +55,12 @@ class GenerationInferenceModel:
                else seq_len_encoder.to(dev, torch.int32).reshape(B).contiguous())
         if cache_kvs is None:
             cache_kvs = self.allocate_caches(B, S + max_length)
-        max_len = cache_kvs[0].shape[3]
+        if getattr(self, "block_attn", False):                   # paged cache: capacity = blocks per sequence x block size
+            if self.block_tables is None or self.block_tables.shape[0] != B:
+                raise ValueError("block_attn: allocate the caches with allocate_caches(batch, max_len) for this batch size")
+            max_len = self.block_tables.shape[1] * cache_kvs[0].shape[2]
+        else:
+            max_len = cache_kvs[0].shape[3]
         if S + max_length > max_len:
             raise ValueError(f"cache max_len {max_len} < prompt {S} + max_length {max_length}")
         eos = torch.tensor([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id or [-1]),

@@ -8,15 +8,20 @@ from typing import Dict, List
 import torch
 
 from .... import ops
-from ..fused_transformer_layers import FusedMultiTransformerBase, FusedMultiTransformerConfig
+from ..fused_transformer_layers import FusedBlockMultiTransformer, FusedMultiTransformerBase, FusedMultiTransformerConfig
 from ..generation_utils import GenerationInferenceModel
 
 BF16 = torch.bfloat16
 
 
 class LlamaForCausalLMInferenceModel(GenerationInferenceModel):
-    def __init__(self, config, device=None):
+    def __init__(self, config, device=None, block_attn: bool = False, block_size: int = 64):
+        """block_attn=True selects the paged KV cache (`--block_attn` of llm/predict/predictor.py:1507-1520:
+        LlamaBlockInferenceModel on FusedBlockMultiTransformer)."""
         self.config = config
+        self.block_attn = bool(block_attn)
+        self.block_size = int(block_size)
+        self.block_tables = None
         c = config
         self.prefix = c.model_type
         fcfg = FusedMultiTransformerConfig(
@@ -24,7 +29,7 @@ class LlamaForCausalLMInferenceModel(GenerationInferenceModel):
             kv_num_heads=c.num_key_value_heads, num_layers=c.num_hidden_layers, epsilon=c.rms_norm_eps,
             rope_theta=c.rope_theta, max_position_embeddings=max(int(getattr(c, "max_position_embeddings", 4096)), 128),
             qkv_bias=(c.model_type == "qwen2"))
-        self.transformer_block = FusedMultiTransformerBase(fcfg, device)
+        self.transformer_block = (FusedBlockMultiTransformer if self.block_attn else FusedMultiTransformerBase)(fcfg, device)
         self.device = self.transformer_block.device
         self.embed_tokens = torch.zeros(c.vocab_size, c.hidden_size, dtype=BF16, device=self.device)
         self.norm_weight = torch.ones(c.hidden_size, dtype=BF16, device=self.device)
@@ -71,7 +76,29 @@ class LlamaForCausalLMInferenceModel(GenerationInferenceModel):
     def allocate_caches(self, batch: int, max_len: int) -> List[torch.Tensor]:
         """cache_kvs = [zeros([2, bsz, kvh, max_len, d])] * L (llm/predict/predictor.py:697-706)."""
         t = self.transformer_block
+        if self.block_attn:
+            return self.allocate_block_caches(batch, max_len)
         return [torch.zeros(2, batch, t.kvh, max_len, t.d, dtype=BF16, device=self.device) for _ in range(t.L)]
+
+    def allocate_block_caches(self, batch: int, max_len: int, max_block_nums: int = 0) -> List[torch.Tensor]:
+        """cache_kvs = [key_cache_0, value_cache_0, ...], each zeros([max_block_nums, kvh, block_size, d])
+        (get_cache_kvs_shape, experimental/transformers/llama/modeling.py; predictor.py:960-964), plus the block tables the
+        predictor builds (predictor.py:923-930): -1 everywhere, then every sequence takes ceil(max_len / block_size) blocks
+        popped from the end of the free list."""
+        t = self.transformer_block
+        bs = self.block_size
+        per_seq = (max_len + bs - 1) // bs
+        n = max(max_block_nums, batch * per_seq)
+        free_list = list(range(n))
+        tables = torch.full((batch, per_seq), -1, dtype=torch.int32)
+        for i in range(batch):
+            for j in range(per_seq):
+                tables[i, j] = free_list.pop()
+        self.block_tables = tables.to(self.device)
+        return [torch.zeros(n, t.kvh, bs, t.d, dtype=BF16, device=self.device) for _ in range(2 * t.L)]
+
+    def _cache_kw(self):
+        return {"block_tables": self.block_tables} if self.block_attn else {}
 
     # ---- forward ----
     def _head(self, hidden):
@@ -81,7 +108,7 @@ class LlamaForCausalLMInferenceModel(GenerationInferenceModel):
     def _prefill(self, input_ids, seq_lens_encoder, caches):
         B, S = input_ids.shape
         emb = ops.embedding_fwd(input_ids.reshape(-1), self.embed_tokens)
-        hidden = self.transformer_block(emb, caches, B=B, S=S, seq_lens_encoder=seq_lens_encoder)
+        hidden = self.transformer_block(emb, caches, B=B, S=S, seq_lens_encoder=seq_lens_encoder, **self._cache_kw())
         # rebuild_padding: keep the last valid position of every sequence
         last = (torch.arange(B, device=self.device) * S + seq_lens_encoder.to(torch.int64) - 1)
         return self._head(hidden.index_select(0, last).contiguous())
@@ -89,7 +116,8 @@ class LlamaForCausalLMInferenceModel(GenerationInferenceModel):
     def _decode(self, tgt_ids, seq_lens_decoder, caches):
         B = tgt_ids.numel()
         emb = ops.embedding_fwd(tgt_ids.reshape(-1), self.embed_tokens)
-        hidden = self.transformer_block(emb, caches, B=B, S=1, seq_lens_decoder=seq_lens_decoder, time_step=0)
+        hidden = self.transformer_block(emb, caches, B=B, S=1, seq_lens_decoder=seq_lens_decoder, time_step=0,
+                                        **self._cache_kw())
         return self._head(hidden)
 
     @torch.no_grad()
@@ -98,5 +126,5 @@ class LlamaForCausalLMInferenceModel(GenerationInferenceModel):
         B, S = input_ids.shape
         caches = self.allocate_caches(B, S)
         emb = ops.embedding_fwd(input_ids.to(self.device).reshape(-1), self.embed_tokens)
-        hidden = self.transformer_block(emb, caches, B=B, S=S, seq_lens_encoder=None)
+        hidden = self.transformer_block(emb, caches, B=B, S=S, seq_lens_encoder=None, **self._cache_kw())
         return self._head(hidden).view(B, S, -1)

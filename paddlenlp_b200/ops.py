@@ -422,6 +422,54 @@ def decode_attention(qkv, cache, seq_lens, nh, kvh, d, softmax_scale=None, out=N
     return out
 
 
+# ---- paged ("block") KV cache: FusedBlockMultiTransformer / append_attention ----------------------------------------
+def _paged_geom(key_cache, value_cache, block_tables):
+    _chk(key_cache, "key_cache"); _chk(value_cache, "value_cache"); _chk(block_tables, "block_tables", torch.int32)
+    assert key_cache.shape == value_cache.shape and key_cache.is_contiguous() and value_cache.is_contiguous()
+    assert block_tables.dim() == 2 and block_tables.is_contiguous()
+    num_blocks, kvh, block_size, d = key_cache.shape
+    return num_blocks, kvh, block_size, d, block_tables.shape[1]
+
+
+def write_cache_kv_paged(qkv, key_cache, value_cache, block_tables, seq_lens, B, S, nh):
+    nb, kvh, bs, d, mb = _paged_geom(key_cache, value_cache, block_tables)
+    call("b200_write_cache_kv_paged", ptr(qkv), ptr(key_cache), ptr(value_cache), ptr(block_tables), ptr(seq_lens), B, S, nh, kvh,
+         d, bs, mb, qkv.stride(0), stream_ptr())
+
+
+def decode_rope_append_paged(qkv, key_cache, value_cache, block_tables, cos, sin, seq_lens, nh, acc_f32=None, bias=None):
+    """RoPE on the new token's q, k + append k, v at position seq_lens[b] of sequence b's block list.  With acc_f32 the packed
+    projection arrives as the fp32 split-K workspace (rounded here, workspace re-zeroed) and `qkv` is created."""
+    nb, kvh, bs, d, mb = _paged_geom(key_cache, value_cache, block_tables)
+    if acc_f32 is not None:
+        B = acc_f32.shape[0]
+        qkv = torch.empty(B, (nh + 2 * kvh) * d, dtype=BF16, device=acc_f32.device)
+    B = qkv.shape[0]
+    call("b200_decode_rope_append_paged", ptr(qkv), ptr(acc_f32), ptr(bias), ptr(key_cache), ptr(value_cache), ptr(block_tables),
+         ptr(cos), ptr(sin), ptr(seq_lens), B, nh, kvh, d, bs, mb, qkv.stride(0), stream_ptr())
+    return qkv
+
+
+def decode_attention_paged(qkv, key_cache, value_cache, block_tables, seq_lens, nh, softmax_scale=None, out=None,
+                           num_splits: int = 0):
+    _chk(qkv, "qkv"); _chk(seq_lens, "seq_lens", torch.int32)
+    nb, kvh, bs, d, mb = _paged_geom(key_cache, value_cache, block_tables)
+    B = qkv.shape[0]
+    if out is None:
+        out = torch.empty(B, nh * d, dtype=BF16, device=qkv.device)
+    if softmax_scale is None:
+        softmax_scale = 1.0 / math.sqrt(d)
+    max_len = mb * bs
+    if num_splits <= 0:
+        num_splits = max(1, min((max_len + 127) // 128, (3 * 148 + B * kvh - 1) // (B * kvh)))
+    ws = None
+    if num_splits > 1:
+        ws = _workspace(_lib.load().b200_decode_attention_workspace_bytes(B, nh, num_splits), qkv.device, "decode_attn")
+    call("b200_decode_attention_paged", ptr(qkv), ptr(key_cache), ptr(value_cache), ptr(block_tables), ptr(seq_lens), ptr(out),
+         ptr(ws), B, nh, kvh, d, nb, bs, mb, qkv.stride(0), float(softmax_scale), num_splits, stream_ptr())
+    return out
+
+
 def get_padding_offset(input_ids, cum_offsets, token_num, seq_lens):
     """get_padding_offset_v2: returns (x_remove_padding, cum_offsets_out, padding_offset, cu_seqlens_q, cu_seqlens_k)."""
     bsz, max_len = input_ids.shape

@@ -329,3 +329,72 @@ def test_generate_with_top_p_sampling():
     assert torch.equal(a, c)
     d, _, _ = m.generate(ids, max_length=10, top_p=0.9, temperature=1.3, seed=43)
     assert not torch.equal(a, d)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# paged ("block") KV cache — FusedBlockMultiTransformer / append_attention layout
+# ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nh,kvh,B,block_size,max_blocks,splits", [(32, 8, 9, 64, 12, 0), (8, 2, 40, 64, 5, 1), (28, 4, 3, 128, 6, 3),
+                                                                    (4, 1, 2, 32, 9, 2)])
+def test_paged_rope_append_and_attention(nh, kvh, B, block_size, max_blocks, splits):
+    o = ops()
+    d = 128
+    rng = np.random.default_rng(nh + B)
+    nb = B * max_blocks + 3
+    perm = rng.permutation(nb)[: B * max_blocks].astype(np.int32).reshape(B, max_blocks)       # scattered physical blocks
+    cap = block_size * max_blocks
+    lens = rng.integers(0, cap - 1, size=B).astype(np.int32)
+    lens[0], lens[-1] = 0, cap - 1                                        # empty history; cache already full (clamped)
+    kc = torch.tensor(rng.standard_normal((nb, kvh, block_size, d)).astype(np.float32)).to(BF16)
+    vc = torch.tensor(rng.standard_normal((nb, kvh, block_size, d)).astype(np.float32)).to(BF16)
+    for b in range(B):                                                    # blocks past a sequence's need are unallocated
+        used = (min(int(lens[b]) + 1, cap) + block_size - 1) // block_size
+        perm[b, used:] = -1
+    qkv = torch.tensor(rng.standard_normal((B, (nh + 2 * kvh) * d)).astype(np.float32)).to(BF16)
+    cos, sin = o.rope_tables(d, cap, 10000.0, DEV)
+    kc_d, vc_d, qkv_d = kc.clone().to(DEV), vc.clone().to(DEV), qkv.clone().to(DEV)
+    bt, ln = t(perm, torch.int32), t(lens, torch.int32)
+    o.decode_rope_append_paged(qkv_d, kc_d, vc_d, bt, cos, sin, ln, nh)
+    # RoPE + append: identical bits to the dense kernel writing into a dense cache
+    dense = torch.zeros(2, B, kvh, cap, d, dtype=BF16, device=DEV)
+    qkv_dense = qkv.clone().to(DEV)
+    o.decode_rope_append(qkv_dense, dense, cos, sin, ln, nh, kvh, d)
+    assert torch.equal(qkv_d, qkv_dense)
+    for b in range(B):
+        p = int(lens[b])
+        if p >= cap:
+            continue
+        blk, off = int(perm[b, p // block_size]), p % block_size
+        assert torch.equal(kc_d[blk, :, off], dense[0, b, :, p]) and torch.equal(vc_d[blk, :, off], dense[1, b, :, p])
+    touched = (kc_d != kc.to(DEV)).any(-1).sum().item()
+    assert touched <= B * kvh                                             # nothing else in the pool was written
+    out = o.decode_attention_paged(qkv_d, kc_d, vc_d, bt, ln, nh, num_splits=splits).float().cpu().numpy()
+    ref = G.paged_decode_attention(qkv_d[:, : nh * d].float().cpu().numpy().reshape(B, nh, d), kc_d.float().cpu().numpy(),
+                                   vc_d.float().cpu().numpy(), perm, lens)
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() / np.abs(ref).max() < 1.5e-2
+
+
+@pytest.mark.parametrize("model_type", ["llama", "qwen2"])
+def test_block_attn_generation_matches_dense_cache(model_type):
+    """generate() on FusedBlockMultiTransformer (scattered 64-row pages) produces the tokens of the dense-cache path."""
+    import paddlenlp_b200.transformers as T
+    from paddlenlp_b200.experimental.transformers import FusedBlockMultiTransformer, LlamaForCausalLMInferenceModel
+
+    cfg = _tiny(model_type)
+    w = R.init_weights(cfg, seed=9)
+    dense, c = _infer_model(cfg, w)
+    paged = LlamaForCausalLMInferenceModel(c, block_attn=True, block_size=64)
+    paged.set_state_dict(w)
+    assert isinstance(paged.transformer_block, FusedBlockMultiTransformer)
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(1, cfg.vocab_size, (5, 37), generator=g)
+    enc = torch.tensor([37, 20, 5, 33, 1], dtype=torch.int32)
+    for i in range(5):
+        ids[i, enc[i]:] = 0
+    a, _, la = dense.generate(ids, seq_len_encoder=enc, max_length=40)
+    caches = paged.allocate_caches(5, 37 + 40)
+    assert len(caches) == 2 * cfg.num_hidden_layers and caches[0].shape == (5 * 2, cfg.num_key_value_heads, 64, 128)
+    assert paged.block_tables.shape == (5, 2) and int(paged.block_tables[0, 0]) == 9        # free_list.pop(): highest id first
+    b, _, lb = paged.generate(ids, seq_len_encoder=enc, max_length=40, cache_kvs=caches)
+    assert torch.equal(a, b) and torch.equal(la, lb)

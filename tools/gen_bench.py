@@ -24,9 +24,10 @@ def main():
     ap.add_argument("--layers", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--block-attn", action="store_true", help="paged KV cache (FusedBlockMultiTransformer, 64-row blocks)")
     a = ap.parse_args()
     cfg = T.LlamaConfig.llama3_8b(num_hidden_layers=a.layers) if a.layers else T.LlamaConfig.llama3_8b()
-    m = LlamaForCausalLMInferenceModel(cfg)
+    m = LlamaForCausalLMInferenceModel(cfg, block_attn=a.block_attn)
     m.init_random(seed=42)
     g = torch.Generator().manual_seed(1234)
     ids = torch.randint(0, cfg.vocab_size, (a.batch, a.prompt), generator=g).cuda()
