@@ -127,6 +127,19 @@ int b200_fa_bwd(const void* q, const void* k, const void* v, const void* o, cons
                 void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t S, int64_t num_heads,
                 int64_t num_kv_heads, int64_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
                 int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv, float softmax_scale, cudaStream_t stream);
+/* FlashMask, causal lower-triangular form: the same two ops with a per-key-column start row
+ * (fusion_ops.py:218-231 -> F.flashmask_attention(q, k, v, startend_row_indices=..., causal=True)):
+ * mask_start_rows [B, S] int32, query row i sees key column c iff c <= i < mask_start_rows[b, c].  For packed SFT samples
+ * ("zero padding", llm/utils/data.py:200-204, paddlenlp/datasets/zero_padding_dataset.py:84-86) it is the end of c's document
+ * and must be non-decreasing in c; kv tiles that a q tile cannot see are skipped, not just masked.  NULL = plain causal. */
+int b200_fa_fwd_flashmask(const void* q, const void* k, const void* v, void* o, float* lse, const int32_t* mask_start_rows,
+                          int64_t B, int64_t S, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t ldq,
+                          int64_t ldk, int64_t ldv, int64_t ldo, float softmax_scale, cudaStream_t stream);
+int b200_fa_bwd_flashmask(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                          const int32_t* mask_start_rows, void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t S,
+                          int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv,
+                          int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv, float softmax_scale,
+                          cudaStream_t stream);
 
 /* ---- Criterion: LlamaPretrainingCriterion (llama/modeling.py:1799-1825) on bf16 logits [tokens, vocab] (ld).
  * fwd : loss_tok[i] = fp32 CE (0 for ignore_index), lse[i]; loss_out[0] = sum(l_i [l_i>0]) / count, loss_out[1] = count.

@@ -153,8 +153,11 @@ def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, mode: str,
     return rnd(x * c + rotate_half(x) * s, mode)
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mode: str) -> torch.Tensor:
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mode: str,
+              mask_start: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Causal GQA attention; q [b,s,nh,d], k/v [b,s,kvh,d] -> [b,s,nh*d].
+    mask_start [b, s] (optional): FlashMask causal-LT start rows (fusion_ops.py:218-231): key column c is hidden from query
+    rows i >= mask_start[b, c]  (packed-document masking, llm/utils/data.py:200-204).
     Rounding points of the flash path (SURVEY.md §8a a5): S, softmax in fp32 with the scale applied to S;
     P rounded to bf16 before P@V; output rounded to bf16."""
     b, s, nh, d = q.shape
@@ -165,6 +168,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mode: str) -> t
     qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
     scores = torch.matmul(qt, kt.transpose(-1, -2)) / math.sqrt(d)
     mask = torch.full((s, s), float("-inf"), device=q.device).triu(1)
+    if mask_start is not None:
+        rows = torch.arange(s, device=q.device)[None, :, None]                       # [1, s(row), 1]
+        hidden = rows >= mask_start.to(q.device)[:, None, :]                         # [b, row, col]
+        mask = mask[None].expand(b, s, s).masked_fill(hidden, float("-inf"))[:, None]
     p = torch.softmax(scores + mask, dim=-1)
     p = rnd(p, mode)
     out = torch.matmul(p, vt).transpose(1, 2).reshape(b, s, nh * d)
@@ -183,7 +190,7 @@ def swiglu(g: torch.Tensor, u: torch.Tensor, mode: str) -> torch.Tensor:
 
 
 def decoder_layer(x: torch.Tensor, w: Dict[str, torch.Tensor], p: str, cfg: RefConfig, cos, sin, mode: str,
-                  position_ids=None, capture: Optional[dict] = None) -> torch.Tensor:
+                  position_ids=None, capture: Optional[dict] = None, mask_start=None) -> torch.Tensor:
     b, s, h = x.shape
     nh, kvh, d = cfg.num_attention_heads, cfg.num_key_value_heads, cfg.head_dim
     n1 = rms_norm(x, w[p + "input_layernorm.weight"], cfg.rms_norm_eps, mode)
@@ -192,7 +199,7 @@ def decoder_layer(x: torch.Tensor, w: Dict[str, torch.Tensor], p: str, cfg: RefC
     v = linear(n1, w[p + "self_attn.v_proj.weight"], w.get(p + "self_attn.v_proj.bias"), mode).reshape(b, s, kvh, d)
     q = apply_rope(q, cos, sin, mode, position_ids)
     k = apply_rope(k, cos, sin, mode, position_ids)
-    a = attention(q, k, v, mode)
+    a = attention(q, k, v, mode, mask_start=mask_start)
     o = linear(a, w[p + "self_attn.o_proj.weight"], None, mode)
     x1 = rnd(x + o, mode)
     n2 = rms_norm(x1, w[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps, mode)

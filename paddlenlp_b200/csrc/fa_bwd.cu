@@ -36,6 +36,7 @@ struct Params {
   float scale, scale_log2;
   const float* lse;     // [B, nh, S]  natural log
   const float* delta;   // [B, nh, S]  rowsum(dO o O)
+  const int* mask_start;   // FlashMask causal-LT start rows [B, S] (see fa_fwd.cu) or nullptr
 };
 
 // TMEM accumulator (this warp's 32 lanes, fp32 columns [32*ch0, 32*(ch0+nch))) -> fp32 staging -> TMA reduce-add of
@@ -90,9 +91,18 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int jt = static_cast<int>(blockIdx.x);     // kv tile; tile 0 has the most work and is scheduled first
   const int hq = blockIdx.y, batch = blockIdx.z;
   const int kv_head = hq / (p.nh / p.kvh);
-  const int n_q = num_tiles - jt;                  // q tiles jt .. num_tiles-1
-  const int n_iter = n_q;
   const int kv0 = jt * 128;
+  // q tiles jt .. hi-1: with a document mask, q tiles that start at or after the end of the last document of this kv tile
+  // see none of its columns (mask_start is non-decreasing; the diagonal tile always remains)
+  int hi = num_tiles;
+  if (p.mask_start != nullptr)
+    hi = min(num_tiles, (__ldg(p.mask_start + static_cast<size_t>(batch) * p.S + min(kv0 + 127, p.S - 1)) + 127) / 128);
+  const int n_iter = hi - jt;
+  __shared__ int s_start[128];                     // mask start row of each column of this kv tile
+  if (threadIdx.x < 128) {
+    const int c = kv0 + static_cast<int>(threadIdx.x);
+    s_start[threadIdx.x] = (p.mask_start != nullptr && c < p.S) ? p.mask_start[static_cast<size_t>(batch) * p.S + c] : 0x7fffffff;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
@@ -182,6 +192,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const float lse2 = row_ok ? p.lse[stat_idx] * 1.4426950408889634f : 0.f;
       const float drow = row_ok ? p.delta[stat_idx] : 0.f;
       const bool diag = (qt == jt);
+      const bool mtile = (p.mask_start != nullptr) && (q0 + 127 >= s_start[0]);   // some column's document ends in / before this q tile
+      const int qrow = q0 + r;
       mbar_wait(s_full, n & 1);
       tc_fence_after();
 #pragma unroll
@@ -196,8 +208,8 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           const int col = ch * 32 + 2 * c;
           float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * c]), p.scale_log2, -lse2));
           float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * c + 1]), p.scale_log2, -lse2));
-          if (!row_ok || (diag && col > r)) p0 = 0.f;
-          if (!row_ok || (diag && col + 1 > r)) p1 = 0.f;
+          if (!row_ok || (diag && col > r) || (mtile && qrow >= s_start[col])) p0 = 0.f;
+          if (!row_ok || (diag && col + 1 > r) || (mtile && qrow >= s_start[col + 1])) p1 = 0.f;
           const float d0 = p0 * (__uint_as_float(dv[2 * c]) - drow) * p.scale;
           const float d1 = p1 * (__uint_as_float(dv[2 * c + 1]) - drow) * p.scale;
           pp[c] = pack_bf16x2(p0, p1);
@@ -306,6 +318,15 @@ extern "C" int b200_fa_bwd(const void* q, const void* k, const void* v, const vo
                            int64_t num_kv_heads, int64_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
                            int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv, float softmax_scale,
                            cudaStream_t stream) {
+  return b200_fa_bwd_flashmask(q, k, v, o, dout, lse, nullptr, dq, dk, dv, workspace, B, S, num_heads, num_kv_heads, head_dim,
+                               ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, softmax_scale, stream);
+}
+
+extern "C" int b200_fa_bwd_flashmask(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                                     const float* lse, const int32_t* mask_start_rows, void* dq, void* dk, void* dv,
+                                     void* workspace, int64_t B, int64_t S, int64_t num_heads, int64_t num_kv_heads,
+                                     int64_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo,
+                                     int64_t lddq, int64_t lddk, int64_t lddv, float softmax_scale, cudaStream_t stream) {
   using namespace b200;
   using namespace b200::fab;
   B200_CHECK_ARG(q && k && v && o && dout && lse && dq && dk && dv && workspace, "fa_bwd: null pointer");
@@ -354,6 +375,7 @@ extern "C" int b200_fa_bwd(const void* q, const void* k, const void* v, const vo
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.lse = lse; p.delta = delta;
+  p.mask_start = mask_start_rows;
   dim3 grid(static_cast<unsigned>((S + 127) / 128), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
   fa_bwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p);
   if ((rc = check_launch("fa_bwd")) != 0) return rc;

@@ -36,6 +36,10 @@ struct Params {
   int S, B, nh, kvh;
   float scale_log2;   // (1/sqrt(d)) * log2(e)
   float* lse;         // [B, nh, S]
+  // FlashMask, causal lower-triangular form (fusion_ops.py:218-231 -> F.flashmask_attention(startend_row_indices, causal=True)):
+  // mask_start[b, c] = first query row that may NOT see key column c (the end of c's packed document, llm/utils/data.py:
+  // 200-204 + zero_padding_dataset.py:84-86); non-decreasing in c.  nullptr = plain causal.
+  const int* mask_start;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -66,7 +70,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int head = blockIdx.y, batch = blockIdx.z;
   const int kv_head = head / (p.nh / p.kvh);
   const int q0 = qt * BQ;
-  const int n_kv = qt + 1;
+  // kv tiles j_lo .. qt.  With a document mask the leading tiles whose every column belongs to a document that ended at or
+  // before this q tile are skipped (mask_start is non-decreasing, so they form a prefix; the diagonal tile is never empty).
+  int j_lo = 0;
+  if (p.mask_start != nullptr) {
+    const int* ms = p.mask_start + static_cast<size_t>(batch) * p.S;
+    while (j_lo < qt && __ldg(ms + min(j_lo * BKV + BKV - 1, p.S - 1)) <= q0) ++j_lo;
+  }
+  const int n_kv = qt + 1 - j_lo;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
@@ -98,12 +109,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&k_empty[st], ph ^ 1u);
         mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
-        tma_load_4d(&tmK, &k_full[st], sK + st * TILE_BYTES, 0, kv_head, j * BKV, batch);
-        tma_load_4d(&tmK, &k_full[st], sK + st * TILE_BYTES + HALF_BYTES, 64, kv_head, j * BKV, batch);
+        tma_load_4d(&tmK, &k_full[st], sK + st * TILE_BYTES, 0, kv_head, (j_lo + j) * BKV, batch);
+        tma_load_4d(&tmK, &k_full[st], sK + st * TILE_BYTES + HALF_BYTES, 64, kv_head, (j_lo + j) * BKV, batch);
         mbar_wait(&v_empty[st], ph ^ 1u);
         mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
-        tma_load_4d(&tmV, &v_full[st], sV + st * TILE_BYTES, 0, kv_head, j * BKV, batch);
-        tma_load_4d(&tmV, &v_full[st], sV + st * TILE_BYTES + HALF_BYTES, 64, kv_head, j * BKV, batch);
+        tma_load_4d(&tmV, &v_full[st], sV + st * TILE_BYTES, 0, kv_head, (j_lo + j) * BKV, batch);
+        tma_load_4d(&tmV, &v_full[st], sV + st * TILE_BYTES + HALF_BYTES, 64, kv_head, (j_lo + j) * BKV, batch);
       }
     }
   } else if (warp == 1) {
@@ -179,11 +190,22 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       // causal mask on the diagonal tile, row max over this thread's 64 columns (raw scores; the positive softmax
       // scale is folded into the exponent below as one FFMA per element)
       float rowmax = -INFINITY;
-      const bool diag = (j == qt);
+      const int jg = j_lo + j;                            // global kv tile index
+      const bool diag = (jg == qt);
       if (diag) {
 #pragma unroll
         for (int c = 0; c < 64; ++c)
           if ((chalf * 64 + c) > r) sv[c] = 0xff800000u;   // -inf
+      }
+      if (p.mask_start != nullptr) {
+        const int* ms = p.mask_start + static_cast<size_t>(batch) * p.S + jg * BKV;
+        if (__ldg(ms) <= q0 + BQ - 1) {                   // some document in this kv tile ends inside / before the q tile
+          const int row = q0 + r;
+          const int cmax = p.S - jg * BKV - chalf * 64;   // columns of this half that exist
+#pragma unroll 8
+          for (int c = 0; c < 64; ++c)
+            if (c < cmax && row >= __ldg(ms + chalf * 64 + c)) sv[c] = 0xff800000u;
+        }
       }
 #pragma unroll
       for (int c = 0; c < 64; ++c) rowmax = fmaxf(rowmax, __uint_as_float(sv[c]));
@@ -207,7 +229,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
       uint32_t pk[32];
       float rs = 0.f;
-      const float neg_m = -m_used;
+      const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;   // a row can be fully masked in its first tiles (documents)
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * c]), p.scale_log2, neg_m));
@@ -299,6 +321,14 @@ static int make_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S, int
 extern "C" int b200_fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int64_t B, int64_t S,
                            int64_t num_heads, int64_t num_kv_heads, int64_t head_dim, int64_t ldq, int64_t ldk,
                            int64_t ldv, int64_t ldo, float softmax_scale, cudaStream_t stream) {
+  return b200_fa_fwd_flashmask(q, k, v, o, lse, nullptr, B, S, num_heads, num_kv_heads, head_dim, ldq, ldk, ldv, ldo,
+                               softmax_scale, stream);
+}
+
+extern "C" int b200_fa_fwd_flashmask(const void* q, const void* k, const void* v, void* o, float* lse,
+                                     const int32_t* mask_start_rows, int64_t B, int64_t S, int64_t num_heads,
+                                     int64_t num_kv_heads, int64_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv,
+                                     int64_t ldo, float softmax_scale, cudaStream_t stream) {
   using namespace b200;
   using namespace b200::fa;
   B200_CHECK_ARG(q && k && v && o && lse, "fa_fwd: null pointer");
@@ -327,6 +357,7 @@ extern "C" int b200_fa_fwd(const void* q, const void* k, const void* v, void* o,
   p.kvh = static_cast<int>(num_kv_heads);
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.lse = lse;
+  p.mask_start = mask_start_rows;
   dim3 grid(static_cast<unsigned>((S + BQ - 1) / BQ), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
   fa_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   return check_launch("fa_fwd");

@@ -243,9 +243,18 @@ def _tok_stride(t: torch.Tensor, heads: int, d: int) -> int:
     return ld
 
 
+def _mask_rows(mask_start, B, S):
+    if mask_start is None:
+        return None
+    _chk(mask_start, "mask_start", torch.int32)
+    assert mask_start.is_contiguous() and mask_start.numel() == B * S, "mask_start must be int32 [B, S]"
+    return mask_start
+
+
 def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: Optional[float] = None,
-                   out: Optional[torch.Tensor] = None):
+                   out: Optional[torch.Tensor] = None, mask_start: Optional[torch.Tensor] = None):
     """Causal GQA attention.  q [B,S,nh,128], k/v [B,S,kvh,128] (may be strided views of a packed QKV buffer).
+    mask_start [B,S] int32 (optional): FlashMask start rows — row i sees column c iff c <= i < mask_start[b, c].
     Returns (o [B,S,nh,128] contiguous, lse [B,nh,S] fp32)."""
     _chk(q, "q"); _chk(k, "k"); _chk(v, "v")
     B, S, nh, d = q.shape
@@ -255,12 +264,13 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_sc
     if out is None:
         out = torch.empty(B, S, nh, d, dtype=BF16, device=q.device)
     lse = torch.empty(B, nh, S, dtype=torch.float32, device=q.device)
-    call("b200_fa_fwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), B, S, nh, kvh, d, _tok_stride(q, nh, d),
-         _tok_stride(k, kvh, d), _tok_stride(v, kvh, d), _tok_stride(out, nh, d), float(softmax_scale), stream_ptr())
+    call("b200_fa_fwd_flashmask", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(_mask_rows(mask_start, B, S)), B, S, nh, kvh,
+         d, _tok_stride(q, nh, d), _tok_stride(k, kvh, d), _tok_stride(v, kvh, d), _tok_stride(out, nh, d),
+         float(softmax_scale), stream_ptr())
     return out, lse
 
 
-def flash_attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, softmax_scale: Optional[float] = None):
+def flash_attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, softmax_scale: Optional[float] = None, mask_start=None):
     """Gradients written into dq/dk/dv (views allowed, e.g. slices of a packed dQKV buffer)."""
     for name, t in (("q", q), ("k", k), ("v", v), ("o", o), ("dout", dout), ("dq", dq), ("dk", dk), ("dv", dv)):
         _chk(t, name)
@@ -270,8 +280,8 @@ def flash_attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, softmax_scale: Optional[fl
     if softmax_scale is None:
         softmax_scale = 1.0 / math.sqrt(d)
     ws = _workspace(_lib.load().b200_fa_bwd_workspace_bytes(B, S, nh, d), q.device, "fa_bwd")
-    call("b200_fa_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(dout), ptr(lse), ptr(dq), ptr(dk), ptr(dv), ptr(ws), B, S, nh,
-         kvh, d, _tok_stride(q, nh, d), _tok_stride(k, kvh, d), _tok_stride(v, kvh, d), _tok_stride(o, nh, d),
+    call("b200_fa_bwd_flashmask", ptr(q), ptr(k), ptr(v), ptr(o), ptr(dout), ptr(lse), ptr(_mask_rows(mask_start, B, S)),
+         ptr(dq), ptr(dk), ptr(dv), ptr(ws), B, S, nh, kvh, d, _tok_stride(q, nh, d), _tok_stride(k, kvh, d), _tok_stride(v, kvh, d), _tok_stride(o, nh, d),
          _tok_stride(dout, nh, d), _tok_stride(dq, nh, d), _tok_stride(dk, kvh, d), _tok_stride(dv, kvh, d),
          float(softmax_scale), stream_ptr())
     return dq, dk, dv

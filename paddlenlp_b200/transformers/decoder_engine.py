@@ -184,7 +184,7 @@ class DecoderEngine:
     # ------------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------------
-    def _layer_fwd(self, i: int, x: torch.Tensor, B: int, S: int, pos, save: Optional[list]):
+    def _layer_fwd(self, i: int, x: torch.Tensor, B: int, S: int, pos, save: Optional[list], mask=None):
         T = B * S
         p = self.p
         n1, rstd1 = ops.rmsnorm_fwd(x, p[f"l{i}.ln1"], self.eps)
@@ -196,7 +196,7 @@ class DecoderEngine:
         q = q4[:, :, :qn].unflatten(2, (self.nh, self.d))
         k = q4[:, :, qn:qn + kn].unflatten(2, (self.kvh, self.d))
         v = q4[:, :, qn + kn:].unflatten(2, (self.kvh, self.d))
-        attn, lse = ops.flash_attn_fwd(q, k, v)
+        attn, lse = ops.flash_attn_fwd(q, k, v, mask_start=mask)
         attn2 = attn.view(T, qn)
         x1 = ops.gemm(attn2, p[f"l{i}.o_w"], residual=x)
         n2, rstd2 = ops.rmsnorm_fwd(x1, p[f"l{i}.ln2"], self.eps)
@@ -220,33 +220,50 @@ class DecoderEngine:
         self._rope_tables(need)
         return B, S, ids, pos
 
-    def hidden_states(self, input_ids, position_ids=None, save: Optional[list] = None):
+    def _prep_mask(self, attn_mask_startend_row_indices, B: int, S: int):
+        """FlashMask start rows -> int32 [B, S] on the device, in the kernels' canonical form: every column is visible at least
+        to its own row.  The reference right-pads the indices with 0 (tokenizer_utils_base.py:3256-3264: padding columns hidden
+        from every row, which leaves the padding rows with an empty softmax); here a padding column becomes a one-token
+        document — same result for every real token, finite values on the (label -100) padding rows."""
+        if attn_mask_startend_row_indices is None:
+            return None
+        ms = attn_mask_startend_row_indices.to(device=self.device, dtype=torch.int32, non_blocking=True).reshape(B, S)
+        own = torch.arange(1, S + 1, dtype=torch.int32, device=self.device)
+        return torch.maximum(ms, own[None, :]).contiguous()
+
+    def hidden_states(self, input_ids, position_ids=None, save: Optional[list] = None, attn_mask_startend_row_indices=None):
         """Embedding + decoder stack + final norm -> ([T, h] normed states, pre-norm states, rstd)."""
         B, S, ids, pos = self._prep_inputs(input_ids, position_ids)
+        mask = self._prep_mask(attn_mask_startend_row_indices, B, S)
+        self._mask = mask
         x = ops.embedding_fwd(ids, self.p["embed"])
         for i in range(self.L):
-            x = self._layer_fwd(i, x, B, S, pos, save)
+            x = self._layer_fwd(i, x, B, S, pos, save, mask)
         hf, rstd_f = ops.rmsnorm_fwd(x, self.p["norm"], self.eps)
         return B, S, ids, pos, x, hf, rstd_f
 
     @torch.no_grad()
-    def forward_logits(self, input_ids, position_ids=None) -> torch.Tensor:
+    def forward_logits(self, input_ids, position_ids=None, attn_mask_startend_row_indices=None) -> torch.Tensor:
         """Inference forward: logits [B, S, V] (bf16).  Nothing is saved for backward."""
-        B, S, ids, pos, x, hf, _ = self.hidden_states(input_ids, position_ids, save=None)
+        B, S, ids, pos, x, hf, _ = self.hidden_states(input_ids, position_ids, save=None,
+                                                      attn_mask_startend_row_indices=attn_mask_startend_row_indices)
         logits = ops.gemm(hf, self.p["head"])
         return logits.view(B, S, self.V)
 
     @torch.no_grad()
-    def forward_loss(self, input_ids, labels, position_ids=None, ignore_index: int = -100, keep_for_backward=True):
+    def forward_loss(self, input_ids, labels, position_ids=None, ignore_index: int = -100, keep_for_backward=True,
+                     attn_mask_startend_row_indices=None):
         """Training forward: returns loss_out (device [2] = masked-mean loss, token count).
-        Activations are kept for backward()."""
+        Activations are kept for backward().  attn_mask_startend_row_indices [B, S]: FlashMask start rows of packed
+        samples (llama/modeling.py:1588-1774 forwards it to every layer's attention)."""
         save: Optional[list] = [] if keep_for_backward else None
-        B, S, ids, pos, x, hf, rstd_f = self.hidden_states(input_ids, position_ids, save=save)
+        B, S, ids, pos, x, hf, rstd_f = self.hidden_states(input_ids, position_ids, save=save,
+                                                           attn_mask_startend_row_indices=attn_mask_startend_row_indices)
         logits = ops.gemm(hf, self.p["head"])
         lab = labels.to(device=self.device, dtype=torch.int64, non_blocking=True).contiguous().view(-1)
         loss_out, loss_tok, lse = ops.ce_fwd(logits, lab, ignore_index)
         if keep_for_backward:
-            self._saved = dict(B=B, S=S, ids=ids, pos=pos, layers=save, x_last=x, hf=hf, rstd_f=rstd_f, logits=logits,
+            self._saved = dict(B=B, S=S, ids=ids, pos=pos, mask=self._mask, layers=save, x_last=x, hf=hf, rstd_f=rstd_f, logits=logits,
                                labels=lab, loss_tok=loss_tok, lse=lse, loss_out=loss_out)
         return loss_out, logits.view(B, S, self.V)
 
@@ -274,14 +291,14 @@ class DecoderEngine:
         del dhf
         layers = st["layers"]
         for i in range(self.L - 1, -1, -1):
-            dx = self._layer_bwd(i, dx, layers[i], B, S, st["pos"], acc)
+            dx = self._layer_bwd(i, dx, layers[i], B, S, st["pos"], acc, st.get("mask"))
             layers[i] = None
         if not acc:
             g["embed"].zero_()
         ops.embedding_bwd(st["ids"], dx, g["embed"])
         self.grads_fresh = False
 
-    def _layer_bwd(self, i, dx2, saved, B, S, pos, acc):
+    def _layer_bwd(self, i, dx2, saved, B, S, pos, acc, mask=None):
         (x, rstd1, n1, qkv, attn2, lse, x1, rstd2, n2, gu, m) = saved
         p, g = self.p, self.g
         T = B * S
@@ -309,7 +326,8 @@ class DecoderEngine:
         dq = d4[:, :, :qn].unflatten(2, (self.nh, self.d))
         dk = d4[:, :, qn:qn + kn].unflatten(2, (self.kvh, self.d))
         dv = d4[:, :, qn + kn:].unflatten(2, (self.kvh, self.d))
-        ops.flash_attn_bwd(q, k, v, attn2.view(B, S, self.nh, self.d), dattn.view(B, S, self.nh, self.d), lse, dq, dk, dv)
+        ops.flash_attn_bwd(q, k, v, attn2.view(B, S, self.nh, self.d), dattn.view(B, S, self.nh, self.d), lse, dq, dk, dv,
+                           mask_start=mask)
         del dattn, attn2, qkv, q, k, v, q4
         cos, sin = self._rope
         ops.rope_inplace(dqkv, cos, sin, S, self.nh + self.kvh, self.d, position_ids=pos, backward=True)

@@ -121,39 +121,48 @@ def fusion_rope(query_states, key_states, value_states, hidden_states, position_
 # ----------------------------------------------------------------------------------------------------------
 class _FlashAttnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, scale):
+    def forward(ctx, q, k, v, scale, mask_rows=None):
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
-        o, lse = ops.flash_attn_fwd(q, k, v, scale)
+        o, lse = ops.flash_attn_fwd(q, k, v, scale, mask_start=mask_rows)
         ctx.save_for_backward(q, k, v, o, lse)
         ctx.scale = scale
+        ctx.mask_rows = mask_rows
         return o
 
     @staticmethod
     def backward(ctx, do):
         q, k, v, o, lse = ctx.saved_tensors
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-        ops.flash_attn_bwd(q, k, v, o, do.contiguous(), lse, dq, dk, dv, ctx.scale)
-        return dq, dk, dv, None
+        ops.flash_attn_bwd(q, k, v, o, do.contiguous(), lse, dq, dk, dv, ctx.scale, mask_start=ctx.mask_rows)
+        return dq, dk, dv, None, None
 
 
 def fusion_flash_attention(query_states, config, key_states, value_states, attention_mask, output_attentions, alibi=None,
                            attn_mask_startend_row_indices=None, sequence_parallel=False, reshard_layer=None,
                            npu_is_casual=False):
     """Causal GQA flash attention; q [b, s, nh, d], k/v [b, s, kvh, d] -> [b, s, nh*d] (or [b*s, nh*d] under
-    `sequence_parallel`, fusion_ops.py:262-265).  The pre-training path always passes attention_mask=None
-    (llama/modeling.py:1679-1699 with a causal mask); anything else is outside the hot path and rejected."""
+    `sequence_parallel`, fusion_ops.py:262-265).  The pre-training path passes attention_mask=None
+    (llama/modeling.py:1679-1699 with a causal mask); packed SFT samples pass `attn_mask_startend_row_indices`
+    (FlashMask); dense masks are outside the hot path and rejected."""
     bsz, q_len, num_heads, head_dim = query_states.shape
     if alibi is not None:
         raise NotImplementedError("alibi is not on the Llama-3 / Qwen2 path")
-    if attention_mask is not None or attn_mask_startend_row_indices is not None:
-        raise NotImplementedError("only the causal (attention_mask=None) flash path is built")
+    if attention_mask is not None:
+        raise NotImplementedError("dense attention masks are not built: causal, or causal + FlashMask start rows")
     if reshard_layer is not None:
         raise NotImplementedError("sep-parallel resharding is outside the data-parallel hot path")
     if output_attentions:
         raise ValueError("flash attention does not return attention weights (fusion_ops.py:209-212)")
     if head_dim != 128:
         raise ValueError(f"head_dim {head_dim} unsupported (128 only)")
-    out = _FlashAttnFn.apply(query_states, key_states, value_states, 1.0 / math.sqrt(head_dim))
+    mask_rows = None
+    if attn_mask_startend_row_indices is not None:
+        # fusion_ops.py:218-231: F.flashmask_attention(..., startend_row_indices=idx.unsqueeze(-1), causal=True); idx is
+        # [b, s] or [b, 1, s].  Canonical form for the kernels: every column visible at least to its own row.
+        idx = attn_mask_startend_row_indices.reshape(bsz, q_len).to(device=query_states.device, dtype=torch.int32)
+        own = torch.arange(1, q_len + 1, dtype=torch.int32, device=idx.device)
+        mask_rows = torch.maximum(idx, own[None, :]).contiguous()
+    out = _FlashAttnFn.apply(query_states, key_states, value_states, 1.0 / math.sqrt(head_dim), mask_rows)
     if sequence_parallel:
         return out.reshape(bsz * q_len, num_heads * head_dim)
     return out.reshape(bsz, q_len, num_heads * head_dim)

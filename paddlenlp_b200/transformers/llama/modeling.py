@@ -78,9 +78,11 @@ class LlamaModel(LlamaPretrainedModel):
 
     @torch.no_grad()
     def forward(self, input_ids=None, position_ids=None, attention_mask=None, inputs_embeds=None, use_cache=False,
-                past_key_values=None, output_attentions=False, output_hidden_states=None, return_dict=False, **kw):
+                past_key_values=None, output_attentions=False, output_hidden_states=None, return_dict=False,
+                attn_mask_startend_row_indices=None, **kw):
         _check_unsupported(attention_mask, inputs_embeds, use_cache, past_key_values, output_attentions)
-        B, S, _, _, _, hf, _ = self.engine.hidden_states(input_ids, position_ids)
+        B, S, _, _, _, hf, _ = self.engine.hidden_states(input_ids, position_ids,
+                                                         attn_mask_startend_row_indices=attn_mask_startend_row_indices)
         hs = hf.view(B, S, -1)
         if return_dict:
             return BaseModelOutputWithPastAndCrossAttentions(last_hidden_state=hs)
@@ -97,18 +99,17 @@ class LlamaForCausalLM(LlamaPretrainedModel):
                 use_cache=False, past_key_values=None, output_attentions=None, output_hidden_states=None,
                 return_dict=None, attn_mask_startend_row_indices=None, **kw):
         _check_unsupported(attention_mask, inputs_embeds, use_cache, past_key_values, output_attentions)
-        if attn_mask_startend_row_indices is not None:
-            raise NotImplementedError("FlashMask packing is a 'next' item (SURVEY.md §8f)")
+        ms = attn_mask_startend_row_indices         # FlashMask start rows of packed samples ([B, S] or [B, 1, S(, 1)])
         loss = None
         if labels is not None and torch.is_grad_enabled():
             loss, logits = _CausalLMLossFn.apply(self._anchor, self.engine, input_ids, labels, position_ids,
-                                                 self.criterion.ignore_index)
+                                                 self.criterion.ignore_index, ms)
         elif labels is not None:
             loss_out, logits = self.engine.forward_loss(input_ids, labels, position_ids, self.criterion.ignore_index,
-                                                        keep_for_backward=False)
+                                                        keep_for_backward=False, attn_mask_startend_row_indices=ms)
             loss = loss_out[0]
         else:
-            logits = self.engine.forward_logits(input_ids, position_ids)
+            logits = self.engine.forward_logits(input_ids, position_ids, attn_mask_startend_row_indices=ms)
         if return_dict:
             return CausalLMOutputWithCrossAttentions(loss=loss, logits=logits)
         return (loss, logits) if loss is not None else (logits,)

@@ -17,8 +17,9 @@ class _CausalLMLossFn(torch.autograd.Function):
     """Bridges `loss.backward()` (trainer.py:2243) to the engine's explicit backward."""
 
     @staticmethod
-    def forward(ctx, anchor, engine, input_ids, labels, position_ids, ignore_index):
-        loss_out, logits = engine.forward_loss(input_ids, labels, position_ids, ignore_index)
+    def forward(ctx, anchor, engine, input_ids, labels, position_ids, ignore_index, mask_rows=None):
+        loss_out, logits = engine.forward_loss(input_ids, labels, position_ids, ignore_index,
+                                               attn_mask_startend_row_indices=mask_rows)
         ctx.engine = engine
         ctx.mark_non_differentiable(logits)
         return loss_out[0].clone(), logits
@@ -27,7 +28,7 @@ class _CausalLMLossFn(torch.autograd.Function):
     def backward(ctx, gloss, _glogits):
         g = gloss.detach().to(torch.float32).reshape(1).contiguous()
         ctx.engine.backward(1.0, g)          # upstream scale stays on the device: no host sync
-        return None, None, None, None, None, None
+        return None, None, None, None, None, None, None
 
 
 class PretrainedModel(nn.Module):

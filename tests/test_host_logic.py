@@ -114,7 +114,7 @@ WORKER = textwrap.dedent("""
     lo, hi = D.shard_rows(16)
     assert (lo, hi) == (rank * 8, rank * 8 + 8)
     torch.distributed.barrier()
-    print("OK", rank)
+    print("OK " + str(rank), flush=True)      # one write per token: the two ranks' lines may interleave only at line ends
 """)
 
 
@@ -132,3 +132,33 @@ def test_data_parallel_exchange_world2_gloo(tmp_path):
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "OK 0" in r.stdout and "OK 1" in r.stdout
+
+
+def test_zero_padding_dataset_and_collator():
+    """Sample packing restated from paddlenlp/datasets/zero_padding_dataset.py and the right-padding collator."""
+    import torch
+
+    from paddlenlp_b200.data import DataCollatorForSeq2Seq
+    from paddlenlp_b200.datasets import ZeroPaddingMapDataset, generate_greedy_packs
+
+    def rec(n, base):
+        return {"input_ids": list(range(base, base + n)), "labels": [-100] * (n // 2) + list(range(n - n // 2)),
+                "position_ids": list(range(n)), "attn_mask_startend_row_indices": [n] * n}
+
+    data = [rec(5, 100), rec(4, 200), rec(20, 300), rec(3, 400), rec(6, 500)]       # the 20-token record exceeds max_length
+    ds = ZeroPaddingMapDataset(data, tokenizer=None, max_length=10)
+    assert len(ds) == 2
+    a, b = ds[0], ds[1]
+    assert a["input_ids"] == list(range(100, 105)) + list(range(200, 204))          # 5 + 4 fit, + 3 would overflow? no: 5+4+3 > 10
+    assert a["attn_mask_startend_row_indices"] == [5] * 5 + [9] * 4                 # each column -> end of its sample
+    assert a["position_ids"] == [0, 1, 2, 3, 4, 0, 1, 2, 3]
+    assert b["input_ids"] == list(range(400, 403)) + list(range(500, 506))
+    assert b["attn_mask_startend_row_indices"] == [3] * 3 + [9] * 6
+    packs = generate_greedy_packs([rec(6, 0), rec(5, 10), rec(4, 20), rec(3, 30), rec(2, 40)], 10)
+    assert sorted(sorted(len(r["input_ids"]) for r in p) for p in packs) == [[2], [3, 6], [4, 5]]
+    g = ZeroPaddingMapDataset(data, max_length=10, greedy_zero_padding=True)
+    assert sorted(len(x["input_ids"]) for x in g) == [9, 9]
+    batch = DataCollatorForSeq2Seq(max_length=12, pad_token_id=7)([a, b])
+    assert batch["input_ids"].shape == (2, 12) and batch["input_ids"][0, -1] == 7 and batch["labels"][0, -1] == -100
+    assert batch["attn_mask_startend_row_indices"].dtype == torch.int32
+    assert batch["attn_mask_startend_row_indices"][0].tolist() == [5] * 5 + [9] * 4 + [0] * 3

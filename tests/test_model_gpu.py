@@ -174,3 +174,73 @@ def test_causality_prefix_invariance():
         b = model(input_ids=ids2.to(DEV))[0]
     assert torch.equal(a[0, :130], b[0, :130])
     assert not torch.equal(a[0, 130:], b[0, 130:])
+
+
+@pytest.mark.parametrize("model_type", ["llama", "qwen2"])
+def test_flashmask_packing_invariance(model_type):
+    """Zero-padding (sample packing): three samples packed into one row with FlashMask start rows and per-sample
+    position ids, right-padded the reference's way (indices padded with 0), give the logits, loss and gradients of the same
+    samples run one by one.  Also checked against the oracle's masked attention end to end."""
+    from paddlenlp_b200.data import DataCollatorForSeq2Seq
+    from paddlenlp_b200.datasets import ZeroPaddingMapDataset
+
+    cfg = tiny_cfg(model_type)
+    w = make_weights(cfg)
+    model = build(cfg, w)
+    g = torch.Generator().manual_seed(11)
+    lens = [150, 37, 201]
+    recs = []
+    for n in lens:
+        ids = torch.randint(1, cfg.vocab_size, (n + 1,), generator=g)
+        lab = ids[1:].clone()
+        lab[: n // 3] = -100                                          # prompt tokens carry no loss (llm/utils/data.py:179-206)
+        recs.append({"input_ids": ids[:-1].tolist(), "labels": lab.tolist()})
+    packed = ZeroPaddingMapDataset(recs, max_length=512)
+    assert len(packed) == 1
+    batch = DataCollatorForSeq2Seq(max_length=512, pad_token_id=0)([packed[0]])
+    assert batch["attn_mask_startend_row_indices"][0, 149] == 150 and batch["attn_mask_startend_row_indices"][0, 400] == 0
+    dev = {k: v.to(DEV) for k, v in batch.items()}
+
+    # packed run
+    model.engine.clear_grad()
+    loss, logits = model(**dev)
+    logits = logits.clone()                                           # backward() reuses the logits buffer for dlogits
+    loss.backward()
+    g_packed = {k: v.clone() for k, v in model.engine.named_views(grads=True).items()}
+    n_valid = sum(int((torch.tensor(r["labels"]) != -100).sum()) for r in recs)
+
+    # the same samples one by one, gradients accumulated with the weights that make the sum the packed mean
+    model.engine.clear_grad()
+    start, loss_sum = 0, 0.0
+    for r in recs:
+        n = len(r["input_ids"])
+        ids = torch.tensor([r["input_ids"]]).to(DEV)
+        lab = torch.tensor([r["labels"]]).to(DEV)
+        nv = int((lab != -100).sum())
+        l1, lg1 = model(input_ids=ids, labels=lab)
+        lg1 = lg1.clone()
+        (l1 * (nv / n_valid)).backward()
+        loss_sum += float(l1.detach()) * nv
+        seg = logits[0, start:start + n].float()
+        assert maxerr(seg, lg1[0]) < 2e-2, (start, maxerr(seg, lg1[0]))
+        if start == 0:
+            assert torch.equal(logits[0, :n], lg1[0])                  # first sample: same tiles, same order -> same bits
+        start += n
+    assert abs(float(loss.detach()) - loss_sum / n_valid) < 2e-3 * abs(float(loss.detach()))
+    g_single = model.engine.named_views(grads=True)
+    pre = cfg.model_type
+    for k in (f"{pre}.layers.0.self_attn.q_proj.weight", f"{pre}.layers.1.self_attn.v_proj.weight",
+              f"{pre}.layers.0.mlp.down_proj.weight", f"{pre}.layers.1.input_layernorm.weight", "lm_head.weight"):
+        assert relerr(g_packed[k], g_single[k]) < 3e-2, (k, relerr(g_packed[k], g_single[k]))
+
+    # oracle with the same mask (bf16 rounding points): logits on the real tokens
+    ms = torch.maximum(batch["attn_mask_startend_row_indices"], torch.arange(1, 513, dtype=torch.int32)[None])
+    wd = {k: v.float() for k, v in w.items()}
+    cos, sin = R.rope_tables(cfg.hidden_size // cfg.num_attention_heads, cfg.max_position_embeddings, cfg.rope_theta)
+    x = wd[f"{pre}.embed_tokens.weight"][batch["input_ids"]]
+    for i in range(cfg.num_hidden_layers):
+        x = R.decoder_layer(x, wd, f"{pre}.layers.{i}.", cfg, cos, sin, "bf16", position_ids=batch["position_ids"], mask_start=ms)
+    ref = R.linear(R.rms_norm(x, wd[f"{pre}.norm.weight"], cfg.rms_norm_eps, "bf16"), wd["lm_head.weight"], None, "bf16")
+    real = sum(lens)
+    e = maxerr(logits[0, :real].cpu(), ref[0, :real])
+    assert e < 3e-2, e

@@ -231,6 +231,53 @@ def test_flash_attention_fwd_bwd(B, S, nh, kvh):
     assert relerr(dv, vf.grad) < 2e-2
 
 
+def _doc_mask(doc_lens, S):
+    """FlashMask start rows of packed documents: column c -> end of c's document (zero_padding_dataset.py:84-86)."""
+    ms = torch.empty(S, dtype=torch.int32)
+    pos = 0
+    for n in doc_lens:
+        ms[pos:pos + n] = pos + n
+        pos += n
+    assert pos == S
+    return ms
+
+
+@pytest.mark.parametrize("S,nh,kvh,docs", [(384, 2, 1, [[100, 284], [128, 128, 128]]), (1024, 4, 2, [[1, 700, 323]]),
+                                           (200, 2, 2, [[7, 57, 136]]), (640, 1, 1, [[256, 1, 383], [640]])])
+def test_flash_attention_flashmask(S, nh, kvh, docs):
+    """Packed-document (FlashMask causal-LT) attention, forward and backward, vs the oracle's masked softmax; a row of
+    [S]*S start rows is plain causal.  Document boundaries on and off the 128-row tile grid, 1-token documents."""
+    o = ops()
+    B, d = len(docs), 128
+    ms = torch.stack([_doc_mask(dl, S) for dl in docs])
+    ld = (nh + 2 * kvh) * d
+    qkv = rand_bf16(B, S, ld, seed=31).to(DEV)
+    q = qkv[:, :, : nh * d].view(B, S, nh, d)
+    k = qkv[:, :, nh * d: (nh + kvh) * d].view(B, S, kvh, d)
+    v = qkv[:, :, (nh + kvh) * d:].view(B, S, kvh, d)
+    out, lse = o.flash_attn_fwd(q, k, v, mask_start=ms.to(DEV))
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ref = R.attention(qf, kf, vf, "fp32", mask_start=ms)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert maxerr(out.reshape(B, S, -1), ref.detach()) < 1.5e-2
+    dout = rand_bf16(B, S, nh, d, seed=32).to(DEV)
+    ref.backward(dout.float().reshape(B, S, -1))
+    dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+    o.flash_attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, mask_start=ms.to(DEV))
+    for name, a, r in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        assert relerr(a, r) < 2e-2, (name, relerr(a, r))
+    # packing invariance: the first document alone gives the same bits for its rows (same tiles, same order)
+    n0 = docs[0][0]
+    if n0 >= 2:
+        solo, _ = o.flash_attn_fwd(q[:1, :n0].contiguous(), k[:1, :n0].contiguous(), v[:1, :n0].contiguous())
+        assert torch.equal(solo, out[:1, :n0])
+    # mask_start = S everywhere == no mask
+    full = torch.full((B, S), S, dtype=torch.int32, device=DEV)
+    a, la = o.flash_attn_fwd(q, k, v, mask_start=full)
+    b, lb = o.flash_attn_fwd(q, k, v)
+    assert torch.equal(a, b) and torch.equal(la, lb)
+
+
 # ------------------------------------------------------------------------------------------------
 def test_cross_entropy():
     o = ops()
