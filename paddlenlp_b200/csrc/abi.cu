@@ -35,6 +35,8 @@ int check_launch(const char* what) {
 
 static int g_pdl = 0;
 bool pdl_enabled() { return g_pdl != 0; }
+static int g_skinny_impl = 1;
+int skinny_gemm_impl() { return g_skinny_impl; }
 
 int sm_count() {
   static int cached[64];
@@ -115,6 +117,12 @@ int b200_abi_version(void) { return B200NLP_ABI_VERSION; }
 int b200_set_pdl(int enable) {
   int old = b200::g_pdl;
   b200::g_pdl = enable ? 1 : 0;
+  return old;
+}
+
+int b200_set_skinny_gemm(int impl) {
+  int old = b200::g_skinny_impl;
+  b200::g_skinny_impl = impl ? 1 : 0;
   return old;
 }
 

@@ -1,0 +1,258 @@
+// Weight-streaming GEMM for the decode step (M <= 128 token rows): swapped operands, two CTAs per SM.
+//
+//   ws[M, N] (fp32, zero on entry) += X[M, K] * W[K, N]        X bf16 [tokens, K];  W bf16 [K, N] or [N, K] ("trans_b")
+//
+// Same contract as epilogue mode 3 of gemm_tcgen05.cu (b200_gemm_bf16_splitk): the consumer kernel rounds the fp32 sums once.
+// Why a second kernel: with 64 token rows the 128x256 tile of the training GEMM wastes half of every UMMA and needs ~200 KB
+// of shared memory per CTA, so consecutive GEMMs of the decode chain can never overlap (one CTA per SM, ~7 us of prologue /
+// ramp / drain per 12-30 us kernel).  Here the WEIGHT tile is the 128-row M operand and the tokens are the N operand:
+//   S^T-style tile  acc[128 features, NT tokens] = W_tile^T (128 x 64k)  x  X_tile^T (64k x NT),  NT = 64 or 128
+//   stage = 16 KB of weights + NT*128 B of activations -> 96 KB ring, 64/128 TMEM columns: two CTAs per SM, so under
+//   programmatic dependent launch the next GEMM is resident, has its weight tiles in flight and the rest of its slice
+//   prefetched to L2 while the previous kernels of the chain are still draining;
+//   K is split over CTAs (work item = feature tile x K range), partial tiles leave through per-warp transposed fp32
+//   staging (reusing the drained ring) and TMA reduce-add into the [tokens, N] workspace.
+#include "../../include/b200nlp.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+namespace skinny {
+
+constexpr int BF = 128;    // output features per work item (UMMA M)
+constexpr int BK = 64;     // k per stage (one 128-byte swizzle row)
+constexpr int UK = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int W_BYTES = BF * BK * 2;   // 16 KB
+
+template <int NT>
+struct Cfg {
+  static constexpr int X_BYTES = NT * BK * 2;
+  static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
+  static constexpr int STAGES = (NT == 64) ? 4 : 3;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;              // 96 KB
+  static constexpr int SMEM_BYTES = RING_BYTES + 256 + 1024;
+  static_assert(4 * NT * 32 * 4 <= RING_BYTES, "epilogue staging must fit in the drained ring");
+};
+
+struct Params {
+  int M, N, K;
+  int split_k, kb_per_split;
+  int w_prefetch;       // PDL: weight tiles of the first stages are loaded before griddepcontrol.wait
+  int l2_prefetch_kb;   // PDL: further weight k-blocks prefetched into L2 before the wait
+};
+
+template <int NT, bool W_KMAJOR>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                   const __grid_constant__ CUtensorMap tmF, const Params p) {
+  using C = Cfg<NT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;    // [STAGES]
+  uint64_t* acc_full = bars + 2 * C::STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x;
+  const int f_tile = item / p.split_k, split = item - f_tile * p.split_k;
+  const int f0 = f_tile * BF;
+  const int num_kb_total = (p.K + BK - 1) / BK;
+  const int kb0 = split * p.kb_per_split;
+  const int nkb = min(num_kb_total, kb0 + p.kb_per_split) - kb0;      // >= 1 by construction
+  pdl_launch_dependents();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmF);
+    for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_ptr_smem, NT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      auto load_w = [&](int s, int kb) {
+        uint8_t* sw = smem + s * C::STAGE_BYTES;
+        const int k0 = kb * BK;
+        if constexpr (W_KMAJOR) {
+          tma_load_2d(&tmW, &full_bar[s], sw, k0, f0);                      // [128 features x 64 k], k contiguous
+        } else {
+          tma_load_2d(&tmW, &full_bar[s], sw, f0, k0);                      // two [64 k x 64 features] boxes
+          tma_load_2d(&tmW, &full_bar[s], sw + 64 * BK * 2, f0 + 64, k0);
+        }
+      };
+      int pre = 0;
+      if (p.w_prefetch) {
+        // the weights do not depend on the previous kernel: put them in flight (and the rest of the slice into L2) first
+        pre = min(C::STAGES, nkb);
+        for (int s = 0; s < pre; ++s) {
+          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          load_w(s, kb0 + s);
+        }
+        const int l2_end = min(nkb, pre + p.l2_prefetch_kb);
+        for (int s = pre; s < l2_end; ++s) {
+          const int k0 = (kb0 + s) * BK;
+          if constexpr (W_KMAJOR) {
+            tma_prefetch_l2_2d(&tmW, k0, f0);
+          } else {
+            tma_prefetch_l2_2d(&tmW, f0, k0);
+            tma_prefetch_l2_2d(&tmW, f0 + 64, k0);
+          }
+        }
+      }
+      pdl_wait();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        if (i >= pre) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          load_w(stage, kb0 + i);
+        }
+        tma_load_2d(&tmX, &full_bar[stage], smem + stage * C::STAGE_BYTES + W_BYTES, (kb0 + i) * BK, 0);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BF, NT, !W_KMAJOR, false);
+      constexpr uint32_t w_lbo = W_KMAJOR ? 16 : 64 * BK * 2, w_adv = W_KMAJOR ? UK * 2 : UK * 128;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sw = smem_u32(smem + stage * C::STAGE_BYTES);
+        const uint32_t sx = sw + W_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UK; ++k)
+          umma_ss<1>(tmem_base, umma_desc_sw128(sw + k * w_adv, w_lbo, 1024), umma_desc_sw128(sx + k * UK * 2, 16, 1024),
+                     idesc, (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ===================================== epilogue =====================================
+    pdl_wait();                                   // the workspace belongs to the previous kernels until now
+    const int q = warp & 3;                       // TMEM lane quadrant: features f0 + 32q .. +31
+    mbar_wait(acc_full, 0);                       // every MMA has completed: all TMA loads landed, the ring is free
+    tc_fence_after();
+    uint8_t* stage_buf = smem + q * (NT * 32 * 4);
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if (f0 + q * 32 < p.N) {
+#pragma unroll
+      for (int ch = 0; ch < NT / 32; ++ch) {
+        if (ch * 32 >= p.M) break;                // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        // transpose through smem: staging row = token, 32 features (128 B) per row, 128B-swizzled like the fp32 tensor map
+        const uint32_t base = smem_u32(stage_buf + ch * 4096) + (lane & 3) * 4;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const uint32_t addr = base + t * 128 + ((((lane >> 2) ^ (t & 7))) << 4);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v[t]) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tmF, stage_buf + ch * 4096, f0 + q * 32, ch * 32);
+          tma_store_commit();
+        }
+      }
+      if (lane == 0) tma_store_wait<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, NT);
+  }
+}
+
+template <int NT, bool W_KMAJOR>
+static int launch(const CUtensorMap& tmW, const CUtensorMap& tmX, const CUtensorMap& tmF, Params p, int items,
+                  cudaStream_t stream) {
+  using C = Cfg<NT>;
+  auto kern = gemm_skinny_kernel<NT, W_KMAJOR>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(gemm_skinny smem=%d): %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  p.w_prefetch = pdl_enabled() ? 1 : 0;
+  // at most ~64 MB of weights parked in L2 ahead of the loads
+  const long long per_kb = static_cast<long long>(W_BYTES) * items;
+  const long long kbs = (64ll << 20) / per_kb;
+  p.l2_prefetch_kb = p.w_prefetch ? static_cast<int>(kbs > 64 ? 64 : kbs) : 0;
+  cudaError_t e = launch_pdl(kern, dim3(static_cast<unsigned>(items)), dim3(NUM_THREADS), C::SMEM_BYTES, stream, tmW, tmX, tmF, p);
+  if (e != cudaSuccess) {
+    set_last_error("gemm_skinny launch: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return check_launch("gemm_skinny");
+}
+
+// ws[M, N] += X[M, K] W ; returns 0 or an error code.  Called by b200_gemm_bf16_splitk for the decode-step shapes.
+int gemm_skinny_f32(const void* X, const void* W, void* workspace, int64_t M, int64_t N, int64_t K, int64_t ldx, int64_t ldw,
+                    bool w_kmajor, int split_k, cudaStream_t stream) {
+  if (!(M > 0 && M <= 128 && N > 0 && K > 0 && N % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0))
+    return fail_arg("gemm_skinny: need 0 < M <= 128, N %% 8 == 0, leading dimensions %% 8 == 0");
+  const int NT = M <= 64 ? 64 : 128;
+  CUtensorMap tmW, tmX, tmF;
+  int rc;
+  {
+    uint64_t dims[2], strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2];
+    if (w_kmajor) { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = BF; }     // W [N, K]
+    else          { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }     // W [K, N]
+    if ((rc = encode_tmap_bf16(&tmW, W, 2, dims, strides, box)) != 0) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldx) * 2};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(NT)};
+    if ((rc = encode_tmap_bf16(&tmX, X, 2, dims, strides, box)) != 0) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(N) * 4};
+    uint32_t box[2] = {32, 32};
+    if ((rc = encode_tmap_f32(&tmF, workspace, 2, dims, strides, box)) != 0) return rc;
+  }
+  Params p = {};
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  const int f_tiles = static_cast<int>((N + BF - 1) / BF);
+  const int num_kb = static_cast<int>((K + BK - 1) / BK);
+  if (split_k <= 0) {
+    // as many work items as fit in one wave of two CTAs per SM, each keeping >= 4 k-blocks
+    split_k = (2 * sm_count()) / f_tiles;
+    if (split_k > num_kb / 4) split_k = num_kb / 4;
+    if (split_k < 1) split_k = 1;
+  }
+  if (split_k > num_kb) split_k = num_kb;
+  p.kb_per_split = (num_kb + split_k - 1) / split_k;
+  p.split_k = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty ranges
+  const int items = f_tiles * p.split_k;
+  if (NT == 64) return w_kmajor ? launch<64, true>(tmW, tmX, tmF, p, items, stream) : launch<64, false>(tmW, tmX, tmF, p, items, stream);
+  return w_kmajor ? launch<128, true>(tmW, tmX, tmF, p, items, stream) : launch<128, false>(tmW, tmX, tmF, p, items, stream);
+}
+
+}  // namespace skinny
+}  // namespace b200

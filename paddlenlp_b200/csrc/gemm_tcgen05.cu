@@ -489,6 +489,10 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const fl
 }
 
 namespace b200 {
+namespace skinny {
+int gemm_skinny_f32(const void* X, const void* W, void* workspace, int64_t M, int64_t N, int64_t K, int64_t ldx, int64_t ldw,
+                    bool w_kmajor, int split_k, cudaStream_t stream);   // gemm_skinny.cu
+}
 namespace gemm {
 // out[m, n] = bf16(ws[m, n] + bias[n]) ; ws is re-zeroed for the next split-K GEMM that uses it
 __global__ void splitk_finish_kernel(float* __restrict__ ws, const float* __restrict__ bias, bf16* __restrict__ out,
@@ -529,6 +533,20 @@ extern "C" int b200_gemm_bf16_splitk(const void* A, const void* B, void* C, cons
   B200_CHECK_ARG(A && B && workspace, "gemm_splitk: null pointer");
   B200_CHECK_ARG(M > 0 && N > 0 && K > 0 && N % 8 == 0, "gemm_splitk: bad dimensions (N must be a multiple of 8)");
   B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0, "gemm_splitk: leading dimensions must be multiples of 8");
+  auto finish = [&]() -> int {
+    if (C == nullptr) return 0;   // C == NULL: the consumer kernel reads (and re-zeroes) the fp32 workspace itself
+    const int64_t total = M * (N / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    splitk_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<float*>(workspace), bias,
+                                                                           static_cast<bf16*>(C), M, N, ldc);
+    return check_launch("gemm_splitk(finish)");
+  };
+  if (!a_mn_major && M <= 128 && skinny_gemm_impl() == 1) {
+    // decode-step shapes: swapped-operand weight-streaming kernel, two CTAs per SM (gemm_skinny.cu)
+    int r = skinny::gemm_skinny_f32(A, B, workspace, M, N, K, lda, ldb, /*w_kmajor=*/!b_mn_major, split_k, stream);
+    return r ? r : finish();
+  }
   CUtensorMap tmA, tmB, tmC, tmF;
   int rc;
   {
@@ -578,13 +596,7 @@ extern "C" int b200_gemm_bf16_splitk(const void* A, const void* B, void* C, cons
   else if (a_mn_major) rc = launch<1, true, false>(tmA, tmB, tmC, tmF, p, 0, stream);
   else if (b_mn_major) rc = launch<1, false, true>(tmA, tmB, tmC, tmF, p, 0, stream);
   else rc = launch<1, false, false>(tmA, tmB, tmC, tmF, p, 0, stream);
-  if (rc || C == nullptr) return rc;   // C == NULL: the consumer kernel reads (and re-zeroes) the fp32 workspace itself
-  const int64_t total = M * (N / 8);
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  splitk_finish_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(static_cast<float*>(workspace), bias,
-                                                                         static_cast<bf16*>(C), M, N, ldc);
-  return check_launch("gemm_splitk(finish)");
+  return rc ? rc : finish();
 }
 
 extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N, int64_t K,

@@ -15,6 +15,7 @@ int fail_arg(const char* fmt, ...);   // records message, returns -1
 int check_launch(const char* what);  // cudaGetLastError() -> return code
 
 int sm_count();  // multiprocessors of the current device (cached per device)
+int skinny_gemm_impl();   // b200_set_skinny_gemm(): 1 = swapped-operand two-CTA/SM kernel (gemm_skinny.cu), 0 = the 128x256 persistent kernel
 bool pdl_enabled();   // b200_set_pdl(): launch GEMMs with programmatic dependent launch (decode-step kernel chains)
 
 // Launch `kern` on `stream`; when PDL is enabled the launch carries the programmatic-stream-serialization attribute, so the

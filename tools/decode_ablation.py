@@ -59,6 +59,7 @@ def main():
         return residual
 
     lib = _lib.load()
+    lib.b200_set_skinny_gemm(int(os.environ.get("B200_SKINNY", "1")))
     results = {}
     for t in (128, 1024, 2040):
         lens = torch.full((B,), t, dtype=torch.int32, device=dev)
