@@ -110,6 +110,9 @@ int b200_rope_inplace(void* x, const float* cos_table, const float* sin_table, c
 /* ---- SwiGLU on a packed [rows, 2*inter] = [gate | up] buffer: replaces Paddle-core swiglu
  * (llama/modeling.py:38-45, 648-650).  bwd writes [dgate | dup] packed the same way. */
 int b200_swiglu_fwd(const void* gate_up, void* out, int64_t rows, int64_t inter, cudaStream_t stream);
+/* Same, gate|up given as the fp32 split-K workspace [rows, 2*inter] of the producing GEMM (rounded to bf16 here, workspace
+ * re-zeroed): the decode step's ffn1 -> fused_bias_act("swiglu") pair (fused_transformer_layers.py:100-168). */
+int b200_swiglu_fwd_f32(float* gate_up_f32_ws, void* out, int64_t rows, int64_t inter, cudaStream_t stream);
 int b200_swiglu_bwd(const void* gate_up, const void* dout, void* dgate_up, int64_t rows, int64_t inter,
                     cudaStream_t stream);
 

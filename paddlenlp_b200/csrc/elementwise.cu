@@ -261,6 +261,36 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
   }
 }
 
+// Same op fed by the fp32 split-K workspace of the producing GEMM [rows, 2*inter]: gate and up are rounded to bf16 first
+// (the Linear output rounding), the workspace is handed back zeroed.
+__global__ void swiglu_fwd_f32_kernel(float* __restrict__ acc, bf16* __restrict__ m, int64_t rows, int inter) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t nchunk_row = inter >> 3;
+  const int64_t total = rows * nchunk_row;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / nchunk_row, c = i % nchunk_row;
+    float4* gp = reinterpret_cast<float4*>(acc + r * 2 * inter) + 2 * c;
+    float4* up = gp + 2 * nchunk_row;
+    const float4 g0 = gp[0], g1 = gp[1], u0 = up[0], u1 = up[1];
+    gp[0] = zero; gp[1] = zero; up[0] = zero; up[1] = zero;
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float uv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    uint4 o;
+    uint32_t* oi = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float ga = bf16_round(gv[2 * j]), gb = bf16_round(gv[2 * j + 1]);
+      const float ua = bf16_round(uv[2 * j]), ub = bf16_round(uv[2 * j + 1]);
+      const float s0 = ga / (1.f + __expf(-ga)), s1 = gb / (1.f + __expf(-gb));
+      oi[j] = pack_bf16x2(s0 * ua, s1 * ub);
+    }
+    st_na_v4(reinterpret_cast<uint4*>(m + r * inter) + c, o);
+  }
+}
+
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dm, bf16* __restrict__ dgu,
                                   int64_t rows, int inter) {
   const int64_t nchunk_row = inter >> 3;
@@ -413,6 +443,18 @@ extern "C" int b200_swiglu_fwd(const void* gate_up, void* out, int64_t rows, int
   launch_pdl(swiglu_fwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, static_cast<const bf16*>(gate_up),
              static_cast<bf16*>(out), rows, (int)inter);
   return check_launch("swiglu_fwd");
+}
+
+extern "C" int b200_swiglu_fwd_f32(float* gate_up_f32_ws, void* out, int64_t rows, int64_t inter, cudaStream_t stream) {
+  B200_CHECK_ARG(gate_up_f32_ws && out, "swiglu_fwd_f32: null pointer");
+  B200_CHECK_ARG(rows > 0 && inter > 0 && inter % 8 == 0, "swiglu_fwd_f32: intermediate size must be a multiple of 8");
+  const int64_t total = rows * (inter / 8);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  launch_pdl(swiglu_fwd_f32_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, gate_up_f32_ws,
+             static_cast<bf16*>(out), rows, (int)inter);
+  return check_launch("swiglu_fwd_f32");
 }
 
 extern "C" int b200_swiglu_bwd(const void* gate_up, const void* dout, void* dgate_up, int64_t rows, int64_t inter,

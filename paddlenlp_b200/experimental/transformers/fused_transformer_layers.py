@@ -151,6 +151,8 @@ class FusedMultiTransformerBase:
                 attn = self._attend(qkv, caches, i, seq_lens_decoder, kw)
                 acc = ops.gemm_skinny_f32(attn, self.linear_weights[i], tag="splitk_h")
                 ln_out, residual = ops.add_rmsnorm_f32(acc, residual, self.ffn_ln_scales[i], eps)
+                # ffn1 [h, 2I] has enough 256-wide column tiles to stream at ~5.5 TB/s from the persistent kernel; the
+                # swapped-operand kernel + swiglu_fwd_f32 measured the same (tools/decode_ablation.py, B200_FFN1=skinny)
                 ffn1 = self._mm(ln_out, self.ffn1_weights[i])
                 act = ops.swiglu_fwd(ffn1)
                 acc = ops.gemm_skinny_f32(act, self.ffn2_weights[i], tag="splitk_h")

@@ -201,6 +201,18 @@ def swiglu_fwd(gate_up: torch.Tensor, out: Optional[torch.Tensor] = None):
     return out
 
 
+def swiglu_fwd_f32(acc_f32: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """SwiGLU fed by the fp32 split-K workspace [rows, 2I] of the ffn1 GEMM (rounded here, workspace re-zeroed)."""
+    _chk(acc_f32, "acc_f32", torch.float32)
+    rows, two_i = acc_f32.shape
+    assert acc_f32.is_contiguous() and two_i % 2 == 0
+    inter = two_i // 2
+    if out is None:
+        out = torch.empty(rows, inter, dtype=BF16, device=acc_f32.device)
+    call("b200_swiglu_fwd_f32", ptr(acc_f32), ptr(out), rows, inter, stream_ptr())
+    return out
+
+
 def swiglu_bwd(gate_up: torch.Tensor, dout: torch.Tensor, dgate_up: Optional[torch.Tensor] = None):
     _chk(gate_up, "gate_up"); _chk(dout, "dout")
     rows, two_i = gate_up.shape

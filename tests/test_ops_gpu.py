@@ -181,6 +181,11 @@ def test_swiglu():
     dgu = o.swiglu_bwd(gu.to(DEV), dm.to(DEV)).cpu()
     assert relerr(dgu[:, :inter], g.grad) < 6e-3
     assert relerr(dgu[:, inter:], u.grad) < 6e-3
+    # fp32-workspace variant (decode step): rounds gate/up once, same bits as the bf16 op, hands the workspace back zeroed
+    acc = (gu.float() * (1 + 2 ** -12)).to(DEV)                # not representable in bf16: exercises the rounding
+    want = o.swiglu_fwd(acc.to(BF16))
+    m2 = o.swiglu_fwd_f32(acc)
+    assert torch.equal(m2, want) and not acc.any()
 
 
 def test_embedding():

@@ -50,8 +50,12 @@ def main():
             if "gemm_f1" in skip:
                 act = fix_act
             else:
-                ffn1 = ops.gemm(ln_out if "norm" not in skip else fix_ln, f1_w[i], cta_group=1)
-                act = fix_act if "swiglu" in skip else ops.swiglu_fwd(ffn1)
+                if os.environ.get("B200_FFN1", "plain") == "skinny":
+                    acc1 = ops.gemm_skinny_f32(ln_out if "norm" not in skip else fix_ln, f1_w[i], tag="splitk_ffn1")
+                    act = fix_act if "swiglu" in skip else ops.swiglu_fwd_f32(acc1)
+                else:
+                    ffn1 = ops.gemm(ln_out if "norm" not in skip else fix_ln, f1_w[i], cta_group=1)
+                    act = fix_act if "swiglu" in skip else ops.swiglu_fwd(ffn1)
             if "gemm_f2" not in skip:
                 acc = ops.gemm_skinny_f32(act, f2_w[i], tag="splitk_h")
                 if "norm" not in skip:
