@@ -62,6 +62,7 @@ __device__ __forceinline__ void reduce_out_tile(uint32_t tsrc, uint8_t* buf, con
   }
 }
 
+template <bool MASK>     // MASK: FlashMask start rows present (kept out of the plain causal instantiation entirely)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -95,13 +96,15 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   // q tiles jt .. hi-1: with a document mask, q tiles that start at or after the end of the last document of this kv tile
   // see none of its columns (mask_start is non-decreasing; the diagonal tile always remains)
   int hi = num_tiles;
-  if (p.mask_start != nullptr)
+  if constexpr (MASK)
     hi = min(num_tiles, (__ldg(p.mask_start + static_cast<size_t>(batch) * p.S + min(kv0 + 127, p.S - 1)) + 127) / 128);
   const int n_iter = hi - jt;
-  __shared__ int s_start[128];                     // mask start row of each column of this kv tile
-  if (threadIdx.x < 128) {
-    const int c = kv0 + static_cast<int>(threadIdx.x);
-    s_start[threadIdx.x] = (p.mask_start != nullptr && c < p.S) ? p.mask_start[static_cast<size_t>(batch) * p.S + c] : 0x7fffffff;
+  __shared__ int s_start[MASK ? 128 : 1];          // mask start row of each column of this kv tile
+  if constexpr (MASK) {
+    if (threadIdx.x < 128) {
+      const int c = kv0 + static_cast<int>(threadIdx.x);
+      s_start[threadIdx.x] = c < p.S ? p.mask_start[static_cast<size_t>(batch) * p.S + c] : 0x7fffffff;
+    }
   }
 
   if (warp == 0 && lane == 0) {
@@ -192,7 +195,7 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const float lse2 = row_ok ? p.lse[stat_idx] * 1.4426950408889634f : 0.f;
       const float drow = row_ok ? p.delta[stat_idx] : 0.f;
       const bool diag = (qt == jt);
-      const bool mtile = (p.mask_start != nullptr) && (q0 + 127 >= s_start[0]);   // some column's document ends in / before this q tile
+      const bool mtile = MASK && (q0 + 127 >= s_start[0]);   // some column's document ends in / before this q tile
       const int qrow = q0 + r;
       mbar_wait(s_full, n & 1);
       tc_fence_after();
@@ -208,8 +211,12 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           const int col = ch * 32 + 2 * c;
           float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * c]), p.scale_log2, -lse2));
           float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * c + 1]), p.scale_log2, -lse2));
-          if (!row_ok || (diag && col > r) || (mtile && qrow >= s_start[col])) p0 = 0.f;
-          if (!row_ok || (diag && col + 1 > r) || (mtile && qrow >= s_start[col + 1])) p1 = 0.f;
+          if (!row_ok || (diag && col > r)) p0 = 0.f;
+          if (!row_ok || (diag && col + 1 > r)) p1 = 0.f;
+          if constexpr (MASK) {
+            if (mtile && qrow >= s_start[col]) p0 = 0.f;
+            if (mtile && qrow >= s_start[col + 1]) p1 = 0.f;
+          }
           const float d0 = p0 * (__uint_as_float(dv[2 * c]) - drow) * p.scale;
           const float d1 = p1 * (__uint_as_float(dv[2 * c + 1]) - drow) * p.scale;
           pp[c] = pack_bf16x2(p0, p1);
@@ -363,7 +370,8 @@ extern "C" int b200_fa_bwd_flashmask(const void* q, const void* k, const void* v
   if ((rc = make_acc_map(&tmdV, dv_acc, B, S, num_kv_heads)) != 0) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    e = cudaFuncSetAttribute(fa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    e = cudaFuncSetAttribute(fa_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fa_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) {
       set_last_error("fa_bwd smem attr: %s", cudaGetErrorString(e));
       return static_cast<int>(e);
@@ -377,7 +385,10 @@ extern "C" int b200_fa_bwd_flashmask(const void* q, const void* k, const void* v
   p.lse = lse; p.delta = delta;
   p.mask_start = mask_start_rows;
   dim3 grid(static_cast<unsigned>((S + 127) / 128), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
-  fa_bwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p);
+  if (mask_start_rows != nullptr)
+    fa_bwd_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p);
+  else
+    fa_bwd_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p);
   if ((rc = check_launch("fa_bwd")) != 0) return rc;
   {
     const int64_t tokens = B * S;

@@ -42,6 +42,7 @@ struct Params {
   const int* mask_start;
 };
 
+template <bool MASK>     // MASK: FlashMask start rows present (kept out of the plain causal instantiation entirely)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
@@ -73,7 +74,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   // kv tiles j_lo .. qt.  With a document mask the leading tiles whose every column belongs to a document that ended at or
   // before this q tile are skipped (mask_start is non-decreasing, so they form a prefix; the diagonal tile is never empty).
   int j_lo = 0;
-  if (p.mask_start != nullptr) {
+  if constexpr (MASK) {
     const int* ms = p.mask_start + static_cast<size_t>(batch) * p.S;
     while (j_lo < qt && __ldg(ms + min(j_lo * BKV + BKV - 1, p.S - 1)) <= q0) ++j_lo;
   }
@@ -197,14 +198,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         for (int c = 0; c < 64; ++c)
           if ((chalf * 64 + c) > r) sv[c] = 0xff800000u;   // -inf
       }
-      if (p.mask_start != nullptr) {
+      if constexpr (MASK) {
         const int* ms = p.mask_start + static_cast<size_t>(batch) * p.S + jg * BKV;
         if (__ldg(ms) <= q0 + BQ - 1) {                   // some document in this kv tile ends inside / before the q tile
           const int row = q0 + r;
           const int cmax = p.S - jg * BKV - chalf * 64;   // columns of this half that exist
-#pragma unroll 8
-          for (int c = 0; c < 64; ++c)
-            if (c < cmax && row >= __ldg(ms + chalf * 64 + c)) sv[c] = 0xff800000u;
+#pragma unroll                                            // full unroll: sv[] must stay in registers
+          for (int c = 0; c < 64; ++c) {
+            const int start = __ldg(ms + chalf * 64 + min(c, cmax - 1));
+            if (c < cmax && row >= start) sv[c] = 0xff800000u;
+          }
         }
       }
 #pragma unroll
@@ -229,7 +232,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
       uint32_t pk[32];
       float rs = 0.f;
-      const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;   // a row can be fully masked in its first tiles (documents)
+      // with documents a row can be fully masked in its first tiles: exp2(-inf - (-inf)) must not be evaluated
+      const float neg_m = (MASK && m_used == -INFINITY) ? 0.f : -m_used;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * c]), p.scale_log2, neg_m));
@@ -345,7 +349,8 @@ extern "C" int b200_fa_fwd_flashmask(const void* q, const void* k, const void* v
   if ((rc = make_map(&tmO, o, B, S, num_heads, ldo)) != 0) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fa_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) {
       set_last_error("fa_fwd smem attr: %s", cudaGetErrorString(e));
       return static_cast<int>(e);
@@ -359,6 +364,7 @@ extern "C" int b200_fa_fwd_flashmask(const void* q, const void* k, const void* v
   p.lse = lse;
   p.mask_start = mask_start_rows;
   dim3 grid(static_cast<unsigned>((S + BQ - 1) / BQ), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
-  fa_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  if (mask_start_rows != nullptr) fa_fwd_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  else fa_fwd_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   return check_launch("fa_fwd");
 }

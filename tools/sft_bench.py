@@ -50,6 +50,8 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=4)
     ap.add_argument("--accum", type=int, default=2)
     ap.add_argument("--layers", type=int, default=0)
+    ap.add_argument("--zero-padding", action="store_true",
+                    help="pack samples into 2048-token rows (ZeroPaddingMapDataset + FlashMask), llm/run_finetune.py --zero_padding")
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -59,8 +61,23 @@ def main():
     cfg = T.Qwen2Config.qwen2_7b(num_hidden_layers=a.layers) if a.layers else T.Qwen2Config.qwen2_7b()
     model = T.AutoModelForCausalLM.from_config(cfg, dtype="bfloat16")
     n = (a.steps + a.warmup) * a.micro_batch * a.accum * args.world_size
-    ds = SyntheticSFT(n, cfg.vocab_size)
-    trainer = Trainer(model=model, args=args, train_dataset=ds)
+    collator = None
+    if a.zero_padding:
+        from paddlenlp_b200.data import DataCollatorForSeq2Seq
+        from paddlenlp_b200.datasets import ZeroPaddingMapDataset
+
+        raw = SyntheticSFT(3 * n, cfg.vocab_size)                    # ~2-3 samples fit one row
+        recs = [{"input_ids": it[0][: it[2]].tolist(), "labels": it[1][: it[2]].tolist()} for it in raw.items]
+        packed = ZeroPaddingMapDataset(recs, max_length=S, greedy_zero_padding=True)
+        packed.new_data = packed.new_data[:n]
+        assert len(packed) >= n, "not enough packed rows"
+        real = [len(r["input_ids"]) for r in packed.new_data]
+        ds = packed
+        ds.items = [(None, None, r) for r in real]
+        collator = DataCollatorForSeq2Seq(max_length=S, pad_token_id=0)
+    else:
+        ds = SyntheticSFT(n, cfg.vocab_size)
+    trainer = Trainer(model=model, args=args, train_dataset=ds, data_collator=collator)
     t0 = time.time()
     trainer.train()
     hist = trainer.state.log_history[a.warmup:]
@@ -68,7 +85,7 @@ def main():
         sps = sum(h["interval_samples_per_second"] for h in hist) / len(hist)
         nonpad = sum(it[2] for it in ds.items) / len(ds.items)
         rec = dict(model="Qwen2-7B" if not a.layers else f"Qwen2-7B width, {a.layers} layers", n_gpus=args.world_size,
-                   seq_len=S, micro_batch=a.micro_batch, grad_accum=a.accum, steps=a.steps,
+                   seq_len=S, zero_padding=bool(a.zero_padding), micro_batch=a.micro_batch, grad_accum=a.accum, steps=a.steps,
                    tokens_per_s=sps * S, nonpad_tokens_per_s=sps * nonpad, loss_first=hist[0]["loss"], loss_last=hist[-1]["loss"],
                    tflops_per_gpu=sps * S / args.world_size * model.get_algorithmic_flops_per_token(S) / 1e12,
                    mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
