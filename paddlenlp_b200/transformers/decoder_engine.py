@@ -229,7 +229,15 @@ class DecoderEngine:
             return None
         ms = attn_mask_startend_row_indices.to(device=self.device, dtype=torch.int32, non_blocking=True).reshape(B, S)
         own = torch.arange(1, S + 1, dtype=torch.int32, device=self.device)
-        return torch.maximum(ms, own[None, :]).contiguous()
+        ms = torch.maximum(ms, own[None, :]).contiguous()
+        if not getattr(self, "_mask_form_checked", False):
+            # one-time (first batch) check of the form the kernels rely on for tile skipping: non-decreasing start rows, i.e.
+            # contiguous packed documents.  Costs one host sync, once per engine.
+            self._mask_form_checked = True
+            if S > 1 and bool((ms[:, 1:] < ms[:, :-1]).any()):
+                raise ValueError("attn_mask_startend_row_indices must be non-decreasing along the sequence (packed contiguous "
+                                 "samples, each column -> end of its sample); general FlashMask patterns are not implemented")
+        return ms
 
     def hidden_states(self, input_ids, position_ids=None, save: Optional[list] = None, attn_mask_startend_row_indices=None):
         """Embedding + decoder stack + final norm -> ([T, h] normed states, pre-norm states, rstd)."""

@@ -244,3 +244,13 @@ def test_flashmask_packing_invariance(model_type):
     real = sum(lens)
     e = maxerr(logits[0, :real].cpu(), ref[0, :real])
     assert e < 3e-2, e
+
+
+def test_flashmask_rejects_non_document_masks():
+    cfg = tiny_cfg()
+    model = build(cfg, make_weights(cfg))
+    ids = torch.randint(1, cfg.vocab_size, (1, 128), generator=torch.Generator().manual_seed(1)).to(DEV)
+    bad = torch.full((1, 128), 128, dtype=torch.int32)
+    bad[0, 40:80] = 60                                                # a start row that decreases again: not a packed layout
+    with pytest.raises(ValueError):
+        model(input_ids=ids, attn_mask_startend_row_indices=bad.to(DEV))
