@@ -233,6 +233,8 @@ def run_native(args):
         b = i % nbatches
         for m in range(accum):
             eng.forward_loss(dev_ids[b, m * mb:(m + 1) * mb], dev_lab[b, m * mb:(m + 1) * mb])
+            if dp is not None and m == accum - 1:
+                dp.prepare_backward()            # last micro-batch: finished gradient ranges are all-reduced during backward
             eng.backward(1.0 / accum)
         if dp is not None:
             dp.sync_gradients()
@@ -246,9 +248,11 @@ def run_native(args):
         for m in range(accum):
             ids = host_ids[b, m * mb:(m + 1) * mb].to(dev, non_blocking=True)
             lab = host_lab[b, m * mb:(m + 1) * mb].to(dev, non_blocking=True)
-            loss, _ = (dp or model)(input_ids=ids, labels=lab)
-            loss = loss / accum
-            loss.backward()
+            ctx = dp.no_sync() if (dp is not None and m < accum - 1) else contextlib.nullcontext()
+            with ctx:                            # trainer.py:1049-1075: accumulation micro-steps skip the exchange
+                loss, _ = (dp or model)(input_ids=ids, labels=lab)
+                loss = loss / accum
+                loss.backward()
             total += loss.detach()
         if dp is not None:
             dp.sync_gradients()

@@ -1,9 +1,10 @@
 """Data-parallel plumbing: one process per GPU, torch.distributed (NCCL over NVLink 5 / NVSwitch) as the carrier.
 
 Replaces the reference's `paddle.distributed.init_parallel_env()` (trainer/training_args.py:1617-1625) and
-`paddle.DataParallel` bucketed reducer / `fused_allreduce_gradients` (trainer.py:1934-1954, 1079-1110) with exactly
-ONE all-reduce(SUM) of the flat bf16 gradient buffer per optimizer step; the 1/world_size mean is folded into the
-optimizer kernel's grad_scale.  Pure replication: no parameter or optimizer-state sharding.
+`paddle.DataParallel` bucketed reducer / `fused_allreduce_gradients` (trainer.py:1934-1954, 1079-1110) with an
+all-reduce(SUM) of the flat bf16 gradient buffer per optimizer step — issued range by range (one decoder layer at a time)
+on a side stream as the last micro-batch's backward finalises them, or as ONE call when overlap is off; the 1/world_size
+mean is folded into the optimizer kernel's grad_scale.  Pure replication: no parameter or optimizer-state sharding.
 """
 from __future__ import annotations
 
@@ -64,19 +65,35 @@ def shard_rows(global_batch: int, rank: Optional[int] = None, world: Optional[in
 
 
 class DataParallel(torch.nn.Module):
-    """paddle.DataParallel stand-in: forwards to the wrapped model, owns the gradient exchange."""
+    """paddle.DataParallel stand-in: forwards to the wrapped model, owns the gradient exchange.
 
-    def __init__(self, layers, find_unused_parameters: bool = False, group=None):
+    The reference's reducer all-reduces 25 MB buckets while backward is still running.  Here the
+    gradients live in one flat buffer that is final piecewise — lm_head first, then decoder layer L-1 ... 0, then the
+    embedding and the norm/bias vectors — during the backward of the LAST micro-batch of an optimizer step.  The engine
+    reports each finished range (`grad_ready_hook`); the range is all-reduced on a side stream while the remaining layers
+    are still being differentiated, and `sync_gradients()` reduces whatever is left and joins.  Micro-batches run under
+    `no_sync()` accumulate locally, exactly like the reference (trainer.py:1049-1075)."""
+
+    def __init__(self, layers, find_unused_parameters: bool = False, group=None, overlap: bool = True):
         super().__init__()
         self._layers = layers
         self.group = group
         self._sync = True
+        self.overlap = overlap
+        self._pending = []          # (lo, hi, work) of ranges already handed to the collective
+        self._comm_stream = None
         engine = getattr(layers, "engine", None)
         if engine is not None:
             broadcast_flat_(engine.flat_params, 0, group)
 
     def forward(self, *a, **kw):
+        self.prepare_backward()
         return self._layers(*a, **kw)
+
+    def prepare_backward(self):
+        """Arm (or disarm, under no_sync) the overlap hook for the next engine.backward()."""
+        eng = self._layers.engine
+        eng.grad_ready_hook = self._on_ready if (self._sync and self.overlap and get_world_size() > 1) else None
 
     @contextlib.contextmanager
     def no_sync(self):
@@ -87,8 +104,38 @@ class DataParallel(torch.nn.Module):
         finally:
             self._sync = old
 
+    def _on_ready(self, lo: int, hi: int):
+        flat = self._layers.engine.flat_grads
+        if hi <= lo:
+            return
+        if flat.is_cuda:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=flat.device)
+            ev = torch.cuda.Event()
+            ev.record()                                   # the range is final at this point of the compute stream
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(ev)
+                work = dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            work = dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._pending.append((lo, hi, work))
+
     def sync_gradients(self):
-        allreduce_flat_(self._layers.engine.flat_grads, self.group)
+        """All-reduce every range of the flat gradient buffer that was not already reduced during backward, then make the
+        current stream wait for all of them."""
+        eng = self._layers.engine
+        eng.grad_ready_hook = None
+        flat = eng.flat_grads
+        if get_world_size() > 1:
+            done = sorted((lo, hi) for lo, hi, _ in self._pending)
+            pos = 0
+            for lo, hi in done + [(flat.numel(), flat.numel())]:
+                if lo > pos:
+                    dist.all_reduce(flat[pos:lo], op=dist.ReduceOp.SUM, group=self.group)
+                pos = max(pos, hi)
+            for _, _, work in self._pending:
+                work.wait()
+        self._pending = []
 
     def __getattr__(self, name):
         try:

@@ -327,7 +327,11 @@ class Trainer:
                         cb.on_step_begin(a, self.state, self.control)
                 last_micro = (step + 1) % accum == 0
                 tok = self.timers.start("forward-backward")
-                tr_loss += self.training_step(model, inputs)
+                if world > 1 and not last_micro:
+                    with model.no_sync():            # trainer.py:1049-1075: accumulation micro-steps skip the exchange
+                        tr_loss += self.training_step(model, inputs)
+                else:
+                    tr_loss += self.training_step(model, inputs)
                 self.timers.stop(tok)
                 if not last_micro:
                     continue

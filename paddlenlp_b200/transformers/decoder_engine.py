@@ -85,6 +85,7 @@ class DecoderEngine:
         self.p = {n: self.flat_params[o:o + math.prod(s)].view(s) for n, (o, s) in self._offsets.items()}
         self.g = {n: self.flat_grads[o:o + math.prod(s)].view(s) for n, (o, s) in self._offsets.items()}
         self.grads_fresh = True          # True: the next backward overwrites instead of accumulating
+        self.grad_ready_hook = None      # callable(lo, hi): flat_grads[lo:hi] is final (set by distributed.DataParallel)
         self._rope = None
         self._saved = None
         self._bias_f32: Dict[int, torch.Tensor] = {}
@@ -291,8 +292,11 @@ class DecoderEngine:
         B, S = st["B"], st["S"]
         dlogits = ops.ce_bwd_(st["logits"], st["labels"], st["loss_tok"], st["lse"], st["loss_out"], grad_scale,
                               grad_scale_dev)
+        hook, self.grad_ready_hook = self.grad_ready_hook, None      # one backward per arming
         dhf = ops.gemm(dlogits, p["head"], trans_b=True)
         ops.gemm(st["hf"], dlogits, out=g["head"], trans_a=True, accumulate=acc)
+        if hook is not None:
+            hook(*self._range("head", "head"))
         del dlogits
         st["logits"] = None
         dx = ops.rmsnorm_bwd(dhf, st["x_last"], p["norm"], st["rstd_f"], g["norm"], accumulate_dw=acc)
@@ -301,10 +305,21 @@ class DecoderEngine:
         for i in range(self.L - 1, -1, -1):
             dx = self._layer_bwd(i, dx, layers[i], B, S, st["pos"], acc, st.get("mask"))
             layers[i] = None
+            if hook is not None:
+                hook(*self._range(f"l{i}.qkv_w", f"l{i}.down_w"))       # this layer's four matrices are contiguous
         if not acc:
             g["embed"].zero_()
         ops.embedding_bwd(st["ids"], dx, g["embed"])
+        if hook is not None:
+            hook(*self._range("embed", "embed"))
+            hook(self.decay_end, self.numel)                            # norm weights / biases of every layer
         self.grads_fresh = False
+
+    def _range(self, first: str, last: str):
+        """[lo, hi) of the flat buffers covering the parameters `first` .. `last` (contiguous in the layout)."""
+        lo = self._offsets[first][0]
+        o, shp = self._offsets[last]
+        return lo, o + _align8(math.prod(shp))
 
     def _layer_bwd(self, i, dx2, saved, B, S, pos, acc, mask=None):
         (x, rstd1, n1, qkv, attn2, lse, x1, rstd2, n2, gu, m) = saved

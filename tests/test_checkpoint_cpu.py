@@ -92,3 +92,20 @@ def test_trainer_state_json_and_last_checkpoint(tmp_path):
         os.makedirs(tmp_path / f"checkpoint-{n}")
     os.makedirs(tmp_path / "checkpoint-11.tmp")
     assert get_last_checkpoint(str(tmp_path)).endswith("checkpoint-10")
+
+
+def test_gradient_ready_ranges_tile_the_flat_buffer():
+    """The ranges the engine reports to the data-parallel exchange during backward (lm_head, each layer's matrices, embedding,
+    vector tail) cover the flat gradient buffer exactly once."""
+    import paddlenlp_b200.transformers as T
+
+    cfg = T.Qwen2Config(vocab_size=64, hidden_size=256, intermediate_size=72, num_hidden_layers=3, num_attention_heads=2,
+                        num_key_value_heads=1, max_position_embeddings=64)
+    eng = T.Qwen2ForCausalLM(cfg, device="cpu").engine
+    rs = [eng._range("head", "head")] + [eng._range(f"l{i}.qkv_w", f"l{i}.down_w") for i in range(3)]
+    rs += [eng._range("embed", "embed"), (eng.decay_end, eng.numel)]
+    pos = 0
+    for lo, hi in sorted(rs):
+        assert lo == pos and hi > lo
+        pos = hi
+    assert pos == eng.numel

@@ -97,6 +97,7 @@ WORKER = textwrap.dedent("""
         def __init__(self):
             self.flat_params = torch.full((1024,), float(rank + 1))
             self.flat_grads = torch.arange(1024, dtype=torch.float32) * (rank + 1)
+            self.grad_ready_hook = None
 
     class FakeModel(torch.nn.Module):
         def __init__(self):
@@ -107,10 +108,23 @@ WORKER = textwrap.dedent("""
     assert torch.equal(m.engine.flat_params, torch.full((1024,), 1.0)), "rank-0 parameter broadcast at wrap time"
     with m.no_sync():
         assert m._sync is False
-    m.sync_gradients()                     # ONE all-reduce(SUM) of the whole gradient buffer
+    m.sync_gradients()                     # nothing was reduced during backward: ONE all-reduce(SUM) of the whole buffer
     assert torch.equal(m.engine.flat_grads, torch.arange(1024, dtype=torch.float32) * 3)
     mean = m.engine.flat_grads * (1.0 / world)      # the 1/world factor lives in the optimizer's grad_scale
     assert torch.equal(mean, torch.arange(1024, dtype=torch.float32) * 1.5)
+    # overlapped exchange: ranges reported final during the last backward are reduced at once, the rest in sync_gradients();
+    # every element is summed exactly once
+    m.engine.flat_grads = torch.arange(1024, dtype=torch.float32) * (rank + 1)
+    with m.no_sync():
+        m.prepare_backward()
+        assert m.engine.grad_ready_hook is None            # accumulation micro-step: no exchange
+    m.prepare_backward()
+    hook = m.engine.grad_ready_hook
+    hook(900, 1024); hook(300, 640); hook(0, 0)
+    assert len(m._pending) == 2
+    m.sync_gradients()
+    assert m.engine.grad_ready_hook is None and m._pending == []
+    assert torch.equal(m.engine.flat_grads, torch.arange(1024, dtype=torch.float32) * 3.0)
     lo, hi = D.shard_rows(16)
     assert (lo, hi) == (rank * 8, rank * 8 + 8)
     torch.distributed.barrier()
