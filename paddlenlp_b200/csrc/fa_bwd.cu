@@ -42,21 +42,24 @@ struct Params {
 // TMEM accumulator (this warp's 32 lanes, fp32 columns [32*ch0, 32*(ch0+nch))) -> fp32 staging -> TMA reduce-add of
 // 32x32 boxes.  One 4 KB staging buffer per warp: the previous reduce must have finished reading it.
 __device__ __forceinline__ void reduce_out_tile(uint32_t tsrc, uint8_t* buf, const CUtensorMap* tm, int lane, int head,
-                                                int row0, int batch, int ch0, int nch) {
-  for (int ch = ch0; ch < ch0 + nch; ++ch) {
-    uint32_t o[32];
-    tmem_ld32(tsrc + ch * 32, o);
-    tmem_ld_wait();
+                                                int row0, int batch, int ch0) {
+  // both 32-column chunks are fetched from TMEM before the single wait (one tcgen05.ld round trip instead of two)
+  uint32_t o[2][32];
+  tmem_ld32(tsrc + ch0 * 32, o[0]);
+  tmem_ld32(tsrc + (ch0 + 1) * 32, o[1]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
     if (lane == 0) tma_store_wait_read<0>();
     __syncwarp();
     const uint32_t row_s = smem_u32(buf) + lane * 128;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-      st_shared_v4(row_s + ((c ^ (lane & 7)) << 4), make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]));
+      st_shared_v4(row_s + ((c ^ (lane & 7)) << 4), make_uint4(o[i][4 * c], o[i][4 * c + 1], o[i][4 * c + 2], o[i][4 * c + 3]));
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_reduce_add_4d(tm, buf, ch * 32, head, row0, batch);
+      tma_reduce_add_4d(tm, buf, (ch0 + i) * 32, head, row0, batch);
       tma_store_commit();
     }
   }
@@ -187,13 +190,23 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
     uint8_t* my_stage = sStage + (warp - 2) * 4096;
+    // row statistics of the NEXT q tile are fetched one iteration ahead (their global-load latency used to sit at the top of
+    // every iteration, in front of the s_full wait)
+    const size_t stat_base = (static_cast<size_t>(batch) * p.nh + hq) * p.S;
+    auto load_stats = [&](int q0n, float& l, float& d) {
+      const bool ok = (q0n + r) < p.S;
+      l = ok ? __ldg(p.lse + stat_base + q0n + r) : 0.f;
+      d = ok ? __ldg(p.delta + stat_base + q0n + r) : 0.f;
+    };
+    float lse_next, drow_next;
+    load_stats(jt * 128, lse_next, drow_next);
     for (int n = 0; n < n_iter; ++n) {
       const int qt = jt + n;
       const int q0 = qt * 128;
       const bool row_ok = (q0 + r) < p.S;
-      const size_t stat_idx = (static_cast<size_t>(batch) * p.nh + hq) * p.S + q0 + r;
-      const float lse2 = row_ok ? p.lse[stat_idx] * 1.4426950408889634f : 0.f;
-      const float drow = row_ok ? p.delta[stat_idx] : 0.f;
+      const float lse2 = lse_next * 1.4426950408889634f;
+      const float drow = drow_next;
+      if (n + 1 < n_iter) load_stats(q0 + 128, lse_next, drow_next);
       const bool diag = (qt == jt);
       const bool mtile = MASK && (q0 + 127 >= s_start[0]);   // some column's document ends in / before this q tile
       const int qrow = q0 + r;
@@ -236,13 +249,13 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       // dQ tile read-out: TMEM -> fp32 staging -> TMA reduce-add into the fp32 dQ buffer (rows >= S are clipped)
       mbar_wait(dq_full, n & 1);
       tc_fence_after();
-      reduce_out_tile(tdP + lane_off, my_stage, &tmdQ, lane, hq, q0 + quad * 32, batch, chalf * 2, 2);
+      reduce_out_tile(tdP + lane_off, my_stage, &tmdQ, lane, hq, q0 + quad * 32, batch, chalf * 2);
       tc_fence_before();
       mbar_arrive(dq_empty);
     }
     // epilogue: this head's dK / dV partials -> fp32 reduce-add (the GQA group's heads sum in L2)
-    reduce_out_tile(tdK + lane_off, my_stage, &tmdK, lane, kv_head, kv0 + quad * 32, batch, chalf * 2, 2);
-    reduce_out_tile(tdV + lane_off, my_stage, &tmdV, lane, kv_head, kv0 + quad * 32, batch, chalf * 2, 2);
+    reduce_out_tile(tdK + lane_off, my_stage, &tmdK, lane, kv_head, kv0 + quad * 32, batch, chalf * 2);
+    reduce_out_tile(tdV + lane_off, my_stage, &tmdV, lane, kv_head, kv0 + quad * 32, batch, chalf * 2);
     if (lane == 0) tma_store_wait<0>();
   }
   tc_fence_before();
