@@ -398,3 +398,35 @@ def test_block_attn_generation_matches_dense_cache(model_type):
     assert paged.block_tables.shape == (5, 2) and int(paged.block_tables[0, 0]) == 9        # free_list.pop(): highest id first
     b, _, lb = paged.generate(ids, seq_len_encoder=enc, max_length=40, cache_kvs=caches)
     assert torch.equal(a, b) and torch.equal(la, lb)
+
+
+@pytest.mark.parametrize("block_attn", [False, True])
+def test_generate_edge_cases(block_attn):
+    """Batch 1 (split-KV auto policy with mostly empty splits), one-token prompts, max_length 1 and 2 (no graph is built),
+    and a cache exactly as long as prompt + max_length; graph and eager runs agree token for token."""
+    from paddlenlp_b200.experimental.transformers import LlamaForCausalLMInferenceModel
+
+    cfg = _tiny()
+    w = R.init_weights(cfg, seed=9)
+    w = {k: (v * 4).to(BF16).float() if k.endswith("weight") and "norm" not in k else v for k, v in w.items()}
+    _, c = _infer_model(cfg, w)
+    m = LlamaForCausalLMInferenceModel(c, block_attn=block_attn)
+    m.set_state_dict(w)
+    g = torch.Generator().manual_seed(3)
+    one = torch.randint(1, cfg.vocab_size, (1, 1), generator=g)
+    for L in (1, 2, 5):
+        a, _, _ = m.generate(one, max_length=L)
+        b, _, _ = m.generate(one, max_length=L, use_cuda_graph=False, use_pdl=False)
+        assert a.shape == (1, L) and torch.equal(a, b) and int(a.min()) >= 0
+    ids = torch.randint(1, cfg.vocab_size, (1, 100), generator=g)
+    caches = m.allocate_caches(1, 100 + 28)                               # exactly full at the last step (128 = one tile)
+    a, _, dec = m.generate(ids, max_length=28, cache_kvs=caches)
+    b, _, _ = m.generate(ids, max_length=28, use_cuda_graph=False)
+    assert torch.equal(a, b) and int(dec[0]) == 100 + 28 - 2
+    ref, margins = G.greedy_generate(ids, w, cfg, 4)
+    for tpos in range(4):
+        if margins[0, tpos] < 2e-2:
+            break
+        assert int(a[0, tpos]) == int(ref[0, tpos])
+    with pytest.raises(ValueError):
+        m.generate(ids, max_length=29, cache_kvs=caches)
