@@ -38,6 +38,8 @@ struct Cfg {
 struct Params {
   int M, N, K;
   int split_k, kb_per_split;
+  int f_tiles;          // feature tiles (work item = feature tile x K range)
+  int split_major;      // item order: 1 = consecutive CTAs take consecutive feature tiles of the same K range
   int w_prefetch;       // PDL: weight tiles of the first stages are loaded before griddepcontrol.wait
   int l2_prefetch_kb;   // PDL: further weight k-blocks prefetched into L2 before the wait
 };
@@ -57,7 +59,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x;
-  const int f_tile = item / p.split_k, split = item - f_tile * p.split_k;
+  int f_tile, split;
+  if (p.split_major) { split = item / p.f_tiles; f_tile = item - split * p.f_tiles; }
+  else { f_tile = item / p.split_k; split = item - f_tile * p.split_k; }
   const int f0 = f_tile * BF;
   const int num_kb_total = (p.K + BK - 1) / BK;
   const int kb0 = split * p.kb_per_split;
@@ -250,6 +254,10 @@ int gemm_skinny_f32(const void* X, const void* W, void* workspace, int64_t M, in
   p.kb_per_split = (num_kb + split_k - 1) / split_k;
   p.split_k = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty ranges
   const int items = f_tiles * p.split_k;
+  p.f_tiles = f_tiles;
+  // measured (tools/decode_ablation.py): with W [K, N] neighbouring CTAs should read neighbouring 256-byte column segments of the
+  // same rows (split-major: o-proj -6 %, ffn2 -2 %); with W [N, K] neighbouring K ranges of the same rows are better
+  p.split_major = w_kmajor ? 0 : 1;
   if (NT == 64) return w_kmajor ? launch<64, true>(tmW, tmX, tmF, p, items, stream) : launch<64, false>(tmW, tmX, tmF, p, items, stream);
   return w_kmajor ? launch<128, true>(tmW, tmX, tmF, p, items, stream) : launch<128, false>(tmW, tmX, tmF, p, items, stream);
 }
