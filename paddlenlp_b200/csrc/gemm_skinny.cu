@@ -15,6 +15,7 @@
 #include "../../include/b200nlp.h"
 #include "common.cuh"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace b200 {
 namespace skinny {
@@ -186,6 +187,224 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stream-K variant (NT = 64): when feature tiles x K ranges do not fill one wave of 2 CTAs/SM evenly (o-proj: 256 of 296 slots;
+// ffn1 / lm_head: hundreds of tiles), the (feature tile, k-block) units are cut into gridDim.x equal contiguous runs instead.  A
+// CTA's run may cross feature-tile boundaries, so it walks 1-3 SEGMENTS (tile, k range): the TMA ring runs on across segments,
+// the accumulator ping-pongs between two TMEM stages, every segment leaves through the same transposed TMA reduce-add.
+// ------------------------------------------------------------------------------------------------
+struct SKCfg {
+  static constexpr int NT = 64;
+  static constexpr int X_BYTES = NT * BK * 2;
+  static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;                // 24 KB
+  static constexpr int STAGES = 3;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;              // 72 KB
+  static constexpr int EPI_BYTES = 4 * 4096;                           // one 32x32 fp32 staging buffer per epilogue warp
+  static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + 256 + 1024;
+};
+
+struct Seg { int f0, kb0, nkb; };
+__device__ __forceinline__ Seg next_seg(long long& u, long long u1, int num_kb) {
+  Seg sg;
+  const int f_tile = static_cast<int>(u / num_kb);
+  sg.kb0 = static_cast<int>(u - static_cast<long long>(f_tile) * num_kb);
+  sg.nkb = static_cast<int>(min(static_cast<long long>(num_kb - sg.kb0), u1 - u));
+  sg.f0 = f_tile * BF;
+  u += sg.nkb;
+  return sg;
+}
+
+template <bool W_KMAJOR>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+gemm_skinny_streamk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                           const __grid_constant__ CUtensorMap tmF, const Params p) {
+  using C = SKCfg;
+  constexpr int NT = C::NT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi = smem + C::RING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + C::EPI_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;    // [STAGES]
+  uint64_t* acc_full = bars + 2 * C::STAGES;     // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const long long total = static_cast<long long>(p.f_tiles) * num_kb;
+  const long long u_begin = total * blockIdx.x / gridDim.x, u_end = total * (blockIdx.x + 1) / gridDim.x;
+  pdl_launch_dependents();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmF);
+    for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_ptr_smem, 2 * NT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      auto load_w = [&](int s, int f0, int kb) {
+        uint8_t* sw = smem + s * C::STAGE_BYTES;
+        const int k0 = kb * BK;
+        if constexpr (W_KMAJOR) {
+          tma_load_2d(&tmW, &full_bar[s], sw, k0, f0);
+        } else {
+          tma_load_2d(&tmW, &full_bar[s], sw, f0, k0);
+          tma_load_2d(&tmW, &full_bar[s], sw + 64 * BK * 2, f0 + 64, k0);
+        }
+      };
+      // weights first (they do not depend on the previous kernel): the first ring stages, then L2 prefetch of the run's next units
+      int pre = 0;
+      if (p.w_prefetch) {
+        long long u = u_begin;
+        int issued_l2 = 0;
+        while (u < u_end && (pre < C::STAGES || issued_l2 < p.l2_prefetch_kb)) {
+          const Seg sg = next_seg(u, u_end, num_kb);
+          for (int i = 0; i < sg.nkb; ++i) {
+            if (pre < C::STAGES) {
+              mbar_arrive_expect_tx(&full_bar[pre], C::STAGE_BYTES);
+              load_w(pre, sg.f0, sg.kb0 + i);
+              ++pre;
+            } else if (issued_l2 < p.l2_prefetch_kb) {
+              const int k0 = (sg.kb0 + i) * BK;
+              if constexpr (W_KMAJOR) {
+                tma_prefetch_l2_2d(&tmW, k0, sg.f0);
+              } else {
+                tma_prefetch_l2_2d(&tmW, sg.f0, k0);
+                tma_prefetch_l2_2d(&tmW, sg.f0 + 64, k0);
+              }
+              ++issued_l2;
+            }
+          }
+        }
+      }
+      pdl_wait();
+      int stage = 0, n = 0;
+      uint32_t phase = 0;
+      for (long long u = u_begin; u < u_end;) {
+        const Seg sg = next_seg(u, u_end, num_kb);
+        for (int i = 0; i < sg.nkb; ++i, ++n) {
+          if (n >= pre) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            load_w(stage, sg.f0, sg.kb0 + i);
+          }
+          tma_load_2d(&tmX, &full_bar[stage], smem + stage * C::STAGE_BYTES + W_BYTES, (sg.kb0 + i) * BK, 0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BF, NT, !W_KMAJOR, false);
+      constexpr uint32_t w_lbo = W_KMAJOR ? 16 : 64 * BK * 2, w_adv = W_KMAJOR ? UK * 2 : UK * 128;
+      int stage = 0, seg = 0;
+      uint32_t phase = 0;
+      for (long long u = u_begin; u < u_end; ++seg) {
+        const Seg sg = next_seg(u, u_end, num_kb);
+        const int as = seg & 1;
+        mbar_wait(&acc_empty[as], ((seg >> 1) & 1) ^ 1u);        // the epilogue drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + static_cast<uint32_t>(as * NT);
+        for (int i = 0; i < sg.nkb; ++i) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sw = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sx = sw + W_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            umma_ss<1>(tacc, umma_desc_sw128(sw + k * w_adv, w_lbo, 1024), umma_desc_sw128(sx + k * UK * 2, 16, 1024), idesc,
+                       (i > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ===================================== epilogue =====================================
+    pdl_wait();
+    const int q = warp & 3;
+    uint8_t* stage_buf = epi + q * 4096;
+    const uint32_t base = smem_u32(stage_buf) + (lane & 3) * 4;
+    int seg = 0;
+    for (long long u = u_begin; u < u_end; ++seg) {
+      const Seg sg = next_seg(u, u_end, num_kb);
+      const int as = seg & 1;
+      mbar_wait(&acc_full[as], (seg >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * NT);
+      uint32_t v[2][32];
+      tmem_ld32(taddr, v[0]);
+      tmem_ld32(taddr + 32, v[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);               // accumulator stage free for the segment after next
+      if (sg.f0 + q * 32 < p.N) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          if (ch * 32 >= p.M) break;
+          if (lane == 0) tma_store_wait_read<0>();               // the previous reduce has finished reading the buffer
+          __syncwarp();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const uint32_t addr = base + t * 128 + ((((lane >> 2) ^ (t & 7))) << 4);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v[ch][t]) : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmF, stage_buf, sg.f0 + q * 32, ch * 32);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 2 * NT);
+  }
+}
+
+template <bool W_KMAJOR>
+static int launch_streamk(const CUtensorMap& tmW, const CUtensorMap& tmX, const CUtensorMap& tmF, Params p, int grid,
+                          cudaStream_t stream) {
+  auto kern = gemm_skinny_streamk_kernel<W_KMAJOR>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SKCfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(gemm_skinny_streamk smem=%d): %s", SKCfg::SMEM_BYTES, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  p.w_prefetch = pdl_enabled() ? 1 : 0;
+  const long long per_kb = static_cast<long long>(W_BYTES) * grid;
+  const long long kbs = (64ll << 20) / per_kb;
+  p.l2_prefetch_kb = p.w_prefetch ? static_cast<int>(kbs > 64 ? 64 : kbs) : 0;
+  cudaError_t e = launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(NUM_THREADS), SKCfg::SMEM_BYTES, stream, tmW, tmX, tmF, p);
+  if (e != cudaSuccess) {
+    set_last_error("gemm_skinny_streamk launch: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return check_launch("gemm_skinny_streamk");
+}
+
 template <int NT, bool W_KMAJOR>
 static int launch(const CUtensorMap& tmW, const CUtensorMap& tmX, const CUtensorMap& tmF, Params p, int items,
                   cudaStream_t stream) {
@@ -255,6 +474,22 @@ int gemm_skinny_f32(const void* X, const void* W, void* workspace, int64_t M, in
   p.split_k = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty ranges
   const int items = f_tiles * p.split_k;
   p.f_tiles = f_tiles;
+  // Stream-K (equal contiguous runs of (tile, k-block) units per CTA) is available but OFF by default: measured in the decode
+  // chain it loses to the plain (tile, K-range) items even where those fill only 256 of 296 slots (o-proj 9.0 vs 8.0 us, ffn1
+  // 41.3 vs 40.3 us; profiles/r01_decode_ablation_streamk.log) — the 3-stage ring and the per-segment accumulator hand-over cost
+  // more than the idle slots.  B200_SKINNY_STREAMK=1 forces it (NT = 64 only).
+  {
+    const int slots = 2 * sm_count();
+    const long long total = static_cast<long long>(f_tiles) * num_kb;
+    const long long waves = (items + slots - 1) / slots;
+    const double eff = static_cast<double>(total) / (static_cast<double>(waves) * p.kb_per_split * slots);
+    static const int force = []() { const char* e = getenv("B200_SKINNY_STREAMK"); return e ? atoi(e) : -1; }();
+    const bool want = force > 0;
+    (void)eff;
+    if (NT == 64 && want && total >= 2ll * slots) {
+      return w_kmajor ? launch_streamk<true>(tmW, tmX, tmF, p, slots, stream) : launch_streamk<false>(tmW, tmX, tmF, p, slots, stream);
+    }
+  }
   // measured (tools/decode_ablation.py): with W [K, N] neighbouring CTAs should read neighbouring 256-byte column segments of the
   // same rows (split-major: o-proj -6 %, ffn2 -2 %); with W [N, K] neighbouring K ranges of the same rows are better
   p.split_major = w_kmajor ? 0 : 1;
