@@ -40,8 +40,9 @@ int b200_device_check(void);
  * barriers, and only waits (griddepcontrol.wait) before touching activations or outputs.  Used for the decode-step chain. */
 int b200_set_pdl(int enable);
 /* Which kernel serves b200_gemm_bf16_splitk for M <= 128 with a row-major A (returns the previous setting; NOT an error
- * code): 1 (default) = the swapped-operand, two-CTA-per-SM weight-streaming kernel (csrc/gemm_skinny.cu), 0 = the persistent
- * 128x256 kernel in split-K mode.  Same results up to fp32 summation order; kept switchable for A/B measurements. */
+ * code): 1 (default) = the swapped-operand, two-CTA-per-SM weight-streaming kernel (csrc/gemm_skinny.cu), 2 = its stream-K
+ * variant (M <= 64), 0 = the persistent 128x256 kernel in split-K mode.  Same results up to fp32 summation order; kept switchable
+ * for A/B measurements. */
 int b200_set_skinny_gemm(int impl);
 
 /* ---- GEMM: replaces paddle.matmul / nn.Linear (cuBLASLt) --------------------------------------------------

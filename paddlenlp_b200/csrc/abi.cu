@@ -122,7 +122,7 @@ int b200_set_pdl(int enable) {
 
 int b200_set_skinny_gemm(int impl) {
   int old = b200::g_skinny_impl;
-  b200::g_skinny_impl = impl ? 1 : 0;
+  b200::g_skinny_impl = impl < 0 ? 0 : (impl > 2 ? 2 : impl);
   return old;
 }
 

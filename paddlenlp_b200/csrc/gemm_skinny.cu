@@ -484,7 +484,7 @@ int gemm_skinny_f32(const void* X, const void* W, void* workspace, int64_t M, in
     const long long waves = (items + slots - 1) / slots;
     const double eff = static_cast<double>(total) / (static_cast<double>(waves) * p.kb_per_split * slots);
     static const int force = []() { const char* e = getenv("B200_SKINNY_STREAMK"); return e ? atoi(e) : -1; }();
-    const bool want = force > 0;
+    const bool want = force > 0 || skinny_gemm_impl() == 2;
     (void)eff;
     if (NT == 64 && want && total >= 2ll * slots) {
       return w_kmajor ? launch_streamk<true>(tmW, tmX, tmF, p, slots, stream) : launch_streamk<false>(tmW, tmX, tmF, p, slots, stream);

@@ -542,7 +542,7 @@ extern "C" int b200_gemm_bf16_splitk(const void* A, const void* B, void* C, cons
                                                                            static_cast<bf16*>(C), M, N, ldc);
     return check_launch("gemm_splitk(finish)");
   };
-  if (!a_mn_major && M <= 128 && skinny_gemm_impl() == 1) {
+  if (!a_mn_major && M <= 128 && skinny_gemm_impl() >= 1) {
     // decode-step shapes: swapped-operand weight-streaming kernel, two CTAs per SM (gemm_skinny.cu)
     int r = skinny::gemm_skinny_f32(A, B, workspace, M, N, K, lda, ldb, /*w_kmajor=*/!b_mn_major, split_k, stream);
     return r ? r : finish();

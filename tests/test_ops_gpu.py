@@ -95,6 +95,26 @@ def test_gemm_skinny_splitk(M, N, K, split, tb):
     assert maxerr(out, ref) < 2 ** -7 and relerr(out, ref) < 4e-3
 
 
+@pytest.mark.parametrize("impl", [0, 2])
+def test_gemm_skinny_alternative_kernels(impl):
+    """b200_set_skinny_gemm: the 128x256 split-K kernel (0) and the stream-K variant (2) give the default kernel's result up to
+    fp32 summation order."""
+    from paddlenlp_b200 import _lib
+    o = ops()
+    lib = _lib.load()
+    try:
+        for M, N, K, tb in ((64, 4096, 4096, False), (64, 6144, 4096, True), (17, 1024, 14336, False), (64, 28672, 512, False)):
+            a = rand_bf16(M, K, seed=41).to(DEV)
+            w = rand_bf16(N, K, seed=42).to(DEV) if tb else rand_bf16(K, N, seed=42).to(DEV)
+            lib.b200_set_skinny_gemm(1)
+            want = o.gemm_skinny(a, w, trans_b=tb).float()
+            lib.b200_set_skinny_gemm(impl)
+            got = o.gemm_skinny(a, w, trans_b=tb).float()
+            assert maxerr(got, want) < 2 ** -7, (M, N, K, tb)
+    finally:
+        lib.b200_set_skinny_gemm(1)
+
+
 def test_gemm_argument_errors():
     o = ops()
     from paddlenlp_b200._lib import B200Error
