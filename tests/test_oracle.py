@@ -114,3 +114,61 @@ def test_adamw_oracle_against_torch_adamw():
                                                weight_decay=0.1, step=t, decay_mask=torch.ones(64, dtype=torch.bool),
                                                max_grad_norm=0.0)
     assert torch.allclose(master, p.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_flashmask_oracle_packing_invariance():
+    """The oracle's FlashMask attention (start rows per key column, fusion_ops.py:218-231): samples packed into one row with
+    per-sample position ids give the logits of the samples evaluated alone — the property the CUDA path is then held to."""
+    cfg = R.RefConfig(vocab_size=128, hidden_size=64, intermediate_size=96, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, max_position_embeddings=128)
+    w = R.init_weights(cfg, seed=3)
+    g = torch.Generator().manual_seed(11)
+    lens = [23, 1, 40]
+    ids = [torch.randint(1, cfg.vocab_size, (n,), generator=g) for n in lens]
+    S = 80
+    packed = torch.zeros(1, S, dtype=torch.long)
+    pos = torch.zeros(1, S, dtype=torch.long)
+    ms = torch.zeros(1, S, dtype=torch.int32)
+    st = 0
+    for t in ids:
+        n = len(t)
+        packed[0, st:st + n], pos[0, st:st + n], ms[0, st:st + n] = t, torch.arange(n), st + n
+        st += n
+    ms = torch.maximum(ms, torch.arange(1, S + 1, dtype=torch.int32)[None])      # padding columns: one-token documents
+    pre = cfg.model_type
+    cos, sin = R.rope_tables(cfg.head_dim, cfg.max_position_embeddings, cfg.rope_theta)
+    x = w[f"{pre}.embed_tokens.weight"][packed]
+    for i in range(cfg.num_hidden_layers):
+        x = R.decoder_layer(x, w, f"{pre}.layers.{i}.", cfg, cos, sin, "fp32", position_ids=pos, mask_start=ms)
+    logits = R.linear(R.rms_norm(x, w[f"{pre}.norm.weight"], cfg.rms_norm_eps, "fp32"), w["lm_head.weight"], None, "fp32")
+    st = 0
+    for t in ids:
+        n = len(t)
+        alone = R.model_forward(t[None], w, cfg, mode="fp32")
+        assert (logits[0, st:st + n] - alone[0]).abs().max() < 1e-5
+        st += n
+    assert torch.isfinite(logits).all()                                           # padding rows are finite too
+
+
+def test_paged_attention_oracle_matches_dense():
+    """generation_ref.paged_decode_attention on scattered blocks == plain attention over the gathered cache."""
+    import numpy as np
+    from oracle import generation_ref as G
+
+    rng = np.random.default_rng(0)
+    B, nh, kvh, d, bs, mb = 3, 4, 2, 16, 8, 5
+    nb = B * mb + 2
+    kc = rng.standard_normal((nb, kvh, bs, d)).astype(np.float32)
+    vc = rng.standard_normal((nb, kvh, bs, d)).astype(np.float32)
+    tables = rng.permutation(nb)[: B * mb].reshape(B, mb).astype(np.int32)
+    lens = np.array([0, 17, mb * bs - 1], np.int32)
+    q = rng.standard_normal((B, nh, d)).astype(np.float32)
+    out = G.paged_decode_attention(q, kc, vc, tables, lens).reshape(B, nh, d)
+    for b in range(B):
+        total = min(int(lens[b]) + 1, mb * bs)
+        K = np.concatenate([kc[tables[b, j]] for j in range(mb)], axis=1)[:, :total]      # [kvh, total, d]
+        V = np.concatenate([vc[tables[b, j]] for j in range(mb)], axis=1)[:, :total]
+        for h in range(nh):
+            s = K[h // 2] @ q[b, h] / np.sqrt(d)
+            p = np.exp(s - s.max())
+            assert np.allclose(out[b, h], (p / p.sum()) @ V[h // 2], atol=1e-5)
