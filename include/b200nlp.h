@@ -114,6 +114,12 @@ int b200_swiglu_fwd(const void* gate_up, void* out, int64_t rows, int64_t inter,
 /* Same, gate|up given as the fp32 split-K workspace [rows, 2*inter] of the producing GEMM (rounded to bf16 here, workspace
  * re-zeroed): the decode step's ffn1 -> fused_bias_act("swiglu") pair (fused_transformer_layers.py:100-168). */
 int b200_swiglu_fwd_f32(float* gate_up_f32_ws, void* out, int64_t rows, int64_t inter, cudaStream_t stream);
+/* Decode-step ffn1 + SwiGLU in one kernel (M <= 64 token rows): act[M, inter] = bf16(silu(g) * u) with g|u = bf16(X W).
+ * W [K, 2*inter] is the ffn1 weight with its columns interleaved per 64 channels — columns [128j, 128j+64) = gate channels
+ * [64j, 64j+64), columns [128j+64, 128j+128) = the matching up channels — so that one 128-feature tile of the swapped-operand
+ * weight-streaming kernel holds both halves (fused_transformer_layers.py:100-168 fused_bias_act("swiglu") after ffn1). */
+int b200_gemm_swiglu_skinny(const void* X, const void* W_interleaved, void* act, int64_t M, int64_t inter, int64_t K,
+                            int64_t ldx, int64_t ldw, cudaStream_t stream);
 int b200_swiglu_bwd(const void* gate_up, const void* dout, void* dgate_up, int64_t rows, int64_t inter,
                     cudaStream_t stream);
 

@@ -43,9 +43,15 @@ struct Params {
   int split_major;      // item order: 1 = consecutive CTAs take consecutive feature tiles of the same K range
   int w_prefetch;       // PDL: weight tiles of the first stages are loaded before griddepcontrol.wait
   int l2_prefetch_kb;   // PDL: further weight k-blocks prefetched into L2 before the wait
+  bf16* act;            // SWIGLU epilogue: output [M, inter] bf16
+  int inter;
 };
 
-template <int NT, bool W_KMAJOR>
+// SWIGLU (ffn1 of the decode step, no K split): the weight columns are interleaved per 64 channels — tile j holds
+// [gate 64j..64j+63 | up 64j..64j+63] — so accumulator lanes 0..63 are gate channels and lanes 64..127 the matching up channels;
+// the epilogue rounds both to bf16 (the Linear output rounding), exchanges the up half through the drained ring and writes
+// bf16(silu(g) * u) straight to act[M, inter]: no fp32 workspace, no separate activation kernel.
+template <int NT, bool W_KMAJOR, bool SWIGLU = false>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                    const __grid_constant__ CUtensorMap tmF, const Params p) {
@@ -155,7 +161,33 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     tc_fence_after();
     uint8_t* stage_buf = smem + q * (NT * 32 * 4);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    if (f0 + q * 32 < p.N) {
+    if constexpr (SWIGLU) {
+      static_assert(!SWIGLU || NT == 64, "SWIGLU epilogue: 64 token columns");
+      float* s_up = reinterpret_cast<float*>(smem);             // [64 tokens][64 channels] fp32
+      uint32_t v[2][32];
+      tmem_ld32(taddr, v[0]);
+      tmem_ld32(taddr + 32, v[1]);
+      tmem_ld_wait();
+      if (q >= 2) {
+#pragma unroll
+        for (int t = 0; t < 64; ++t) s_up[t * 64 + (q - 2) * 32 + lane] = __uint_as_float(v[t >> 5][t & 31]);
+      }
+      named_bar_sync(1, 128);
+      if (q < 2) {
+        const int ch = (f0 >> 1) + q * 32 + lane;               // channel of this lane's gate row
+        if (ch < p.inter) {
+#pragma unroll
+          for (int t = 0; t < 64; ++t) {
+            if (t < p.M) {
+              const float g = bf16_round(__uint_as_float(v[t >> 5][t & 31]));
+              const float u = bf16_round(s_up[t * 64 + q * 32 + lane]);
+              const float sg = g / (1.f + __expf(-g));
+              p.act[static_cast<size_t>(t) * p.inter + ch] = __float2bfloat16_rn(sg * u);
+            }
+          }
+        }
+      }
+    } else if (f0 + q * 32 < p.N) {
 #pragma unroll
       for (int ch = 0; ch < NT / 32; ++ch) {
         if (ch * 32 >= p.M) break;                // warp-uniform
@@ -405,11 +437,11 @@ static int launch_streamk(const CUtensorMap& tmW, const CUtensorMap& tmX, const 
   return check_launch("gemm_skinny_streamk");
 }
 
-template <int NT, bool W_KMAJOR>
+template <int NT, bool W_KMAJOR, bool SWIGLU = false>
 static int launch(const CUtensorMap& tmW, const CUtensorMap& tmX, const CUtensorMap& tmF, Params p, int items,
                   cudaStream_t stream) {
   using C = Cfg<NT>;
-  auto kern = gemm_skinny_kernel<NT, W_KMAJOR>;
+  auto kern = gemm_skinny_kernel<NT, W_KMAJOR, SWIGLU>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -497,5 +529,43 @@ int gemm_skinny_f32(const void* X, const void* W, void* workspace, int64_t M, in
   return w_kmajor ? launch<128, true>(tmW, tmX, tmF, p, items, stream) : launch<128, false>(tmW, tmX, tmF, p, items, stream);
 }
 
+// act[M, inter] = bf16(silu(g) * u), g|u = bf16(X W) with W [K, 2*inter] in the 64-interleaved column layout described above.
+int gemm_swiglu_skinny(const void* X, const void* W, void* act, int64_t M, int64_t inter, int64_t K, int64_t ldx, int64_t ldw,
+                       cudaStream_t stream) {
+  if (!(M > 0 && M <= 64 && inter > 0 && inter % 64 == 0 && K > 0 && ldx % 8 == 0 && ldw % 8 == 0))
+    return fail_arg("gemm_swiglu_skinny: need 0 < M <= 64, inter %% 64 == 0, leading dimensions %% 8 == 0");
+  const int64_t N = 2 * inter;
+  CUtensorMap tmW, tmX;
+  int rc;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(K)}, strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {64, BK};
+    if ((rc = encode_tmap_bf16(&tmW, W, 2, dims, strides, box)) != 0) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldx) * 2};
+    uint32_t box[2] = {BK, 64};
+    if ((rc = encode_tmap_bf16(&tmX, X, 2, dims, strides, box)) != 0) return rc;
+  }
+  Params p = {};
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  const int num_kb = static_cast<int>((K + BK - 1) / BK);
+  p.split_k = 1;
+  p.kb_per_split = num_kb;
+  p.f_tiles = static_cast<int>(N / BF);
+  p.split_major = 0;
+  p.act = static_cast<bf16*>(act);
+  p.inter = static_cast<int>(inter);
+  return launch<64, false, true>(tmW, tmX, tmX, p, p.f_tiles, stream);    // the fp32 workspace map is unused
+}
+
 }  // namespace skinny
 }  // namespace b200
+
+extern "C" int b200_gemm_swiglu_skinny(const void* X, const void* W_interleaved, void* act, int64_t M, int64_t inter, int64_t K,
+                                       int64_t ldx, int64_t ldw, cudaStream_t stream) {
+  using namespace b200;
+  B200_CHECK_ARG(X && W_interleaved && act, "gemm_swiglu_skinny: null pointer");
+  return skinny::gemm_swiglu_skinny(X, W_interleaved, act, M, inter, K, ldx, ldw, stream);
+}

@@ -64,6 +64,7 @@ class LlamaForCausalLMInferenceModel(GenerationInferenceModel):
             t.ffn2_weights[i].copy_(g(lp + "mlp.down_proj.weight"))
             t.ln_scales[i].copy_(g(lp + "input_layernorm.weight"))
             t.ffn_ln_scales[i].copy_(g(lp + "post_attention_layernorm.weight"))
+        t.weights_changed()
 
     @torch.no_grad()
     def init_random(self, seed: int = 42, std: float = 0.02):
@@ -72,6 +73,7 @@ class LlamaForCausalLMInferenceModel(GenerationInferenceModel):
         t = self.transformer_block
         for w in [self.embed_tokens, self.lm_head_weight] + t.qkv_weights + t.linear_weights + t.ffn1_weights + t.ffn2_weights:
             w.normal_(0.0, std, generator=gen)
+        t.weights_changed()
 
     def allocate_caches(self, batch: int, max_len: int) -> List[torch.Tensor]:
         """cache_kvs = [zeros([2, bsz, kvh, max_len, d])] * L (llm/predict/predictor.py:697-706)."""

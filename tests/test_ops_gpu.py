@@ -115,6 +115,23 @@ def test_gemm_skinny_alternative_kernels(impl):
         lib.b200_set_skinny_gemm(1)
 
 
+@pytest.mark.parametrize("M,inter,K", [(64, 14336, 4096), (5, 192, 328), (33, 18944, 3584)])
+def test_gemm_swiglu_skinny(M, inter, K):
+    """Decode ffn1 + SwiGLU in one kernel == GEMM (bf16 output) followed by the SwiGLU kernel, on the interleaved weight."""
+    o = ops()
+    x = rand_bf16(M, K, seed=51).to(DEV)
+    w = rand_bf16(K, 2 * inter, seed=52, scale=0.05).to(DEV)
+    wil = o.interleave_gate_up(w)
+    assert torch.equal(wil[:, :64], w[:, :64]) and torch.equal(wil[:, 64:128], w[:, inter:inter + 64])
+    assert torch.equal(wil[:, 128:192], w[:, 64:128])
+    got = o.gemm_swiglu_skinny(x, wil)
+    want = o.swiglu_fwd(o.gemm(x, w, cta_group=1))
+    ref = R.swiglu(R.linear(x.float().cpu(), w[:, :inter].float().cpu(), None, "bf16"),
+                   R.linear(x.float().cpu(), w[:, inter:].float().cpu(), None, "bf16"), "bf16")
+    assert maxerr(got.cpu(), ref) < 2 ** -6
+    assert (got != want).float().mean().item() < 0.02          # same rounding points; fp32 summation order may flip a few ulps
+
+
 def test_gemm_argument_errors():
     o = ops()
     from paddlenlp_b200._lib import B200Error
