@@ -430,3 +430,16 @@ def test_generate_edge_cases(block_attn):
         assert int(a[0, tpos]) == int(ref[0, tpos])
     with pytest.raises(ValueError):
         m.generate(ids, max_length=29, cache_kvs=caches)
+
+
+def test_generate_with_fused_ffn1_swiglu_option():
+    """FusedMultiTransformerBase.fuse_ffn1_swiglu (off by default: measured slower) generates the same tokens."""
+    cfg = _tiny()
+    w = R.init_weights(cfg, seed=9)
+    w = {k: (v * 4).to(BF16).float() if k.endswith("weight") and "norm" not in k else v for k, v in w.items()}
+    m, _ = _infer_model(cfg, w)
+    ids = torch.randint(1, cfg.vocab_size, (4, 16), generator=torch.Generator().manual_seed(8))
+    a, _, _ = m.generate(ids, max_length=12)
+    m.transformer_block.fuse_ffn1_swiglu = True
+    b, _, _ = m.generate(ids, max_length=12)
+    assert (a == b).float().mean().item() > 0.9 and torch.equal(a[:, :3], b[:, :3])
