@@ -434,7 +434,8 @@ def test_generate_edge_cases(block_attn):
 
 def test_generate_with_fused_ffn1_swiglu_option():
     """FusedMultiTransformerBase.fuse_ffn1_swiglu (off by default: measured slower) generates the same tokens."""
-    cfg = _tiny()
+    cfg = R.RefConfig(vocab_size=512, hidden_size=256, intermediate_size=704, num_hidden_layers=2, num_attention_heads=2,
+                      num_key_value_heads=1, rope_theta=10000.0, max_position_embeddings=128, rms_norm_eps=1e-5)
     w = R.init_weights(cfg, seed=9)
     w = {k: (v * 4).to(BF16).float() if k.endswith("weight") and "norm" not in k else v for k, v in w.items()}
     m, _ = _infer_model(cfg, w)
