@@ -55,6 +55,31 @@ def main():
         except Exception as e:  # library comparison only
             rec["fa2_error"] = str(e)[:200]
         print(json.dumps(rec), flush=True)
+    # FlashMask (packed samples): Qwen2-7B SFT row of 2048 tokens holding documents of 700 / 900 / 448 tokens; useful flops only
+    B, S, nh, kvh, d = 4, 2048, 28, 4, 128
+    docs = [700, 900, 448]
+    ms = torch.empty(S, dtype=torch.int32)
+    pos, useful = 0, 0
+    for n in docs:
+        ms[pos:pos + n] = pos + n
+        pos += n
+        useful += n * n
+    ms = ms[None].expand(B, S).contiguous().to(dev)
+    ld = (nh + 2 * kvh) * d
+    qkv = torch.randn(B, S, ld, device=dev).to(torch.bfloat16)
+    q = qkv[:, :, : nh * d].view(B, S, nh, d)
+    k = qkv[:, :, nh * d: (nh + kvh) * d].view(B, S, kvh, d)
+    v = qkv[:, :, (nh + kvh) * d:].view(B, S, kvh, d)
+    out, lse = ops.flash_attn_fwd(q, k, v, mask_start=ms)
+    dout = torch.randn_like(out)
+    dq, dk, dv = torch.empty_like(out), torch.empty(B, S, kvh, d, device=dev, dtype=torch.bfloat16), torch.empty(B, S, kvh, d, device=dev, dtype=torch.bfloat16)
+    t_f = timeit(lambda: ops.flash_attn_fwd(q, k, v, out=out, mask_start=ms))
+    t_b = timeit(lambda: ops.flash_attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, mask_start=ms))
+    t_fc = timeit(lambda: ops.flash_attn_fwd(q, k, v, out=out))
+    t_bc = timeit(lambda: ops.flash_attn_bwd(q, k, v, out, dout, lse, dq, dk, dv))
+    fl = 4.0 * B * nh * useful * d / 2
+    print(json.dumps(dict(flashmask_docs=docs, shape=[B, S, nh, kvh], fwd_ms=t_f, bwd_ms=t_b, plain_causal_fwd_ms=t_fc,
+                          plain_causal_bwd_ms=t_bc, useful_fwd_tflops=fl / t_f / 1e9, useful_bwd_tflops=2.5 * fl / t_b / 1e9)), flush=True)
 
 
 if __name__ == "__main__":
