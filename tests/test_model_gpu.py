@@ -254,3 +254,39 @@ def test_flashmask_rejects_non_document_masks():
     bad[0, 40:80] = 60                                                # a start row that decreases again: not a packed layout
     with pytest.raises(ValueError):
         model(input_ids=ids, attn_mask_startend_row_indices=bad.to(DEV))
+
+
+def test_full_width_single_layer_llama3_8b_shapes():
+    """SURVEY §8d parity input: one decoder layer at the FULL Llama-3-8B width (h 4096, 32 q / 8 kv heads, I 14336; vocab and
+    sequence shortened so that the CPU oracle finishes in seconds) — logits, loss and the layer's weight gradients vs the
+    bf16-rounding oracle, with the oracle's own bf16-vs-fp32 distance as the noise floor."""
+    cfg = R.RefConfig(vocab_size=4096, hidden_size=4096, intermediate_size=14336, num_hidden_layers=1, num_attention_heads=32,
+                      num_key_value_heads=8, rms_norm_eps=1e-5, rope_theta=500000.0, max_position_embeddings=1024)
+    w = R.init_weights(cfg, seed=21)
+    w["lm_head.weight"] = (w["lm_head.weight"] * 8).to(torch.bfloat16).float()   # decisive logits at the 0.02 init scale
+    model = build(cfg, w)
+    tok = torch.randint(0, cfg.vocab_size, (1, 1025), generator=torch.Generator().manual_seed(22))
+    ids, labels = tok[:, :-1].contiguous(), tok[:, 1:].contiguous()
+    loss, logits = model(input_ids=ids.to(DEV), labels=labels.to(DEV))
+    logits = logits.float().cpu().clone()
+    ref16 = R.model_forward(ids, w, cfg, mode="bf16")
+    ref32 = R.model_forward(ids, w, cfg, mode="fp32")
+    floor_rel = relerr(ref16, ref32)
+    e_rel, e_max = relerr(logits, ref16), maxerr(logits, ref16)
+    print(f"[full width] logits rel {e_rel:.2e} max {e_max:.2e}; oracle bf16-vs-fp32 floor rel {floor_rel:.2e}")
+    assert relerr(logits, ref32) <= 1.25 * floor_rel + 5e-4
+    assert e_rel <= max(2.0 * floor_rel, 2e-3)
+    am, am_ref = logits.argmax(-1), ref16.argmax(-1)
+    top2 = ref16.topk(2, dim=-1).values
+    decisive = (top2[..., 0] - top2[..., 1]) > 2 * e_max * ref16.abs().max()
+    assert bool((am == am_ref)[decisive].all()) and (am == am_ref).float().mean().item() > 0.95
+    ref_loss = R.criterion(ref16, labels)
+    assert abs(loss.item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item())
+    model.engine.clear_grad()
+    loss.backward()
+    _, _, gref = R.loss_and_grads(ids, labels, w, cfg, mode="bf16")
+    grads = model.engine.named_views(grads=True)
+    for k in ("llama.layers.0.self_attn.q_proj.weight", "llama.layers.0.self_attn.v_proj.weight", "llama.layers.0.mlp.up_proj.weight",
+              "llama.layers.0.mlp.down_proj.weight", "llama.layers.0.input_layernorm.weight"):
+        e = relerr(grads[k].cpu(), gref[k])
+        assert e < 3e-2, (k, e)
