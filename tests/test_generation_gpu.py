@@ -444,3 +444,47 @@ def test_generate_with_fused_ffn1_swiglu_option():
     m.transformer_block.fuse_ffn1_swiglu = True
     b, _, _ = m.generate(ids, max_length=12)
     assert (a == b).float().mean().item() > 0.9 and torch.equal(a[:, :3], b[:, :3])
+
+
+def test_full_width_decode_matches_uncached_forward():
+    """KV-cache consistency (tests/transformers/llama/test_modeling.py:171-219) at the FULL Llama-3-8B layer width, batch 64:
+    prefill logits match the training-path forward, and three decode steps (swapped-operand GEMMs at N = 6144 / 4096 /
+    28672, K = 14336; tcgen05 decode attention with 4 query heads per kv head) reproduce the uncached forward of the grown
+    sequence within bf16 noise, with identical decisive arg-max."""
+    import paddlenlp_b200.transformers as T
+    from paddlenlp_b200.experimental.transformers import LlamaForCausalLMInferenceModel
+
+    kw = dict(vocab_size=4096, hidden_size=4096, intermediate_size=14336, num_hidden_layers=1, num_attention_heads=32,
+              num_key_value_heads=8, rms_norm_eps=1e-5, rope_theta=500000.0, max_position_embeddings=512)
+    cfg = R.RefConfig(**kw)
+    w = R.init_weights(cfg, seed=31)
+    w["lm_head.weight"] = (w["lm_head.weight"] * 8).to(BF16).float()
+    train = T.LlamaForCausalLM(T.LlamaConfig(**kw))
+    train.set_state_dict(w)
+    for block_attn in (False, True):
+        inf = LlamaForCausalLMInferenceModel(T.LlamaConfig(**kw), block_attn=block_attn)
+        inf.set_state_dict(w)
+        B, S = 64, 130
+        g = torch.Generator().manual_seed(32)
+        ids = torch.randint(0, cfg.vocab_size, (B, S), generator=g).to(DEV)
+        enc = torch.full((B,), S, dtype=torch.int32, device=DEV)
+        caches = inf.allocate_caches(B, S + 8)
+        lg = inf._prefill(ids, enc, caches)
+        full = train.engine.forward_logits(ids)
+        # same decoder kernels in the same order; only the 64-row lm_head takes the split-K kernel (fp32 summation order)
+        e0 = ((lg.float() - full[:, -1].float()).abs().max() / full[:, -1].float().abs().max()).item()
+        assert e0 < 5e-3, e0
+        seq = ids
+        lens = enc.clone()
+        for step in range(3):
+            nxt = lg.float().argmax(-1)
+            seq = torch.cat([seq, nxt[:, None]], dim=1)
+            lg = inf._decode(nxt, lens, caches)
+            lens += 1
+            ref = train.engine.forward_logits(seq)[:, -1].float()
+            err = ((lg.float() - ref).abs().max() / ref.abs().max()).item()
+            assert err < 2e-2, (block_attn, step, err)
+            top2 = ref.topk(2, dim=-1).values
+            decisive = (top2[:, 0] - top2[:, 1]) > 4 * err * ref.abs().max()
+            assert bool((lg.float().argmax(-1) == ref.argmax(-1))[decisive].all())
+            assert decisive.float().mean().item() > 0.5
