@@ -8,9 +8,17 @@
 One "step" = one optimizer step over per-GPU batch 8 x seq 4096 synthetic tokens (4 micro-batches of 2 sequences with
 gradient accumulation into the flat gradient buffer — the Trainer's gradient_accumulation_steps semantics,
 trainer.py:1045-1091), including the data-parallel gradient all-reduce and the AdamW update; nothing is skipped.
+Every step sees a FRESH random batch (drawn on the CPU from one seeded generator before the timed region).
 Prints ONE JSON line (rank 0).  `value` has inputs resident in HBM; `e2e` runs the same step through the public
 Trainer-facing API (model(input_ids, labels) -> loss.backward() -> optimizer.step()) with pinned-host inputs, the H2D
 copies and a D2H read of the loss inside the timed region.
+
+The same line also carries BASELINE.json configs[3] and configs[4] under `other_configs` (skip with --only-pretrain):
+  sft     Qwen2-7B full-parameter SFT, seq 2048, through Trainer.train() (pure data parallel over the launched ranks)
+  decode  Llama-3-8B generation, batch 64, prompt 128 -> +1920, FusedMultiTransformer KV-cache path (rank 0, N=1 only:
+          the decode path does not shard — replicas only)
+and `breakdown`: the in-step device time of every kernel family (CUDA events around each C-ABI call during one extra
+step after the timed region; GEMM is additionally timed live INSIDE the timed region for `roofline`).
 """
 from __future__ import annotations
 
@@ -112,16 +120,20 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # CPU baseline (oracle port): one decoder layer fwd+bwd + lm_head/criterion fwd+bwd on a bounded token sample
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(layer_tokens: int = 512, head_tokens: int = 128, threads: int | None = None):
+def cpu_reference_sample(layer_tokens: int = 512, head_tokens: int = 128, attn_heads: int = 8, threads: int | None = None):
     """Times the oracle (oracle/llama_ref.py, bf16-rounding mode) on the host cores and extrapolates tokens/s of the
-    full Llama-3-8B step: tokens/s = 1 / (32 * t_layer/token + t_head/token).  Attention is evaluated at
-    seq = layer_tokens (not 4096), which under-counts its ~7 % share; stated in `sample`."""
+    full Llama-3-8B step:  tokens/s = 1 / (32 * (t_layer/token + t_attn4096/token) + t_head/token)  where
+      t_layer     = fwd+bwd of ONE full-width decoder layer on `layer_tokens` tokens (its own attention runs at that short
+                    length: ~1 % of the layer's work),
+      t_attn4096  = fwd+bwd of the causal GQA attention at the REAL sequence length 4096 on `attn_heads` of the 32 q heads
+                    (attn_heads/4 kv heads), scaled to 32 heads,
+      t_head      = final norm + lm_head + criterion fwd+bwd on `head_tokens` tokens."""
     import torch
 
     from oracle import llama_ref as R
 
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores, regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     cores = torch.get_num_threads()
     cfg = R.llama3_8b()
     g = torch.Generator().manual_seed(0)
@@ -145,6 +157,16 @@ def cpu_reference_sample(layer_tokens: int = 512, head_tokens: int = 128, thread
     y = R.decoder_layer(x, w, p, cfg, cos, sin, "bf16")
     y.sum().backward()
     t_layer = time.perf_counter() - t0
+    # attention at the real sequence length
+    rep = cfg.num_attention_heads // cfg.num_key_value_heads
+    akv = max(1, attn_heads // rep)
+    q = torch.randn(1, SEQ, akv * rep, d, generator=g).requires_grad_(True)
+    k = torch.randn(1, SEQ, akv, d, generator=g).requires_grad_(True)
+    v = torch.randn(1, SEQ, akv, d, generator=g).requires_grad_(True)
+    t0 = time.perf_counter()
+    R.attention(q, k, v, "bf16").sum().backward()
+    t_attn = (time.perf_counter() - t0) * (cfg.num_attention_heads / (akv * rep))
+    del q, k, v
     head = cache["head"].detach().requires_grad_(True)
     hs = torch.randn(1, head_tokens, h, generator=g).requires_grad_(True)
     labels = torch.randint(0, cfg.vocab_size, (1, head_tokens), generator=g)
@@ -152,12 +174,13 @@ def cpu_reference_sample(layer_tokens: int = 512, head_tokens: int = 128, thread
     logits = R.linear(R.rms_norm(hs, torch.ones(h), cfg.rms_norm_eps, "bf16"), head, None, "bf16")
     R.criterion(logits, labels).backward()
     t_head = time.perf_counter() - t0
-    per_token = cfg.num_hidden_layers * t_layer / layer_tokens + t_head / head_tokens
+    per_token = cfg.num_hidden_layers * (t_layer / layer_tokens + t_attn / SEQ) + t_head / head_tokens
     return dict(value=1.0 / per_token, unit="tokens/s", cores=cores, kind="port",
                 sample=(f"oracle/llama_ref.py (torch CPU, bf16-rounding mode) fwd+bwd of ONE full-width decoder layer on "
-                        f"{layer_tokens} tokens ({t_layer:.2f} s) + final-norm/lm_head/criterion on {head_tokens} tokens "
-                        f"({t_head:.2f} s); extrapolated x32 layers; optimizer step not included"),
-                seconds=t_layer + t_head)
+                        f"{layer_tokens} tokens ({t_layer:.2f} s) + causal GQA attention fwd+bwd at seq {SEQ} on {akv * rep} of "
+                        f"{cfg.num_attention_heads} q heads (scaled to all heads: {t_attn:.2f} s) + final-norm/lm_head/criterion "
+                        f"on {head_tokens} tokens ({t_head:.2f} s); extrapolated x32 layers; optimizer step not included"),
+                seconds=t_layer + t_attn * (akv * rep) / cfg.num_attention_heads + t_head)
 
 
 def run_reference(args):
@@ -187,6 +210,32 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # native arm
 # ----------------------------------------------------------------------------------------------------------------
+# kernel family of every C-ABI entry point the training step calls (for `breakdown`)
+FAMILY = {
+    "b200_gemm_bf16_ex": "gemm (tcgen05)", "b200_gemm_bf16": "gemm (tcgen05)",
+    "b200_fa_fwd_flashmask": "attention fwd (tcgen05)", "b200_fa_fwd": "attention fwd (tcgen05)",
+    "b200_fa_bwd_flashmask": "attention bwd (tcgen05)", "b200_fa_bwd": "attention bwd (tcgen05)",
+    "b200_rmsnorm_fwd": "rmsnorm", "b200_rmsnorm_bwd": "rmsnorm", "b200_rope_inplace": "rope",
+    "b200_swiglu_fwd": "swiglu", "b200_swiglu_bwd": "swiglu", "b200_embedding_fwd": "embedding",
+    "b200_embedding_bwd": "embedding", "b200_ce_fwd": "cross-entropy", "b200_ce_bwd": "cross-entropy",
+    "b200_grad_sqnorm": "optimizer (|g|^2 + AdamW)", "b200_adamw_step": "optimizer (|g|^2 + AdamW)",
+    "b200_colsum_bf16": "bias grad",
+}
+
+
+def free_device_memory():
+    import gc
+
+    import torch
+
+    from paddlenlp_b200 import ops
+
+    ops._workspaces.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -219,20 +268,34 @@ def run_native(args):
     accum = PER_GPU_BATCH // mb
     tokens_per_step = PER_GPU_BATCH * SEQ * world
 
-    # synthetic data: global batch drawn on the CPU with a fixed seed; rank r owns rows r*8 .. r*8+7
+    # synthetic data: a FRESH global batch for every step (warm-up, timed, breakdown and e2e steps all differ), drawn on the
+    # CPU from one seeded generator; rank r owns rows r*8 .. r*8+7 of each global batch
     g = torch.Generator().manual_seed(1234)
-    nbatches = 2
-    tok = torch.randint(0, cfg.vocab_size, (nbatches, PER_GPU_BATCH * world, SEQ + 1), generator=g)
+    n_resident = args.warmup + args.steps + 1               # +1: the breakdown step
+    n_e2e = args.steps
     lo, hi = dist_env.shard_rows(PER_GPU_BATCH * world, rank, world)
-    host_ids = tok[:, lo:hi, :-1].contiguous().pin_memory()
-    host_lab = tok[:, lo:hi, 1:].contiguous().pin_memory()
-    dev_ids, dev_lab = host_ids.to(dev), host_lab.to(dev)
+
+    def draw(n):
+        rows = []
+        for _ in range(n):
+            tok = torch.randint(0, cfg.vocab_size, (PER_GPU_BATCH * world, SEQ + 1), generator=g)
+            rows.append(tok[lo:hi].clone())
+        return torch.stack(rows)
+
+    tok_res = draw(n_resident)
+    dev_ids, dev_lab = tok_res[:, :, :-1].contiguous().to(dev), tok_res[:, :, 1:].contiguous().to(dev)
+    tok_e2e = draw(n_e2e)
+    host_ids = tok_e2e[:, :, :-1].contiguous().pin_memory()
+    host_lab = tok_e2e[:, :, 1:].contiguous().pin_memory()
+    del tok_res, tok_e2e
     l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    step_losses = []        # device scalars of the first micro-batch of every resident step (read after the timed region)
 
     def step_resident(i):
-        b = i % nbatches
         for m in range(accum):
-            eng.forward_loss(dev_ids[b, m * mb:(m + 1) * mb], dev_lab[b, m * mb:(m + 1) * mb])
+            loss_out = eng.forward_loss(dev_ids[i, m * mb:(m + 1) * mb], dev_lab[i, m * mb:(m + 1) * mb])[0]
+            if m == 0:
+                step_losses.append(loss_out)
             if dp is not None and m == accum - 1:
                 dp.prepare_backward()            # last micro-batch: finished gradient ranges are all-reduced during backward
             eng.backward(1.0 / accum)
@@ -243,11 +306,10 @@ def run_native(args):
     def step_e2e(i):
         """Public API path: pinned host batch -> H2D -> model(input_ids, labels) -> loss.backward() -> all-reduce ->
         optimizer.step(); the step's loss is read back to the host."""
-        b = i % nbatches
         total = torch.zeros((), device=dev)
         for m in range(accum):
-            ids = host_ids[b, m * mb:(m + 1) * mb].to(dev, non_blocking=True)
-            lab = host_lab[b, m * mb:(m + 1) * mb].to(dev, non_blocking=True)
+            ids = host_ids[i, m * mb:(m + 1) * mb].to(dev, non_blocking=True)
+            lab = host_lab[i, m * mb:(m + 1) * mb].to(dev, non_blocking=True)
             ctx = dp.no_sync() if (dp is not None and m < accum - 1) else contextlib.nullcontext()
             with ctx:                            # trainer.py:1049-1075: accumulation micro-steps skip the exchange
                 loss, _ = (dp or model)(input_ids=ids, labels=lab)
@@ -264,13 +326,13 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, k):
+    def timed(fn, k, first=0):
         """K steps bracketed by barrier + synchronize; device time by CUDA events; max over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(k):
-            fn(i)
+            fn(first + i)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -292,7 +354,7 @@ def run_native(args):
             e0.record()
             yield
             e1.record()
-            gemm_events.append((e0, e1, 2.0 * a[5] * a[6] * a[7]))
+            gemm_events.append((e0, e1, 2.0 * a[5] * a[6] * a[7], (int(a[5]), int(a[6]), int(a[7]))))
         else:
             yield
 
@@ -301,19 +363,51 @@ def run_native(args):
         sampler.start()
     launches0 = _lib.launch_count
     _lib.call_hook = hook if rank == 0 else None
-    ms = timed(step_resident, args.steps)
+    ms = timed(step_resident, args.steps, first=args.warmup)
     _lib.call_hook = None
     launches = _lib.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
-    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in gemm_events)
-    gemm_flops = sum(f for _, _, f in gemm_events)
+    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in gemm_events)
+    gemm_flops = sum(f for _, _, f, _ in gemm_events)
     n_gemm = len(gemm_events)
+    per_shape = {}
+    for e0, e1, f, shp in gemm_events:
+        r = per_shape.setdefault(shp, [0, 0.0, 0.0])
+        r[0] += 1; r[1] += e0.elapsed_time(e1); r[2] += f
+    gemm_events.clear()
+
+    # one extra step with CUDA events around EVERY C-ABI call: in-step time of each kernel family (all ranks run it — the
+    # gradient exchange is collective — rank 0 records)
+    fam_events = []
+
+    @contextlib.contextmanager
+    def hook_all(name, a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        fam_events.append((FAMILY.get(name, name), e0, e1))
+
+    _lib.call_hook = hook_all if rank == 0 else None
+    ms_bd = timed(step_resident, 1, first=args.warmup + args.steps)
+    _lib.call_hook = None
+    breakdown = None
+    if rank == 0:
+        fam = {}
+        for name, e0, e1 in fam_events:
+            r = fam.setdefault(name, [0, 0.0])
+            r[0] += 1; r[1] += e0.elapsed_time(e1)
+        covered = sum(v[1] for v in fam.values())
+        breakdown = {"step_ms": ms_bd, "note": "one extra step, CUDA events around every C-ABI call (adds ~2 event records per call)",
+                     "families": {k: {"calls": v[0], "ms": round(v[1], 3), "share": round(v[1] / ms_bd, 4)}
+                                  for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])},
+                     "uncovered_ms (launch gaps, torch fill/copy, NCCL)": round(ms_bd - covered, 3)}
+    fam_events.clear()
+    first_losses = [float(t[0]) for t in step_losses[:1] + step_losses[args.warmup:args.warmup + 1] + step_losses[-1:]]
 
     losses = []
     ms_e2e = timed(lambda i: losses.append(step_e2e(i)), args.steps)
 
-    if rank != 0:
-        return
     peaks = load_peaks()
     ms_per_step = ms / args.steps
     value = tokens_per_step / (ms_per_step / 1e3)
@@ -321,31 +415,81 @@ def run_native(args):
     flops_per_token = model.get_algorithmic_flops_per_token(SEQ)
     tf_per_gpu = value / world * flops_per_token / 1e12
     gemm_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
-    out = {
-        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {"workload": "Llama-3-8B bf16 pretrain step, per-GPU batch 8 x seq 4096 (BASELINE.json configs[1]; "
-                               "configs[2] at 8 GPUs)",
-                   "model": "Llama-3-8B" if not args.layers else f"Llama-3-8B width, {args.layers} layers (DEBUG, not the metric)",
-                   "global_batch": PER_GPU_BATCH * world, "seq_len": SEQ, "micro_batch": mb, "grad_accum": accum,
-                   "parallelism": f"dp{world}", "optimizer": "AdamW fp32 master + global-norm clip, in the timed step",
-                   "l2": "inputs (weights 16 GB, activations) exceed the 126 MB L2; a 192 MB flush precedes the timed region"},
-        "clocks": clocks,
-        "gpu_launches": launches,
-        "hbm_peak_allocated_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
-        "model_tflops_per_gpu": tf_per_gpu,
-        "mfu": {"algorithmic_gflop_per_token": flops_per_token / 1e9, "vs_nominal_2250": tf_per_gpu / 2250.0,
-                "vs_measured_burst": tf_per_gpu / peaks["bf16_burst"], "vs_measured_sustained": tf_per_gpu / peaks["bf16_sustained"]},
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all projection/lm_head GEMMs fwd+bwd)",
-                     "achieved": gemm_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": (gemm_tf / peaks["bf16_sustained"]) if gemm_tf else None, "peak_source": peaks["source"] + ", sustained",
-                     "launches_timed": n_gemm, "avg_launch_ms": gemm_ms / max(1, n_gemm), "share_of_step": gemm_ms / ms,
-                     "algorithmic_flops_per_launch": gemm_flops / max(1, n_gemm),
-                     "traffic": gemm_traffic_from_profile(), "traffic_unit": "bytes/launch (ncu --set full, profiles/r01_ncu_summary.md)"},
-        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(PER_GPU_BATCH * SEQ * 8 * 2),
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": losses[-1] if losses else None},
-    }
+    hbm_peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    out = None
+    if rank == 0:
+        traffic = gemm_traffic_from_profile()
+        out = {
+            "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "Llama-3-8B bf16 pretrain step, per-GPU batch 8 x seq 4096 (BASELINE.json configs[1]; "
+                                   "configs[2] at 8 GPUs)",
+                       "model": "Llama-3-8B" if not args.layers else f"Llama-3-8B width, {args.layers} layers (DEBUG, not the metric)",
+                       "global_batch": PER_GPU_BATCH * world, "seq_len": SEQ, "micro_batch": mb, "grad_accum": accum,
+                       "parallelism": f"dp{world}", "optimizer": "AdamW fp32 master + global-norm clip, in the timed step",
+                       "batches": "a fresh uniform-random batch every step (seed 1234, drawn on the CPU before the timed region)",
+                       "l2": "inputs (weights 16 GB, activations) exceed the 126 MB L2; a 192 MB flush precedes the timed region"},
+            "clocks": clocks,
+            "gpu_launches": launches,
+            "hbm_peak_allocated_gb": hbm_peak_gb,
+            "first_loss": first_losses[0] if first_losses else None,      # ~ ln(vocab) = 11.76 at the reference init
+            "loss_trace": {"first_warmup_step": first_losses[0] if first_losses else None,
+                           "first_timed_step": first_losses[1] if len(first_losses) > 1 else None,
+                           "last_step": first_losses[-1] if first_losses else None, "ln_vocab": 11.7618},
+            "model_tflops_per_gpu": tf_per_gpu,
+            "clock_normalised": {"sm_mhz_over_max": (clocks["sm_mhz"] / clocks["sm_max_mhz"]) if clocks and clocks.get("sm_mhz") else None,
+                                 "model_tflops_per_gpu_per_ghz": (tf_per_gpu / (clocks["sm_mhz"] / 1e3)) if clocks and clocks.get("sm_mhz") else None,
+                                 "note": "the step runs under sw_power_cap: compare rounds/boxes by TFLOP/s per GHz of median SM clock"},
+            "mfu": {"algorithmic_gflop_per_token": flops_per_token / 1e9, "vs_nominal_2250": tf_per_gpu / 2250.0,
+                    "vs_measured_burst": tf_per_gpu / peaks["bf16_burst"], "vs_measured_sustained": tf_per_gpu / peaks["bf16_sustained"]},
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all projection/lm_head GEMMs fwd+bwd)",
+                         "achieved": gemm_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": (gemm_tf / peaks["bf16_sustained"]) if gemm_tf else None, "peak_source": peaks["source"] + ", sustained",
+                         "launches_timed": n_gemm, "avg_launch_ms": gemm_ms / max(1, n_gemm), "share_of_step": gemm_ms / ms,
+                         "algorithmic_flops_per_launch": gemm_flops / max(1, n_gemm),
+                         "traffic": traffic, "traffic_unit": "bytes/launch (ncu --set full, profiles/r01_ncu_summary.md)",
+                         "per_shape_MNK": {f"{k[0]}x{k[1]}x{k[2]}": {"launches": v[0], "ms_per_launch": round(v[1] / v[0], 4),
+                                                                       "tflops": round(v[2] / (v[1] / 1e3) / 1e12, 1)}
+                                           for k, v in sorted(per_shape.items(), key=lambda kv: -kv[1][1])}},
+            "breakdown": breakdown,
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": int(PER_GPU_BATCH * SEQ * 8 * 2),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "first_loss": losses[0] if losses else None,
+                    "last_loss": losses[-1] if losses else None},
+        }
+
+    # ---- BASELINE.json configs[3] (Qwen2-7B SFT, all ranks) and configs[4] (decode, rank 0 at N=1) in the same process ----
+    if not args.only_pretrain and not args.layers:
+        others = {}
+        del model, eng, opt, dp, dev_ids, dev_lab, host_ids, host_lab, l2_flush
+        step_losses.clear()
+        free_device_memory()
+        try:
+            from tools import sft_bench
+            rec = sft_bench.run(steps=args.sft_steps, warmup=2, micro_batch=4, accum=2, zero_padding=False, quiet=True)
+            if rank == 0:
+                others["sft"] = rec
+        except Exception as e:  # the extra configs must never take the headline number down with them
+            if rank == 0:
+                others["sft"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+        free_device_memory()
+        if world == 1:
+            try:
+                from tools import gen_bench
+                others["decode"] = gen_bench.run()
+            except Exception as e:
+                others["decode"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+            free_device_memory()
+        if rank == 0:
+            out["other_configs"] = others
+            if isinstance(others.get("decode"), dict) and "decode_tokens_per_s" in others["decode"]:
+                out["decode_tok_s"] = others["decode"]["decode_tokens_per_s"]
+                out["decode_roofline_frac"] = others["decode"]["roofline_frac"]
+            if isinstance(others.get("sft"), dict) and "tokens_per_s" in others["sft"]:
+                out["sft_tok_s"] = others["sft"]["tokens_per_s"]
+
+    if rank != 0:
+        return
     if world == 1 and not args.no_cpu_baseline:
         try:
             cb = cpu_reference_sample()
@@ -365,6 +509,8 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=2, choices=[1, 2, 4, 8])
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-pretrain", action="store_true", help="skip the Qwen2-7B SFT and Llama-3-8B decode sub-benchmarks")
+    ap.add_argument("--sft-steps", type=int, default=4)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -39,6 +39,11 @@ int b200_device_check(void);
  * may start while the previous kernel of the stream is still draining — it prefetches its weight tiles and sets up TMEM /
  * barriers, and only waits (griddepcontrol.wait) before touching activations or outputs.  Used for the decode-step chain. */
 int b200_set_pdl(int enable);
+/* Which kernel serves the plain-causal b200_fa_fwd (returns the previous setting; NOT an error code): 2 (default) = two
+ * 128-row q tiles per CTA with P kept in tensor memory (csrc/fa_fwd2.cu), 1 = one q tile per CTA (csrc/fa_fwd.cu, which
+ * also serves every FlashMask call).  Same rounding points; kept switchable for A/B measurements.  The initial value can
+ * be set with the environment variable B200_FA_FWD_IMPL. */
+int b200_set_fa_fwd_impl(int impl);
 /* Which kernel serves b200_gemm_bf16_splitk for M <= 128 with a row-major A (returns the previous setting; NOT an error
  * code): 1 (default) = the swapped-operand, two-CTA-per-SM weight-streaming kernel (csrc/gemm_skinny.cu), 2 = its stream-K
  * variant (M <= 64), 0 = the persistent 128x256 kernel in split-K mode.  Same results up to fp32 summation order; kept switchable

@@ -53,6 +53,7 @@ class RefConfig:
     max_position_embeddings: int = 8192
     qkv_bias: bool = False          # Qwen2
     model_type: str = "llama"
+    rope_scaling: Optional[dict] = None   # {"rope_type": "llama3", ...} or {"type": "linear"|"ntk"|"dynamic_ntk", "factor": f}
 
     @property
     def head_dim(self) -> int:
@@ -126,10 +127,37 @@ def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float, mode: str) -> to
     return rnd(y * weight, mode)
 
 
-def rope_tables(head_dim: int, seq_len: int, theta: float, device="cpu"):
+def rope_inv_freq(head_dim: int, theta: float, scaling: Optional[dict] = None, seq_len: int = 0,
+                  max_position_embeddings: int = 0) -> torch.Tensor:
+    """Inverse frequencies of the reference's rotary variants (llama/modeling.py):
+    plain :409-411; Llama3RotaryEmbedding :535-553 (wavelength bands, smooth interpolation between them);
+    LlamaNTKScalingRotaryEmbedding :467-470 (base * f**(d/(d-2))); LlamaDynamicNTKScalingRotaryEmbedding :482-487 (the same
+    with alpha = f*seq/max_pos - (f-1), only when seq_len > max_position_embeddings)."""
+    kind = None if not scaling else (scaling.get("rope_type") or scaling.get("type"))
+    base = float(theta)
+    if kind == "ntk":
+        base = base * float(scaling["factor"]) ** (head_dim / (head_dim - 2))
+    elif kind == "dynamic_ntk" and max_position_embeddings and seq_len > max_position_embeddings:
+        f = float(scaling["factor"])
+        base = base * ((f * seq_len / max_position_embeddings) - (f - 1)) ** (head_dim / (head_dim - 2))
+    inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    if kind == "llama3":
+        factor, lo, hi = float(scaling["factor"]), float(scaling["low_freq_factor"]), float(scaling["high_freq_factor"])
+        orig = float(scaling["original_max_position_embeddings"])
+        wavelen = 2 * math.pi / inv_freq
+        smooth = (orig / wavelen - lo) / (hi - lo)
+        mid = (1 - smooth) * inv_freq / factor + smooth * inv_freq
+        inv_freq = torch.where(wavelen < orig / hi, inv_freq, torch.where(wavelen > orig / lo, inv_freq / factor, mid))
+    return inv_freq
+
+
+def rope_tables(head_dim: int, seq_len: int, theta: float, device="cpu", scaling: Optional[dict] = None,
+                max_position_embeddings: int = 0):
     # modeling.py:409-423: inv_freq = 1 / base**(arange(0,dim,2)/dim); emb = concat([freqs, freqs]); cos/sin fp32.
-    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    inv_freq = rope_inv_freq(head_dim, theta, scaling, seq_len, max_position_embeddings)
     t = torch.arange(seq_len, dtype=torch.float32)
+    if scaling and (scaling.get("rope_type") or scaling.get("type")) == "linear":
+        t = t / float(scaling["factor"])              # LlamaLinearScalingRotaryEmbedding :446-450
     freqs = torch.einsum("i,j->ij", t, inv_freq)
     emb = torch.cat([freqs, freqs], dim=-1)
     return emb.cos().to(device), emb.sin().to(device)  # [S, d]; always computed on the CPU first
@@ -219,7 +247,7 @@ def model_forward(input_ids: torch.Tensor, w: Dict[str, torch.Tensor], cfg: RefC
     pre = cfg.model_type
     x = w[f"{pre}.embed_tokens.weight"][input_ids]
     cos, sin = rope_tables(cfg.head_dim, max(input_ids.shape[1], int(position_ids.max()) + 1 if position_ids is not None else 0),
-                           cfg.rope_theta, x.device)
+                           cfg.rope_theta, x.device, scaling=cfg.rope_scaling, max_position_embeddings=cfg.max_position_embeddings)
     for i in range(cfg.num_hidden_layers):
         x = decoder_layer(x, w, f"{pre}.layers.{i}.", cfg, cos, sin, mode, position_ids)
     hf = rms_norm(x, w[f"{pre}.norm.weight"], cfg.rms_norm_eps, mode)

@@ -1,4 +1,5 @@
 // C-ABI plumbing: error string, version, device checks, tensor-map encoding.
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -37,6 +38,14 @@ static int g_pdl = 0;
 bool pdl_enabled() { return g_pdl != 0; }
 static int g_skinny_impl = 1;
 int skinny_gemm_impl() { return g_skinny_impl; }
+// attention kernel generations: forward 2 = two q tiles per CTA (fa_fwd2.cu), 1 = one q tile per CTA (fa_fwd.cu);
+// the initial value can be overridden with B200_FA_FWD_IMPL / B200_FA_BWD_IMPL for A/B runs of unmodified scripts
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+static int g_fa_fwd_impl = env_int("B200_FA_FWD_IMPL", 2);
+int fa_fwd_impl() { return g_fa_fwd_impl; }
 
 int sm_count() {
   static int cached[64];
@@ -117,6 +126,12 @@ int b200_abi_version(void) { return B200NLP_ABI_VERSION; }
 int b200_set_pdl(int enable) {
   int old = b200::g_pdl;
   b200::g_pdl = enable ? 1 : 0;
+  return old;
+}
+
+int b200_set_fa_fwd_impl(int impl) {
+  int old = b200::g_fa_fwd_impl;
+  b200::g_fa_fwd_impl = impl == 1 ? 1 : 2;
   return old;
 }
 

@@ -1,0 +1,360 @@
+// Causal GQA flash-attention forward, second generation (head_dim 128): two 128-row q tiles per CTA.
+//
+//   O = softmax(Q K^T / sqrt(d) + causal) V ,  LSE saved for the backward.   Same contract as fa_fwd.cu.
+//
+// Why a second kernel.  The first one (fa_fwd.cu: one q tile per CTA, two threads per row, P staged through shared
+// memory) spends ~3800 cycles per 128x128 kv tile against 1024 cycles of tensor work (ncu: tensor pipe 26.7 %): the 8
+// softmax warps run in lock-step (named barrier for the row-max exchange), so the MUFU phase (16 ex2/clk/SM = 1024
+// cycles per tile) never overlaps the load / max / pack / store phases, and the MMA pipe idles while they run.
+// Here
+//   * a CTA owns TWO q tiles A and B (256 q rows of one (batch, head)); each has its own softmax warpgroup, and the
+//     MMA warp alternates  PV_A(j), QK_A(j+1), PV_B(j), QK_B(j+1)  so tile A's softmax runs under tile B's MMAs
+//     and vice versa;  K/V tiles are fetched once per CTA for both q tiles (half the L2 traffic per q row);
+//   * one thread owns one q row (TMEM lane): row max / row sum need no cross-thread exchange and no block barrier;
+//   * P never touches shared memory: it is written back to TMEM as packed bf16 over the S columns it came from
+//     (tcgen05.st) and consumed as the TMEM A operand of the PV MMA (tcgen05.mma with A in tensor memory);
+//   * the scale-and-subtract and the row sum use the packed fp32x2 pipe (fma.rn.f32x2 / add.f32x2).
+//
+//   warp 0        TMA producer: Q_A, Q_B once; K_j, V_j alternating through ONE 5-stage ring of 32 KB tiles
+//   warp 1        MMA issuer
+//   warps 2..5    softmax of tile A (rows q0 .. q0+127), one thread per row
+//   warps 6..9    softmax of tile B (rows q0+128 .. q0+255)
+//   TMEM (512 columns): S_A|P_A [0,128)  S_B|P_B [128,256)  O_A [256,384)  O_B [384,512)
+//
+// Rounding points are those of fa_fwd.cu (and of the reference's flash path): S and the softmax in
+// fp32 with the scale applied to S, P rounded to bf16 before P@V, O accumulated in fp32 and rounded to bf16 once.
+// Replaces F.scaled_dot_product_attention(is_causal=True) (paddlenlp/transformers/llama/fusion_ops.py:240-246).
+#include "../../include/b200nlp.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace b200 {
+namespace fa2 {
+
+constexpr int D = 128;
+constexpr int TILE_BYTES = 128 * 128 * 2;   // 32 KB: one 128x128 bf16 tile = two 64-column halves of 16 KB
+constexpr int HALF_BYTES = TILE_BYTES / 2;
+constexpr int NST = 5;                      // K/V ring stages
+constexpr int NUM_THREADS = 320;
+constexpr int BAR_BYTES = 512;
+constexpr int SMEM_BYTES = (2 + NST) * TILE_BYTES + BAR_BYTES + 1024;   // Q_A, Q_B, ring, barriers, align slack
+constexpr float RESCALE_THRESHOLD = 8.f;    // log2 units: O is rescaled only when the row max grew by more than 2^8
+
+struct Params {
+  int S, B, nh, kvh;
+  float scale_log2;   // (1/sqrt(d)) * log2(e)
+  float* lse;         // [B, nh, S]
+};
+
+// (x0, x1) = (a0, a1) * s + c    on the packed fp32x2 pipe
+__device__ __forceinline__ void fma2(float& x0, float& x1, float a0, float a1, float s, float c) {
+  asm("{\n\t.reg .b64 ra, rs, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rs, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
+      "fma.rn.f32x2 rd, ra, rs, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(x0), "=f"(x1)
+      : "f"(a0), "f"(a1), "f"(s), "f"(c));
+}
+// (acc0, acc1) += (a0, a1)
+__device__ __forceinline__ void add2(float& acc0, float& acc1, float a0, float a1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "+f"(acc0), "+f"(acc1)
+      : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                          // [2] tiles: A, B (reused as the O staging of the same tile)
+  uint8_t* sKV = smem + 2 * TILE_BYTES;        // [NST] ring: item 2j = K_j, item 2j+1 = V_j
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + NST) * TILE_BYTES);
+  uint64_t* q_full = bars;                     // [2]
+  uint64_t* kv_full = bars + 2;                // [NST]
+  uint64_t* kv_empty = bars + 2 + NST;         // [NST]
+  uint64_t* s_full = bars + 2 + 2 * NST;       // [2]  MMA -> softmax: S_t(j) complete (and every earlier MMA)
+  uint64_t* p_full = s_full + 2;               // [2]  softmax -> MMA: P_t(j) in TMEM, O_t rescaled
+  uint64_t* o_full = p_full + 2;               // [2]  MMA -> softmax: last PV of tile t complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_qb = (p.S + 255) / 256;
+  const int qb = num_qb - 1 - static_cast<int>(blockIdx.x);   // heavy blocks first
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int kv_head = head / (p.nh / p.kvh);
+  const int q0 = qb * 256;
+  const bool b_active = (q0 + 128) < p.S;
+  const int nA = 2 * qb + 1;                   // kv tiles 0 .. 2qb     (diagonal = last)
+  const int nB = b_active ? 2 * qb + 2 : 0;    // kv tiles 0 .. 2qb+1   (diagonal = last)
+  const int n_kv = b_active ? nB : nA;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+    }
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&q_full[0], TILE_BYTES);
+      tma_load_4d(&tmQ, &q_full[0], sQ, 0, head, q0, batch);
+      tma_load_4d(&tmQ, &q_full[0], sQ + HALF_BYTES, 64, head, q0, batch);
+      if (b_active) {
+        mbar_arrive_expect_tx(&q_full[1], TILE_BYTES);
+        tma_load_4d(&tmQ, &q_full[1], sQ + TILE_BYTES, 0, head, q0 + 128, batch);
+        tma_load_4d(&tmQ, &q_full[1], sQ + TILE_BYTES + HALF_BYTES, 64, head, q0 + 128, batch);
+      }
+      for (int it = 0; it < 2 * n_kv; ++it) {
+        const int st = it % NST;
+        const uint32_t use = static_cast<uint32_t>(it / NST);
+        mbar_wait(&kv_empty[st], (use & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&kv_full[st], TILE_BYTES);
+        uint8_t* dst = sKV + st * TILE_BYTES;
+        const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
+        const int row = (it >> 1) * 128;
+        tma_load_4d(tm, &kv_full[st], dst, 0, kv_head, row, batch);
+        tma_load_4d(tm, &kv_full[st], dst + HALF_BYTES, 64, kv_head, row, batch);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);   // A = Q (smem, K-major), B = K (K-major)
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, false, true);    // A = P (TMEM), B = V (MN-major)
+      auto wait_kv = [&](int it) { mbar_wait(&kv_full[it % NST], static_cast<uint32_t>(it / NST) & 1u); };
+      auto free_kv = [&](int it) { umma_commit(&kv_empty[it % NST]); };
+      auto issue_qk = [&](int t, int j) {          // S_t = Q_t K_j^T
+        const uint32_t sQ_a = smem_u32(sQ + t * TILE_BYTES);
+        const uint32_t sK_a = smem_u32(sKV + ((2 * j) % NST) * TILE_BYTES);
+        const uint32_t tS = tmem_base + static_cast<uint32_t>(t * 128);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
+          umma_ss<1>(tS, umma_desc_sw128(sQ_a + off, 16, 1024), umma_desc_sw128(sK_a + off, 16, 1024), idesc_qk,
+                     kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j) {          // O_t (+)= P_t V_j ; P_t = packed bf16 in the first 64 columns of S_t
+        const uint32_t sV_a = smem_u32(sKV + ((2 * j + 1) % NST) * TILE_BYTES);
+        const uint32_t tP = tmem_base + static_cast<uint32_t>(t * 128);
+        const uint32_t tO = tmem_base + 256u + static_cast<uint32_t>(t * 128);
+#pragma unroll
+        for (int kk = 0; kk < 128 / 16; ++kk)
+          umma_ts(tO, tP + kk * 8, umma_desc_sw128(sV_a + kk * 2048, HALF_BYTES, 1024), idesc_pv,
+                  (j > 0 || kk > 0) ? 1u : 0u);
+      };
+      mbar_wait(&q_full[0], 0);
+      wait_kv(0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      if (b_active) {
+        mbar_wait(&q_full[1], 0);
+        tc_fence_after();
+        issue_qk(1, 0);
+      }
+      free_kv(0);
+      for (int j = 0; j < n_kv; ++j) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int nt = t == 0 ? nA : nB;
+          if (j < nt) {
+            mbar_wait(&p_full[t], j & 1);
+            wait_kv(2 * j + 1);
+            tc_fence_after();
+            issue_pv(t, j);
+            if (j + 1 < nt) {
+              wait_kv(2 * j + 2);
+              tc_fence_after();
+              issue_qk(t, j + 1);
+            } else {
+              umma_commit(&o_full[t]);
+            }
+          }
+        }
+        // both tiles have issued everything that reads V_j and K_{j+1}: hand the stages back when those MMAs retire
+        free_kv(2 * j + 1);
+        if (j + 1 < n_kv) free_kv(2 * j + 2);
+      }
+    }
+  } else {
+    // ------------------------------- softmax / epilogue: one thread per q row -------------------------------
+    const int t = (warp - 2) >> 2;                        // 0: tile A, 1: tile B
+    const int nt = t == 0 ? nA : nB;
+    if (nt > 0) {
+      const int quad = warp & 3;                          // TMEM lane quadrant this warp may touch
+      const int r = quad * 32 + lane;                     // row within the tile == TMEM lane
+      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+      const uint32_t tS = tmem_base + lane_off + static_cast<uint32_t>(t * 128);
+      const uint32_t tO = tmem_base + lane_off + 256u + static_cast<uint32_t>(t * 128);
+      const int q0t = q0 + t * 128;
+      float m_used = -INFINITY, l0 = 0.f, l1 = 0.f;
+      for (int j = 0; j < nt; ++j) {
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        uint32_t sv[128];
+        {
+          uint32_t(*c)[32] = reinterpret_cast<uint32_t(*)[32]>(sv);
+          tmem_ld32(tS, c[0]); tmem_ld32(tS + 32, c[1]); tmem_ld32(tS + 64, c[2]); tmem_ld32(tS + 96, c[3]);
+          tmem_ld_wait();
+        }
+        if (j == nt - 1) {                                // diagonal tile: columns beyond the row are masked
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c > r) sv[c] = 0xff800000u;               // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 128; c += 8) {
+          mx0 = max3(mx0, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+          mx1 = max3(mx1, __uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3]));
+          mx2 = max3(mx2, __uint_as_float(sv[c + 4]), __uint_as_float(sv[c + 5]));
+          mx3 = max3(mx3, __uint_as_float(sv[c + 6]), __uint_as_float(sv[c + 7]));
+        }
+        const float rowmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;   // scale > 0
+        bool need = false;
+        float factor = 1.f;
+        if (j == 0) {
+          m_used = rowmax;
+        } else if (rowmax > m_used + RESCALE_THRESHOLD) {
+          need = true;
+          factor = fast_exp2(m_used - rowmax);
+          l0 *= factor; l1 *= factor;
+          m_used = rowmax;
+        }
+        const bool rescale = __any_sync(0xffffffffu, need);
+        const float neg_m = -m_used;
+        uint32_t pk[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          float x0, x1;
+          fma2(x0, x1, __uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1]), p.scale_log2, neg_m);
+          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+          add2(l0, l1, p0, p1);
+          pk[c] = pack_bf16x2(p0, p1);
+        }
+        // P over the first 64 columns of this row's S (every S value of the row is already in registers)
+        {
+          uint32_t(*c)[32] = reinterpret_cast<uint32_t(*)[32]>(pk);
+          tmem_st32(tS, c[0]); tmem_st32(tS + 32, c[1]);
+        }
+        if (rescale) {
+          // s_full(j) tracks every MMA issued before QK_t(j), PV_t(j-1) included, and PV_t(j) waits for the arrive below:
+          // the O accumulator of this tile is quiescent here
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t o[32];
+            tmem_ld32(tO + ch * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
+            tmem_st32(tO + ch * 32, o);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+      }
+      // epilogue: O / l -> bf16 -> swizzled smem (this tile's Q buffer) -> TMA store ; LSE
+      const float l = l0 + l1;
+      const float inv_l = 1.f / l;
+      mbar_wait(&o_full[t], 0);
+      tc_fence_after();
+      const uint32_t sO_a = smem_u32(sQ + t * TILE_BYTES);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(tO + ch * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const int k = (ch & 1) * 4 + c8;     // 16-byte chunk within the 128-byte half row; half = ch >> 1
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[c8 * 8 + 0]) * inv_l, __uint_as_float(o[c8 * 8 + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[c8 * 8 + 2]) * inv_l, __uint_as_float(o[c8 * 8 + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[c8 * 8 + 4]) * inv_l, __uint_as_float(o[c8 * 8 + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[c8 * 8 + 6]) * inv_l, __uint_as_float(o[c8 * 8 + 7]) * inv_l);
+          st_shared_v4(sO_a + (ch >> 1) * HALF_BYTES + r * 128 + ((k ^ (r & 7)) << 4), v);
+        }
+      }
+      if (q0t + r < p.S)
+        p.lse[(static_cast<size_t>(batch) * p.nh + head) * p.S + q0t + r] = (m_used + log2f(l)) * 0.6931471805599453f;
+      fence_proxy_async_smem();
+      named_bar_sync(1 + t, 128);
+      if ((warp == 2 || warp == 6) && lane == 0) {
+        tma_store_4d(&tmO, sQ + t * TILE_BYTES, 0, head, q0t, batch);
+        tma_store_4d(&tmO, sQ + t * TILE_BYTES + HALF_BYTES, 64, head, q0t, batch);
+        tma_store_commit();
+        tma_store_wait<0>();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// 4-D map over a [B, S, heads, 128] bf16 view with token stride `ld` (elements): dims {128, heads, S, B}, 64x128 boxes.
+static int make_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S, int64_t heads, int64_t ld) {
+  uint64_t dims[4] = {128, static_cast<uint64_t>(heads), static_cast<uint64_t>(S), static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {128 * 2, static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(S) * ld * 2};
+  uint32_t box[4] = {64, 1, 128, 1};
+  return encode_tmap_bf16(tm, base, 4, dims, strides, box);
+}
+
+}  // namespace fa2
+
+// Plain-causal forward through the two-tile kernel; called by b200_fa_fwd_flashmask (fa_fwd.cu) when no mask is given.
+int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* lse, int64_t B, int64_t S, int64_t num_heads,
+                   int64_t num_kv_heads, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float softmax_scale,
+                   cudaStream_t stream) {
+  using namespace fa2;
+  CUtensorMap tmQ, tmK, tmV, tmO;
+  int rc;
+  if ((rc = make_map(&tmQ, q, B, S, num_heads, ldq)) != 0) return rc;
+  if ((rc = make_map(&tmK, k, B, S, num_kv_heads, ldk)) != 0) return rc;
+  if ((rc = make_map(&tmV, v, B, S, num_kv_heads, ldv)) != 0) return rc;
+  if ((rc = make_map(&tmO, o, B, S, num_heads, ldo)) != 0) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("fa_fwd2 smem attr: %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  Params p;
+  p.S = static_cast<int>(S); p.B = static_cast<int>(B); p.nh = static_cast<int>(num_heads);
+  p.kvh = static_cast<int>(num_kv_heads);
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.lse = lse;
+  dim3 grid(static_cast<unsigned>((S + 255) / 256), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
+  fa_fwd2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  return check_launch("fa_fwd2");
+}
+
+}  // namespace b200

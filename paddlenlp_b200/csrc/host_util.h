@@ -16,6 +16,11 @@ int check_launch(const char* what);  // cudaGetLastError() -> return code
 
 int sm_count();  // multiprocessors of the current device (cached per device)
 int skinny_gemm_impl();   // b200_set_skinny_gemm(): 1 = swapped-operand two-CTA/SM kernel (gemm_skinny.cu), 0 = the 128x256 persistent kernel
+int fa_fwd_impl();         // b200_set_fa_fwd_impl(): 2 = two-q-tile kernel (fa_fwd2.cu, plain causal), 1 = fa_fwd.cu for everything
+// fa_fwd2.cu: plain-causal forward (same argument meaning as b200_fa_fwd)
+int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* lse, int64_t B, int64_t S, int64_t num_heads,
+                   int64_t num_kv_heads, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float softmax_scale,
+                   cudaStream_t stream);
 bool pdl_enabled();   // b200_set_pdl(): launch GEMMs with programmatic dependent launch (decode-step kernel chains)
 
 // Launch `kern` on `stream`; when PDL is enabled the launch carries the programmatic-stream-serialization attribute, so the

@@ -82,6 +82,13 @@ class FusedMultiTransformerBase:
         self._ffn1_il: List[Optional[torch.Tensor]] = [None] * self.L   # decode-step copy of ffn1_weight, columns interleaved per 64
         self.rope = ops.rope_tables(self.d, c.max_position_embeddings, float(c.rope_theta), self.device)
 
+    def ensure_rope(self, positions: int):
+        """Grow the fp32 cos/sin tables to cover `positions` rows.  The decode kernels index them with the running sequence
+        length (decode_rope_append reads row seq_len of the tables): a cache longer than config.max_position_embeddings
+        must not read past the tables.  Call outside CUDA-graph capture (generate() does, before the first step)."""
+        if self.rope[0].shape[0] < positions:
+            self.rope = ops.rope_tables(self.d, int(positions), float(self.config.rope_theta), self.device)
+
     def _bias(self, i):
         if self.qkv_biases[i] is None:
             return None

@@ -63,6 +63,11 @@ class GenerationInferenceModel:
             max_len = cache_kvs[0].shape[3]
         if S + max_length > max_len:
             raise ValueError(f"cache max_len {max_len} < prompt {S} + max_length {max_length}")
+        # the rotary tables must cover every position the decode steps will index (they have max_position_embeddings rows at
+        # construction; the KV cache may be longer): grow them now, before any kernel or graph captures their pointers
+        tb = getattr(self, "transformer_block", None)
+        if tb is not None and hasattr(tb, "ensure_rope"):
+            tb.ensure_rope(S + max_length)
         eos = torch.tensor([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id or [-1]),
                            dtype=torch.int64, device=dev)
         st = dict(

@@ -162,11 +162,55 @@ def colsum(a: torch.Tensor, out: torch.Tensor, accumulate: bool = True):
 # ----------------------------------------------------------------------------------------------------------
 # RoPE
 # ----------------------------------------------------------------------------------------------------------
-def rope_tables(head_dim: int, max_pos: int, theta: float, device):
+def rope_inv_freq(head_dim: int, theta: float, scaling: Optional[dict] = None, seq_len: int = 0,
+                  max_position_embeddings: int = 0) -> torch.Tensor:
+    """fp32 inverse frequencies [head_dim/2] on the CPU for the reference's rotary variants (llama/modeling.py):
+      None / {}                          LlamaRotaryEmbedding                    :402-439
+      {"rope_type": "llama3", factor, low_freq_factor, high_freq_factor, original_max_position_embeddings}
+                                         Llama3RotaryEmbedding                   :520-554  (Llama-3.1 wavelength bands)
+      {"type": "ntk", "factor": f}       LlamaNTKScalingRotaryEmbedding          :464-470  (base * f^(d/(d-2)))
+      {"type": "dynamic_ntk", "factor"}  LlamaDynamicNTKScalingRotaryEmbedding   :473-517  (base rescaled only when
+                                         seq_len > max_position_embeddings)
+      {"type": "linear", "factor": f}    handled in rope_tables (positions / f)  :440-461"""
+    kind = None if not scaling else (scaling.get("rope_type") or scaling.get("type"))
+    base = float(theta)
+    d = head_dim
+    if kind == "ntk":
+        base = base * float(scaling["factor"]) ** (d / (d - 2))
+    elif kind == "dynamic_ntk" and max_position_embeddings and seq_len > max_position_embeddings:
+        f = float(scaling["factor"])
+        alpha = (f * seq_len / max_position_embeddings) - (f - 1)
+        base = base * alpha ** (d / (d - 2))
+    inv_freq = 1.0 / (base ** (torch.arange(0, d, 2, dtype=torch.float32) / d))
+    if kind == "llama3":
+        factor = float(scaling["factor"])
+        lo, hi = float(scaling["low_freq_factor"]), float(scaling["high_freq_factor"])
+        orig = float(scaling["original_max_position_embeddings"])
+        low_wavelen, high_wavelen = orig / lo, orig / hi
+        out = []
+        for freq in inv_freq:                          # per-frequency loop in fp32 tensor arithmetic, as the reference (:540-552)
+            wavelen = 2 * math.pi / freq
+            if wavelen < high_wavelen:
+                out.append(freq)
+            elif wavelen > low_wavelen:
+                out.append(freq / factor)
+            else:
+                smooth = (orig / wavelen - lo) / (hi - lo)
+                out.append((1 - smooth) * freq / factor + smooth * freq)
+        inv_freq = torch.stack(out).to(torch.float32)
+    elif kind not in (None, "ntk", "dynamic_ntk", "linear", "default"):
+        raise ValueError(f"Unknown RoPE scaling type {kind}")       # llama/modeling.py:864
+    return inv_freq
+
+
+def rope_tables(head_dim: int, max_pos: int, theta: float, device, scaling: Optional[dict] = None,
+                max_position_embeddings: int = 0):
     """fp32 cos/sin tables [max_pos, head_dim/2], computed on the CPU exactly as the reference does
     (llama/modeling.py:409-423) so that host and device share bits, then uploaded once."""
-    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    inv_freq = rope_inv_freq(head_dim, theta, scaling, seq_len=max_pos, max_position_embeddings=max_position_embeddings)
     t = torch.arange(max_pos, dtype=torch.float32)
+    if scaling and (scaling.get("rope_type") or scaling.get("type")) == "linear":
+        t = t / float(scaling["factor"])
     freqs = torch.einsum("i,j->ij", t, inv_freq)
     return freqs.cos().contiguous().to(device), freqs.sin().contiguous().to(device)
 

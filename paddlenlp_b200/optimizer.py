@@ -49,6 +49,21 @@ class ConstantLR(LRScheduler):
         return self.base_lr
 
 
+class ConstantLRWithWarmup(LRScheduler):
+    """get_scheduler("constant_with_warmup") (trainer_utils.py get_constant_schedule_with_warmup): linear ramp from 0 over
+    `num_warmup_steps`, then the base learning rate."""
+
+    def __init__(self, learning_rate, num_warmup_steps):
+        super().__init__(learning_rate)
+        self.warmup = int(num_warmup_steps)
+
+    def get_lr(self):
+        s = self.last_epoch
+        if s < self.warmup:
+            return self.base_lr * float(s) / float(max(1, self.warmup))
+        return self.base_lr
+
+
 class LinearDecayWithWarmup(LRScheduler):
     """get_scheduler("linear"): linear warm-up then linear decay to 0 at num_training_steps."""
 
@@ -107,8 +122,10 @@ def get_scheduler(name, learning_rate, num_warmup_steps=0, num_training_steps=No
         return LinearDecayWithWarmup(learning_rate, num_training_steps, num_warmup_steps)
     if name == "cosine":
         return CosineDecayWithWarmup(learning_rate, num_training_steps, num_warmup_steps, num_cycles)
-    if name in ("constant", "constant_with_warmup"):
+    if name == "constant":
         return ConstantLR(learning_rate)
+    if name == "constant_with_warmup":
+        return ConstantLRWithWarmup(learning_rate, num_warmup_steps)
     raise ValueError(f"unknown lr_scheduler_type {name}")
 
 
@@ -181,8 +198,10 @@ class AdamW:
         eng = self.engine
         m1 = eng.named_views(flat=self.exp_avg)
         m2 = eng.named_views(flat=self.exp_avg_sq)
-        b1 = torch.tensor([self.beta1 ** self.step_count], dtype=torch.float32)
-        b2 = torch.tensor([self.beta2 ** self.step_count], dtype=torch.float32)
+        # Paddle's accumulators start at beta and are multiplied by beta AFTER each update: after `step` steps they hold
+        # beta ** (step + 1) (the value the NEXT step's bias correction uses)
+        b1 = torch.tensor([self.beta1 ** (self.step_count + 1)], dtype=torch.float32)
+        b2 = torch.tensor([self.beta2 ** (self.step_count + 1)], dtype=torch.float32)
         out: Dict[str, torch.Tensor] = {}
         for k in m1:
             out[k + "/moment1_0"] = m1[k]
@@ -196,7 +215,7 @@ class AdamW:
 
     def load_named_state(self, optim_items, master_items, step: Optional[int] = None):
         """`optim_items` / `master_items`: iterables of (key, host tensor) in the layout above.  The step count comes from
-        `step` when given, else from beta1_pow_acc (beta1 ** step)."""
+        `step` when given, else from beta1_pow_acc (= beta1 ** (step + 1), Paddle's post-update convention)."""
         eng = self.engine
         m1 = eng.named_views(flat=self.exp_avg)
         m2 = eng.named_views(flat=self.exp_avg_sq)
@@ -213,7 +232,7 @@ class AdamW:
                 elif kind == "beta1_pow_acc_0":
                     v = float(t.reshape(-1)[0])
                     if 0.0 < v < 1.0:
-                        pow_step = round(math.log(v) / math.log(self.beta1))
+                        pow_step = max(0, round(math.log(v) / math.log(self.beta1)) - 1)
                     elif v == 1.0:
                         pow_step = 0
                     continue

@@ -133,6 +133,34 @@ class _PhaseTimers:
         return out
 
 
+class IterableDatasetShard(torch.utils.data.IterableDataset):
+    """trainer_utils.py IterableDatasetShard: every process iterates the whole stream; of each group of
+    `batch_size * num_processes` samples, process i keeps samples [i * batch_size, (i + 1) * batch_size).  A trailing partial
+    group is dropped (drop_last) or completed by wrapping around to the first samples."""
+
+    def __init__(self, dataset, batch_size: int = 1, drop_last: bool = False, num_processes: int = 1, process_index: int = 0):
+        self.dataset, self.batch_size, self.drop_last = dataset, batch_size, drop_last
+        self.num_processes, self.process_index = num_processes, process_index
+
+    def __iter__(self):
+        real = self.batch_size * self.num_processes
+        lo, hi = self.process_index * self.batch_size, (self.process_index + 1) * self.batch_size
+        first, cur = None, []
+        for el in self.dataset:
+            cur.append(el)
+            if len(cur) == real:
+                yield from cur[lo:hi]
+                if first is None:
+                    first = list(cur)
+                cur = []
+        if cur and not self.drop_last:
+            if first is None:
+                first = list(cur)
+            while len(cur) < real:
+                cur += first
+            yield from cur[lo:hi]
+
+
 def default_data_collator(features: List[Dict[str, Any]]) -> Dict[str, torch.Tensor]:
     out = {}
     for k in features[0]:
@@ -163,16 +191,23 @@ class Trainer:
 
     # ------------------------------------------------------------------------------------------------
     def get_train_dataloader(self):
+        """trainer.py:1457-1530 (_get_train_sampler / get_train_dataloader): a SHUFFLING batch sampler — `BatchSampler(shuffle=True)`
+        for one process, `DistributedBatchSampler(shuffle=True)` across ranks — re-seeded per epoch (`set_epoch`) so that resume
+        can skip the consumed batches deterministically; an IterableDataset is sharded by rank (`IterableDatasetShard`)."""
         a = self.args
         ds = self.train_dataset
         if ds is None:
             raise ValueError("Trainer: training requires a train_dataset.")
         world, rank = a.dataset_world_size, a.dataset_rank
         if isinstance(ds, torch.utils.data.IterableDataset):
+            if world > 1:
+                ds = IterableDatasetShard(ds, batch_size=a.per_device_train_batch_size, drop_last=a.dataloader_drop_last,
+                                          num_processes=world, process_index=rank)
             return torch.utils.data.DataLoader(ds, batch_size=a.per_device_train_batch_size, collate_fn=self.data_collator,
                                                num_workers=a.dataloader_num_workers, pin_memory=True)
-        sampler = torch.utils.data.distributed.DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=False,
-                                                                   drop_last=a.dataloader_drop_last) if world > 1 else None
+        # DistributedSampler with one replica is a seeded shuffling sampler with set_epoch(): the same class serves both cases
+        sampler = torch.utils.data.distributed.DistributedSampler(ds, num_replicas=max(1, world), rank=rank if world > 1 else 0,
+                                                                   shuffle=True, seed=int(a.seed), drop_last=a.dataloader_drop_last)
         return torch.utils.data.DataLoader(ds, batch_size=a.per_device_train_batch_size, sampler=sampler, shuffle=False,
                                            collate_fn=self.data_collator, drop_last=a.dataloader_drop_last,
                                            num_workers=a.dataloader_num_workers, pin_memory=True)
@@ -227,12 +262,30 @@ class Trainer:
         return out
 
     def compute_loss(self, model, inputs, return_outputs=False):
-        """trainer.py:2157-2197: criterion(outputs, labels) when a criterion is given, else the model's own loss."""
+        """trainer.py:2157-2197: criterion(outputs, labels) when a criterion is given, else the model's own loss.
+
+        With the built-in pre-training criterion (LlamaPretrainingCriterion / Qwen2PretrainingCriterion: masked-mean fp32 CE)
+        the labels are handed to the model so that the fused head + criterion path runs (same value, no second logits
+        buffer) with the criterion's ignore_index.  Any other callable receives differentiable logits: the model keeps its
+        activations and `loss.backward()` feeds d(logits) into the engine's explicit backward."""
         if self.criterion is not None:
+            from ..transformers.llama.modeling import LlamaPretrainingCriterion
+
+            inputs = dict(inputs)
             labels = inputs.pop("labels")
-            outputs = model(**inputs)
-            logits = outputs[0] if isinstance(outputs, (tuple, list)) else outputs.logits
-            loss = self.criterion(logits, labels)
+            inner = getattr(model, "_layers", model)
+            if isinstance(self.criterion, LlamaPretrainingCriterion) and hasattr(inner, "criterion"):
+                old = inner.criterion.ignore_index
+                inner.criterion.ignore_index = self.criterion.ignore_index
+                try:
+                    outputs = model(**inputs, labels=labels)
+                finally:
+                    inner.criterion.ignore_index = old
+                loss = outputs[0] if isinstance(outputs, (tuple, list)) else outputs.loss
+            else:
+                outputs = model(**inputs)
+                logits = outputs[0] if isinstance(outputs, (tuple, list)) else outputs.logits
+                loss = self.criterion(logits, labels)
         else:
             outputs = model(**inputs)
             loss = outputs[0] if isinstance(outputs, (tuple, list)) else outputs.loss
@@ -443,12 +496,12 @@ class Trainer:
             if self._engine().device.type == "cuda":
                 torch.cuda.synchronize(self._engine().device)
             m = getattr(self.model, "_layers", self.model)
-            m.save_pretrained(tmp)
+            m.save_pretrained(tmp, unified_checkpoint=True)
             if not a.save_only_model:
                 cu.save_sharded(self.optimizer.named_optimizer_state(), tmp, cu.SAFE_OPTIMIZER_NAME,
-                                cu.SAFE_OPTIMIZER_INDEX_NAME)
+                                cu.SAFE_OPTIMIZER_INDEX_NAME, always_index=True)
                 cu.save_sharded(self.optimizer.named_master_weights(), tmp, cu.SAFE_MASTER_WEIGHTS_NAME,
-                                cu.SAFE_MASTER_WEIGHTS_INDEX_NAME)
+                                cu.SAFE_MASTER_WEIGHTS_INDEX_NAME, always_index=True)
                 torch.save(self.lr_scheduler.state_dict(), os.path.join(tmp, SCHEDULER_NAME))
             self.state.save_to_json(os.path.join(tmp, TRAINER_STATE_NAME))
             with open(os.path.join(tmp, TRAINING_ARGS_NAME), "w", encoding="utf-8") as f:

@@ -94,9 +94,12 @@ def _shard_name(base: str, i: int, n: int) -> str:
 
 
 def save_sharded(tensors: Dict[str, torch.Tensor], directory: str, weights_name: str = SAFE_WEIGHTS_NAME,
-                 index_name: str = SAFE_WEIGHTS_INDEX_NAME, max_shard_size="5GB") -> List[str]:
+                 index_name: str = SAFE_WEIGHTS_INDEX_NAME, max_shard_size="5GB", always_index: bool = False) -> List[str]:
     """Writes `tensors` (any device; each is copied to the host when its shard is written, so peak host memory is one
-    shard) and returns the list of files written."""
+    shard) and returns the list of files written.  A single shard is written as the bare `weights_name` (what
+    `save_pretrained` / shard_checkpoint do, model_utils.py:562-640) unless `always_index`: the Trainer's unified checkpoint
+    always writes `<stem>-00001-of-0000N<ext>` plus the index, and its loader requires the index
+    (trainer/plugins/unified_checkpoint.py:301-423, select_model_weight_index)."""
     from safetensors.torch import save_file
 
     os.makedirs(directory, exist_ok=True)
@@ -107,7 +110,7 @@ def save_sharded(tensors: Dict[str, torch.Tensor], directory: str, weights_name:
         if stale == weights_name or stale == index_name or re.fullmatch(re.escape(stem) + r"-\d{5}-of-\d{5}" + re.escape(ext), stale):
             os.remove(os.path.join(directory, stale))
     written = []
-    if len(shards) == 1:
+    if len(shards) == 1 and not always_index:
         save_file({k: tensors[k].detach().cpu().contiguous() for k in shards[0]}, os.path.join(directory, weights_name),
                   metadata={"format": "pt"})
         return [weights_name]

@@ -58,6 +58,13 @@ class DecoderEngine:
         if self.h % 8 or self.I % 8 or self.V % 8:
             raise ValueError("hidden_size, intermediate_size and vocab_size must be multiples of 8")
         self.qkv_n = (self.nh + 2 * self.kvh) * self.d
+        # recompute (llama/modeling.py:1706-1733 `recompute_training_full`): keep only each layer's input and re-run the
+        # layer forward inside backward.  Only the "full" granularity exists here (the "full_attn" / "core_attn" splits
+        # exist to trade memory against the reference's unfused attention; the fused attention keeps no S x S tensor).
+        self.recompute = bool(getattr(config, "recompute", False))
+        gran = getattr(config, "recompute_granularity", "full") or "full"
+        if self.recompute and gran != "full":
+            raise NotImplementedError(f"recompute_granularity={gran!r}: only 'full' (whole decoder layer) is implemented")
 
         # ---- flat layout: [matrices | vectors] ----
         mats: List[Tuple[str, Tuple[int, ...]]] = [("embed", (self.V, self.h))]
@@ -96,9 +103,19 @@ class DecoderEngine:
     def num_parameters(self) -> int:
         return sum(math.prod(s) for _, s in self._offsets.values())
 
-    def init_weights(self, seed: int = 42):
+    def init_weights(self, seed: int = 42, on_host: Optional[bool] = None):
         """Reference init (llama/modeling.py:1386-1436): N(0, initializer_range) for every Linear / Embedding /
-        lm_head weight, o_proj and down_proj scaled by 1/sqrt(2L), RMSNorm weights 1, biases 0."""
+        lm_head weight, o_proj and down_proj scaled by 1/sqrt(2L), RMSNorm weights 1, biases 0.
+
+        on_host=True draws every tensor in fp32 from ONE seeded CPU generator in the reference's parameter order
+        (embed_tokens, then per layer q, k, v, o[, q/k/v bias = 0], gate, up, down, then lm_head), applies the 1/sqrt(2L)
+        factor in fp32 and rounds to bf16 once — so a CPU restatement that draws the same way holds the same bits
+        (SURVEY.md §8a row a10).  Default: host for models below 2^28 parameters, device draws (bf16 normals straight
+        into the flat buffer, same distribution, no 30 GB fp32 host round trip) above."""
+        if on_host is None:
+            on_host = bool(getattr(self.cfg, "init_on_host", self.num_parameters() < (1 << 28)))
+        if on_host:
+            return self._init_weights_host(seed)
         gen = torch.Generator(device=self.device)
         gen.manual_seed(seed)
         std = self.cfg.initializer_range
@@ -116,6 +133,38 @@ class DecoderEngine:
             if self.qkv_bias:
                 self.p[f"l{i}.qkv_b"].zero_()
         self.p["norm"].fill_(1.0)
+        self._bias_f32.clear()
+
+    def _init_weights_host(self, seed: int):
+        g = torch.Generator().manual_seed(seed)
+        std = float(self.cfg.initializer_range)
+        factor = 1.0 / math.sqrt(2 * self.L)
+        qn, kn = self.nh * self.d, self.kvh * self.d
+
+        def draw(*shape, scale=1.0):
+            t = torch.randn(*shape, generator=g, dtype=torch.float32) * std
+            if scale != 1.0:
+                t = t * scale
+            return t.to(BF16)
+
+        with torch.no_grad():
+            self.p["embed"].copy_(draw(self.V, self.h))
+            for i in range(self.L):
+                w = self.p[f"l{i}.qkv_w"]
+                w[:, :qn].copy_(draw(self.h, qn))
+                w[:, qn:qn + kn].copy_(draw(self.h, kn))
+                w[:, qn + kn:].copy_(draw(self.h, kn))
+                self.p[f"l{i}.o_w"].copy_(draw(qn, self.h, scale=factor))
+                gu = self.p[f"l{i}.gu_w"]
+                gu[:, :self.I].copy_(draw(self.h, self.I))
+                gu[:, self.I:].copy_(draw(self.h, self.I))
+                self.p[f"l{i}.down_w"].copy_(draw(self.I, self.h, scale=factor))
+                self.p[f"l{i}.ln1"].fill_(1.0)
+                self.p[f"l{i}.ln2"].fill_(1.0)
+                if self.qkv_bias:
+                    self.p[f"l{i}.qkv_b"].zero_()
+            self.p["norm"].fill_(1.0)
+            self.p["head"].copy_(draw(self.h, self.V))
         self._bias_f32.clear()
 
     def named_views(self, grads: bool = False, flat: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
@@ -178,8 +227,13 @@ class DecoderEngine:
 
     def _rope_tables(self, need_pos: int):
         if self._rope is None or self._rope[0].shape[0] < need_pos:
-            n = max(need_pos, int(getattr(self.cfg, "max_position_embeddings", 0) or 0))
-            self._rope = ops.rope_tables(self.d, n, float(self.cfg.rope_theta), self.device)
+            mpe = int(getattr(self.cfg, "max_position_embeddings", 0) or 0)
+            n = max(need_pos, mpe)
+            spec = self.cfg.rope_scaling_spec() if hasattr(self.cfg, "rope_scaling_spec") else None
+            if spec and spec.get("type") == "linear":
+                n = max(n, int(mpe * float(spec["factor"])))             # llama/modeling.py:443: table covers mpe * factor
+            self._rope = ops.rope_tables(self.d, n, float(self.cfg.rope_theta), self.device, scaling=spec,
+                                         max_position_embeddings=mpe)
         return self._rope
 
     # ------------------------------------------------------------------------------------------------
@@ -206,6 +260,13 @@ class DecoderEngine:
         x2 = ops.gemm(m, p[f"l{i}.down_w"], residual=x1)
         if save is not None:
             save.append((x, rstd1, n1, qkv, attn2, lse, x1, rstd2, n2, gu, m))
+        return x2
+
+    def _layer_fwd_ckpt(self, i: int, x: torch.Tensor, B: int, S: int, pos, save: Optional[list], mask=None):
+        """Recompute mode: run the layer without keeping its activations; remember only the layer input."""
+        x2 = self._layer_fwd(i, x, B, S, pos, None, mask)
+        if save is not None:
+            save.append((x,))
         return x2
 
     def _prep_inputs(self, input_ids: torch.Tensor, position_ids: Optional[torch.Tensor]):
@@ -246,8 +307,9 @@ class DecoderEngine:
         mask = self._prep_mask(attn_mask_startend_row_indices, B, S)
         self._mask = mask
         x = ops.embedding_fwd(ids, self.p["embed"])
+        layer = self._layer_fwd_ckpt if (self.recompute and save is not None) else self._layer_fwd
         for i in range(self.L):
-            x = self._layer_fwd(i, x, B, S, pos, save, mask)
+            x = layer(i, x, B, S, pos, save, mask)
         hf, rstd_f = ops.rmsnorm_fwd(x, self.p["norm"], self.eps)
         return B, S, ids, pos, x, hf, rstd_f
 
@@ -276,13 +338,27 @@ class DecoderEngine:
                                labels=lab, loss_tok=loss_tok, lse=lse, loss_out=loss_out)
         return loss_out, logits.view(B, S, self.V)
 
+    @torch.no_grad()
+    def forward_logits_train(self, input_ids, position_ids=None, attn_mask_startend_row_indices=None) -> torch.Tensor:
+        """Training forward WITHOUT the fused criterion: logits [B, S, V] (bf16) with the activations kept, for a caller-side
+        loss (Trainer(criterion=<any callable>), trainer.py:2157-2197).  backward(dlogits=...) completes the step."""
+        save: list = []
+        B, S, ids, pos, x, hf, rstd_f = self.hidden_states(input_ids, position_ids, save=save,
+                                                           attn_mask_startend_row_indices=attn_mask_startend_row_indices)
+        logits = ops.gemm(hf, self.p["head"])
+        self._saved = dict(B=B, S=S, ids=ids, pos=pos, mask=self._mask, layers=save, x_last=x, hf=hf, rstd_f=rstd_f,
+                           logits=None, labels=None)
+        return logits.view(B, S, self.V)
+
     # ------------------------------------------------------------------------------------------------
     # backward
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def backward(self, grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None):
-        """Backward of the last forward_loss(): gradients are accumulated into flat_grads (or overwrite it if
-        grads_fresh).  The logits buffer is consumed (overwritten by dlogits)."""
+    def backward(self, grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None,
+                 dlogits: Optional[torch.Tensor] = None):
+        """Backward of the last forward_loss() (or forward_logits_train() + caller-supplied `dlogits` [T, V] bf16): gradients
+        are accumulated into flat_grads (or overwrite it if grads_fresh).  The logits buffer is consumed (overwritten by
+        dlogits)."""
         st = self._saved
         if st is None:
             raise RuntimeError("backward() without a preceding forward_loss()")
@@ -290,8 +366,17 @@ class DecoderEngine:
         acc = not self.grads_fresh
         p, g = self.p, self.g
         B, S = st["B"], st["S"]
-        dlogits = ops.ce_bwd_(st["logits"], st["labels"], st["loss_tok"], st["lse"], st["loss_out"], grad_scale,
-                              grad_scale_dev)
+        if st["labels"] is None:
+            if dlogits is None:
+                raise RuntimeError("backward() after forward_logits_train() needs dlogits")
+            dlogits = dlogits.reshape(B * S, self.V)
+            if dlogits.dtype != BF16 or not dlogits.is_contiguous():
+                dlogits = dlogits.to(BF16).contiguous()
+            if grad_scale != 1.0:
+                dlogits = dlogits * grad_scale
+        else:
+            dlogits = ops.ce_bwd_(st["logits"], st["labels"], st["loss_tok"], st["lse"], st["loss_out"], grad_scale,
+                                  grad_scale_dev)
         hook, self.grad_ready_hook = self.grad_ready_hook, None      # one backward per arming
         dhf = ops.gemm(dlogits, p["head"], trans_b=True)
         ops.gemm(st["hf"], dlogits, out=g["head"], trans_a=True, accumulate=acc)
@@ -322,6 +407,10 @@ class DecoderEngine:
         return lo, o + _align8(math.prod(shp))
 
     def _layer_bwd(self, i, dx2, saved, B, S, pos, acc, mask=None):
+        if len(saved) == 1:                      # recompute: rebuild this layer's activations from its input
+            tmp: list = []
+            self._layer_fwd(i, saved[0], B, S, pos, tmp, mask)
+            saved = tmp[0]
         (x, rstd1, n1, qkv, attn2, lse, x1, rstd2, n2, gu, m) = saved
         p, g = self.p, self.g
         T = B * S

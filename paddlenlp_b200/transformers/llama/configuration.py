@@ -11,7 +11,8 @@ class LlamaConfig(PretrainedConfig):
                  seq_length=2048, num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=None,
                  initializer_range=0.02, rms_norm_eps=1e-6, rope_theta=10000.0, use_cache=True,
                  fuse_attention_qkv=False, fuse_attention_ffn=False, pad_token_id=0, bos_token_id=1, eos_token_id=2,
-                 tie_word_embeddings=False, alibi=False, rope_scaling_factor=1.0, rope_scaling_type=None, **kwargs):
+                 tie_word_embeddings=False, alibi=False, rope_scaling_factor=1.0, rope_scaling_type=None, rope_scaling=None,
+                 **kwargs):
         self.vocab_size = vocab_size
         self.hidden_size = hidden_size
         self.intermediate_size = intermediate_size
@@ -29,6 +30,9 @@ class LlamaConfig(PretrainedConfig):
         self.alibi = alibi
         self.rope_scaling_factor = rope_scaling_factor
         self.rope_scaling_type = rope_scaling_type
+        self.rope_scaling = rope_scaling                       # {"rope_type": "llama3", ...} (HF Llama-3.1 config.json)
+        if rope_scaling_type not in (None, "linear", "ntk", "dynamic_ntk"):
+            raise ValueError(f"Unknown RoPE scaling type {rope_scaling_type}")      # llama/modeling.py:864
         if alibi:
             raise NotImplementedError("alibi attention bias is outside the hot path this build covers")
         if tie_word_embeddings:
@@ -39,6 +43,16 @@ class LlamaConfig(PretrainedConfig):
     @property
     def rope(self):
         return not self.alibi
+
+    def rope_scaling_spec(self):
+        """The rotary variant `_init_rope` would pick (llama/modeling.py:821-864) as a dict for ops.rope_tables, or None."""
+        rs = getattr(self, "rope_scaling", None)
+        if rs is not None and rs.get("rope_type", None) == "llama3":
+            return dict(rs)
+        t = getattr(self, "rope_scaling_type", None)
+        if t is None:
+            return None
+        return {"type": t, "factor": float(self.rope_scaling_factor)}
 
     # public presets used by bench / tests (hyper-parameters from the public model cards, SURVEY.md §8)
     @classmethod

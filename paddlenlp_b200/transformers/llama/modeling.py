@@ -16,7 +16,7 @@ import torch
 
 from ... import ops
 from ..model_outputs import BaseModelOutputWithPastAndCrossAttentions, CausalLMOutputWithCrossAttentions
-from ..model_utils import PretrainedModel, _CausalLMLossFn
+from ..model_utils import PretrainedModel, _CausalLMLogitsFn, _CausalLMLossFn
 from .configuration import LlamaConfig
 
 __all__ = ["LlamaModel", "LlamaPretrainedModel", "LlamaForCausalLM", "LlamaPretrainingCriterion"]
@@ -60,8 +60,38 @@ def _check_unsupported(attention_mask, inputs_embeds, use_cache, past_key_values
     if output_attentions:
         raise NotImplementedError("output_attentions: flash attention never materialises the attention matrix")
     if attention_mask is not None and attention_mask.dim() > 2:
-        raise NotImplementedError("dense 3-D/4-D attention masks: only causal attention is implemented "
-                                  "(right-padded batches with labels -100 on pads are exact under a causal mask)")
+        raise NotImplementedError("dense 3-D/4-D attention masks: pass attn_mask_startend_row_indices (FlashMask) for packed "
+                                  "samples or a 2-D [batch, seq] padding mask")
+
+
+def _mask_rows_from_padding_mask(attention_mask: torch.Tensor) -> torch.Tensor:
+    """2-D `[batch, src_len]` padding mask (1 = attend, 0 = padding) -> FlashMask causal start rows.
+
+    The reference expands it to `[b, 1, tgt, src]` and ANDs it with the causal mask (llama/modeling.py:1517-1552,
+    qwen2/modeling.py:950-973): key column c is hidden from every query row when mask[b, c] == 0.  In start-row form that
+    is start[c] = c + 1 (the column stays visible to its own — padding — row only, which keeps that row's softmax
+    non-empty; its output carries label -100 / is discarded by the caller).  A trailing run of padding columns (right
+    padding) is already invisible to every real row under the causal mask and is left at S.  This covers left- and
+    right-padded batches (the Llama tokenizer pads on the left, llama/tokenizer.py:52); zeros in the middle of a row give
+    non-monotonic start rows and are rejected by the engine's form check.  No host sync."""
+    m = attention_mask != 0
+    B, S = m.shape
+    dev = m.device
+    later_real = torch.flip(torch.cumsum(torch.flip(m.to(torch.int32), dims=[1]), dim=1), dims=[1]) > 0   # any real col >= c
+    own = torch.arange(1, S + 1, dtype=torch.int32, device=dev)[None, :].expand(B, S)
+    full = torch.full((B, S), S, dtype=torch.int32, device=dev)
+    return torch.where(m | ~later_real, full, own).contiguous()
+
+
+def _resolve_mask(attention_mask, attn_mask_startend_row_indices):
+    """attn_mask_startend_row_indices wins when both are given (llama/modeling.py:1683-1688)."""
+    if attn_mask_startend_row_indices is not None:
+        return attn_mask_startend_row_indices
+    if attention_mask is not None:
+        if attention_mask.dim() != 2:
+            raise NotImplementedError("attention_mask must be 2-D [batch, seq]")
+        return _mask_rows_from_padding_mask(attention_mask)
+    return None
 
 
 class LlamaPretrainedModel(PretrainedModel):
@@ -81,8 +111,8 @@ class LlamaModel(LlamaPretrainedModel):
                 past_key_values=None, output_attentions=False, output_hidden_states=None, return_dict=False,
                 attn_mask_startend_row_indices=None, **kw):
         _check_unsupported(attention_mask, inputs_embeds, use_cache, past_key_values, output_attentions)
-        B, S, _, _, _, hf, _ = self.engine.hidden_states(input_ids, position_ids,
-                                                         attn_mask_startend_row_indices=attn_mask_startend_row_indices)
+        ms = _resolve_mask(attention_mask, attn_mask_startend_row_indices)
+        B, S, _, _, _, hf, _ = self.engine.hidden_states(input_ids, position_ids, attn_mask_startend_row_indices=ms)
         hs = hf.view(B, S, -1)
         if return_dict:
             return BaseModelOutputWithPastAndCrossAttentions(last_hidden_state=hs)
@@ -99,7 +129,8 @@ class LlamaForCausalLM(LlamaPretrainedModel):
                 use_cache=False, past_key_values=None, output_attentions=None, output_hidden_states=None,
                 return_dict=None, attn_mask_startend_row_indices=None, **kw):
         _check_unsupported(attention_mask, inputs_embeds, use_cache, past_key_values, output_attentions)
-        ms = attn_mask_startend_row_indices         # FlashMask start rows of packed samples ([B, S] or [B, 1, S(, 1)])
+        # FlashMask start rows of packed samples ([B, S] or [B, 1, S(, 1)]), or derived from a 2-D padding mask
+        ms = _resolve_mask(attention_mask, attn_mask_startend_row_indices)
         loss = None
         if labels is not None and torch.is_grad_enabled():
             loss, logits = _CausalLMLossFn.apply(self._anchor, self.engine, input_ids, labels, position_ids,
@@ -108,6 +139,10 @@ class LlamaForCausalLM(LlamaPretrainedModel):
             loss_out, logits = self.engine.forward_loss(input_ids, labels, position_ids, self.criterion.ignore_index,
                                                         keep_for_backward=False, attn_mask_startend_row_indices=ms)
             loss = loss_out[0]
+        elif torch.is_grad_enabled() and self.training:
+            # no labels, gradient mode, train(): logits stay differentiable (the caller applies its own criterion and calls
+            # loss.backward(), trainer.py:2157-2197); use torch.no_grad() / .eval() for inference
+            logits = _CausalLMLogitsFn.apply(self._anchor, self.engine, input_ids, position_ids, ms)
         else:
             logits = self.engine.forward_logits(input_ids, position_ids, attn_mask_startend_row_indices=ms)
         if return_dict:

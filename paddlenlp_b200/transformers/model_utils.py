@@ -31,6 +31,22 @@ class _CausalLMLossFn(torch.autograd.Function):
         return None, None, None, None, None, None, None
 
 
+class _CausalLMLogitsFn(torch.autograd.Function):
+    """Differentiable logits for a caller-side criterion: forward keeps the engine's activations, backward feeds d(logits)
+    into the engine's explicit backward (gradients land in the flat gradient buffer, like the fused path)."""
+
+    @staticmethod
+    def forward(ctx, anchor, engine, input_ids, position_ids, mask_rows=None):
+        logits = engine.forward_logits_train(input_ids, position_ids, attn_mask_startend_row_indices=mask_rows)
+        ctx.engine = engine
+        return logits
+
+    @staticmethod
+    def backward(ctx, glogits):
+        ctx.engine.backward(1.0, None, dlogits=glogits)
+        return None, None, None, None, None
+
+
 class PretrainedModel(nn.Module):
     config_class = None
     base_model_prefix = ""
@@ -38,6 +54,7 @@ class PretrainedModel(nn.Module):
     def __init__(self, config):
         super().__init__()
         self.config = config
+        self.training = True
 
     # -- construction -------------------------------------------------------------------------------
     def _build_engine(self, config, device=None):
@@ -117,7 +134,7 @@ class PretrainedModel(nn.Module):
         self.engine.params_changed()
 
     def save_pretrained(self, save_directory: str, max_shard_size="5GB", safe_serialization: bool = True,
-                        hf_format: bool = False):
+                        hf_format: bool = False, unified_checkpoint: bool = False):
         """config.json + safetensors shards + index (model_utils.py save_pretrained / shard_checkpoint :562-640).
         `hf_format=True` writes HuggingFace names and `[out, in]` Linear layouts instead of the Paddle ones."""
         from . import conversion_utils as cu
@@ -130,7 +147,8 @@ class PretrainedModel(nn.Module):
             return
         if hf_format:
             sd = cu.paddle_to_hf_state_dict(sd, self.engine.prefix)
-        cu.save_sharded(sd, save_directory, max_shard_size=max_shard_size)
+        # unified_checkpoint: always `model-0000i-of-0000N.safetensors` + index, even for one shard (the Trainer's layout)
+        cu.save_sharded(sd, save_directory, max_shard_size=max_shard_size, always_index=unified_checkpoint)
 
     # -- parameters ---------------------------------------------------------------------------------
     def named_parameters(self, prefix: str = "", recurse: bool = True, remove_duplicate: bool = True):
@@ -153,9 +171,14 @@ class PretrainedModel(nn.Module):
         return self.engine.num_parameters()
 
     def recompute_enable(self):
-        # model_utils.py:1140.  Activation memory is bounded by micro-batching here (gradient accumulation into the
-        # flat buffer) rather than by recomputation; accepted for API compatibility.
+        """model_utils.py:1140: activation recomputation — every decoder layer keeps only its input and is re-run in
+        backward (llama/modeling.py:1706-1733, granularity "full")."""
         self.config.recompute = True
+        self.engine.recompute = True
+
+    def recompute_disable(self):
+        self.config.recompute = False
+        self.engine.recompute = False
 
     def train(self, mode: bool = True):
         self.training = mode

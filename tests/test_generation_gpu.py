@@ -488,3 +488,27 @@ def test_full_width_decode_matches_uncached_forward():
             decisive = (top2[:, 0] - top2[:, 1]) > 4 * err * ref.abs().max()
             assert bool((lg.float().argmax(-1) == ref.argmax(-1))[decisive].all())
             assert decisive.float().mean().item() > 0.5
+
+
+def test_generate_beyond_max_position_embeddings_grows_rope_tables():
+    """the decode kernels index the fp32 cos/sin tables with the running sequence length; a KV cache longer than
+    config.max_position_embeddings must not read past them.  generate() grows the tables: a model configured with 128
+    positions generates, beyond position 128, the same tokens as one configured with 512."""
+    import paddlenlp_b200.transformers as T
+    from oracle import llama_ref as R
+    from paddlenlp_b200.experimental.transformers import LlamaForCausalLMInferenceModel
+
+    kw = dict(vocab_size=512, hidden_size=256, intermediate_size=688, num_hidden_layers=2, num_attention_heads=2,
+              num_key_value_heads=1, rms_norm_eps=1e-5, rope_theta=500000.0)
+    cfg = R.RefConfig(max_position_embeddings=512, **kw)
+    w = R.init_weights(cfg, seed=3)
+    w = {k: (v * 4).to(torch.bfloat16).float() if k.endswith("weight") and "norm" not in k else v for k, v in w.items()}
+    prompt = torch.randint(0, 512, (2, 100), generator=torch.Generator().manual_seed(4))
+    outs = []
+    for mpe in (128, 512):
+        m = LlamaForCausalLMInferenceModel(T.LlamaConfig(max_position_embeddings=mpe, **kw))
+        m.set_state_dict(w)
+        out, _, _ = m.generate(prompt, max_length=60, eos_token_id=-1)
+        assert m.transformer_block.rope[0].shape[0] >= 160
+        outs.append(out.cpu())
+    assert torch.equal(outs[0], outs[1])

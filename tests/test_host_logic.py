@@ -176,3 +176,91 @@ def test_zero_padding_dataset_and_collator():
     assert batch["input_ids"].shape == (2, 12) and batch["input_ids"][0, -1] == 7 and batch["labels"][0, -1] == -100
     assert batch["attn_mask_startend_row_indices"].dtype == torch.int32
     assert batch["attn_mask_startend_row_indices"][0].tolist() == [5] * 5 + [9] * 4 + [0] * 3
+
+
+def test_rope_scaling_variants_match_hf_and_oracle():
+    """llama/modeling.py:440-554 rotary variants: the product tables (paddlenlp_b200.ops.rope_tables) against HuggingFace's
+    ROPE_INIT_FUNCTIONS (independent implementation of the same published formulas) and against the oracle restatement."""
+    import transformers
+    from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
+
+    from oracle import llama_ref as R
+    from paddlenlp_b200 import ops
+    import paddlenlp_b200.transformers as T
+
+    l3 = {"rope_type": "llama3", "factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
+          "original_max_position_embeddings": 8192}
+    hf = transformers.LlamaConfig(hidden_size=4096, num_attention_heads=32, rope_theta=500000.0, max_position_embeddings=131072,
+                                  rope_scaling=dict(l3))
+    inv_hf, _ = ROPE_INIT_FUNCTIONS["llama3"](hf, "cpu")
+    assert torch.equal(ops.rope_inv_freq(128, 500000.0, l3), inv_hf)
+    assert torch.equal(R.rope_inv_freq(128, 500000.0, l3), inv_hf)
+    # config plumbing: rope_scaling dict (HF Llama-3.1 config.json) and the reference's rope_scaling_type / factor pair
+    assert T.LlamaConfig(rope_scaling=dict(l3)).rope_scaling_spec() == l3
+    assert T.LlamaConfig(rope_scaling_type="linear", rope_scaling_factor=4.0).rope_scaling_spec() == {"type": "linear", "factor": 4.0}
+    assert T.LlamaConfig().rope_scaling_spec() is None
+    with pytest.raises(ValueError):
+        T.LlamaConfig(rope_scaling_type="yarn")
+    # linear: positions / factor (:446-450); HF divides inv_freq instead — same angles up to one fp32 rounding
+    cos, sin = ops.rope_tables(128, 64, 10000.0, "cpu", scaling={"type": "linear", "factor": 4.0})
+    t = torch.arange(64, dtype=torch.float32)
+    want = torch.einsum("i,j->ij", t, ops.rope_inv_freq(128, 10000.0) / 4.0)
+    assert (cos - want.cos()).abs().max() < 1e-5 and (sin - want.sin()).abs().max() < 1e-5
+    # ntk: base * f^(d/(d-2)) (:467-470)
+    assert torch.allclose(ops.rope_inv_freq(128, 10000.0, {"type": "ntk", "factor": 2.0}),
+                          ops.rope_inv_freq(128, 10000.0 * 2.0 ** (128 / 126)))
+    # dynamic ntk: unchanged up to max_position_embeddings, rescaled base beyond (:482-487) — HF "dynamic" is the same formula
+    d = {"type": "dynamic_ntk", "factor": 2.0}
+    assert torch.equal(ops.rope_inv_freq(128, 10000.0, d, seq_len=2048, max_position_embeddings=2048), ops.rope_inv_freq(128, 10000.0))
+    hfd = transformers.LlamaConfig(hidden_size=4096, num_attention_heads=32, rope_theta=10000.0, max_position_embeddings=2048,
+                                   rope_scaling={"rope_type": "dynamic", "factor": 2.0})
+    inv_d, _ = ROPE_INIT_FUNCTIONS["dynamic"](hfd, "cpu", seq_len=4096)
+    assert torch.allclose(ops.rope_inv_freq(128, 10000.0, d, seq_len=4096, max_position_embeddings=2048), inv_d, rtol=1e-6, atol=0)
+    for sc in (l3, {"type": "linear", "factor": 4.0}, {"type": "ntk", "factor": 2.0}):
+        a = ops.rope_tables(128, 96, 500000.0, "cpu", scaling=sc)
+        b = R.rope_tables(128, 96, 500000.0, scaling=sc)
+        assert torch.equal(a[0], b[0][:, :64]) and torch.equal(a[1], b[1][:, :64])
+
+
+def test_padding_mask_to_flashmask_start_rows():
+    """2-D [batch, seq] padding masks (llama/modeling.py:1517-1552) as FlashMask start rows: left padding hides the pad columns
+    from every later row; right padding is a no-op under the causal mask; no other pattern is produced."""
+    from paddlenlp_b200.transformers.llama.modeling import _mask_rows_from_padding_mask
+
+    m = torch.tensor([[0, 0, 0, 1, 1, 1, 1, 1],      # left padded by 3
+                      [1, 1, 1, 1, 1, 0, 0, 0],      # right padded by 3
+                      [1, 1, 1, 1, 1, 1, 1, 1]])
+    ms = _mask_rows_from_padding_mask(m)
+    assert ms.dtype == torch.int32
+    assert ms.tolist() == [[1, 2, 3, 8, 8, 8, 8, 8], [8] * 8, [8] * 8]
+    # dense check against the reference's expanded mask: row i sees column c iff c <= i and mask[c] (for real rows)
+    S = 8
+    for b in range(3):
+        for i in range(S):
+            if not m[b, i]:
+                continue
+            for c in range(S):
+                ref_visible = (c <= i) and bool(m[b, c])
+                ours = (c <= i) and (i < int(ms[b, c]))
+                assert ref_visible == ours, (b, i, c)
+
+
+def test_constant_with_warmup_schedule_and_iterable_shard():
+    from paddlenlp_b200.optimizer import get_scheduler
+    from paddlenlp_b200.trainer.trainer import IterableDatasetShard
+
+    s = get_scheduler("constant_with_warmup", 1e-3, num_warmup_steps=4, num_training_steps=100)
+    vals = []
+    for _ in range(8):
+        vals.append(s.get_lr()); s.step()
+    assert vals[:5] == [0.0, 2.5e-4, 5e-4, 7.5e-4, 1e-3] and vals[5:] == [1e-3] * 3      # linear ramp from 0, then constant
+    assert get_scheduler("constant", 1e-3, num_warmup_steps=4).get_lr() == 1e-3
+
+    class Stream(torch.utils.data.IterableDataset):
+        def __iter__(self):
+            return iter(range(22))
+
+    shards = [list(IterableDatasetShard(Stream(), batch_size=2, drop_last=True, num_processes=3, process_index=r)) for r in range(3)]
+    assert shards == [[0, 1, 6, 7, 12, 13], [2, 3, 8, 9, 14, 15], [4, 5, 10, 11, 16, 17]]      # disjoint, every world-th batch
+    tail = [list(IterableDatasetShard(Stream(), batch_size=2, drop_last=False, num_processes=3, process_index=r)) for r in range(3)]
+    assert tail[0][-2:] == [18, 19] and tail[1][-2:] == [20, 21] and tail[2][-2:] == [0, 1]  # partial group completed by wrapping

@@ -154,3 +154,50 @@ def test_checkpoint_resume(tmp_path):
     assert res.optimizer.get_lr() == orig.optimizer.get_lr()
     a, b = res.optimizer.master, orig.optimizer.master
     assert ((a - b).norm() / b.norm()).item() < 1e-4
+
+
+def test_trainer_with_criterion_argument(tmp_path):
+    """Trainer(model, criterion, ...) — the call pattern of llm/run_pretrain.py:541-551: with the built-in
+    pre-training criterion the fused head + criterion path runs; an arbitrary callable receives differentiable logits and
+    loss.backward() reaches the engine.  Both train, and their first losses equal the model's own loss."""
+    import paddlenlp_b200.transformers as T
+    from paddlenlp_b200.trainer import Trainer, TrainingArguments
+
+    def run(criterion):
+        torch.manual_seed(0)
+        model = tiny()
+        args = TrainingArguments(output_dir=str(tmp_path), per_device_train_batch_size=2, gradient_accumulation_steps=2,
+                                 max_steps=6, learning_rate=2e-3, weight_decay=0.01, warmup_steps=1, logging_steps=1,
+                                 max_seq_length=128, lr_scheduler_type="linear")
+        tr = Trainer(model=model, criterion=criterion, args=args, train_dataset=ToyDataset(8, 128, 512))
+        tr.train()
+        return [h["loss"] for h in tr.state.log_history]
+
+    def torch_criterion(logits, labels):            # any callable: plain torch CE on the differentiable logits
+        return torch.nn.functional.cross_entropy(logits.float().reshape(-1, logits.shape[-1]), labels.reshape(-1).to(logits.device))
+
+    base = run(None)
+    fused = run(T.LlamaPretrainingCriterion(ignore_index=-100))
+    custom = run(torch_criterion)
+    assert fused == base                                             # same kernels, same order -> same logged losses
+    assert abs(custom[0] - base[0]) < 2e-3 * abs(base[0])            # same first loss (torch CE vs the CE kernel)
+    assert custom[-1] < custom[0] - 0.3 and fused[-1] < fused[0] - 0.3
+
+
+def test_train_sampler_shuffles_and_resumes_deterministically(tmp_path):
+    """trainer.py:1457-1530: the train sampler shuffles (seeded by args.seed, re-seeded per epoch); two Trainers with the same
+    seed see the same order, a different seed a different one."""
+    from paddlenlp_b200.trainer import Trainer, TrainingArguments
+
+    def order(seed, epoch):
+        args = TrainingArguments(output_dir=str(tmp_path), per_device_train_batch_size=2, max_steps=4, seed=seed)
+        tr = Trainer(model=tiny(), args=args, train_dataset=ToyDataset(16, 128, 512))
+        dl = tr.get_train_dataloader()
+        dl.sampler.set_epoch(epoch)
+        return [tuple(b["input_ids"][:, 0].tolist()) for b in dl]
+
+    a, b, c, d = order(42, 0), order(42, 0), order(43, 0), order(42, 1)
+    ds = ToyDataset(16, 128, 512)
+    in_file_order = [tuple(ds.tok[i:i + 2, 0].tolist()) for i in range(0, 16, 2)]
+    assert a == b and a != c and a != d and a != in_file_order
+    assert sorted(x for t in a for x in t) == sorted(x for t in in_file_order for x in t)

@@ -16,16 +16,15 @@ import paddlenlp_b200.transformers as T  # noqa: E402
 from paddlenlp_b200.experimental.transformers import LlamaForCausalLMInferenceModel  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--prompt", type=int, default=128)
-    ap.add_argument("--gen", type=int, default=1920)
-    ap.add_argument("--layers", type=int, default=0)
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-pdl", action="store_true")
-    ap.add_argument("--block-attn", action="store_true", help="paged KV cache (FusedBlockMultiTransformer, 64-row blocks)")
-    a = ap.parse_args()
+def run(batch=64, prompt=128, gen=1920, layers=0, graph=True, pdl=True, block_attn=False):
+    class A:
+        pass
+    a = A()
+    a.batch, a.prompt, a.gen, a.layers, a.no_graph, a.no_pdl, a.block_attn = batch, prompt, gen, layers, not graph, not pdl, block_attn
+    return _run(a)
+
+
+def _run(a):
     cfg = T.LlamaConfig.llama3_8b(num_hidden_layers=a.layers) if a.layers else T.LlamaConfig.llama3_8b()
     m = LlamaForCausalLMInferenceModel(cfg, block_attn=a.block_attn)
     m.init_random(seed=42)
@@ -62,11 +61,28 @@ def main():
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
     ms_step = decode_ms / steps
     achieved = bytes_per_step / (ms_step / 1e3) / 1e9
-    rec = dict(batch=a.batch, prompt=a.prompt, gen=a.gen, layers=L, prefill_ms=prefill_ms, decode_ms=decode_ms, ms_per_step=ms_step,
+    rec = dict(workload="Llama-3-8B generation decode, batch 64, prompt 128 -> +1920, FusedMultiTransformer KV-cache path "
+                        "(BASELINE.json configs[4])" if (a.batch, a.prompt, a.gen, a.layers) == (64, 128, 1920, 0) else "custom",
+               batch=a.batch, prompt=a.prompt, gen=a.gen, layers=L, paged_kv=bool(a.block_attn), prefill_ms=prefill_ms, decode_ms=decode_ms,
+               ms_per_step=ms_step,
                decode_tokens_per_s=a.batch * steps / (decode_ms / 1e3), bytes_per_step_gb=bytes_per_step / 1e9,
                achieved_gbs=achieved, hbm_peak_gbs=peaks["hbm_gbs"], roofline_frac=achieved / peaks["hbm_gbs"],
                graph=not a.no_graph, pdl=not a.no_pdl, mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, last_tokens=out[0, -4:].tolist())
-    print(json.dumps(rec), flush=True)
+    del m, caches
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--prompt", type=int, default=128)
+    ap.add_argument("--gen", type=int, default=1920)
+    ap.add_argument("--layers", type=int, default=0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--block-attn", action="store_true", help="paged KV cache (FusedBlockMultiTransformer, 64-row blocks)")
+    a = ap.parse_args()
+    print(json.dumps(_run(a)), flush=True)
 
 
 if __name__ == "__main__":

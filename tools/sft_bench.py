@@ -43,26 +43,18 @@ class SyntheticSFT(torch.utils.data.Dataset):
         return {"input_ids": self.items[i][0], "labels": self.items[i][1]}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=4)
-    ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--micro-batch", type=int, default=4)
-    ap.add_argument("--accum", type=int, default=2)
-    ap.add_argument("--layers", type=int, default=0)
-    ap.add_argument("--zero-padding", action="store_true",
-                    help="pack samples into 2048-token rows (ZeroPaddingMapDataset + FlashMask), llm/run_finetune.py --zero_padding")
-    a = ap.parse_args()
+def run(steps=4, warmup=2, micro_batch=4, accum=2, layers=0, zero_padding=False, quiet=False):
+    """Train `warmup + steps` optimizer steps through Trainer.train(); returns the record (rank 0) / None (other ranks)."""
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    args = TrainingArguments(output_dir="/tmp/sft_out", per_device_train_batch_size=a.micro_batch,
-                             gradient_accumulation_steps=a.accum, max_steps=a.steps + a.warmup, learning_rate=3e-5,
+    args = TrainingArguments(output_dir="/tmp/sft_out", per_device_train_batch_size=micro_batch,
+                             gradient_accumulation_steps=accum, max_steps=steps + warmup, learning_rate=3e-5,
                              weight_decay=0.01, warmup_steps=1, logging_steps=1, max_seq_length=S, lr_scheduler_type="linear")
-    cfg = T.Qwen2Config.qwen2_7b(num_hidden_layers=a.layers) if a.layers else T.Qwen2Config.qwen2_7b()
+    cfg = T.Qwen2Config.qwen2_7b(num_hidden_layers=layers) if layers else T.Qwen2Config.qwen2_7b()
     model = T.AutoModelForCausalLM.from_config(cfg, dtype="bfloat16")
-    n = (a.steps + a.warmup) * a.micro_batch * a.accum * args.world_size
+    n = (steps + warmup) * micro_batch * accum * args.world_size
     collator = None
-    if a.zero_padding:
+    if zero_padding:
         from paddlenlp_b200.data import DataCollatorForSeq2Seq
         from paddlenlp_b200.datasets import ZeroPaddingMapDataset
 
@@ -78,18 +70,44 @@ def main():
     else:
         ds = SyntheticSFT(n, cfg.vocab_size)
     trainer = Trainer(model=model, args=args, train_dataset=ds, data_collator=collator)
-    t0 = time.time()
+    if quiet:
+        from paddlenlp_b200.trainer.trainer import PrinterCallback
+        trainer.callbacks = [c for c in trainer.callbacks if not isinstance(c, PrinterCallback)]
     trainer.train()
-    hist = trainer.state.log_history[a.warmup:]
+    hist = trainer.state.log_history[warmup:]
+    rec = None
     if args.process_index == 0:
         sps = sum(h["interval_samples_per_second"] for h in hist) / len(hist)
         nonpad = sum(it[2] for it in ds.items) / len(ds.items)
-        rec = dict(model="Qwen2-7B" if not a.layers else f"Qwen2-7B width, {a.layers} layers", n_gpus=args.world_size,
-                   seq_len=S, zero_padding=bool(a.zero_padding), micro_batch=a.micro_batch, grad_accum=a.accum, steps=a.steps,
+        rec = dict(workload="Qwen2-7B full-parameter SFT bf16 through Trainer.train(), synthetic instruction pairs "
+                            "(BASELINE.json configs[3])",
+                   model="Qwen2-7B" if not layers else f"Qwen2-7B width, {layers} layers", n_gpus=args.world_size,
+                   seq_len=S, zero_padding=bool(zero_padding), micro_batch=micro_batch, grad_accum=accum, steps=steps,
+                   global_batch=micro_batch * accum * args.world_size,
                    tokens_per_s=sps * S, nonpad_tokens_per_s=sps * nonpad, loss_first=hist[0]["loss"], loss_last=hist[-1]["loss"],
                    tflops_per_gpu=sps * S / args.world_size * model.get_algorithmic_flops_per_token(S) / 1e12,
+                   timing="host wall clock between log steps (Trainer speed_metrics, logging_steps=1 => one loss read per step)",
                    mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
+    del trainer, model
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--micro-batch", type=int, default=4)
+    ap.add_argument("--accum", type=int, default=2)
+    ap.add_argument("--layers", type=int, default=0)
+    ap.add_argument("--zero-padding", action="store_true",
+                    help="pack samples into 2048-token rows (ZeroPaddingMapDataset + FlashMask), llm/run_finetune.py --zero_padding")
+    a = ap.parse_args()
+    rec = run(a.steps, a.warmup, a.micro_batch, a.accum, a.layers, a.zero_padding)
+    if rec is not None:
         print(json.dumps(rec), flush=True)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
