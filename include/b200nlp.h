@@ -276,6 +276,33 @@ int b200_token_penalty_multi_scores(const int64_t* pre_ids, float* logits, const
 /* set_stop_value_multi_ends: v1 mode 2 csrc/gpu/stop_generation_multi_ends.cu:45-56 ; v2 …_v2.cu:35-59 */
 int b200_set_stop_value_multi_ends(bool* stop_flags, int64_t* topk_ids, int64_t* next_tokens, const int64_t* end_ids,
                                    const int32_t* seq_lens, int64_t bs, int64_t end_length, int v2, cudaStream_t stream);
+/* fused_get_rotary_embedding(input_ids, position_ids, head_dim_shape_tensor, prompt_num, theta, use_neox):
+ * csrc/gpu/fused_get_rope.cu:40-223, called experimental/transformers/llama/modeling.py:799-803.
+ * position_ids int64 [bsz, max_position_seq_length]; rope_embedding fp32 [2, bsz, 1, max_seq_length, head_dim] (cos, sin) with
+ * angle = position_ids[b, s + prompt_num] * powf(theta, -2j/head_dim); use_neox != 0: value j at columns j and j + head_dim/2
+ * (rotate-half, Llama/Qwen2), use_neox == 0: at columns 2j, 2j+1.  max_seq_length is input_ids.shape[1] in the reference. */
+int b200_fused_get_rotary_embedding(const int64_t* position_ids, float* rope_embedding, int64_t bsz, int64_t max_seq_length,
+                                    int64_t max_position_seq_length, int64_t head_dim, int64_t prompt_num, float theta,
+                                    int use_neox, cudaStream_t stream);
+
+/* step_paddle: csrc/gpu/step.cu:19-283 (free_and_dispatch_block + recover_block) — continuous-batching block bookkeeping of the
+ * paged KV cache, called once per decode step: finished sequences return their decoder blocks to free_list; running sequences
+ * that step into an unallocated block get one (pre-empting the largest holders into step_block_list when the list runs dry);
+ * parked sequences are recovered when blocks are available again (lengths / stop flag / input_ids rebuilt from pre_ids).
+ * All arguments are updated in place like the reference op (every tensor is an input aliased to an output there).  Sizes:
+ * bsz = seq_lens_this_time.shape[0] (<= 1024), block_num_per_seq = block_tables.shape[1], length = input_ids.shape[1],
+ * pre_id_length = pre_ids.shape[1]; the reference attribute `encoder_decoder_block_num` is unused by its kernels and omitted.
+ * ONE launch, no host synchronisation (the reference copies recover_lens to the host between its two kernels); list order
+ * is by sequence index (deterministic; the reference's atomics leave it timing dependent). */
+int b200_step_paddle(bool* stop_flags, int32_t* seq_lens_this_time, const int32_t* ori_seq_lens_encoder,
+                     int32_t* seq_lens_encoder, int32_t* seq_lens_decoder, int32_t* block_tables, int32_t* encoder_block_lens,
+                     bool* is_block_step, int32_t* step_block_list, int32_t* step_lens, int32_t* recover_block_list,
+                     int32_t* recover_lens, int32_t* need_block_list, int32_t* need_block_len, int32_t* used_list_len,
+                     int32_t* free_list, int32_t* free_list_len, int64_t* input_ids, const int64_t* pre_ids,
+                     const int64_t* step_idx, const int64_t* next_tokens, int64_t bsz, int64_t block_size,
+                     int64_t block_num_per_seq, int64_t length, int64_t pre_id_length, int64_t first_token_id,
+                     cudaStream_t stream);
+
 /* update_inputs: csrc/gpu/update_inputs.cu:18-82 */
 int b200_update_inputs(bool* not_need_stop, int32_t* seq_lens_this_time, int32_t* seq_lens_encoder,
                        int32_t* seq_lens_decoder, int64_t* input_ids, const int64_t* stop_nums, const bool* stop_flags,

@@ -218,3 +218,110 @@ def paged_decode_attention(q, key_cache, value_cache, block_tables, seq_lens, sc
             p = np.exp(s - s.max())
             out[b, h] = (p / p.sum()) @ V[:, h // rep]
     return out.reshape(B, nh * d)
+
+
+# csrc/gpu/fused_get_rope.cu:40-75 (use_neox=True: value j at columns j and j + d/2) / :97-138 (interleaved pairs)
+def fused_get_rotary_embedding(input_ids_shape, position_ids, head_dim, prompt_num=0, theta=10000.0, use_neox=True):
+    """fp32 arithmetic like the kernel: powf(theta, -2j/d) with the exponent formed as -(2j) * (1/d), angle = float(pos) * inv_freq."""
+    bsz, seq = int(input_ids_shape[0]), int(input_ids_shape[1])
+    half = head_dim // 2
+    inv_head_dim = np.float32(1.0) / np.float32(head_dim)
+    expo = (-(2 * np.arange(half)).astype(np.float32)) * inv_head_dim
+    inv_freq = np.power(np.float32(theta), expo, dtype=np.float32)
+    pos = np.asarray(position_ids)[:, prompt_num:prompt_num + seq].astype(np.float32)          # [bsz, seq]
+    freqs = (pos[:, :, None] * inv_freq[None, None, :]).astype(np.float32)
+    c, s = np.cos(freqs, dtype=np.float32), np.sin(freqs, dtype=np.float32)
+    out = np.empty((2, bsz, 1, seq, head_dim), np.float32)
+    if use_neox:
+        out[0, :, 0, :, :half], out[0, :, 0, :, half:] = c, c
+        out[1, :, 0, :, :half], out[1, :, 0, :, half:] = s, s
+    else:
+        out[0, :, 0, :, 0::2], out[0, :, 0, :, 1::2] = c, c
+        out[1, :, 0, :, 0::2], out[1, :, 0, :, 1::2] = s, s
+    return out
+
+
+# csrc/gpu/step.cu:19-214 (free_and_dispatch_block + recover_block), executed in sequence-index order.
+# PARITY UNPINNED: the reference holds no test or known-answer vector for step_paddle, and its kernels order the free list with
+# atomicAdd / atomicSub across threads (timing dependent).  This restatement runs the threads in index order — one of the orders
+# the reference can produce — and is checked on its invariants (tests/test_generation_oracle.py): every cache block is owned by
+# exactly one of {free list, one sequence's table}, requests are served iff a block is free, pre-emption picks the largest holder.
+def step_paddle(st, block_size, first_token_id=0):
+    """`st`: dict of numpy arrays named like the reference op's inputs; updated IN PLACE (every input aliases an output)."""
+    sf, stt, ose, sle, sld = st["stop_flags"], st["seq_lens_this_time"], st["ori_seq_lens_encoder"], st["seq_lens_encoder"], st["seq_lens_decoder"]
+    bt, ebl, ibs = st["block_tables"], st["encoder_block_lens"], st["is_block_step"]
+    sbl, sl, rbl, rl = st["step_block_list"], st["step_lens"], st["recover_block_list"], st["recover_lens"]
+    nbl, nl, ull, fl, fll = st["need_block_list"], st["need_block_len"], st["used_list_len"], st["free_list"], st["free_list_len"]
+    ids, pre, sidx, nxt = st["input_ids"], st["pre_ids"], st["step_idx"], st["next_tokens"]
+    bsz = stt.shape[0]
+    length = ids.shape[1]
+    max_decoder_block_num = length // block_size
+    # 1. free finished sequences / collect requests                                   (:41-67)
+    for tid in range(bsz):
+        if sf[tid] and not ibs[tid]:
+            e, used = int(ebl[tid]), int(ull[tid])
+            if used > 0:
+                ori = int(fll[0]); fll[0] += used
+                for i in range(used):
+                    fl[ori + i] = bt[tid, e + i]
+                    bt[tid, e + i] = -1
+                ebl[tid] = 0
+                ull[tid] = 0
+        elif sld[tid] != 0 and bt[tid, sld[tid] // block_size] == -1:
+            nbl[int(nl[0])] = tid
+            nl[0] += 1
+    # 2. pre-empt the largest holders until the requests fit                            (:73-103; cub::ArgMax: ties -> lowest index)
+    while nl[0] > fll[0]:
+        used = np.array([int(ull[t]) if not ibs[t] else 0 for t in range(bsz)])
+        k = int(np.argmax(used)); v = int(used[k])
+        if v <= 0:
+            break                      # nothing to reclaim: the reference kernel would spin; the CUDA port breaks out as well
+        e = int(ebl[k])
+        for i in range(v):
+            fl[int(fll[0]) + i] = bt[k, e + i]
+            bt[k, e + i] = -1
+        sbl[int(sl[0])] = k
+        sl[0] += 1
+        fll[0] += v
+        sf[k] = True; ibs[k] = True; stt[k] = 0; sld[k] = 0
+    # 3. one block per surviving request from the tail of the free list                 (:105-117)
+    for t in range(int(nl[0])):
+        rid = int(nbl[t])
+        if not sf[rid]:
+            ull[rid] += 1
+            ori = int(fll[0]); fll[0] -= 1
+            bt[rid, sld[rid] // block_size] = fl[ori - 1]
+        nbl[t] = -1
+    # 4. which parked sequences fit again                                              (:119-150)
+    ori_free, ori_step_len = int(fll[0]), int(sl[0])
+    if ori_step_len > 0:
+        sid = int(sbl[ori_step_len - 1]); tmp = int(ull[sid])
+        used_len = tmp + 1 if tmp < max_decoder_block_num else tmp
+        while ori_step_len > 0 and ori_free >= used_len:
+            rbl[int(rl[0])] = sid
+            ibs[sid] = False
+            ull[sid] = used_len
+            ori_free -= used_len
+            sbl[ori_step_len - 1] = -1
+            sl[0] -= 1; rl[0] += 1
+            ori_step_len = int(sl[0])
+            if ori_step_len > 0:
+                sid = int(sbl[ori_step_len - 1]); tmp = int(ull[sid])
+                used_len = tmp + 1 if tmp < max_decoder_block_num else tmp
+    nl[0] = 0
+    # 5. recover_block                                                                  (:154-214)
+    for b in range(int(rl[0])):
+        rid = int(rbl[b])
+        oe, sn = int(ose[rid]), int(sidx[rid])
+        seq_len = oe + sn
+        e, used = int(ebl[rid]), int(ull[rid])
+        ori = int(fll[0]); fll[0] -= used
+        for i in range(used):
+            bt[rid, e + i] = fl[ori - i - 1]
+        for i in range(sn - 1):
+            ids[rid, oe + i] = pre[rid, i + 1]
+        stt[rid] = seq_len; sle[rid] = seq_len; sf[rid] = False
+        ids[rid, oe + sn - 1] = nxt[rid]
+        ids[rid, 0] = first_token_id
+    rl[0] = 0
+    return st

@@ -1097,3 +1097,297 @@ extern "C" int b200_top_p_sampling_reject(const float* probs, const float* top_p
                                                                                (int)bs, (int)max_rounds);
   return check_launch("top_p_sampling_reject");
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// fused_get_rotary_embedding (csrc/gpu/fused_get_rope.cu:40-223): position ids -> fp32 cos / sin tables
+//   out [2, bsz, 1, seq, head_dim]:  out[0] = cos, out[1] = sin of  position_ids[b, s + prompt_num] * theta^(-2j/head_dim)
+//   use_neox != 0 ("neox" in csrc naming == rotate-half, the Llama / Qwen2 convention, SURVEY.md §8 naming trap):
+//       value j is stored at columns j and j + head_dim/2;   use_neox == 0: at columns 2j and 2j+1 (interleaved pairs).
+// One thread per (b, s, j): powf / cosf / sinf in fp32 like the reference kernel; the two copies of each value are written as
+// one 8-byte store in the interleaved layout and as two coalesced 4-byte stores in the half-split layout.
+// ------------------------------------------------------------------------------------------------------------------
+namespace b200 {
+namespace gen {
+__global__ void __launch_bounds__(256) fused_get_rope_kernel(const int64_t* __restrict__ position_ids, float* __restrict__ out,
+                                                            int bsz, int seq, int pos_stride, int head_dim, int prompt_num,
+                                                            float inv_head_dim, float theta, int use_neox) {
+  const int half = head_dim >> 1;
+  const int64_t total = static_cast<int64_t>(bsz) * seq * half;
+  const int64_t sin_base = static_cast<int64_t>(bsz) * seq * head_dim;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t bs_idx = idx / half;
+    const int j = static_cast<int>(idx - bs_idx * half);
+    const int b = static_cast<int>(bs_idx / seq), s_ = static_cast<int>(bs_idx - static_cast<int64_t>(b) * seq);
+    const float exponent = -static_cast<float>(2 * j) * inv_head_dim;
+    const float inv_freq = powf(theta, exponent);
+    const float f = static_cast<float>(position_ids[static_cast<int64_t>(b) * pos_stride + s_ + prompt_num]) * inv_freq;
+    const float c = cosf(f), sn = sinf(f);
+    const int64_t row = bs_idx * head_dim;
+    if (use_neox) {
+      out[row + j] = c; out[row + j + half] = c;
+      out[sin_base + row + j] = sn; out[sin_base + row + j + half] = sn;
+    } else {
+      *reinterpret_cast<float2*>(out + row + 2 * j) = make_float2(c, c);
+      *reinterpret_cast<float2*>(out + sin_base + row + 2 * j) = make_float2(sn, sn);
+    }
+  }
+}
+}  // namespace gen
+}  // namespace b200
+
+extern "C" int b200_fused_get_rotary_embedding(const int64_t* position_ids, float* rope_embedding, int64_t bsz,
+                                               int64_t max_seq_length, int64_t max_position_seq_length, int64_t head_dim,
+                                               int64_t prompt_num, float theta, int use_neox, cudaStream_t stream) {
+  using namespace b200;
+  B200_CHECK_ARG(position_ids && rope_embedding, "fused_get_rotary_embedding: null pointer");
+  B200_CHECK_ARG(bsz > 0 && max_seq_length > 0 && head_dim > 0 && head_dim % 2 == 0 && prompt_num >= 0 &&
+                     max_seq_length + prompt_num <= max_position_seq_length,
+                 "fused_get_rotary_embedding: need even head_dim and seq + prompt_num <= position_ids row length "
+                 "(bsz=%lld seq=%lld pos_len=%lld head_dim=%lld prompt_num=%lld)",
+                 (long long)bsz, (long long)max_seq_length, (long long)max_position_seq_length, (long long)head_dim,
+                 (long long)prompt_num);
+  const int64_t total = bsz * max_seq_length * (head_dim / 2);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  gen::fused_get_rope_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      position_ids, rope_embedding, (int)bsz, (int)max_seq_length, (int)max_position_seq_length, (int)head_dim, (int)prompt_num,
+      1.0f / static_cast<float>(head_dim), theta, use_neox);
+  return check_launch("fused_get_rotary_embedding");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// step_paddle (csrc/gpu/step.cu:19-283): continuous-batching block bookkeeping of the paged KV cache, one call per decode step.
+//   1. finished sequences hand their decoder blocks back to the free list; running sequences whose next token falls into an
+//      unallocated block register a request                                              (free_and_dispatch_block :41-67)
+//   2. while requests outnumber free blocks, the running sequence holding the most decoder blocks is pre-empted ("block
+//      step"): its decoder blocks are freed and it is parked in step_block_list            (:73-103)
+//   3. every surviving request receives one block from the tail of the free list            (:105-117)
+//   4. parked sequences are recovered, last-parked first, while the free list can hold their decoder blocks plus one (:119-150)
+//   5. a recovered sequence is re-armed for a fresh prefill over prompt + generated tokens: lengths, stop flag, input ids
+//      rebuilt from pre_ids, its decoder blocks re-attached                                 (recover_block :154-214)
+// The reference runs 1-4 in one 512-thread CTA with atomicAdd/atomicSub on the list lengths (so the ORDER of blocks in the
+// free list depends on thread timing), copies recover_len to the host, and launches step 5 with that grid.  Here everything is
+// ONE launch of one CTA: list positions come from block-wide prefix sums in sequence-index order (deterministic, and one of the
+// orders the reference's atomics can produce), the arg-max is a shuffle reduction (ties -> lowest index, as cub::ArgMax), and
+// step 5 loops over the recovered sequences inside the same CTA — no host round trip.
+// ------------------------------------------------------------------------------------------------------------------
+namespace b200 {
+namespace gen {
+
+constexpr int STEP_THREADS = 1024;
+
+// exclusive prefix sum over the CTA (value per thread) + total; all STEP_THREADS threads must call
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  __syncthreads();                       // s_warp may still be read from a previous call
+  if (lane == 31) s_warp[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int x = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += n;
+    }
+    s_warp[lane] = x;                    // inclusive over warps
+  }
+  __syncthreads();
+  const int base = w == 0 ? 0 : s_warp[w - 1];
+  *total = s_warp[31];
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(STEP_THREADS, 1)
+step_paddle_kernel(bool* stop_flags, int* seq_lens_this_time, const int* ori_seq_lens_encoder, int* seq_lens_encoder,
+                   int* seq_lens_decoder, int* block_tables, int* encoder_block_lens, bool* is_block_step, int* step_block_list,
+                   int* step_len, int* recover_block_list, int* recover_len, int* need_block_list, int* need_block_len,
+                   int* used_list_len, int* free_list, int* free_list_len, int64_t* input_ids, const int64_t* pre_ids,
+                   const int64_t* step_idx, const int64_t* next_tokens, int bsz, int block_size, int block_num_per_seq, int length,
+                   int pre_id_length, int64_t first_token_id) {
+  __shared__ int s_warp[32];
+  __shared__ int s_key[32], s_val[32];
+  __shared__ int s_free_len, s_need_len, s_best_key, s_best_val;
+  const int tid = threadIdx.x;
+  const int max_decoder_block_num = length / block_size;
+  int* tbl = block_tables + static_cast<int64_t>(tid < bsz ? tid : 0) * block_num_per_seq;
+
+  // ---- 1. free finished sequences / collect block requests (positions by prefix sum, in sequence order) ----
+  int n_free = 0, need = 0, enc_len = 0;
+  if (tid < bsz) {
+    if (stop_flags[tid] && !is_block_step[tid]) {
+      n_free = used_list_len[tid];
+      enc_len = encoder_block_lens[tid];
+    } else if (seq_lens_decoder[tid] != 0 && tbl[seq_lens_decoder[tid] / block_size] == -1) {
+      need = 1;
+    }
+  }
+  int total_free, total_need;
+  const int free_pos = block_exclusive_scan(n_free, s_warp, &total_free);
+  const int need_pos = block_exclusive_scan(need, s_warp, &total_need);
+  const int free0 = *free_list_len, need0 = *need_block_len;
+  if (n_free > 0) {
+    for (int i = 0; i < n_free; ++i) {
+      free_list[free0 + free_pos + i] = tbl[enc_len + i];
+      tbl[enc_len + i] = -1;
+    }
+    encoder_block_lens[tid] = 0;
+    used_list_len[tid] = 0;
+  }
+  if (need) need_block_list[need0 + need_pos] = tid;
+  __syncthreads();
+  if (tid == 0) {
+    s_free_len = free0 + total_free;
+    s_need_len = need0 + total_need;
+  }
+  __syncthreads();
+
+  // ---- 2. pre-empt the largest holders until the requests fit ----
+  while (s_need_len > s_free_len) {
+    int key = tid, val = (tid < bsz && !is_block_step[tid]) ? used_list_len[tid] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int k2 = __shfl_xor_sync(0xffffffffu, key, o), v2 = __shfl_xor_sync(0xffffffffu, val, o);
+      if (v2 > val || (v2 == val && k2 < key)) { key = k2; val = v2; }
+    }
+    if ((tid & 31) == 0) { s_key[tid >> 5] = key; s_val[tid >> 5] = val; }
+    __syncthreads();
+    if (tid < 32) {
+      key = s_key[tid]; val = s_val[tid];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const int k2 = __shfl_xor_sync(0xffffffffu, key, o), v2 = __shfl_xor_sync(0xffffffffu, val, o);
+        if (v2 > val || (v2 == val && k2 < key)) { key = k2; val = v2; }
+      }
+      if (tid == 0) { s_best_key = key; s_best_val = val; }
+    }
+    __syncthreads();
+    if (s_best_val <= 0) break;          // nothing left to reclaim (the reference would spin here forever)
+    if (tid == 0) {
+      const int k = s_best_key, v = s_best_val;
+      int* t2 = block_tables + static_cast<int64_t>(k) * block_num_per_seq;
+      const int e = encoder_block_lens[k];
+      for (int i = 0; i < v; ++i) {
+        free_list[s_free_len + i] = t2[e + i];
+        t2[e + i] = -1;
+      }
+      step_block_list[*step_len] = k;
+      *step_len += 1;
+      s_free_len += v;
+      stop_flags[k] = true;
+      is_block_step[k] = true;
+      seq_lens_this_time[k] = 0;
+      seq_lens_decoder[k] = 0;
+    }
+    __syncthreads();
+  }
+
+  // ---- 3. one block per surviving request, taken from the tail of the free list in request order ----
+  int req = -1, active = 0;
+  if (tid < s_need_len) {
+    req = need_block_list[tid];
+    active = !stop_flags[req];
+  }
+  int total_active;
+  const int apos = block_exclusive_scan(active, s_warp, &total_active);
+  if (active) {
+    used_list_len[req] += 1;
+    int* t2 = block_tables + static_cast<int64_t>(req) * block_num_per_seq;
+    t2[seq_lens_decoder[req] / block_size] = free_list[s_free_len - 1 - apos];
+  }
+  if (tid < s_need_len) need_block_list[tid] = -1;
+  __syncthreads();
+
+  // ---- 4. which parked sequences fit again (last parked first; one spare block each) ----
+  if (tid == 0) {
+    s_free_len -= total_active;
+    int ori_free = s_free_len;
+    int ori_step_len = *step_len;
+    if (ori_step_len > 0) {
+      int sid = step_block_list[ori_step_len - 1];
+      int tmp_used = used_list_len[sid];
+      int used_len = tmp_used < max_decoder_block_num ? tmp_used + 1 : tmp_used;
+      while (ori_step_len > 0 && ori_free >= used_len) {
+        recover_block_list[*recover_len] = sid;
+        is_block_step[sid] = false;
+        used_list_len[sid] = used_len;
+        ori_free -= used_len;
+        step_block_list[ori_step_len - 1] = -1;
+        *step_len -= 1;
+        *recover_len += 1;
+        ori_step_len = *step_len;
+        if (ori_step_len > 0) {
+          sid = step_block_list[ori_step_len - 1];
+          tmp_used = used_list_len[sid];
+          used_len = tmp_used < max_decoder_block_num ? tmp_used + 1 : tmp_used;
+        }
+      }
+    }
+    *need_block_len = 0;
+  }
+  __syncthreads();
+
+  // ---- 5. re-arm the recovered sequences (recover_block), in recover-list order ----
+  const int n_rec = *recover_len;
+  for (int r = 0; r < n_rec; ++r) {
+    const int rid = recover_block_list[r];
+    const int ori_enc = ori_seq_lens_encoder[rid];
+    const int step_now = static_cast<int>(step_idx[rid]);
+    const int seq_len = ori_enc + step_now;
+    const int e = encoder_block_lens[rid];
+    const int used = used_list_len[rid];
+    int* t2 = block_tables + static_cast<int64_t>(rid) * block_num_per_seq;
+    int64_t* ids = input_ids + static_cast<int64_t>(rid) * length;
+    const int64_t* pre = pre_ids + static_cast<int64_t>(rid) * pre_id_length;
+    const int ori_free = s_free_len;
+    for (int i = tid; i < used; i += STEP_THREADS) t2[e + i] = free_list[ori_free - i - 1];
+    for (int i = tid; i < step_now - 1; i += STEP_THREADS) ids[ori_enc + i] = pre[i + 1];
+    __syncthreads();                      // the element writes below overwrite positions of the loops above
+    if (tid == 0) {
+      seq_lens_this_time[rid] = seq_len;
+      seq_lens_encoder[rid] = seq_len;
+      stop_flags[rid] = false;
+      ids[ori_enc + step_now - 1] = next_tokens[rid];
+      ids[0] = first_token_id;
+      s_free_len = ori_free - used;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    *recover_len = 0;
+    *free_list_len = s_free_len;
+  }
+}
+}  // namespace gen
+}  // namespace b200
+
+extern "C" int b200_step_paddle(bool* stop_flags, int32_t* seq_lens_this_time, const int32_t* ori_seq_lens_encoder,
+                                int32_t* seq_lens_encoder, int32_t* seq_lens_decoder, int32_t* block_tables,
+                                int32_t* encoder_block_lens, bool* is_block_step, int32_t* step_block_list, int32_t* step_lens,
+                                int32_t* recover_block_list, int32_t* recover_lens, int32_t* need_block_list,
+                                int32_t* need_block_len, int32_t* used_list_len, int32_t* free_list, int32_t* free_list_len,
+                                int64_t* input_ids, const int64_t* pre_ids, const int64_t* step_idx, const int64_t* next_tokens,
+                                int64_t bsz, int64_t block_size, int64_t block_num_per_seq, int64_t length, int64_t pre_id_length,
+                                int64_t first_token_id, cudaStream_t stream) {
+  using namespace b200;
+  B200_CHECK_ARG(stop_flags && seq_lens_this_time && ori_seq_lens_encoder && seq_lens_encoder && seq_lens_decoder && block_tables &&
+                     encoder_block_lens && is_block_step && step_block_list && step_lens && recover_block_list && recover_lens &&
+                     need_block_list && need_block_len && used_list_len && free_list && free_list_len && input_ids && pre_ids &&
+                     step_idx && next_tokens,
+                 "step_paddle: null pointer");
+  B200_CHECK_ARG(bsz > 0 && bsz <= gen::STEP_THREADS && block_size > 0 && block_num_per_seq > 0 && length > 0 && pre_id_length > 0,
+                 "step_paddle: need 0 < bsz <= %d and positive sizes", gen::STEP_THREADS);
+  gen::step_paddle_kernel<<<1, gen::STEP_THREADS, 0, stream>>>(
+      stop_flags, seq_lens_this_time, ori_seq_lens_encoder, seq_lens_encoder, seq_lens_decoder, block_tables, encoder_block_lens,
+      is_block_step, step_block_list, step_lens, recover_block_list, recover_lens, need_block_list, need_block_len, used_list_len,
+      free_list, free_list_len, input_ids, pre_ids, step_idx, next_tokens, (int)bsz, (int)block_size, (int)block_num_per_seq,
+      (int)length, (int)pre_id_length, first_token_id);
+  return check_launch("step_paddle");
+}

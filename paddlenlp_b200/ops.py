@@ -560,6 +560,22 @@ def decode_attention_paged(qkv, key_cache, value_cache, block_tables, seq_lens, 
     return out
 
 
+def fused_get_rotary_embedding(input_ids, position_ids, head_dim_shape_tensor, prompt_num: int = 0, theta: float = 10000.0,
+                               use_neox: bool = True) -> torch.Tensor:
+    """fused_get_rotary_embedding op of the reference (csrc/gpu/fused_get_rope.cu:159-223; same positional arguments):
+    input_ids [bsz, seq] (only its shape is used), position_ids int64 [bsz, >= seq + prompt_num], head_dim_shape_tensor: any
+    tensor whose FIRST dimension is head_dim (the reference's shape-carrier trick) or an int.
+    Returns fp32 [2, bsz, 1, seq, head_dim] (cos, sin)."""
+    _chk(position_ids, "position_ids", torch.int64)
+    bsz, seq = input_ids.shape[0], input_ids.shape[1]
+    head_dim = int(head_dim_shape_tensor) if isinstance(head_dim_shape_tensor, int) else int(head_dim_shape_tensor.shape[0])
+    assert position_ids.dim() == 2 and position_ids.is_contiguous() and position_ids.shape[0] == bsz
+    out = torch.empty(2, bsz, 1, seq, head_dim, dtype=torch.float32, device=position_ids.device)
+    call("b200_fused_get_rotary_embedding", ptr(position_ids), ptr(out), bsz, seq, position_ids.shape[1], head_dim,
+         int(prompt_num), float(theta), 1 if use_neox else 0, stream_ptr())
+    return out
+
+
 def get_padding_offset(input_ids, cum_offsets, token_num, seq_lens):
     """get_padding_offset_v2: returns (x_remove_padding, cum_offsets_out, padding_offset, cu_seqlens_q, cu_seqlens_k)."""
     bsz, max_len = input_ids.shape
@@ -620,6 +636,25 @@ def update_inputs(stop_flags, not_need_stop, seq_lens_this_time, seq_lens_encode
     call("b200_update_inputs", ptr(not_need_stop), ptr(seq_lens_this_time), ptr(seq_lens_encoder), ptr(seq_lens_decoder),
          ptr(input_ids), ptr(stop_nums), ptr(stop_flags), ptr(is_block_step), ptr(next_tokens), seq_lens_this_time.numel(),
          stop_flags.numel(), input_ids.shape[1], stream_ptr())
+
+
+def step_paddle(stop_flags, seq_lens_this_time, ori_seq_lens_encoder, seq_lens_encoder, seq_lens_decoder, block_tables,
+                encoder_block_lens, is_block_step, step_block_list, step_lens, recover_block_list, recover_lens, need_block_list,
+                need_block_len, used_list_len, free_list, free_list_len, input_ids, pre_ids, step_idx, next_tokens, block_size: int,
+                encoder_decoder_block_num: int = 0, first_token_id: int = 0):
+    """step_paddle(...) of the reference (csrc/gpu/step.cu:216-283; same argument order and in-place semantics)."""
+    for name, t, dt in (("stop_flags", stop_flags, torch.bool), ("is_block_step", is_block_step, torch.bool),
+                        ("seq_lens_this_time", seq_lens_this_time, torch.int32), ("block_tables", block_tables, torch.int32),
+                        ("free_list", free_list, torch.int32), ("input_ids", input_ids, torch.int64), ("pre_ids", pre_ids, torch.int64),
+                        ("step_idx", step_idx, torch.int64), ("next_tokens", next_tokens, torch.int64)):
+        _chk(t, name, dt)
+        assert t.is_contiguous(), name
+    bsz = seq_lens_this_time.shape[0]
+    call("b200_step_paddle", ptr(stop_flags), ptr(seq_lens_this_time), ptr(ori_seq_lens_encoder), ptr(seq_lens_encoder),
+         ptr(seq_lens_decoder), ptr(block_tables), ptr(encoder_block_lens), ptr(is_block_step), ptr(step_block_list), ptr(step_lens),
+         ptr(recover_block_list), ptr(recover_lens), ptr(need_block_list), ptr(need_block_len), ptr(used_list_len), ptr(free_list),
+         ptr(free_list_len), ptr(input_ids), ptr(pre_ids), ptr(step_idx), ptr(next_tokens), bsz, int(block_size),
+         block_tables.shape[1], input_ids.shape[1], pre_ids.shape[1], int(first_token_id), stream_ptr())
 
 
 def generate_step_update(next_tokens, stop_flags, step_idx, max_dec_len, seq_len_decoder, pre_ids, eos_ids, out_tokens,

@@ -512,3 +512,58 @@ def test_generate_beyond_max_position_embeddings_grows_rope_tables():
         assert m.transformer_block.rope[0].shape[0] >= 160
         outs.append(out.cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("use_neox", [True, False])
+def test_fused_get_rotary_embedding_op(use_neox):
+    """fused_get_rotary_embedding (csrc/gpu/fused_get_rope.cu:40-223, called experimental/transformers/llama/modeling.py:799-803)
+    vs the numpy restatement.  powf / cosf / sinf are not correctly rounded on either side: one ulp of the inverse frequency
+    (2^-23 relative) times the position bounds the angle error, hence the position-proportional tolerance."""
+    import numpy as np
+
+    from oracle import generation_ref as G
+    from paddlenlp_b200 import ops
+
+    bsz, seq, d, prompt_num, theta = 3, 200, 128, 7, 500000.0
+    pos = torch.arange(0, 2048, dtype=torch.int64)[None].repeat(bsz, 1).contiguous()
+    pos[1] += 1000                                                     # per-sequence offsets
+    ids = torch.zeros(bsz, seq, dtype=torch.int64)
+    out = ops.fused_get_rotary_embedding(ids.to(DEV), pos.to(DEV), torch.zeros(d), prompt_num, theta, use_neox).cpu().numpy()
+    ref = G.fused_get_rotary_embedding((bsz, seq), pos.numpy(), d, prompt_num, theta, use_neox)
+    assert out.shape == (2, bsz, 1, seq, d)
+    p = pos[:, prompt_num:prompt_num + seq].numpy().astype(np.float64)[None, :, None, :, None]
+    tol = 4e-7 * np.maximum(p, 1.0) + 2e-6
+    assert (np.abs(out - ref) <= tol).all(), float(np.abs(out - ref).max())
+    if use_neox:                                                       # the layout the Llama / Qwen2 rotate-half kernels expect
+        assert np.array_equal(out[..., :d // 2], out[..., d // 2:])
+    else:
+        assert np.array_equal(out[..., 0::2], out[..., 1::2])
+    with pytest.raises(Exception):
+        ops.fused_get_rotary_embedding(ids.to(DEV), pos[:, :100].contiguous().to(DEV), torch.zeros(d), prompt_num, theta, use_neox)
+
+
+def test_step_paddle_matches_oracle_bit_exact():
+    """step_paddle (csrc/gpu/step.cu:19-283) on a tight block pool: after every call ALL 21 state tensors equal the oracle's
+    (sequence-index order on both sides), through freeing, on-demand allocation, pre-emption and recovery."""
+    import numpy as np
+
+    import step_sim as sim
+    from oracle import generation_ref as G
+    from paddlenlp_b200 import ops
+
+    bs, nb, max_dec = 4, 22, 24
+    sim.BLOCK_SIZE_FOR_CHECK[0] = bs
+    events = 0
+    for seed in range(4):
+        st, rng = sim.make_state(seed, block_size=bs, num_blocks=nb, max_dec=max_dec)
+        for step in range(50):
+            sim.between_steps(st, rng, bs, max_dec)
+            dev = {k: torch.from_numpy(v.copy()).to(DEV) for k, v in st.items()}
+            ops.step_paddle(*[dev[k] for k in sim.ORDER], block_size=bs, first_token_id=1)
+            parked_before = int(st["step_lens"][0])
+            G.step_paddle(st, bs, first_token_id=1)
+            events += int(st["step_lens"][0]) != parked_before
+            for k in sim.ORDER:
+                assert np.array_equal(dev[k].cpu().numpy(), st[k]), (seed, step, k, dev[k].cpu().numpy(), st[k])
+            sim.check_invariants(st, nb)
+    assert events > 0

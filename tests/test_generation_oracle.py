@@ -88,3 +88,49 @@ def test_top_p_sampling_reject_oracle_properties():
     for b in range(bs):
         cdf = np.cumsum(p[b], dtype=np.float32)
         assert ids[b] == int(np.nonzero(cdf > u[0, b])[0][0])
+
+
+def test_fused_get_rotary_embedding_oracle_layout():
+    """csrc/gpu/fused_get_rope.cu:40-75: [2, bsz, 1, seq, d] fp32, half-split ("neox" == rotate-half in csrc naming) layout equal to
+    the training path's concat([freqs, freqs]) tables (llama/modeling.py:409-423) at the same positions."""
+    import numpy as np
+
+    from oracle import generation_ref as G
+    from oracle import llama_ref as R
+
+    pos = np.arange(40, dtype=np.int64)[None].repeat(3, 0)
+    out = G.fused_get_rotary_embedding((3, 32), pos, 128, prompt_num=5, theta=500000.0, use_neox=True)
+    cos, sin = R.rope_tables(128, 40, 500000.0)
+    assert out.shape == (2, 3, 1, 32, 128)
+    assert np.abs(out[0, 1, 0] - cos[5:37].numpy()).max() < 2e-5 and np.abs(out[1, 2, 0] - sin[5:37].numpy()).max() < 2e-5
+    il = G.fused_get_rotary_embedding((3, 32), pos, 128, prompt_num=5, theta=500000.0, use_neox=False)
+    assert np.array_equal(il[0, :, 0, :, 0::2], out[0, :, 0, :, :64]) and np.array_equal(il[1, :, 0, :, 1::2], out[1, :, 0, :, 64:])
+
+
+def test_step_paddle_oracle_invariants():
+    """step_paddle restatement (csrc/gpu/step.cu:19-214; parity unpinned in the reference — no test, timing-dependent list order)
+    on a tight block pool: block conservation, no lost requests, pre-emption and recovery both occur."""
+    import numpy as np
+
+    import step_sim as sim
+    from oracle import generation_ref as G
+
+    bs, nb, max_dec = 4, 22, 24
+    sim.BLOCK_SIZE_FOR_CHECK[0] = bs
+    preempted = recovered = freed = 0
+    for seed in range(6):
+        st, rng = sim.make_state(seed, block_size=bs, num_blocks=nb, max_dec=max_dec)
+        for _ in range(60):
+            sim.between_steps(st, rng, bs, max_dec)
+            before_step, before_free = int(st["step_lens"][0]), int(st["free_list_len"][0])
+            was_parked = st["is_block_step"].copy()
+            G.step_paddle(st, bs, first_token_id=1)
+            sim.check_invariants(st, nb)
+            preempted += int(st["step_lens"][0]) > before_step
+            recovered += int((was_parked & ~st["is_block_step"]).sum())
+            freed += int(st["free_list_len"][0]) > before_free
+            for b in np.nonzero(was_parked & ~st["is_block_step"])[0]:      # a recovered sequence is re-armed for a full prefill
+                n = int(st["ori_seq_lens_encoder"][b] + st["step_idx"][b])
+                assert not st["stop_flags"][b] and st["seq_lens_encoder"][b] == n and st["seq_lens_this_time"][b] == n
+                assert st["input_ids"][b, 0] == 1 and st["input_ids"][b, n - 1] == st["next_tokens"][b]
+    assert preempted > 0 and recovered > 0 and freed > 0, (preempted, recovered, freed)

@@ -10,7 +10,7 @@ if grep -q "failed" $OUT/${TAG}_fa_tests.log; then
   echo "attention tests failed: falling back to forward generation 1 for the rest of this session" >> $OUT/${TAG}_fa_tests.log
   export B200_FA_FWD_IMPL=1
 fi
-timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_ops_gpu.py::test_flash_attention_fwd_bwd \
+timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_ops_gpu.py::test_flash_attention_fwd_bwd \
   --deselect tests/test_ops_gpu.py::test_flash_attention_bench_shapes -rA 2>&1 | grep -v "^PASSED" | tail -120 > $OUT/${TAG}_tests.log
 timeout 600 python tools/fa_bench.py > $OUT/${TAG}_fa_bench.log 2>&1
 B200_FA_FWD_IMPL=1 timeout 600 python tools/fa_bench.py > $OUT/${TAG}_fa_bench_impl1.log 2>&1
