@@ -303,6 +303,14 @@ int b200_step_paddle(bool* stop_flags, int32_t* seq_lens_this_time, const int32_
                      int64_t block_num_per_seq, int64_t length, int64_t pre_id_length, int64_t first_token_id,
                      cudaStream_t stream);
 
+/* save_output(x, not_need_stop, rank_id) replacement: csrc/gpu/save_with_output_msg.cc:28-52 (producer) / csrc/gpu/get_output.cc
+ * (consumer), reader loop paddlenlp/utils/llm_utils.py:753-776.  Writes the step's message {flag, bsz, tokens...} (flag 1 =
+ * running, -1 = finished: *stop_count >= bs or step >= last_step) into slot (step % num_slots) of `ring`, an int32 buffer of
+ * num_slots x slot_stride in pinned device-mapped host memory, and publishes it by storing step + 1 into the slot's first word
+ * last; `step_counter` (device int64) is the running step and is incremented.  No host synchronisation; graph-replayable. */
+int b200_save_output_stream(const int64_t* next_tokens, const int32_t* stop_count, int32_t* ring, int64_t slot_stride,
+                            int64_t num_slots, int64_t* step_counter, int64_t last_step, int64_t bs, cudaStream_t stream);
+
 /* update_inputs: csrc/gpu/update_inputs.cu:18-82 */
 int b200_update_inputs(bool* not_need_stop, int32_t* seq_lens_this_time, int32_t* seq_lens_encoder,
                        int32_t* seq_lens_decoder, int64_t* input_ids, const int64_t* stop_nums, const bool* stop_flags,

@@ -75,6 +75,7 @@ _SIGNATURES = {
     "b200_set_stop_value_multi_ends": [P, P, P, P, P, I64, I64, I, P],
     "b200_fused_get_rotary_embedding": [P, P, I64, I64, I64, I64, I64, F, I, P],
     "b200_step_paddle": [P] * 21 + [I64] * 6 + [P],
+    "b200_save_output_stream": [P, P, P, I64, I64, P, I64, I64, P],
     "b200_update_inputs": [P, P, P, P, P, P, P, P, P, I64, I64, I64, P],
     "b200_generate_step_update": [P, P, P, P, P, P, I64, P, I64, P, I64, I64, P, P, I64, P],
     "b200_argmax_f32": [P, P, I64, I64, I64, P],

@@ -1391,3 +1391,47 @@ extern "C" int b200_step_paddle(bool* stop_flags, int32_t* seq_lens_this_time, c
       (int)length, (int)pre_id_length, first_token_id);
   return check_launch("step_paddle");
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// save_output / get_output replacement (csrc/gpu/save_with_output_msg.cc:28-52, csrc/gpu/get_output.cc:28-60).
+// The reference copies the step's tokens to the host synchronously (two blocking D2H copies per decode step) and pushes them
+// into a SysV message queue as  int mtext[MAX_BSZ + 2] = {not_need_stop ? 1 : -1, bsz, tokens...}.  Here the decode step's own
+// stream writes the same message straight into a ring of slots in PINNED, DEVICE-MAPPED host memory — no copy engine, no host
+// synchronisation, CUDA-graph replayable — and publishes it by storing the step's sequence number into the slot header LAST
+// (after __threadfence_system()); a host reader thread polls the header (paddlenlp_b200/experimental/transformers/token_stream.py).
+//   slot layout (int32):  [0] seq = step + 1 (0 = never written)   [1] flag (1 running / -1 finished)   [2] bsz   [3 ..] tokens
+// ------------------------------------------------------------------------------------------------------------------
+namespace b200 {
+namespace gen {
+__global__ void __launch_bounds__(512) save_output_stream_kernel(const int64_t* __restrict__ tokens, const int32_t* __restrict__ stop_count,
+                                                                 volatile int32_t* ring, int64_t slot_stride, int64_t num_slots,
+                                                                 int64_t* step_counter, int64_t last_step, int bs) {
+  const int64_t step = *step_counter;
+  volatile int32_t* slot = ring + (step % num_slots) * slot_stride;
+  for (int i = threadIdx.x; i < bs; i += blockDim.x) slot[3 + i] = static_cast<int32_t>(tokens[i]);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const bool finished = (stop_count != nullptr && *stop_count >= bs) || (last_step >= 0 && step >= last_step);
+    slot[1] = finished ? -1 : 1;
+    slot[2] = bs;
+    __threadfence_system();
+    slot[0] = static_cast<int32_t>(step + 1);
+    __threadfence_system();
+    *step_counter = step + 1;
+  }
+}
+}  // namespace gen
+}  // namespace b200
+
+extern "C" int b200_save_output_stream(const int64_t* next_tokens, const int32_t* stop_count, int32_t* ring, int64_t slot_stride,
+                                       int64_t num_slots, int64_t* step_counter, int64_t last_step, int64_t bs,
+                                       cudaStream_t stream) {
+  using namespace b200;
+  B200_CHECK_ARG(next_tokens && ring && step_counter, "save_output_stream: null pointer");
+  B200_CHECK_ARG(bs > 0 && num_slots > 0 && slot_stride >= bs + 3, "save_output_stream: need slot_stride >= bs + 3 (bs=%lld stride=%lld)",
+                 (long long)bs, (long long)slot_stride);
+  gen::save_output_stream_kernel<<<1, 512, 0, stream>>>(next_tokens, stop_count, ring, slot_stride, num_slots, step_counter,
+                                                        last_step, (int)bs);
+  return check_launch("save_output_stream");
+}

@@ -3,3 +3,4 @@ from .fused_transformer_layers import FusedBlockMultiTransformer, FusedMultiTran
 from .generation_utils import GenerationInferenceModel
 from .llama.modeling import LlamaForCausalLMInferenceModel
 
+from .token_stream import TokenStream, TokenStreamOverrun

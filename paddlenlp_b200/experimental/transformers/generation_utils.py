@@ -43,9 +43,12 @@ class GenerationInferenceModel:
                  eos_token_id=None, cache_kvs: Optional[List[torch.Tensor]] = None, temperature: float = 1.0,
                  top_p: float = 0.0, penalty_score: float = 1.0, frequency_score: float = 0.0, presence_score: float = 0.0,
                  min_length: int = 0, use_cuda_graph: bool = True, sync_interval: int = 16, use_pdl: bool = True, seed: int = 0,
-                 **kwargs):
+                 token_stream=None, **kwargs):
         """input_ids [B, S] (right padded); returns (ids [B, max_length], stop_flags, seq_len_decoder).
-        top_p in (0, 1]: sample from the top-p nucleus (seed != 0 makes the draw reproducible); top_p 0: greedy."""
+        top_p in (0, 1]: sample from the top-p nucleus (seed != 0 makes the draw reproducible); top_p 0: greedy.
+        token_stream: a token_stream.TokenStream — every step's tokens are published to its pinned-host ring from inside
+        the (graph-replayed) decode step, the replacement of save_with_output / save_output (generation_utils.py:353-361,
+        :711-713): a reader thread sees step t while step t+1 is computed, with no host synchronisation in this loop."""
         if top_p is not None and not (0.0 <= float(top_p) <= 1.0):
             raise ValueError(f"top_p must be in [0, 1], got {top_p}")
         dev = self.device
@@ -97,7 +100,11 @@ class GenerationInferenceModel:
             # decode step appends at the right cache position.
             ops.generate_step_update(next_tokens, st["stop_flags"], st["step_idx"], st["max_dec_len"], st["seq_len_decoder"],
                                      st["pre_ids"], st["eos"], st["out"], st["stop_count"], out_col_dev=st["col"])
+            if token_stream is not None:
+                token_stream.push(next_tokens, st["stop_count"])
 
+        if token_stream is not None:
+            token_stream.reset(total_steps=max_length)
         # ---- prefill ("encoder" step) ----
         logits = self._prefill(ids, enc, cache_kvs)              # [B, V], last valid position of each prompt
         tgt = self._choose(logits, st)

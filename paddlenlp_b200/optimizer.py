@@ -94,9 +94,10 @@ class CosineDecayWithWarmup(LRScheduler):
 class LinearAnnealingWithWarmupDecay(LRScheduler):
     """llm/run_pretrain.py:520-536 schedule family: warm-up to max_lr, linear anneal to min_lr over decay_step."""
 
-    def __init__(self, max_lr, min_lr, warmup_step, decay_step):
+    def __init__(self, max_lr, min_lr, warmup_step, decay_step, last_epoch=0, verbose=False):
         super().__init__(max_lr)
         self.max_lr, self.min_lr, self.warmup_step, self.decay_step = max_lr, min_lr, warmup_step, decay_step
+        self.last_epoch = int(last_epoch)
 
     def _coeff(self, ratio):
         return 1.0 - ratio
@@ -117,7 +118,7 @@ class CosineAnnealingWithWarmupDecay(LinearAnnealingWithWarmupDecay):
 
 
 def get_scheduler(name, learning_rate, num_warmup_steps=0, num_training_steps=None, num_cycles=0.5, **_):
-    name = str(name).lower()
+    name = str(getattr(name, "value", name)).lower()         # SchedulerType enum or plain string
     if name == "linear":
         return LinearDecayWithWarmup(learning_rate, num_training_steps, num_warmup_steps)
     if name == "cosine":

@@ -33,9 +33,13 @@ class PdArgumentParser(argparse.ArgumentParser):
         self.dataclass_types = list(dataclass_types)
         import typing
 
+        seen = set()
         for dt in self.dataclass_types:
             hints = typing.get_type_hints(dt)
             for f in dataclasses.fields(dt):
+                if f.name in seen:          # a name shared by two argument classes (e.g. max_seq_length: DataArguments and this
+                    continue                # build's TrainingArguments) is parsed once and handed to both
+                seen.add(f.name)
                 tp = _base_type(hints.get(f.name, str))
                 kw = {}
                 if tp is bool:

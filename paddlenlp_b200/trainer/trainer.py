@@ -161,6 +161,34 @@ class IterableDatasetShard(torch.utils.data.IterableDataset):
             yield from cur[lo:hi]
 
 
+def set_seed(seed: int = 1234, topo=None):
+    """trainer_utils.py set_seed (pure data parallel: the same seed on every rank; data order is de-correlated by the sampler)."""
+    import numpy as np
+
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def speed_metrics(split, start_time, num_samples=None, num_steps=None, seq_length=None, model_flops=None):
+    """trainer_utils.py:351-380 — the runtime / samples-per-second / tokens-per-second-per-device / hardware-TFLOPS keys."""
+    runtime = time.time() - start_time
+    result = {f"{split}_runtime": round(runtime, 4)}
+    if num_samples is not None:
+        sps = num_samples / runtime
+        result[f"{split}_samples_per_second"] = round(sps, 4)
+        if seq_length is not None:
+            tps = sps * seq_length / dist_env.get_world_size()
+            result[f"{split}_tokens_per_second_per_device"] = round(tps, 4)
+            if model_flops is not None:
+                result[f"{split}_hardware_tflops_per_device"] = round(tps * model_flops / seq_length / 2 ** 40, 2)
+    if num_steps is not None:
+        result[f"{split}_steps_per_second"] = round(num_steps / runtime, 4)
+    return result
+
+
 def default_data_collator(features: List[Dict[str, Any]]) -> Dict[str, torch.Tensor]:
     out = {}
     for k in features[0]:
@@ -205,12 +233,24 @@ class Trainer:
                                           num_processes=world, process_index=rank)
             return torch.utils.data.DataLoader(ds, batch_size=a.per_device_train_batch_size, collate_fn=self.data_collator,
                                                num_workers=a.dataloader_num_workers, pin_memory=True)
-        # DistributedSampler with one replica is a seeded shuffling sampler with set_epoch(): the same class serves both cases
-        sampler = torch.utils.data.distributed.DistributedSampler(ds, num_replicas=max(1, world), rank=rank if world > 1 else 0,
-                                                                   shuffle=True, seed=int(a.seed), drop_last=a.dataloader_drop_last)
+        sampler = self._get_train_sampler()
+        if hasattr(sampler, "batch_size") and not isinstance(sampler, torch.utils.data.Sampler):
+            # a BATCH sampler (paddlenlp.utils.batch_sampler.DistributedBatchSampler — what run_pretrain.py:341-349 returns)
+            return torch.utils.data.DataLoader(ds, batch_sampler=sampler, collate_fn=self.data_collator,
+                                               num_workers=a.dataloader_num_workers, pin_memory=True)
         return torch.utils.data.DataLoader(ds, batch_size=a.per_device_train_batch_size, sampler=sampler, shuffle=False,
                                            collate_fn=self.data_collator, drop_last=a.dataloader_drop_last,
                                            num_workers=a.dataloader_num_workers, pin_memory=True)
+
+    def _get_train_sampler(self, shuffle: bool = True):
+        """trainer.py:1328-1347.  Subclasses override it the way llm/run_pretrain.py:341-349 does (PretrainingTrainer keeps the
+        file order: shuffle=False).  DistributedSampler with one replica is a seeded shuffling sampler with set_epoch(): the same
+        class serves the single-process and the data-parallel case."""
+        a = self.args
+        world, rank = a.dataset_world_size, a.dataset_rank
+        return torch.utils.data.distributed.DistributedSampler(self.train_dataset, num_replicas=max(1, world),
+                                                               rank=rank if world > 1 else 0, shuffle=shuffle, seed=int(a.seed),
+                                                               drop_last=a.dataloader_drop_last)
 
     def create_optimizer_and_scheduler(self, num_training_steps: int):
         self.create_scheduler(num_training_steps)
@@ -358,9 +398,10 @@ class Trainer:
         done = False
         logged_step = self.state.global_step
         for epoch in range(epochs_trained, epochs):
-            sampler = getattr(dl, "sampler", None)
-            if hasattr(sampler, "set_epoch"):
-                sampler.set_epoch(epoch)
+            for sampler in (getattr(dl, "batch_sampler", None), getattr(dl, "sampler", None)):
+                if hasattr(sampler, "set_epoch"):
+                    sampler.set_epoch(epoch)
+                    break
             it = iter(dl)
             step = -1
             if epoch == epochs_trained and skip_batches:
@@ -455,6 +496,27 @@ class Trainer:
         for cb in self.callbacks:
             cb.on_train_end(a, self.state, self.control)
         return TrainOutput(self.state.global_step, logged_loss_total / gs, metrics)
+
+    def log_metrics(self, split: str, metrics: Dict[str, float]):
+        """trainer_utils.py log_metrics: formatted dump of a metrics dict (rank 0)."""
+        if self.args.process_index != 0:
+            return
+        print(f"***** {split} metrics *****", flush=True)
+        width = max((len(str(k)) for k in metrics), default=0)
+        for k in sorted(metrics):
+            print(f"  {str(k):<{width}} = {metrics[k]}", flush=True)
+
+    def save_metrics(self, split: str, metrics: Dict[str, float], combined: bool = True):
+        if self.args.process_index != 0:
+            return
+        os.makedirs(self.args.output_dir, exist_ok=True)
+        with open(os.path.join(self.args.output_dir, f"{split}_results.json"), "w") as f:
+            json.dump(metrics, f, indent=4, sort_keys=True)
+
+    def save_state(self):
+        if self.args.process_index == 0:
+            os.makedirs(self.args.output_dir, exist_ok=True)
+            self.state.save_to_json(os.path.join(self.args.output_dir, TRAINER_STATE_NAME))
 
     def log(self, logs: Dict[str, float]):
         self.state.log_history.append(dict(logs))

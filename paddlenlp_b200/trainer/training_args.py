@@ -14,6 +14,15 @@ from typing import Optional
 from .. import distributed as dist_env
 
 
+class _SchedulerName(str):
+    """A plain string that also answers `.value` (the reference's SchedulerType enum member: run_pretrain.py:518 reads
+    `training_args.lr_scheduler_type.value`)."""
+
+    @property
+    def value(self):
+        return str(self)
+
+
 @dataclass
 class TrainingArguments:
     output_dir: str = "./output"
@@ -56,6 +65,18 @@ class TrainingArguments:
     ignore_data_skip: bool = False
     device: str = "gpu"
     max_seq_length: Optional[int] = None
+    # fields the reference's training scripts read (llm/run_pretrain.py:358-575); inert on the pure data-parallel path
+    overwrite_output_dir: bool = False
+    do_eval: bool = False
+    do_predict: bool = False
+    autotuner_benchmark: bool = False
+    sequence_parallel: bool = False
+    fuse_sequence_parallel_allreduce: bool = False
+    enable_linear_fused_grad_add: bool = False
+    no_recompute_layers: Optional[list] = None
+    sharding_parallel_config: Optional[str] = None
+    should_load_dataset: bool = True
+    unified_checkpoint: bool = True
     # parallelism knobs accepted for compatibility; only the pure-DP values are implemented
     tensor_parallel_degree: int = 1
     pipeline_parallel_degree: int = 1
@@ -80,7 +101,19 @@ class TrainingArguments:
             raise NotImplementedError("sharding (ZeRO) stages: pure data-parallel replication only")
         if self.device not in ("gpu", "cuda"):
             raise NotImplementedError("device must be 'gpu': there is no CPU / XPU / NPU path")
+        if self.sequence_parallel or self.enable_linear_fused_grad_add:
+            raise NotImplementedError("sequence_parallel / enable_linear_fused_grad_add belong to the tensor-parallel path")
+        self.lr_scheduler_type = _SchedulerName(getattr(self.lr_scheduler_type, "value", self.lr_scheduler_type))
         dist_env.init_parallel_env()
+
+    def print_config(self, args=None, key=""):
+        """training_args.py print_config: dump an arguments object (rank 0)."""
+        if self.process_index != 0:
+            return
+        obj = self if args is None else args
+        print("=" * 60 + f"\n{key or type(obj).__name__} Configuration Arguments".center(60))
+        for k, v in sorted(vars(obj).items()):
+            print(f"{k:30}: {v}")
 
     # -- derived (training_args.py:1006-1064) --
     @property
@@ -120,7 +153,9 @@ class TrainingArguments:
         return self.process_index == 0
 
     def to_dict(self):
-        return asdict(self)
+        d = asdict(self)
+        d["lr_scheduler_type"] = str(self.lr_scheduler_type)
+        return d
 
     def to_json_string(self):
         return json.dumps(self.to_dict(), indent=2)

@@ -99,3 +99,14 @@ class LlmMetaConfig:
         for k in LLM_META_SWITCHES:
             if hasattr(args, k):
                 setattr(config, k, getattr(args, k))
+
+
+def llmmetaclass(cls):
+    """configuration_utils.py:294-310: class decorator that adds the LlmMetaConfig switches as dataclass fields of an
+    arguments class (run_pretrain.py:60 `@llmmetaclass @dataclass class PreTrainingArguments(TrainingArguments)`).  The
+    TrainingArguments of this build already carries the switches that have a meaning on the single native path; the decorator
+    adds any missing one as a plain class attribute with its default so that `set_llm_config` finds it."""
+    for k, v in LLM_META_SWITCHES.items():
+        if not hasattr(cls, k):
+            setattr(cls, k, v)
+    return cls

@@ -567,3 +567,52 @@ def test_step_paddle_matches_oracle_bit_exact():
                 assert np.array_equal(dev[k].cpu().numpy(), st[k]), (seed, step, k, dev[k].cpu().numpy(), st[k])
             sim.check_invariants(st, nb)
     assert events > 0
+
+
+def test_streaming_token_output():
+    """save_output / get_output replacement (csrc/gpu/save_with_output_msg.cc:28-52, get_output.cc, llm_utils.py:753-776): a
+    reader thread receives every step's {flag, bsz, tokens} message from the pinned-host ring WHILE generation is running —
+    the loop itself never synchronises — and the concatenated messages equal generate()'s return value."""
+    import time
+
+    import paddlenlp_b200.transformers as T
+    from paddlenlp_b200.experimental.transformers import LlamaForCausalLMInferenceModel, TokenStream
+
+    cfg = T.LlamaConfig(vocab_size=512, hidden_size=256, intermediate_size=688, num_hidden_layers=2, num_attention_heads=2,
+                        num_key_value_heads=1, rms_norm_eps=1e-5, rope_theta=500000.0, max_position_embeddings=1024)
+    m = LlamaForCausalLMInferenceModel(cfg)
+    m.init_random(seed=3)
+    prompt = torch.randint(0, 512, (5, 16), generator=torch.Generator().manual_seed(2))
+    stream = TokenStream(max_bsz=8, num_slots=64)                       # ring much shorter than the generation: slots are reused
+    assert stream.get_output(False) == [-2, 0]                          # nothing yet: the reference's "read none" answer
+    n_steps = 600
+    arrivals = []
+    reader = stream.start_reader(on_message=lambda i, msg: arrivals.append(time.time()))
+    out, _, _ = m.generate(prompt, max_length=n_steps, eos_token_id=-1, token_stream=stream)
+    t_enqueued = time.time()
+    reader.join(timeout=60)
+    torch.cuda.synchronize()
+    assert reader.error is None, reader.error
+    msgs = reader.result
+    assert len(msgs) == n_steps and all(len(x) == 5 for x in msgs)
+    got = torch.tensor(msgs).t()                                        # [bsz, steps]
+    assert torch.equal(got, out.cpu())
+    # streamed: the first message was on the host long before the last one (it did not wait for the end of the generation)
+    assert arrivals[0] < arrivals[-1] - 0.5 * (arrivals[-1] - arrivals[0]) and arrivals[n_steps // 4] < arrivals[-1]
+    print(f"[stream] first message {arrivals[0] - t_enqueued:+.3f} s, last {arrivals[-1] - t_enqueued:+.3f} s relative to generate() returning")
+    # the finished flag: -1 on the final message only
+    stream2 = TokenStream(max_bsz=8, num_slots=1024)
+    out2, _, _ = m.generate(prompt, max_length=40, eos_token_id=-1, token_stream=stream2)
+    flags = []
+    while True:
+        msg = stream2.get_output(True)
+        flags.append(msg[0])
+        if msg[0] == -1:
+            break
+    assert flags == [1] * 39 + [-1] and stream2.get_output(False) == [-2, 0]
+    # a reader that falls a whole ring behind is told so instead of silently reading newer data
+    stream3 = TokenStream(max_bsz=8, num_slots=8)
+    m.generate(prompt, max_length=40, eos_token_id=-1, token_stream=stream3)
+    torch.cuda.synchronize()
+    with pytest.raises(Exception):
+        stream3.get_output(False)

@@ -201,3 +201,38 @@ def test_train_sampler_shuffles_and_resumes_deterministically(tmp_path):
     in_file_order = [tuple(ds.tok[i:i + 2, 0].tolist()) for i in range(0, 16, 2)]
     assert a == b and a != c and a != d and a != in_file_order
     assert sorted(x for t in a for x in t) == sorted(x for t in in_file_order for x in t)
+
+
+def test_reference_style_script_runs_unchanged(tmp_path):
+    """Boundary (SURVEY §8b / north_star "drop-in"): a script with llm/run_pretrain.py's own `paddlenlp.*` import block, argument
+    dataclasses, Trainer subclass and main() flow (tests/pretrain_like_script.py) runs unchanged through the `paddlenlp` shim,
+    driven by the reference's argv style, and trains."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg_dir = tmp_path / "model"
+    cfg_dir.mkdir()
+    (cfg_dir / "config.json").write_text(json.dumps(dict(
+        model_type="llama", vocab_size=512, hidden_size=256, intermediate_size=688, num_hidden_layers=2, num_attention_heads=2,
+        num_key_value_heads=1, max_position_embeddings=128, rms_norm_eps=1e-5, rope_theta=500000.0)))
+    argv = ["--model_name_or_path", str(cfg_dir), "--output_dir", str(tmp_path / "out"), "--per_device_train_batch_size", "2",
+            "--gradient_accumulation_steps", "2", "--max_steps", "8", "--learning_rate", "2e-3", "--min_learning_rate", "2e-4",
+            "--warmup_steps", "1", "--logging_steps", "2", "--max_seq_length", "128", "--lr_scheduler_type", "cosine",
+            "--weight_decay", "0.01", "--bf16", "true", "--fp16_opt_level", "O2", "--recompute", "true", "--do_train", "true",
+            "--save_steps", "4", "--save_total_limit", "1"]
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "pretrain_like_script.py")] + argv, capture_output=True,
+                       text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("FINAL_LOSS_HISTORY")][-1]
+    hist = json.loads(line.split(" ", 1)[1])
+    assert len(hist) == 4 and hist[-1] < hist[0]
+    out = tmp_path / "out"
+    assert (out / "model.safetensors").exists() and (out / "train_results.json").exists() and (out / "trainer_state.json").exists()
+    ck = out / "checkpoint-8"
+    assert (ck / "model-00001-of-00001.safetensors").exists() and (ck / "model.safetensors.index.json").exists()
+    assert (ck / "optimizer-00001-of-00001.safetensors").exists() and (ck / "optimizer.safetensors.index.json").exists()
+    assert not (out / "checkpoint-4").exists()                          # save_total_limit = 1
