@@ -132,8 +132,15 @@ def cpu_reference_sample(layer_tokens: int = 512, head_tokens: int = 128, attn_h
 
     from oracle import llama_ref as R
 
-    # all host cores, regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1)
-    torch.set_num_threads(threads or os.cpu_count() or 1)
+    # all PHYSICAL host cores, regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1; one thread per hardware thread
+    # of a 2-way SMT host is slower for these GEMMs than one per core: measured 14.0 s vs ~3 s for the 512-token layer)
+    if not threads:
+        try:
+            import psutil
+            threads = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+        except Exception:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     cores = torch.get_num_threads()
     cfg = R.llama3_8b()
     g = torch.Generator().manual_seed(0)
@@ -234,6 +241,7 @@ def free_device_memory():
     gc.collect()
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
 
 
 def run_native(args):

@@ -44,6 +44,10 @@ int b200_set_pdl(int enable);
  * also serves every FlashMask call).  Same rounding points; kept switchable for A/B measurements.  The initial value can
  * be set with the environment variable B200_FA_FWD_IMPL. */
 int b200_set_fa_fwd_impl(int impl);
+/* Same for the plain-causal b200_fa_bwd: 2 (default) = transposed score tiles (kv on the UMMA M dimension), 64-row q steps,
+ * S^T double-buffered, P^T kept in tensor memory (csrc/fa_bwd2.cu); 1 = csrc/fa_bwd.cu (also every FlashMask call).
+ * Environment override: B200_FA_BWD_IMPL. */
+int b200_set_fa_bwd_impl(int impl);
 /* Which kernel serves b200_gemm_bf16_splitk for M <= 128 with a row-major A (returns the previous setting; NOT an error
  * code): 1 (default) = the swapped-operand, two-CTA-per-SM weight-streaming kernel (csrc/gemm_skinny.cu), 2 = its stream-K
  * variant (M <= 64), 0 = the persistent 128x256 kernel in split-K mode.  Same results up to fp32 summation order; kept switchable

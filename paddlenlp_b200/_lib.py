@@ -26,6 +26,7 @@ _SIGNATURES = {
     "b200_set_pdl": [I],
     "b200_set_skinny_gemm": [I],
     "b200_set_fa_fwd_impl": [I],
+    "b200_set_fa_bwd_impl": [I],
     "b200_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, P],
     "b200_gemm_bf16_ex": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I, I, I, I, I, P],
     "b200_gemm_splitk_workspace_bytes": [I64, I64],
@@ -129,7 +130,7 @@ class B200Error(RuntimeError):
 KERNELS_PER_CALL = {
     "b200_gemm_bf16": 1, "b200_gemm_bf16_ex": 1, "b200_gemm_bf16_splitk": 2, "b200_rmsnorm_fwd": 1, "b200_rmsnorm_bwd": 2, "b200_colsum_bf16": 2,
     "b200_rope_inplace": 1, "b200_swiglu_fwd": 1, "b200_swiglu_bwd": 1, "b200_embedding_fwd": 1, "b200_embedding_bwd": 1,
-    "b200_fa_fwd": 1, "b200_fa_bwd": 3, "b200_fa_fwd_flashmask": 1, "b200_fa_bwd_flashmask": 3, "b200_ce_fwd": 2, "b200_ce_bwd": 1, "b200_argmax_bf16": 1, "b200_grad_sqnorm": 2,
+    "b200_fa_fwd": 1, "b200_fa_bwd": 5, "b200_fa_fwd_flashmask": 1, "b200_fa_bwd_flashmask": 5, "b200_ce_fwd": 2, "b200_ce_bwd": 1, "b200_argmax_bf16": 1, "b200_grad_sqnorm": 2,
     "b200_adamw_step": 1, "b200_bf16_to_f32": 1, "b200_token_penalty_multi_scores": 2, "b200_generate_step_update": 2, "b200_decode_attention": 2, "b200_decode_attention_tc": 2, "b200_decode_attention_paged": 2,
 }
 launch_count = 0       # kernels launched through this module since import

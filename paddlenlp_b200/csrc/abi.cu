@@ -46,6 +46,9 @@ static int env_int(const char* name, int dflt) {
 }
 static int g_fa_fwd_impl = env_int("B200_FA_FWD_IMPL", 2);
 int fa_fwd_impl() { return g_fa_fwd_impl; }
+// backward 2 = transposed tiles, software-pipelined (fa_bwd2.cu), 1 = fa_bwd.cu
+static int g_fa_bwd_impl = env_int("B200_FA_BWD_IMPL", 2);
+int fa_bwd_impl() { return g_fa_bwd_impl; }
 
 int sm_count() {
   static int cached[64];
@@ -132,6 +135,12 @@ int b200_set_pdl(int enable) {
 int b200_set_fa_fwd_impl(int impl) {
   int old = b200::g_fa_fwd_impl;
   b200::g_fa_fwd_impl = impl == 1 ? 1 : 2;
+  return old;
+}
+
+int b200_set_fa_bwd_impl(int impl) {
+  int old = b200::g_fa_bwd_impl;
+  b200::g_fa_bwd_impl = impl == 1 ? 1 : 2;
   return old;
 }
 

@@ -329,8 +329,10 @@ static int make_acc_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S,
 }  // namespace b200
 
 extern "C" int64_t b200_fa_bwd_workspace_bytes(int64_t B, int64_t S, int64_t num_heads, int64_t head_dim) {
-  // fp32 dQ accumulation buffer + fp32 dK/dV accumulation buffers (at most num_heads wide) + delta
-  return 3 * B * S * num_heads * head_dim * 4 + B * num_heads * S * 4;
+  // fp32 dQ accumulation buffer + fp32 dK/dV accumulation buffers (at most num_heads wide) + per-row statistics; sized for both
+  // kernel generations: fa_bwd2.cu pads the sequence to a multiple of 64 and keeps two floats of statistics per row
+  const int64_t Spad = (S + 63) / 64 * 64;
+  return 3 * B * Spad * num_heads * head_dim * 4 + B * num_heads * Spad * 8;
 }
 
 extern "C" int b200_fa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
@@ -355,6 +357,9 @@ extern "C" int b200_fa_bwd_flashmask(const void* q, const void* k, const void* v
   B200_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 &&
                      lddk % 8 == 0 && lddv % 8 == 0,
                  "fa_bwd: token strides must be multiples of 8");
+  if (mask_start_rows == nullptr && fa_bwd_impl() == 2)    // plain causal: transposed, software-pipelined kernel (fa_bwd2.cu)
+    return launch_fa_bwd2(q, k, v, o, dout, lse, dq, dk, dv, workspace, B, S, num_heads, num_kv_heads, ldq, ldk, ldv, ldo, lddo,
+                          lddq, lddk, lddv, softmax_scale, stream);
   float* dq_acc = static_cast<float*>(workspace);
   float* dk_acc = dq_acc + B * S * num_heads * 128;
   float* dv_acc = dk_acc + B * S * num_kv_heads * 128;

@@ -21,6 +21,12 @@ int fa_fwd_impl();         // b200_set_fa_fwd_impl(): 2 = two-q-tile kernel (fa_
 int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* lse, int64_t B, int64_t S, int64_t num_heads,
                    int64_t num_kv_heads, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float softmax_scale,
                    cudaStream_t stream);
+int fa_bwd_impl();         // b200_set_fa_bwd_impl(): 2 = transposed pipelined kernel (fa_bwd2.cu, plain causal), 1 = fa_bwd.cu
+// fa_bwd2.cu: plain-causal backward (same argument meaning as b200_fa_bwd)
+int launch_fa_bwd2(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq,
+                   void* dk, void* dv, void* workspace, int64_t B, int64_t S, int64_t num_heads, int64_t num_kv_heads,
+                   int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv,
+                   float softmax_scale, cudaStream_t stream);
 bool pdl_enabled();   // b200_set_pdl(): launch GEMMs with programmatic dependent launch (decode-step kernel chains)
 
 // Launch `kern` on `stream`; when PDL is enabled the launch carries the programmatic-stream-serialization attribute, so the

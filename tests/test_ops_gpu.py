@@ -242,13 +242,16 @@ def test_embedding():
 # ------------------------------------------------------------------------------------------------
 @pytest.fixture
 def fa_fwd_impl(request):
-    """Select the plain-causal forward kernel generation (b200_set_fa_fwd_impl) for one test, then restore."""
+    """Select the plain-causal attention kernel generation (b200_set_fa_fwd_impl / b200_set_fa_bwd_impl: 2 = fa_fwd2.cu +
+    fa_bwd2.cu, 1 = fa_fwd.cu + fa_bwd.cu) for one test, then restore."""
     from paddlenlp_b200 import _lib
 
     lib = _lib.load()
-    old = lib.b200_set_fa_fwd_impl(request.param)
+    old_f = lib.b200_set_fa_fwd_impl(request.param)
+    old_b = lib.b200_set_fa_bwd_impl(request.param)
     yield request.param
-    lib.b200_set_fa_fwd_impl(old)
+    lib.b200_set_fa_fwd_impl(old_f)
+    lib.b200_set_fa_bwd_impl(old_b)
 
 
 @pytest.mark.parametrize("fa_fwd_impl", [2, 1], indirect=True)
@@ -374,6 +377,30 @@ def test_flash_attention_bench_shapes(B, S, nh, kvh, fa_fwd_impl):
             assert e < 2e-2, (name, b, e)
         del ref, qf, kf, vf, lse_ref
     print(f"[fa {B}x{S}x{nh}/{kvh} impl {fa_fwd_impl}] grad rel err {worst}")
+
+
+def test_flash_attention_bwd_impls_agree():
+    """Both backward generations from the same forward state: gradients agree to summation-order noise (ragged S, GQA)."""
+    from paddlenlp_b200 import _lib
+    o = ops()
+    lib = _lib.load()
+    B, S, nh, kvh, d = 2, 1000, 4, 2, 128
+    q, k, v = rand_bf16(B, S, nh, d, seed=81).to(DEV), rand_bf16(B, S, kvh, d, seed=82).to(DEV), rand_bf16(B, S, kvh, d, seed=83).to(DEV)
+    out, lse = o.flash_attn_fwd(q, k, v)
+    dout = rand_bf16(B, S, nh, d, seed=84).to(DEV)
+    res = {}
+    old = lib.b200_set_fa_bwd_impl(1)
+    try:
+        for impl in (1, 2):
+            lib.b200_set_fa_bwd_impl(impl)
+            dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+            o.flash_attn_bwd(q, k, v, out, dout, lse, dq, dk, dv)
+            res[impl] = (dq, dk, dv)
+    finally:
+        lib.b200_set_fa_bwd_impl(old)
+    for name, a, b in zip(("dq", "dk", "dv"), res[2], res[1]):
+        assert torch.isfinite(a.float()).all(), name
+        assert relerr(a, b) < 5e-3, (name, relerr(a, b))
 
 
 def test_flash_attention_fwd_impls_agree():

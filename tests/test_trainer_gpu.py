@@ -120,11 +120,14 @@ def test_checkpoint_resume(tmp_path):
     assert get_last_checkpoint(str(tmp_path / "orig")).endswith("checkpoint-6")
     assert sorted(os.listdir(tmp_path / "orig")) == [f"checkpoint-{i}" for i in (3, 4, 5, 6)]
     ck = str(tmp_path / "orig" / "checkpoint-3")
-    assert {"config.json", "model.safetensors", "optimizer.safetensors", "master_weights.safetensors", "scheduler.pdparams",
-            "trainer_state.json", "rng_state.pth", "training_args.json"} <= set(os.listdir(ck))
+    # unified-checkpoint layout: always `<stem>-0000i-of-0000N.safetensors` + index, even for one shard
+    assert {"config.json", "model-00001-of-00001.safetensors", "model.safetensors.index.json", "optimizer-00001-of-00001.safetensors",
+            "optimizer.safetensors.index.json", "master_weights-00001-of-00001.safetensors", "master_weights.safetensors.index.json",
+            "scheduler.pdparams", "trainer_state.json", "rng_state.pth", "training_args.json"} <= set(os.listdir(ck))
     assert json.load(open(os.path.join(ck, "trainer_state.json")))["global_step"] == 3
     opt_file = cu.load_sharded(ck, cu.SAFE_OPTIMIZER_NAME, cu.SAFE_OPTIMIZER_INDEX_NAME)
-    assert abs(float(opt_file["lm_head.weight/beta1_pow_acc_0"]) - 0.9 ** 3) < 1e-7
+    # Paddle's accumulators hold beta ** (step + 1) after `step` updates (post-update convention)
+    assert abs(float(opt_file["lm_head.weight/beta1_pow_acc_0"]) - 0.9 ** 4) < 1e-7
     assert "qwen2.layers.1.self_attn.k_proj.bias/moment2_0" in opt_file
 
     # (1) restore only: every buffer equals the file contents bit for bit
@@ -179,7 +182,8 @@ def test_trainer_with_criterion_argument(tmp_path):
     base = run(None)
     fused = run(T.LlamaPretrainingCriterion(ignore_index=-100))
     custom = run(torch_criterion)
-    assert fused == base                                             # same kernels, same order -> same logged losses
+    assert fused[:2] == base[:2]                                     # same kernels, same order -> same bits until the attention
+    assert max(abs(a - b) for a, b in zip(fused, base)) < 2e-3       # backward's reduce-add order shows up in the weights
     assert abs(custom[0] - base[0]) < 2e-3 * abs(base[0])            # same first loss (torch CE vs the CE kernel)
     assert custom[-1] < custom[0] - 0.3 and fused[-1] < fused[0] - 0.3
 
