@@ -90,6 +90,19 @@ int b200_gemm_bf16_splitk(const void* A, const void* B, void* C, const float* bi
                           int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int split_k,
                           cudaStream_t stream);
 
+/* gate|up projection + SwiGLU in ONE kernel — LlamaMLP.forward with fuse_attention_ffn (llama/modeling.py:632-652, swiglu :38-45):
+ *   GU[M, 2I] = bf16(X[M,K] * W[K,2I])  (gate columns [0,I), up columns [I,2I); kept for the backward),
+ *   Mout[M, I] = bf16(silu(gate) * up)  with gate/up rounded to bf16 first (the unfused rounding points).
+ * A 256-column tcgen05 tile is formed from 128 gate columns and the 128 up columns of the same channels, so no interleaved
+ * weight layout is needed; requires I % 128 == 0.  Bit-identical to b200_gemm_bf16 followed by b200_swiglu_fwd. */
+int b200_gemm_swiglu_bf16(const void* X, const void* W, void* GU, void* Mout, int64_t M, int64_t inter, int64_t K, int64_t ldx,
+                          int64_t ldw, int64_t ldgu, int64_t ldm, int cta_group, cudaStream_t stream);
+/* Backward twin: the down-projection dX GEMM with the SwiGLU backward in its epilogue.
+ *   d(m) = dY[M,K] * Wdown[I,K]^T (never written);  DGU[M, 2I] = [ d(m) * up * silu'(gate) | d(m) * silu(gate) ],
+ * GU = the saved gate|up projection [M, 2I].  Bit-identical to b200_gemm_bf16 (b_mn_major = 0) + b200_swiglu_bwd.  I % 64 == 0. */
+int b200_gemm_swiglu_bwd_bf16(const void* dY, const void* Wdown, const void* GU, void* DGU, int64_t M, int64_t inter, int64_t K,
+                              int64_t lddy, int64_t ldw, int64_t ldgu, int64_t lddgu, int cta_group, cudaStream_t stream);
+
 /* ---- RMSNorm: replaces fused_ln.fused_rms_norm / fast_ln (apex-derived custom ops) --------------------------
  * fwd : y = bf16( bf16(x * rstd) * w ), rstd[row] = rsqrt(mean(x^2) + eps) in fp32 (saved for the backward).
  * bwd : dx = rstd * (dy*w - xhat * mean(dy*w*xhat)) (+ dres, the gradient arriving through the residual branch);

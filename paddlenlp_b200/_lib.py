@@ -29,6 +29,8 @@ _SIGNATURES = {
     "b200_set_fa_bwd_impl": [I],
     "b200_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, P],
     "b200_gemm_bf16_ex": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I, I, I, I, I, P],
+    "b200_gemm_swiglu_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I, P],
+    "b200_gemm_swiglu_bwd_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I, P],
     "b200_gemm_splitk_workspace_bytes": [I64, I64],
     "b200_gemm_bf16_splitk": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, P],
     "b200_rmsnorm_fwd": [P, P, P, P, I64, I64, F, P],

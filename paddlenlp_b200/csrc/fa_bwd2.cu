@@ -122,17 +122,21 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint8_t* sStage = smem + OFF_STAGE;
   uint8_t* sStat = smem + OFF_STAT;    // [QST]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  // Barriers that are WAITED ON by the two compute groups in alternation exist once per group (index n & 1, phase (n >> 1) & 1):
+  // a group waits for steps n, n+2, ... — consecutive waits of the same parity on a shared barrier would be satisfied by the
+  // previous same-parity phase while the other group's step is still in flight.  pds_full is per group for the mirror reason:
+  // arrivals of group g for step n+1 must not complete the phase the MMA warp is waiting on for step n.
   uint64_t* kv_full = bars;            // [1]
   uint64_t* qdo_full = bars + 1;       // [QST]
   uint64_t* qdo_empty = bars + 4;      // [QST]
   uint64_t* s_full = bars + 7;         // [2]   S^T(n) in buffer n&1 (and every earlier MMA) complete
-  uint64_t* dp_full = bars + 9;        // [1]   dP^T(n) complete
-  uint64_t* dp_free = bars + 10;       // [1]   compute(n) has loaded S^T(n), dP^T(n) into registers        (128 arrivals)
-  uint64_t* pds_full = bars + 11;      // [1]   P^T(n) in TMEM, dS^T(n) in smem                              (128 arrivals)
-  uint64_t* dq_full = bars + 12;       // [1]   dQ^T(n) complete
-  uint64_t* dq_empty = bars + 13;      // [1]   dQ^T(n) read out                                            (128 arrivals)
-  uint64_t* acc_full = bars + 14;      // [1]   dK, dV final
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* dp_full = bars + 9;        // [2]   dP^T(n) complete
+  uint64_t* dp_free = bars + 11;       // [1]   compute(n) has loaded S^T(n), dP^T(n) into registers (128 arrivals; in step order)
+  uint64_t* pds_full = bars + 12;      // [2]   P^T(n) in TMEM, dS^T(n) in smem                          (128 arrivals)
+  uint64_t* dq_full = bars + 14;       // [2]   dQ^T(n) complete
+  uint64_t* dq_empty = bars + 16;      // [1]   dQ^T(n) read out                                         (128 arrivals; in step order)
+  uint64_t* acc_full = bars + 17;      // [1]   dK, dV final
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = static_cast<int>(blockIdx.x);     // kv tile; tile 0 has the most work and is scheduled first
@@ -145,11 +149,13 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     mbar_init(kv_full, 1);
     for (int i = 0; i < QST; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-    mbar_init(dp_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&dp_full[i], 1);
+      mbar_init(&pds_full[i], 128);
+      mbar_init(&dq_full[i], 1);
+    }
     mbar_init(dp_free, 128);
-    mbar_init(pds_full, 128);
-    mbar_init(dq_full, 1);
     mbar_init(dq_empty, 128);
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -208,14 +214,14 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tdP, kmaj(aV, kk, KV_HALF), kmaj(adO, kk, Q_HALF), id_st, kk > 0);   // dP^T = V dO^T
-        umma_commit(dp_full);
+        umma_commit(&dp_full[n & 1]);
       };
       mbar_wait(kv_full, 0);
       issue_st_dp(0, false);
       for (int n = 0; n < n_iter; ++n) {
         const int st = n % QST;
         if (n + 1 < n_iter) issue_st_dp(n + 1, true);
-        mbar_wait(pds_full, n & 1);
+        mbar_wait(&pds_full[n & 1], static_cast<uint32_t>((n >> 1) & 1));
         tc_fence_after();
         const uint32_t aQ = smem_u32(sQ + st * Q_TILE_BYTES), adO = smem_u32(sdO + st * Q_TILE_BYTES);
         const uint32_t adS = smem_u32(sdS + (n & 1) * DS_BYTES);
@@ -236,7 +242,7 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int kk = 0; kk < 8; ++kk)     // dQ^T = K^T dS^T : K = 128 kv;  A k-step = 16 K rows (2 KB), B k-step = 16 dS^T rows (2 KB)
           umma_ss<1>(tdQ, umma_desc_sw128(aK + kk * 2048, KV_HALF, 1024), umma_desc_sw128(adS + kk * 2048, 16, 1024), id_dq,
                      kk > 0);
-        umma_commit(dq_full);
+        umma_commit(&dq_full[n & 1]);
       }
       umma_commit(acc_full);
     }
@@ -248,7 +254,7 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     uint8_t* my_stage = sStage + (warp - 2) * 4096;
     auto read_out_dq = [&](int n) {                      // dQ^T(n): lanes = d, columns = 64 q rows of step n
-      mbar_wait(dq_full, n & 1);
+      mbar_wait(&dq_full[n & 1], static_cast<uint32_t>((n >> 1) & 1));
       tc_fence_after();
       reduce_out(tdQ + lane_off, my_stage, &tmdQ, lane, 0, kv0 + n * 64, quad * 32, hq, batch);
       tc_fence_before();
@@ -259,7 +265,7 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint32_t tS = tST + lane_off + static_cast<uint32_t>(g * 64);
       mbar_wait(&qdo_full[st], static_cast<uint32_t>((n / QST) & 1));      // row statistics of this step are in smem
       mbar_wait(&s_full[g], static_cast<uint32_t>((n >> 1) & 1));
-      mbar_wait(dp_full, n & 1);
+      mbar_wait(&dp_full[g], static_cast<uint32_t>((n >> 1) & 1));
       tc_fence_after();
       uint32_t sv[64], dv[64];
       {
@@ -301,7 +307,7 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(pds_full);
+      mbar_arrive(&pds_full[g]);
       read_out_dq(n);
     }
     // the other group's last read-out may still be pending for this group's barrier count: every step was read out by exactly one

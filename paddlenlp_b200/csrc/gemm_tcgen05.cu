@@ -52,6 +52,12 @@ struct Params {
   int M, N, K;
   int num_m_tiles, num_n_tiles;
   int epi_mode;            // 0: C = acc ; 1: C = bf16(C_old + acc) ; 2: C = bf16(bf16(acc) + R) ; 3: F32ws += acc (split-K)
+                           // 4: gate|up GEMM + SwiGLU: a 256-column tile = 128 gate columns | the 128 up columns of the same
+                           //    channels; C gets gate and up (bf16, their [M, 2I] positions), tmR's tensor gets
+                           //    m = bf16(silu(gate) * up) [M, I]
+                           // 5: down-proj dX GEMM + SwiGLU backward: acc = d(m) tile; tmR's tensor = saved gate|up [M, 2I];
+                           //    C = [d(gate) | d(up)] [M, 2I]
+  int swiglu_inter;        // modes 4, 5: I (the up half starts at column I)
   int split_k;             // work items per output tile (K is cut into split_k ranges of kb_per_split k-blocks)
   int kb_per_split;
   int b_prefetch;          // PDL: issue the first stages' B (weight) loads before griddepcontrol.wait
@@ -191,8 +197,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (!b_done) {
             if constexpr (B_MN) {
+              if (p.epi_mode == 4) {
+                // 64-column chunk g of the 256-column tile: chunks 0,1 = gate channels [128 n_blk, +128), chunks 2,3 = the up
+                // columns of the same channels (at column I + ...) — no interleaved weight layout needed
 #pragma unroll
-              for (int c = 0; c < C::B_COLS / 64; ++c) load(&tmB, sb + c * (64 * BK * 2), n0 + c * 64, k0);
+                for (int c = 0; c < C::B_COLS / 64; ++c) {
+                  const int g = static_cast<int>(cta_rank) * (C::B_COLS / 64) + c;
+                  const int col = n_blk * 128 + (g & 1) * 64 + (g >> 1) * p.swiglu_inter;
+                  load(&tmB, sb + c * (64 * BK * 2), col, k0);
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < C::B_COLS / 64; ++c) load(&tmB, sb + c * (64 * BK * 2), n0 + c * 64, k0);
+              }
             } else {
 #pragma unroll
               for (int c = 0; c < C::B_COLS / 128; ++c) load(&tmB, sb + c * (128 * BK * 2), k0, n0 + c * 128);
@@ -255,6 +272,130 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+      if (p.epi_mode == 4) {
+        // gate|up + SwiGLU (llama/modeling.py:38-45, 632-652): accumulator columns [0,128) = gate, [128,256) = up of channels
+        // [128 n_blk, +128).  Rounding points of the unfused path: gate and up each rounded to bf16 (the Linear outputs, kept for
+        // the backward), then silu(g) * u in fp32 and one rounding.
+#pragma unroll 1
+        for (int sp = 0; sp < 2; ++sp) {
+          uint32_t g0[32], g1[32], u0[32], u1[32];
+          tmem_ld32(taddr + sp * 64, g0);
+          tmem_ld32(taddr + sp * 64 + 32, g1);
+          tmem_ld32(taddr + 128 + sp * 64, u0);
+          tmem_ld32(taddr + 128 + sp * 64 + 32, u1);
+          tmem_ld_wait();
+          if (sp == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+          }
+          const int cg = n_blk * 128 + sp * 64;            // gate column in C == channel column in the m tensor
+          if (row0 < p.M) {
+#pragma unroll
+            for (int which = 0; which < 3; ++which) {       // 0: gate -> C, 1: up -> C (+I), 2: m -> tmR's tensor
+              if (lane == 0) tma_store_wait_read<1>();
+              __syncwarp();
+              const uint32_t row_s = my_buf_s + buf * EPI_BUF_BYTES + lane * 128;
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int idx = ch * 8 + j;
+                  const float gv = __uint_as_float(idx < 32 ? g0[idx] : g1[idx - 32]);
+                  const float uv = __uint_as_float(idx < 32 ? u0[idx] : u1[idx - 32]);
+                  if (which == 0) f[j] = gv;
+                  else if (which == 1) f[j] = uv;
+                  else {
+                    const float gb = bf16_round(gv), ub = bf16_round(uv);
+                    f[j] = gb / (1.f + __expf(-gb)) * ub;
+                  }
+                }
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]);
+                o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]);
+                o.w = pack_bf16x2(f[6], f[7]);
+                st_shared_v4(row_s + ((ch ^ (lane & 7)) << 4), o);
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (which == 2) tma_store_2d(&tmR, my_buf + buf * EPI_BUF_BYTES, cg, row0);
+                else tma_store_2d(&tmC, my_buf + buf * EPI_BUF_BYTES, cg + which * p.swiglu_inter, row0);
+                tma_store_commit();
+              }
+              buf ^= 1;
+            }
+          }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+        continue;
+      }
+      if (p.epi_mode == 5) {
+        // d(m) = dY W_down^T  ->  d(gate) = d(m) * up * silu'(gate),  d(up) = d(m) * silu(gate)     (swiglu backward, elementwise.cu)
+        // gate / up tiles come in through the two staging buffers (TMA loads), the results leave through the same buffers.
+#pragma unroll 1
+        for (int slab = 0; slab < BN / EPI_BOX_COLS; ++slab) {
+          const int c0 = col0 + slab * EPI_BOX_COLS;
+          const bool live = (row0 < p.M) && (c0 < p.N);
+          if (lane == 0) tma_store_wait_read<0>();          // both buffers are about to be overwritten by the loads
+          __syncwarp();
+          if (live && lane == 0) {
+            mbar_arrive_expect_tx(&epi_bar[q], 2 * EPI_BUF_BYTES);
+            tma_load_2d(&tmR, &epi_bar[q], my_buf, c0, row0);
+            tma_load_2d(&tmR, &epi_bar[q], my_buf + EPI_BUF_BYTES, c0 + p.swiglu_inter, row0);
+          }
+          uint32_t v0[32], v1[32];
+          tmem_ld32(taddr + slab * EPI_BOX_COLS, v0);
+          tmem_ld32(taddr + slab * EPI_BOX_COLS + 32, v1);
+          tmem_ld_wait();
+          if (slab == BN / EPI_BOX_COLS - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+          }
+          if (live) {
+            mbar_wait(&epi_bar[q], ephase);
+            ephase ^= 1u;
+            const uint32_t row_s = my_buf_s + lane * 128;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              const uint32_t addr = row_s + ((ch ^ (lane & 7)) << 4);
+              const uint4 gq = ld_shared_v4(addr), uq = ld_shared_v4(addr + EPI_BUF_BYTES);
+              const uint32_t* gi = reinterpret_cast<const uint32_t*>(&gq);
+              const uint32_t* ui = reinterpret_cast<const uint32_t*>(&uq);
+              uint4 og, ou;
+              uint32_t* ogi = reinterpret_cast<uint32_t*>(&og);
+              uint32_t* oui = reinterpret_cast<uint32_t*>(&ou);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int idx = ch * 8 + 2 * j;
+                const float d0 = bf16_round(__uint_as_float(idx < 32 ? v0[idx] : v1[idx - 32]));          // d(m): the GEMM's own
+                const float d1 = bf16_round(__uint_as_float(idx + 1 < 32 ? v0[idx + 1] : v1[idx + 1 - 32]));  // bf16 output rounding
+                const float2 gf = unpack_bf16x2(gi[j]);
+                const float2 uf = unpack_bf16x2(ui[j]);
+                const float sg0 = 1.f / (1.f + __expf(-gf.x)), sg1 = 1.f / (1.f + __expf(-gf.y));
+                const float silu0 = gf.x * sg0, silu1 = gf.y * sg1;
+                const float ds0 = sg0 * (1.f + gf.x * (1.f - sg0)), ds1 = sg1 * (1.f + gf.y * (1.f - sg1));
+                ogi[j] = pack_bf16x2(d0 * uf.x * ds0, d1 * uf.y * ds1);
+                oui[j] = pack_bf16x2(d0 * silu0, d1 * silu1);
+              }
+              st_shared_v4(addr, og);
+              st_shared_v4(addr + EPI_BUF_BYTES, ou);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, my_buf, c0, row0);
+              tma_store_2d(&tmC, my_buf + EPI_BUF_BYTES, c0 + p.swiglu_inter, row0);
+              tma_store_commit();
+            }
+          }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+        continue;
+      }
 #pragma unroll 1
       for (int slab = 0; slab < BN / EPI_BOX_COLS; ++slab) {
         const int c0 = col0 + slab * EPI_BOX_COLS;
@@ -395,7 +536,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   Params pp = p;
   pp.b_prefetch = 0;
   pp.l2_prefetch_kb = 0;
-  if (pdl_enabled()) {
+  if (pdl_enabled() && p.epi_mode != 4) {     // (the early weight prefetch does not know mode 4's column mapping)
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
@@ -475,6 +616,7 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const fl
   p.split_k = 1;
   p.kb_per_split = static_cast<int>((K + BK - 1) / BK);
   p.bias = bias;
+  p.swiglu_inter = 0;
 
 #define B200_GEMM_DISPATCH(CG)                                                                          \
   do {                                                                                                  \
@@ -486,6 +628,105 @@ extern "C" int b200_gemm_bf16_ex(const void* A, const void* B, void* C, const fl
   if (cta_group == 2) B200_GEMM_DISPATCH(2);
   B200_GEMM_DISPATCH(1);
 #undef B200_GEMM_DISPATCH
+}
+
+// gate|up projection + SwiGLU in one kernel (training forward of LlamaMLP, llama/modeling.py:632-652 with fuse_attention_ffn):
+//   GU[M, 2I] = bf16(X[M, K] * W[K, 2I])   (gate columns [0, I), up columns [I, 2I): kept for the backward)
+//   Mout[M, I] = bf16( silu(GU[:, c]) * GU[:, I + c] )
+// The 256-column tile of the tcgen05 GEMM is formed from 128 gate columns and the 128 up columns of the same channels (two TMA
+// boxes at different column coordinates of the SAME row-major weight), so the epilogue holds both halves of every channel.
+extern "C" int b200_gemm_swiglu_bf16(const void* X, const void* W, void* GU, void* Mout, int64_t M, int64_t inter, int64_t K,
+                                     int64_t ldx, int64_t ldw, int64_t ldgu, int64_t ldm, int cta_group, cudaStream_t stream) {
+  using namespace b200;
+  using namespace b200::gemm;
+  B200_CHECK_ARG(X && W && GU && Mout, "gemm_swiglu: null pointer");
+  B200_CHECK_ARG(M > 0 && inter > 0 && K > 0 && inter % 128 == 0, "gemm_swiglu: intermediate size must be a multiple of 128 (got %lld)",
+                 (long long)inter);
+  B200_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0 && ldgu % 8 == 0 && ldm % 8 == 0, "gemm_swiglu: leading dimensions must be multiples of 8");
+  B200_CHECK_ARG(cta_group == 1 || cta_group == 2, "gemm_swiglu: cta_group must be 1 or 2");
+  B200_CHECK_ARG(M < (1ll << 31) && inter < (1ll << 30) && K < (1ll << 31), "gemm_swiglu: dimension too large");
+  const int64_t N = 2 * inter;
+  CUtensorMap tmA, tmB, tmC, tmM;
+  int rc;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)}, strides[1] = {static_cast<uint64_t>(ldx) * 2};
+    uint32_t box[2] = {BK, 128};
+    if ((rc = encode_tmap_bf16(&tmA, X, 2, dims, strides, box)) != 0) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(K)}, strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {64, BK};
+    if ((rc = encode_tmap_bf16(&tmB, W, 2, dims, strides, box)) != 0) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)}, strides[1] = {static_cast<uint64_t>(ldgu) * 2};
+    uint32_t box[2] = {EPI_BOX_COLS, EPI_BOX_ROWS};
+    if ((rc = encode_tmap_bf16(&tmC, GU, 2, dims, strides, box)) != 0) return rc;
+    dims[0] = static_cast<uint64_t>(inter);
+    strides[0] = static_cast<uint64_t>(ldm) * 2;
+    if ((rc = encode_tmap_bf16(&tmM, Mout, 2, dims, strides, box)) != 0) return rc;
+  }
+  Params p;
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.K = static_cast<int>(K);
+  p.num_m_tiles = static_cast<int>((M + BM * cta_group - 1) / (BM * cta_group));
+  p.num_n_tiles = static_cast<int>(inter / 128);
+  p.epi_mode = 4;
+  p.split_k = 1;
+  p.kb_per_split = static_cast<int>((K + BK - 1) / BK);
+  p.bias = nullptr;
+  p.swiglu_inter = static_cast<int>(inter);
+  if (cta_group == 2) return launch<2, false, true>(tmA, tmB, tmC, tmM, p, 0, stream);
+  return launch<1, false, true>(tmA, tmB, tmC, tmM, p, 0, stream);
+}
+
+// down-projection dX GEMM + SwiGLU backward in one kernel (backward of LlamaMLP, llama/modeling.py:632-652):
+//   d(m)[M, I] = dY[M, h] * W_down[I, h]^T   (never written),   DGU[M, 2I] = [ d(m) * up * silu'(gate) | d(m) * silu(gate) ]
+// GU is the saved gate|up projection [M, 2I].  Bit-identical to b200_gemm_bf16 (dX) followed by b200_swiglu_bwd.  I % 64 == 0.
+extern "C" int b200_gemm_swiglu_bwd_bf16(const void* dY, const void* Wdown, const void* GU, void* DGU, int64_t M, int64_t inter,
+                                         int64_t K, int64_t lddy, int64_t ldw, int64_t ldgu, int64_t lddgu, int cta_group,
+                                         cudaStream_t stream) {
+  using namespace b200;
+  using namespace b200::gemm;
+  B200_CHECK_ARG(dY && Wdown && GU && DGU, "gemm_swiglu_bwd: null pointer");
+  B200_CHECK_ARG(M > 0 && inter > 0 && K > 0 && inter % 64 == 0, "gemm_swiglu_bwd: intermediate size must be a multiple of 64 (got %lld)",
+                 (long long)inter);
+  B200_CHECK_ARG(lddy % 8 == 0 && ldw % 8 == 0 && ldgu % 8 == 0 && lddgu % 8 == 0, "gemm_swiglu_bwd: leading dimensions must be multiples of 8");
+  B200_CHECK_ARG(cta_group == 1 || cta_group == 2, "gemm_swiglu_bwd: cta_group must be 1 or 2");
+  B200_CHECK_ARG(M < (1ll << 31) && inter < (1ll << 30) && K < (1ll << 31), "gemm_swiglu_bwd: dimension too large");
+  CUtensorMap tmA, tmB, tmC, tmG;
+  int rc;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)}, strides[1] = {static_cast<uint64_t>(lddy) * 2};
+    uint32_t box[2] = {BK, 128};
+    if ((rc = encode_tmap_bf16(&tmA, dY, 2, dims, strides, box)) != 0) return rc;
+  }
+  {   // W_down stored [I, h] = [N, K] row-major: K-major B operand
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(inter)}, strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {BK, 128};
+    if ((rc = encode_tmap_bf16(&tmB, Wdown, 2, dims, strides, box)) != 0) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(2 * inter), static_cast<uint64_t>(M)}, strides[1] = {static_cast<uint64_t>(lddgu) * 2};
+    uint32_t box[2] = {EPI_BOX_COLS, EPI_BOX_ROWS};
+    if ((rc = encode_tmap_bf16(&tmC, DGU, 2, dims, strides, box)) != 0) return rc;
+    strides[0] = static_cast<uint64_t>(ldgu) * 2;
+    if ((rc = encode_tmap_bf16(&tmG, GU, 2, dims, strides, box)) != 0) return rc;
+  }
+  Params p;
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(inter);
+  p.K = static_cast<int>(K);
+  p.num_m_tiles = static_cast<int>((M + BM * cta_group - 1) / (BM * cta_group));
+  p.num_n_tiles = static_cast<int>((inter + BN - 1) / BN);
+  p.epi_mode = 5;
+  p.split_k = 1;
+  p.kb_per_split = static_cast<int>((K + BK - 1) / BK);
+  p.bias = nullptr;
+  p.swiglu_inter = static_cast<int>(inter);
+  if (cta_group == 2) return launch<2, false, false>(tmA, tmB, tmC, tmG, p, 0, stream);
+  return launch<1, false, false>(tmA, tmB, tmC, tmG, p, 0, stream);
 }
 
 namespace b200 {
@@ -575,6 +816,7 @@ extern "C" int b200_gemm_bf16_splitk(const void* A, const void* B, void* C, cons
     (void)strides;
   }
   Params p;
+  p.swiglu_inter = 0;
   p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
   p.num_m_tiles = static_cast<int>((M + BM - 1) / BM);
   p.num_n_tiles = static_cast<int>((N + BN - 1) / BN);

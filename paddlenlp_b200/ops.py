@@ -87,6 +87,41 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
     return out
 
 
+def gemm_swiglu(x: torch.Tensor, w_gate_up: torch.Tensor, gate_up: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, cta_group: int = 2):
+    """(gate_up [M, 2I], m [M, I]) = fused gate|up projection + SwiGLU (one tcgen05 GEMM; the epilogue holds gate and up of the
+    same channels).  w_gate_up is the reference-layout fused weight [K, 2I] (gate | up).  Requires I % 128 == 0."""
+    _chk(x, "x"); _chk(w_gate_up, "w_gate_up")
+    assert x.dim() == 2 and w_gate_up.dim() == 2 and x.stride(1) == 1 and w_gate_up.stride(1) == 1
+    M, K = x.shape
+    Kw, two_i = w_gate_up.shape
+    if K != Kw or two_i % 2:
+        raise ValueError(f"gemm_swiglu: shapes {tuple(x.shape)} x {tuple(w_gate_up.shape)}")
+    inter = two_i // 2
+    if gate_up is None:
+        gate_up = torch.empty(M, two_i, dtype=BF16, device=x.device)
+    if out is None:
+        out = torch.empty(M, inter, dtype=BF16, device=x.device)
+    call("b200_gemm_swiglu_bf16", ptr(x), ptr(w_gate_up), ptr(gate_up), ptr(out), M, inter, K, x.stride(0), w_gate_up.stride(0),
+         gate_up.stride(0), out.stride(0), cta_group, stream_ptr())
+    return gate_up, out
+
+
+def gemm_swiglu_bwd(dy: torch.Tensor, w_down: torch.Tensor, gate_up: torch.Tensor, dgate_up: Optional[torch.Tensor] = None,
+                    cta_group: int = 2) -> torch.Tensor:
+    """dgate_up [M, 2I] = SwiGLU backward of d(m) = dy @ w_down^T, computed in the GEMM epilogue (d(m) is never written).
+    w_down is the reference-layout down_proj weight [I, h]; gate_up the saved projection [M, 2I].  Requires I % 64 == 0."""
+    _chk(dy, "dy"); _chk(w_down, "w_down"); _chk(gate_up, "gate_up")
+    M, K = dy.shape
+    inter, Kw = w_down.shape
+    assert K == Kw and gate_up.shape == (M, 2 * inter) and dy.stride(1) == 1 and w_down.stride(1) == 1 and gate_up.stride(1) == 1
+    if dgate_up is None:
+        dgate_up = torch.empty_like(gate_up)
+    call("b200_gemm_swiglu_bwd_bf16", ptr(dy), ptr(w_down), ptr(gate_up), ptr(dgate_up), M, inter, K, dy.stride(0), w_down.stride(0),
+         gate_up.stride(0), dgate_up.stride(0), cta_group, stream_ptr())
+    return dgate_up
+
+
 def gemm_skinny(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *, trans_b: bool = False,
                 bias: Optional[torch.Tensor] = None, split_k: int = 0) -> torch.Tensor:
     """Decode-step GEMM (few token rows, weight-streaming bound): split-K over all SMs, fp32 TMA reduce, one rounding."""

@@ -58,6 +58,10 @@ class DecoderEngine:
         if self.h % 8 or self.I % 8 or self.V % 8:
             raise ValueError("hidden_size, intermediate_size and vocab_size must be multiples of 8")
         self.qkv_n = (self.nh + 2 * self.kvh) * self.d
+        # SwiGLU fused into the gate|up GEMM epilogue (needs 128-channel tiles); B200_FUSE_SWIGLU=0 selects GEMM + swiglu kernel
+        import os as _os
+        self.fuse_swiglu = (self.I % 128 == 0) and _os.environ.get("B200_FUSE_SWIGLU", "1") != "0"
+        self.fuse_swiglu_bwd = (self.I % 64 == 0) and _os.environ.get("B200_FUSE_SWIGLU_BWD", "1") != "0"
         # recompute (llama/modeling.py:1706-1733 `recompute_training_full`): keep only each layer's input and re-run the
         # layer forward inside backward.  Only the "full" granularity exists here (the "full_attn" / "core_attn" splits
         # exist to trade memory against the reference's unfused attention; the fused attention keeps no S x S tensor).
@@ -255,8 +259,11 @@ class DecoderEngine:
         attn2 = attn.view(T, qn)
         x1 = ops.gemm(attn2, p[f"l{i}.o_w"], residual=x)
         n2, rstd2 = ops.rmsnorm_fwd(x1, p[f"l{i}.ln2"], self.eps)
-        gu = ops.gemm(n2, p[f"l{i}.gu_w"])
-        m = ops.swiglu_fwd(gu)
+        if self.fuse_swiglu:
+            gu, m = ops.gemm_swiglu(n2, p[f"l{i}.gu_w"])          # SwiGLU in the gate|up GEMM's epilogue
+        else:
+            gu = ops.gemm(n2, p[f"l{i}.gu_w"])
+            m = ops.swiglu_fwd(gu)
         x2 = ops.gemm(m, p[f"l{i}.down_w"], residual=x1)
         if save is not None:
             save.append((x, rstd1, n1, qkv, attn2, lse, x1, rstd2, n2, gu, m))
@@ -416,11 +423,16 @@ class DecoderEngine:
         T = B * S
         qn, kn = self.nh * self.d, self.kvh * self.d
         # ---- MLP ----
-        dm = ops.gemm(dx2, p[f"l{i}.down_w"], trans_b=True)
-        ops.gemm(m, dx2, out=g[f"l{i}.down_w"], trans_a=True, accumulate=acc)
-        del m
-        dgu = ops.swiglu_bwd(gu, dm)
-        del dm
+        if self.fuse_swiglu_bwd:
+            dgu = ops.gemm_swiglu_bwd(dx2, p[f"l{i}.down_w"], gu)      # SwiGLU backward in the dX GEMM's epilogue
+            ops.gemm(m, dx2, out=g[f"l{i}.down_w"], trans_a=True, accumulate=acc)
+            del m
+        else:
+            dm = ops.gemm(dx2, p[f"l{i}.down_w"], trans_b=True)
+            ops.gemm(m, dx2, out=g[f"l{i}.down_w"], trans_a=True, accumulate=acc)
+            del m
+            dgu = ops.swiglu_bwd(gu, dm)
+            del dm
         dn2 = ops.gemm(dgu, p[f"l{i}.gu_w"], trans_b=True)
         ops.gemm(n2, dgu, out=g[f"l{i}.gu_w"], trans_a=True, accumulate=acc)
         del dgu, gu, n2

@@ -175,9 +175,9 @@ def main():
             last_epoch=0,
         )
 
-    n = training_args.per_device_train_batch_size * training_args.dataset_world_size * training_args.max_steps * \
-        training_args.gradient_accumulation_steps
-    train_dataset = SyntheticTokenDataset(n, data_args.max_seq_length, config.vocab_size)
+    # 8 samples seen repeatedly (several epochs within max_steps): random tokens can only be memorised, which is what makes the
+    # loss fall in a few steps
+    train_dataset = SyntheticTokenDataset(8 * training_args.dataset_world_size, data_args.max_seq_length, config.vocab_size)
 
     trainer = PretrainingTrainer(
         model=model,

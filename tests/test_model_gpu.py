@@ -301,7 +301,20 @@ def test_full_width_single_layer_llama3_8b_shapes():
 # Parity at the BENCHMARKED shape (SURVEY §8d "Parity inputs"): full Llama-3-8B layer width at S = 4096.
 # The oracle is evaluated on the GPU in fp32 torch (it is a checker: cuBLAS fp32, TF32 off) — on the CPU these sizes take minutes.
 # ------------------------------------------------------------------------------------------------
-def _oracle_on_device(cfg, w, ids, labels, want_grads=True):
+def _chunked_linear(x, wt, bias, mode):
+    """R.linear with the K dimension summed in 4 chunks: the same rounding points, a different fp32 accumulation order."""
+    K = wt.shape[0]
+    step = (K + 3) // 4
+    y = None
+    for s0 in range(0, K, step):
+        part = x[..., s0:s0 + step] @ wt[s0:s0 + step]
+        y = part if y is None else y + part
+    if bias is not None:
+        y = y + bias
+    return R.rnd(y, mode)
+
+
+def _oracle_on_device(cfg, w, ids, labels, want_grads=True, reorder_grads=False):
     assert not torch.backends.cuda.matmul.allow_tf32
     wd = {k: v.to(DEV) for k, v in w.items()}
     ids_d, lab_d = ids.to(DEV), labels.to(DEV)
@@ -313,6 +326,14 @@ def _oracle_on_device(cfg, w, ids, labels, want_grads=True):
         with torch.no_grad():
             ref16 = R.model_forward(ids_d, wd, cfg, mode="bf16")
         ref_loss, gref = R.criterion(ref16, lab_d), None
+    if reorder_grads:
+        orig = R.linear
+        R.linear = _chunked_linear
+        try:
+            _, _, gref2 = R.loss_and_grads(ids_d, lab_d, wd, cfg, mode="bf16")
+        finally:
+            R.linear = orig
+        return ref16, ref32, ref_loss, gref, gref2
     return ref16, ref32, ref_loss, gref
 
 
@@ -376,25 +397,31 @@ def test_two_layer_full_width_real_vocab_s4096():
     tok = torch.randint(0, cfg.vocab_size, (2, 4097), generator=torch.Generator().manual_seed(42))
     ids, labels = tok[:, :-1].contiguous(), tok[:, 1:].contiguous()
     model.engine.clear_grad()
-    gsum = None
+    gsum = gsum2 = None
     for mb in range(2):                                   # two micro-batches of one sequence, loss / 2 each (bench: / accum)
         i1, l1 = ids[mb:mb + 1], labels[mb:mb + 1]
         loss, logits = model(input_ids=i1.to(DEV), labels=l1.to(DEV))
         logits = logits.float().clone()
-        ref16, ref32, ref_loss, gref = _oracle_on_device(cfg, w, i1, l1)
+        ref16, ref32, ref_loss, gref, gref2 = _oracle_on_device(cfg, w, i1, l1, reorder_grads=True)
         _check_logits_loss_argmax(f"2 layers, V=128256, S=4096, micro-batch {mb}", logits, loss.detach(), ref16, ref32, ref_loss)
         del ref16, ref32, logits
         (loss / 2).backward()
         gsum = {k: v / 2 for k, v in gref.items()} if gsum is None else {k: gsum[k] + gref[k] / 2 for k in gref}
-        del gref
+        gsum2 = {k: v / 2 for k, v in gref2.items()} if gsum2 is None else {k: gsum2[k] + gref2[k] / 2 for k in gref2}
+        del gref, gref2
     grads = model.engine.named_views(grads=True)
+    # Gradient tolerance = the oracle's OWN sensitivity to the fp32 accumulation order, measured: with logits of magnitude ~40
+    # (lm_head x 8 for decisive arg-max) one bf16 ulp of a logit is 0.25, i.e. exp(+-0.25) = +-25 % on that probability, so two
+    # correct bf16 evaluations disagree on d(logits) by percents — the same oracle with every Linear summed in 4 K-chunks gives
+    # the floor, and the CUDA path must stay within 2x of it (3e-2 where the floor is small).
     worst = 0.0
     for k in ("lm_head.weight", "llama.norm.weight", "llama.layers.1.mlp.down_proj.weight", "llama.layers.1.self_attn.q_proj.weight",
               "llama.layers.0.self_attn.v_proj.weight", "llama.layers.0.mlp.gate_proj.weight", "llama.layers.0.input_layernorm.weight",
               "llama.embed_tokens.weight"):
-        e = relerr(grads[k], gsum[k])
+        e, floor = relerr(grads[k], gsum[k]), relerr(gsum2[k], gsum[k])
+        print(f"[2 layers, V=128256] grad {k}: rel err {e:.2e}; oracle re-ordering floor {floor:.2e}")
         worst = max(worst, e)
-        assert e < 3e-2, (k, e)
+        assert e < max(3e-2, 2.0 * floor), (k, e, floor)
     print(f"[2 layers, V=128256] worst accumulated-gradient rel err {worst:.2e}")
 
 
@@ -405,17 +432,7 @@ def test_reorder_noise_floor_at_depth():
     the CUDA path at depth 32 must sit no further from the oracle than 2 x the oracle's own re-ordering distance, and both are
     printed beside the bf16-vs-fp32 distance."""
     orig_linear = R.linear
-
-    def chunked_linear(x, wt, bias, mode):
-        K = wt.shape[0]
-        step = (K + 3) // 4
-        y = None
-        for s0 in range(0, K, step):
-            part = x[..., s0:s0 + step] @ wt[s0:s0 + step]
-            y = part if y is None else y + part
-        if bias is not None:
-            y = y + bias
-        return R.rnd(y, mode)
+    chunked_linear = _chunked_linear
 
     rows = []
     for L in (2, 8, 32):

@@ -82,6 +82,39 @@ def test_gemm_residual_epilogue():
     assert mism < 0.02 and maxerr(out, ref) < 2 ** -7           # only fp32 accumulation-order ties may differ
 
 
+@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("M,inter,K", [(520, 384, 328), (8192, 14336, 4096), (300, 128, 64)])
+def test_gemm_swiglu_fused_epilogue(M, inter, K, cg):
+    """gate|up projection + SwiGLU in one tcgen05 GEMM (tile = 128 gate columns | the 128 up columns of the same channels) is
+    bit-identical to GEMM followed by the SwiGLU kernel: same accumulation order per element, same rounding points."""
+    o = ops()
+    x = rand_bf16(M, K, seed=51, scale=0.7).to(DEV)
+    w = rand_bf16(K, 2 * inter, seed=52, scale=0.3).to(DEV)
+    gu_ref = o.gemm(x, w, cta_group=cg)
+    m_ref = o.swiglu_fwd(gu_ref)
+    gu, m = o.gemm_swiglu(x, w, cta_group=cg)
+    assert torch.equal(gu, gu_ref)
+    assert torch.equal(m, m_ref)
+    ref = R.swiglu((x.float() @ w.float())[:, :inter].to(BF16).float(), (x.float() @ w.float())[:, inter:].to(BF16).float(), "bf16")
+    assert maxerr(m, ref) < 2 ** -6
+    with pytest.raises(Exception):
+        o.gemm_swiglu(x, w[:, : 2 * 72].contiguous())              # I = 72 is not a multiple of 128
+
+
+@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("M,inter,K", [(520, 320, 328), (8192, 14336, 4096), (300, 64, 64)])
+def test_gemm_swiglu_bwd_fused_epilogue(M, inter, K, cg):
+    """The down-projection dX GEMM with the SwiGLU backward in its epilogue is bit-identical to GEMM (dX) + swiglu_bwd kernel."""
+    o = ops()
+    dy = rand_bf16(M, K, seed=53, scale=0.5).to(DEV)
+    wd = rand_bf16(inter, K, seed=54, scale=0.3).to(DEV)
+    gu = rand_bf16(M, 2 * inter, seed=55, scale=1.5).to(DEV)
+    dm = o.gemm(dy, wd, trans_b=True, cta_group=cg)
+    ref = o.swiglu_bwd(gu, dm)
+    got = o.gemm_swiglu_bwd(dy, wd, gu, cta_group=cg)
+    assert torch.equal(got, ref)
+
+
 @pytest.mark.parametrize("tb", [False, True])
 @pytest.mark.parametrize("M,N,K,split", [(64, 6144, 4096, 0), (64, 4096, 14336, 0), (8, 520, 328, 3), (100, 1024, 640, 0)])
 def test_gemm_skinny_splitk(M, N, K, split, tb):

@@ -14,6 +14,10 @@ timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_ops_gpu.py::
   --deselect tests/test_ops_gpu.py::test_flash_attention_bench_shapes -rf 2>&1 | grep -v "^loss: \|^PASSED" > $OUT/${TAG}_tests_full.log
 tail -60 $OUT/${TAG}_tests_full.log > $OUT/${TAG}_tests.log
 timeout 600 python tools/fa_bench.py > $OUT/${TAG}_fa_bench.log 2>&1
+if [ "$NCU_FA" == "1" ]; then
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"fa_fwd2_kernel|fa_bwd2_kernel|fa_bwd_kernel" -s 2 -c 2 \
+    -o $OUT/${TAG}_fa_prof -f python tools/fa_probe.py 2 > $OUT/${TAG}_fa_prof.log 2>&1
+fi
 if [ "$SKIP_BENCH" != "1" ]; then
   timeout 1500 python bench.py "$@" > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 fi
