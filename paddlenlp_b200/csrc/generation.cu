@@ -183,53 +183,74 @@ __global__ void decode_rope_append_kernel(bf16* __restrict__ qkv, float* __restr
                                           const CacheView cv, const float* __restrict__ cos_t,
                                           const float* __restrict__ sin_t, const int* __restrict__ seq_lens, int nh,
                                           int64_t ld) {
+  // ONE pass, no block barrier: thread = one (head, 8-column chunk pair) of q / k, or one 8-column chunk of v.  Each thread takes
+  // its inputs from the fp32 split-K accumulation (rounded to bf16 first: the Linear output rounding) or from the bf16 projection,
+  // rotates in registers and writes the projection row and the cache once.  (The first version materialised the bf16 row, hit a
+  // __syncthreads and read it back: two dependent global round trips per launch — 11.6 us for 64 rows in the decode chain.)
   const int kvh = cv.kvh, d = cv.d, max_len = cv.max_len;
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x;
   const int pos = seq_lens[b];
+  const bool pos_ok = pos >= 0 && pos < max_len;
   const int half = d >> 1;
   const int per_head = half >> 3;
+  const int n_rope = (nh + kvh) * per_head;
   const int idx = threadIdx.x;
   bf16* row = qkv + static_cast<size_t>(b) * ld;
   float* arow = acc_f32 ? acc_f32 + static_cast<size_t>(b) * (nh + 2 * kvh) * d : nullptr;
-  if (arow != nullptr) {
-    // materialise the bf16 projection first (all columns), then rotate in place exactly like the bf16 path
-    for (int c = idx; c < ((nh + 2 * kvh) * d) >> 3; c += blockDim.x)
-      *reinterpret_cast<uint4*>(row + c * 8) = take_f32_chunk(arow, bias, c * 8);
-    __syncthreads();
-  }
-  if (pos < 0 || pos >= max_len) return;
-  if (idx < (nh + kvh) * per_head) {
+  if (idx < n_rope) {
     const int head = idx / per_head;
     const int j8 = (idx % per_head) * 8;
     bf16* base = row + head * d;
-    uint4 a = *reinterpret_cast<const uint4*>(base + j8);
-    uint4 bb = *reinterpret_cast<const uint4*>(base + half + j8);
-    const float* cp = cos_t + static_cast<size_t>(pos) * half + j8;
-    const float* sp = sin_t + static_cast<size_t>(pos) * half + j8;
-    uint32_t* ai = reinterpret_cast<uint32_t*>(&a);
-    uint32_t* bi = reinterpret_cast<uint32_t*>(&bb);
+    uint4 a, bb;
+    if (arow != nullptr) {
+      a = take_f32_chunk(arow, bias, head * d + j8);
+      bb = take_f32_chunk(arow, bias, head * d + half + j8);
+    } else {
+      if (!pos_ok) return;
+      a = *reinterpret_cast<const uint4*>(base + j8);
+      bb = *reinterpret_cast<const uint4*>(base + half + j8);
+    }
+    if (pos_ok) {
+      const float4* cp = reinterpret_cast<const float4*>(cos_t + static_cast<size_t>(pos) * half + j8);
+      const float4* sp = reinterpret_cast<const float4*>(sin_t + static_cast<size_t>(pos) * half + j8);
+      const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+      const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      uint32_t* ai = reinterpret_cast<uint32_t*>(&a);
+      uint32_t* bi = reinterpret_cast<uint32_t*>(&bb);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 x1 = unpack_bf16x2(ai[j]), x2 = unpack_bf16x2(bi[j]);
-      const float c0 = __ldg(cp + 2 * j), c1 = __ldg(cp + 2 * j + 1), s0 = __ldg(sp + 2 * j), s1 = __ldg(sp + 2 * j + 1);
-      ai[j] = pack_bf16x2(x1.x * c0 - x2.x * s0, x1.y * c1 - x2.y * s1);
-      bi[j] = pack_bf16x2(x2.x * c0 + x1.x * s0, x2.y * c1 + x1.y * s1);
+      for (int j = 0; j < 4; ++j) {
+        const float2 x1 = unpack_bf16x2(ai[j]), x2 = unpack_bf16x2(bi[j]);
+        ai[j] = pack_bf16x2(x1.x * cs[2 * j] - x2.x * sn[2 * j], x1.y * cs[2 * j + 1] - x2.y * sn[2 * j + 1]);
+        bi[j] = pack_bf16x2(x2.x * cs[2 * j] + x1.x * sn[2 * j], x2.y * cs[2 * j + 1] + x1.y * sn[2 * j + 1]);
+      }
     }
     *reinterpret_cast<uint4*>(base + j8) = a;
     *reinterpret_cast<uint4*>(base + half + j8) = bb;
-    if (head >= nh) {   // rotated k -> cache
+    if (pos_ok && head >= nh) {   // rotated k -> cache
       bf16* dst = cv.row(false, b, head - nh, pos);
       *reinterpret_cast<uint4*>(dst + j8) = a;
       *reinterpret_cast<uint4*>(dst + half + j8) = bb;
     }
-  }
-  // v -> cache (16-byte chunks)
-  for (int c = idx; c < (kvh * d) >> 3; c += blockDim.x) {
-    const int head = (c * 8) / d, off = (c * 8) % d;
-    const uint4 v = *reinterpret_cast<const uint4*>(row + (nh + kvh) * d + c * 8);
-    *reinterpret_cast<uint4*>(cv.row(true, b, head, pos) + off) = v;
+  } else {
+    // v -> projection row (fp32 path) and cache (16-byte chunks)
+    const int c = idx - n_rope;
+    if (c >= (kvh * d) >> 3) return;
+    const int col = (nh + kvh) * d + c * 8;
+    uint4 v;
+    if (arow != nullptr) {
+      v = take_f32_chunk(arow, bias, col);
+      *reinterpret_cast<uint4*>(row + col) = v;
+    } else {
+      if (!pos_ok) return;
+      v = *reinterpret_cast<const uint4*>(row + col);
+    }
+    if (pos_ok) {
+      const int head = (c * 8) / d, off = (c * 8) % d;
+      *reinterpret_cast<uint4*>(cv.row(true, b, head, pos) + off) = v;
+    }
   }
 }
 
@@ -888,7 +909,7 @@ static int rope_append_launch(void* qkv, float* acc_f32_ws, const float* bias, c
                               const float* sin_table, const int32_t* seq_lens, int64_t B, int64_t num_heads, int64_t ld,
                               cudaStream_t stream) {
   B200_CHECK_ARG(cv.d % 16 == 0 && ld % 8 == 0, "decode_rope_append: head_dim %% 16, ld %% 8");
-  const int threads_needed = static_cast<int>((num_heads + cv.kvh) * (cv.d / 16));
+  const int threads_needed = static_cast<int>((num_heads + cv.kvh) * (cv.d / 16) + (cv.kvh * cv.d) / 8);   // rope pairs + v chunks
   B200_CHECK_ARG(threads_needed <= 1024, "decode_rope_append: too many heads");
   const int threads = (threads_needed + 31) / 32 * 32;
   launch_pdl(decode_rope_append_kernel, dim3(static_cast<unsigned>(B)), dim3(threads), 0, stream, static_cast<bf16*>(qkv),
