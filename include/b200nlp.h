@@ -328,6 +328,27 @@ int b200_step_paddle(bool* stop_flags, int32_t* seq_lens_this_time, const int32_
 int b200_save_output_stream(const int64_t* next_tokens, const int32_t* stop_count, int32_t* ring, int64_t slot_stride,
                             int64_t num_slots, int64_t* step_counter, int64_t last_step, int64_t bs, cudaStream_t stream);
 
+/* append_attention(qkv, key_cache, value_cache, seq_lens_encoder, seq_lens_decoder, seq_lens_this_time, padding_offsets,
+ * cum_offsets, block_tables, ..., rotary_embs, ...): csrc/gpu/append_attention.cu:428-851, called
+ * fused_transformer_layers.py:2215-2262 (FusedBlockMultiTransformer.compute_attn with config.append_attn).  ONE entry point for a
+ * mixed batch over the paged KV cache: sequence b contributes seq_lens_this_time[b] rows of the packed projection
+ * qkv [token_num, ldq] (rows cu_seqlens_q[b] ..), at absolute positions seq_lens_decoder[b] + i.  RoPE (rotate-half, tables
+ * [rope_positions, 64] fp32) is applied to q and k in place, k and v are appended to the pages, and every row attends to cache
+ * positions [0, its own]: prompts and prompt CHUNKS on top of a cached prefix (seq_lens_encoder[b] > 0 or more than one row)
+ * through the tcgen05 flash kernel with page-gathered K/V, single decode rows through the decode kernel.  out [token_num, ldo].
+ * max_q_len >= max(seq_lens_this_time) (host bound for the grid; the reference passes max_enc_len_this_time the same way).
+ * cu_seqlens_q replaces padding_offsets / cum_offsets (same information; get_padding_offset produces it).
+ * No host synchronisation.  Workspace: b200_append_attention_workspace_bytes(). */
+int64_t b200_append_attention_workspace_bytes(int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim,
+                                              int64_t num_splits);
+int b200_append_attention(void* qkv, void* key_cache, void* value_cache, const int32_t* seq_lens_encoder,
+                          const int32_t* seq_lens_decoder, const int32_t* seq_lens_this_time, const int32_t* cu_seqlens_q,
+                          const int32_t* block_tables, const float* cos_table, const float* sin_table, void* out, void* workspace,
+                          int64_t B, int64_t token_num, int64_t max_q_len, int64_t num_heads, int64_t num_kv_heads,
+                          int64_t head_dim, int64_t num_blocks, int64_t block_size, int64_t max_blocks_per_seq,
+                          int64_t rope_positions, int64_t ldq, int64_t ldo, float softmax_scale, int64_t num_splits,
+                          cudaStream_t stream);
+
 /* update_inputs: csrc/gpu/update_inputs.cu:18-82 */
 int b200_update_inputs(bool* not_need_stop, int32_t* seq_lens_this_time, int32_t* seq_lens_encoder,
                        int32_t* seq_lens_decoder, int64_t* input_ids, const int64_t* stop_nums, const bool* stop_flags,

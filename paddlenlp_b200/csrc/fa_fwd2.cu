@@ -44,6 +44,17 @@ struct Params {
   int S, B, nh, kvh;
   float scale_log2;   // (1/sqrt(d)) * log2(e)
   float* lse;         // [B, nh, S]
+  // PAGED instantiation (prefill half of append_attention, csrc/gpu/append_attention.cu:428-851): sequence b contributes
+  // seq_this[b] new query rows (token rows cu_q[b] .. of the packed projection) at absolute positions seq_dec[b] + i and attends to
+  // cache positions [0, seq_dec[b] + i] of its pages; key/value caches [num_blocks, kvh, block_size, 128]
+  const int* cu_q;
+  const int* seq_dec;
+  const int* seq_this;
+  const int* seq_enc;
+  const int* block_tables;
+  int max_blocks, block_size;
+  bf16* out;          // [token_num, ldo]
+  int64_t ldo;
 };
 
 // (x0, x1) = (a0, a1) * s + c    on the packed fp32x2 pipe
@@ -66,6 +77,7 @@ __device__ __forceinline__ void add2(float& acc0, float& acc1, float a0, float a
 }
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
+template <bool PAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
@@ -83,14 +95,30 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_qb = (p.S + 255) / 256;
-  const int qb = num_qb - 1 - static_cast<int>(blockIdx.x);   // heavy blocks first
   const int head = blockIdx.y, batch = blockIdx.z;
   const int kv_head = head / (p.nh / p.kvh);
-  const int q0 = qb * 256;
-  const bool b_active = (q0 + 128) < p.S;
-  const int nA = 2 * qb + 1;                   // kv tiles 0 .. 2qb     (diagonal = last)
-  const int nB = b_active ? 2 * qb + 2 : 0;    // kv tiles 0 .. 2qb+1   (diagonal = last)
+  int q0, nA, nB, pos0 = 0, n_rows = p.S, tok0 = 0;
+  bool b_active;
+  if constexpr (PAGED) {
+    n_rows = p.seq_this[batch];
+    // decode rows (one new token on top of a cache, no prompt) belong to the decode kernel; idle slots to nobody
+    if (n_rows <= 0 || (n_rows == 1 && p.seq_enc[batch] <= 0)) return;
+    const int qb = (n_rows + 255) / 256 - 1 - static_cast<int>(blockIdx.x);
+    if (qb < 0) return;
+    pos0 = p.seq_dec[batch];
+    tok0 = p.cu_q[batch];
+    q0 = qb * 256;
+    b_active = (q0 + 128) < n_rows;
+    nA = (pos0 + min(q0 + 127, n_rows - 1)) / 128 + 1;          // kv tiles that tile A's last row can see
+    nB = b_active ? (pos0 + min(q0 + 255, n_rows - 1)) / 128 + 1 : 0;
+  } else {
+    const int num_qb = (p.S + 255) / 256;
+    const int qb = num_qb - 1 - static_cast<int>(blockIdx.x);   // heavy blocks first
+    q0 = qb * 256;
+    b_active = (q0 + 128) < p.S;
+    nA = 2 * qb + 1;                   // kv tiles 0 .. 2qb     (diagonal = last)
+    nB = b_active ? 2 * qb + 2 : 0;    // kv tiles 0 .. 2qb+1   (diagonal = last)
+  }
   const int n_kv = b_active ? nB : nA;
 
   if (warp == 0 && lane == 0) {
@@ -108,6 +136,14 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_ptr_smem, 512);
+  if constexpr (PAGED) {
+    // pages past the end of a sequence are not fetched: the ring must hold finite values there (P = 0 for those columns, but
+    // 0 * NaN = NaN in the PV accumulation)
+    if (warp >= 2) {
+      for (int i = threadIdx.x - 64; i < NST * TILE_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sKV)[i] = make_uint4(0, 0, 0, 0);
+      fence_proxy_async_smem();
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -116,24 +152,57 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(&q_full[0], TILE_BYTES);
-      tma_load_4d(&tmQ, &q_full[0], sQ, 0, head, q0, batch);
-      tma_load_4d(&tmQ, &q_full[0], sQ + HALF_BYTES, 64, head, q0, batch);
-      if (b_active) {
-        mbar_arrive_expect_tx(&q_full[1], TILE_BYTES);
-        tma_load_4d(&tmQ, &q_full[1], sQ + TILE_BYTES, 0, head, q0 + 128, batch);
-        tma_load_4d(&tmQ, &q_full[1], sQ + TILE_BYTES + HALF_BYTES, 64, head, q0 + 128, batch);
-      }
-      for (int it = 0; it < 2 * n_kv; ++it) {
-        const int st = it % NST;
-        const uint32_t use = static_cast<uint32_t>(it / NST);
-        mbar_wait(&kv_empty[st], (use & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[st], TILE_BYTES);
-        uint8_t* dst = sKV + st * TILE_BYTES;
-        const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
-        const int row = (it >> 1) * 128;
-        tma_load_4d(tm, &kv_full[st], dst, 0, kv_head, row, batch);
-        tma_load_4d(tm, &kv_full[st], dst + HALF_BYTES, 64, kv_head, row, batch);
+      if constexpr (PAGED) {
+        mbar_arrive_expect_tx(&q_full[0], TILE_BYTES);
+        tma_load_3d(&tmQ, &q_full[0], sQ, 0, head, tok0 + q0);
+        tma_load_3d(&tmQ, &q_full[0], sQ + HALF_BYTES, 64, head, tok0 + q0);
+        if (b_active) {
+          mbar_arrive_expect_tx(&q_full[1], TILE_BYTES);
+          tma_load_3d(&tmQ, &q_full[1], sQ + TILE_BYTES, 0, head, tok0 + q0 + 128);
+          tma_load_3d(&tmQ, &q_full[1], sQ + TILE_BYTES + HALF_BYTES, 64, head, tok0 + q0 + 128);
+        }
+        const int kv_total = pos0 + n_rows;                 // cache positions that exist for this sequence after the append
+        const int ppt = 128 / p.block_size;
+        const uint32_t page_bytes = static_cast<uint32_t>(p.block_size) * D * 2;
+        for (int it = 0; it < 2 * n_kv; ++it) {
+          const int st = it % NST;
+          const uint32_t use = static_cast<uint32_t>(it / NST);
+          const int t0 = (it >> 1) * 128;
+          int phys[4];
+          int npages = 0;
+          for (int pg = 0; pg < ppt; ++pg) {
+            const int tpos = t0 + pg * p.block_size;
+            if (tpos < kv_total) phys[npages++] = __ldg(p.block_tables + static_cast<size_t>(batch) * p.max_blocks + tpos / p.block_size);
+          }
+          mbar_wait(&kv_empty[st], (use & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&kv_full[st], page_bytes * npages);
+          uint8_t* dst = sKV + st * TILE_BYTES;
+          const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
+          for (int pg = 0; pg < npages; ++pg) {
+            tma_load_4d(tm, &kv_full[st], dst + pg * (page_bytes / 2), 0, 0, kv_head, phys[pg]);
+            tma_load_4d(tm, &kv_full[st], dst + pg * (page_bytes / 2) + HALF_BYTES, 64, 0, kv_head, phys[pg]);
+          }
+        }
+      } else {
+        mbar_arrive_expect_tx(&q_full[0], TILE_BYTES);
+        tma_load_4d(&tmQ, &q_full[0], sQ, 0, head, q0, batch);
+        tma_load_4d(&tmQ, &q_full[0], sQ + HALF_BYTES, 64, head, q0, batch);
+        if (b_active) {
+          mbar_arrive_expect_tx(&q_full[1], TILE_BYTES);
+          tma_load_4d(&tmQ, &q_full[1], sQ + TILE_BYTES, 0, head, q0 + 128, batch);
+          tma_load_4d(&tmQ, &q_full[1], sQ + TILE_BYTES + HALF_BYTES, 64, head, q0 + 128, batch);
+        }
+        for (int it = 0; it < 2 * n_kv; ++it) {
+          const int st = it % NST;
+          const uint32_t use = static_cast<uint32_t>(it / NST);
+          mbar_wait(&kv_empty[st], (use & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&kv_full[st], TILE_BYTES);
+          uint8_t* dst = sKV + st * TILE_BYTES;
+          const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
+          const int row = (it >> 1) * 128;
+          tma_load_4d(tm, &kv_full[st], dst, 0, kv_head, row, batch);
+          tma_load_4d(tm, &kv_full[st], dst + HALF_BYTES, 64, kv_head, row, batch);
+        }
       }
     }
   } else if (warp == 1) {
@@ -218,7 +287,16 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tmem_ld32(tS, c[0]); tmem_ld32(tS + 32, c[1]); tmem_ld32(tS + 64, c[2]); tmem_ld32(tS + 96, c[3]);
           tmem_ld_wait();
         }
-        if (j == nt - 1) {                                // diagonal tile: columns beyond the row are masked
+        if constexpr (PAGED) {
+          // row r sits at absolute position pos0 + q0t + r and sees cache positions <= that: column c of kv tile j is position
+          // 128 j + c.  With a cached prefix the diagonal band is not tile aligned: up to two kv tiles per q tile need the mask.
+          if (128 * j + 127 > pos0 + q0t) {
+            const int lim = pos0 + q0t + r - 128 * j;
+#pragma unroll
+            for (int c = 0; c < 128; ++c)
+              if (c > lim) sv[c] = 0xff800000u;           // -inf
+          }
+        } else if (j == nt - 1) {                         // diagonal tile: columns beyond the row are masked
 #pragma unroll
           for (int c = 0; c < 128; ++c)
             if (c > r) sv[c] = 0xff800000u;               // -inf
@@ -280,32 +358,55 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const float inv_l = 1.f / l;
       mbar_wait(&o_full[t], 0);
       tc_fence_after();
-      const uint32_t sO_a = smem_u32(sQ + t * TILE_BYTES);
+      if constexpr (PAGED) {
+        // packed token rows: a tile may end inside the batch's next sequence, so rows are stored one by one (256 bytes each)
+        const bool valid = q0t + r < n_rows;
+        bf16* orow = p.out + static_cast<size_t>(tok0 + q0t + r) * p.ldo + head * 128;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t o[32];
-        tmem_ld32(tO + ch * 32, o);
-        tmem_ld_wait();
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tO + ch * 32, o);
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          const int k = (ch & 1) * 4 + c8;     // 16-byte chunk within the 128-byte half row; half = ch >> 1
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[c8 * 8 + 0]) * inv_l, __uint_as_float(o[c8 * 8 + 1]) * inv_l);
-          v.y = pack_bf16x2(__uint_as_float(o[c8 * 8 + 2]) * inv_l, __uint_as_float(o[c8 * 8 + 3]) * inv_l);
-          v.z = pack_bf16x2(__uint_as_float(o[c8 * 8 + 4]) * inv_l, __uint_as_float(o[c8 * 8 + 5]) * inv_l);
-          v.w = pack_bf16x2(__uint_as_float(o[c8 * 8 + 6]) * inv_l, __uint_as_float(o[c8 * 8 + 7]) * inv_l);
-          st_shared_v4(sO_a + (ch >> 1) * HALF_BYTES + r * 128 + ((k ^ (r & 7)) << 4), v);
+            for (int c8 = 0; c8 < 4; ++c8) {
+              uint4 v;
+              v.x = pack_bf16x2(__uint_as_float(o[c8 * 8 + 0]) * inv_l, __uint_as_float(o[c8 * 8 + 1]) * inv_l);
+              v.y = pack_bf16x2(__uint_as_float(o[c8 * 8 + 2]) * inv_l, __uint_as_float(o[c8 * 8 + 3]) * inv_l);
+              v.z = pack_bf16x2(__uint_as_float(o[c8 * 8 + 4]) * inv_l, __uint_as_float(o[c8 * 8 + 5]) * inv_l);
+              v.w = pack_bf16x2(__uint_as_float(o[c8 * 8 + 6]) * inv_l, __uint_as_float(o[c8 * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + ch * 32 + c8 * 8) = v;
+            }
+          }
         }
-      }
-      if (q0t + r < p.S)
-        p.lse[(static_cast<size_t>(batch) * p.nh + head) * p.S + q0t + r] = (m_used + log2f(l)) * 0.6931471805599453f;
-      fence_proxy_async_smem();
-      named_bar_sync(1 + t, 128);
-      if ((warp == 2 || warp == 6) && lane == 0) {
-        tma_store_4d(&tmO, sQ + t * TILE_BYTES, 0, head, q0t, batch);
-        tma_store_4d(&tmO, sQ + t * TILE_BYTES + HALF_BYTES, 64, head, q0t, batch);
-        tma_store_commit();
-        tma_store_wait<0>();
+      } else {
+        const uint32_t sO_a = smem_u32(sQ + t * TILE_BYTES);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tO + ch * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            const int k = (ch & 1) * 4 + c8;     // 16-byte chunk within the 128-byte half row; half = ch >> 1
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[c8 * 8 + 0]) * inv_l, __uint_as_float(o[c8 * 8 + 1]) * inv_l);
+            v.y = pack_bf16x2(__uint_as_float(o[c8 * 8 + 2]) * inv_l, __uint_as_float(o[c8 * 8 + 3]) * inv_l);
+            v.z = pack_bf16x2(__uint_as_float(o[c8 * 8 + 4]) * inv_l, __uint_as_float(o[c8 * 8 + 5]) * inv_l);
+            v.w = pack_bf16x2(__uint_as_float(o[c8 * 8 + 6]) * inv_l, __uint_as_float(o[c8 * 8 + 7]) * inv_l);
+            st_shared_v4(sO_a + (ch >> 1) * HALF_BYTES + r * 128 + ((k ^ (r & 7)) << 4), v);
+          }
+        }
+        if (q0t + r < p.S)
+          p.lse[(static_cast<size_t>(batch) * p.nh + head) * p.S + q0t + r] = (m_used + log2f(l)) * 0.6931471805599453f;
+        fence_proxy_async_smem();
+        named_bar_sync(1 + t, 128);
+        if ((warp == 2 || warp == 6) && lane == 0) {
+          tma_store_4d(&tmO, sQ + t * TILE_BYTES, 0, head, q0t, batch);
+          tma_store_4d(&tmO, sQ + t * TILE_BYTES + HALF_BYTES, 64, head, q0t, batch);
+          tma_store_commit();
+          tma_store_wait<0>();
+        }
       }
     }
   }
@@ -340,7 +441,7 @@ int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* 
   if ((rc = make_map(&tmO, o, B, S, num_heads, ldo)) != 0) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) {
       set_last_error("fa_fwd2 smem attr: %s", cudaGetErrorString(e));
       return static_cast<int>(e);
@@ -353,8 +454,58 @@ int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* 
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.lse = lse;
   dim3 grid(static_cast<unsigned>((S + 255) / 256), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
-  fa_fwd2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  p.cu_q = p.seq_dec = p.seq_this = p.seq_enc = p.block_tables = nullptr;
+  p.max_blocks = p.block_size = 0; p.out = nullptr; p.ldo = 0;
+  fa_fwd2_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   return check_launch("fa_fwd2");
+}
+
+// Prefill half of append_attention: causal attention of the NEW token rows of every prompt / prompt-chunk sequence over its paged
+// cache (cached prefix + the rows themselves, already appended).  qkv: packed projection [token_num, ldq] (q heads first, rotated);
+// key / value caches [num_blocks, kvh, block_size, 128]; out [token_num, ldo].  max_q_len bounds seq_lens_this_time (grid size).
+int launch_fa_prefill_paged(const void* qkv, const void* key_cache, const void* value_cache, void* out, const int32_t* cu_seqlens_q,
+                            const int32_t* seq_lens_encoder, const int32_t* seq_lens_decoder, const int32_t* seq_lens_this_time,
+                            const int32_t* block_tables, int64_t B, int64_t token_num, int64_t max_q_len, int64_t num_heads,
+                            int64_t num_kv_heads, int64_t num_blocks, int64_t block_size, int64_t max_blocks_per_seq, int64_t ldq,
+                            int64_t ldo, float softmax_scale, cudaStream_t stream) {
+  using namespace fa2;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  {
+    uint64_t dims[3] = {128, static_cast<uint64_t>(num_heads), static_cast<uint64_t>(token_num)};
+    uint64_t strides[2] = {128 * 2, static_cast<uint64_t>(ldq) * 2};
+    uint32_t box[3] = {64, 1, 128};
+    if ((rc = encode_tmap_bf16(&tmQ, qkv, 3, dims, strides, box)) != 0) return rc;
+  }
+  {
+    uint64_t dims[4] = {128, static_cast<uint64_t>(block_size), static_cast<uint64_t>(num_kv_heads), static_cast<uint64_t>(num_blocks)};
+    uint64_t strides[3] = {128 * 2, static_cast<uint64_t>(block_size) * 128 * 2,
+                           static_cast<uint64_t>(num_kv_heads) * block_size * 128 * 2};
+    uint32_t box[4] = {64, static_cast<uint32_t>(block_size), 1, 1};
+    if ((rc = encode_tmap_bf16(&tmK, key_cache, 4, dims, strides, box)) != 0) return rc;
+    if ((rc = encode_tmap_bf16(&tmV, value_cache, 4, dims, strides, box)) != 0) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_last_error("fa_prefill_paged smem attr: %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  Params p;
+  p.S = static_cast<int>(max_q_len); p.B = static_cast<int>(B); p.nh = static_cast<int>(num_heads);
+  p.kvh = static_cast<int>(num_kv_heads);
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.lse = nullptr;
+  p.cu_q = cu_seqlens_q; p.seq_dec = seq_lens_decoder; p.seq_this = seq_lens_this_time; p.seq_enc = seq_lens_encoder;
+  p.block_tables = block_tables;
+  p.max_blocks = static_cast<int>(max_blocks_per_seq); p.block_size = static_cast<int>(block_size);
+  p.out = static_cast<bf16*>(out); p.ldo = ldo;
+  dim3 grid(static_cast<unsigned>((max_q_len + 255) / 256), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
+  fa_fwd2_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmQ, p);
+  return check_launch("fa_prefill_paged");
 }
 
 }  // namespace b200

@@ -1456,3 +1456,158 @@ extern "C" int b200_save_output_stream(const int64_t* next_tokens, const int32_t
                                                         last_step, (int)bs);
   return check_launch("save_output_stream");
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// append_attention (csrc/gpu/append_attention.cu:428-851; encoder / decoder cache writers append_attn/
+// encoder_write_cache_with_rope_impl.cuh:22-690, decoder_write_cache_with_rope_kernel.cu; tile planning
+// get_block_shape_and_split_kv_block.cu:23-294): ONE entry point for a mixed batch over the paged KV cache.  Sequence b
+// contributes seq_lens_this_time[b] token rows of the packed (remove-padding) QKV projection, at absolute positions
+// seq_lens_decoder[b] + i:
+//     prompt / prompt CHUNK   (seq_lens_encoder[b] > 0, or more than one row): rows attend to the cached prefix + themselves
+//     decode                  (one row, seq_lens_encoder[b] == 0)
+//     idle slot               (seq_lens_this_time[b] == 0)
+//   1. append_rope_write_kernel  RoPE (rotate-half) on q, k of EVERY new row in place + k, v appended to the pages (one launch
+//                                for prompt and decode rows alike); decode rows' q are also gathered into a dense [B, ld] buffer
+//   2. fa_fwd2_kernel<PAGED>     prompt rows: tcgen05 flash attention, q tiles of 2 x 128 rows, K/V tiles gathered page by page
+//                                with TMA, causal band offset by the cached prefix (chunked prefill)
+//   3. decode_attention_tc<PAGED> decode rows (the decode step's kernel; sequences of the other kinds have length -1 = no work)
+//   4. scatter of the decode rows' outputs back to their token rows
+// No host synchronisation: each kernel decides from the device-resident length arrays which sequences are its own (the
+// reference plans tiles on the device too, but copies the plan sizes to the host).
+// ------------------------------------------------------------------------------------------------------------------
+namespace b200 {
+namespace gen {
+
+__global__ void append_rope_write_kernel(bf16* __restrict__ qkv, const CacheView cv, const float* __restrict__ cos_t,
+                                         const float* __restrict__ sin_t, const int* __restrict__ cu_q,
+                                         const int* __restrict__ seq_enc, const int* __restrict__ seq_dec,
+                                         const int* __restrict__ seq_this, bf16* __restrict__ q_dec, int* __restrict__ dec_len, int B,
+                                         int nh, int max_pos, int64_t ld) {
+  const int kvh = cv.kvh, d = cv.d;
+  const int tok = blockIdx.x;
+  // which sequence owns this token row: the last b with cu_q[b] <= tok
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(cu_q + mid) <= tok) lo = mid; else hi = mid;
+  }
+  const int b = lo;
+  const int i = tok - __ldg(cu_q + b);
+  const int n = __ldg(seq_this + b);
+  if (i >= n) return;                                   // (padding rows between sequences, if the caller left any)
+  const int pos = __ldg(seq_dec + b) + i;
+  const bool is_decode = (n == 1) && (__ldg(seq_enc + b) <= 0);
+  if (threadIdx.x == 0 && i == 0) dec_len[b] = is_decode ? pos : -1;
+  if (pos < 0 || pos >= cv.max_len || pos >= max_pos) return;
+  const int half = d >> 1;
+  const int per_head = half >> 3;
+  const int n_rope = (nh + kvh) * per_head;
+  const int idx = threadIdx.x;
+  bf16* row = qkv + static_cast<size_t>(tok) * ld;
+  if (idx < n_rope) {
+    const int head = idx / per_head;
+    const int j8 = (idx % per_head) * 8;
+    bf16* base = row + head * d;
+    uint4 a = *reinterpret_cast<const uint4*>(base + j8);
+    uint4 bb = *reinterpret_cast<const uint4*>(base + half + j8);
+    const float4* cp = reinterpret_cast<const float4*>(cos_t + static_cast<size_t>(pos) * half + j8);
+    const float4* sp = reinterpret_cast<const float4*>(sin_t + static_cast<size_t>(pos) * half + j8);
+    const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+    const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    uint32_t* ai = reinterpret_cast<uint32_t*>(&a);
+    uint32_t* bi = reinterpret_cast<uint32_t*>(&bb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x1 = unpack_bf16x2(ai[j]), x2 = unpack_bf16x2(bi[j]);
+      ai[j] = pack_bf16x2(x1.x * cs[2 * j] - x2.x * sn[2 * j], x1.y * cs[2 * j + 1] - x2.y * sn[2 * j + 1]);
+      bi[j] = pack_bf16x2(x2.x * cs[2 * j] + x1.x * sn[2 * j], x2.y * cs[2 * j + 1] + x1.y * sn[2 * j + 1]);
+    }
+    *reinterpret_cast<uint4*>(base + j8) = a;
+    *reinterpret_cast<uint4*>(base + half + j8) = bb;
+    if (head >= nh) {
+      bf16* dst = cv.row(false, b, head - nh, pos);
+      *reinterpret_cast<uint4*>(dst + j8) = a;
+      *reinterpret_cast<uint4*>(dst + half + j8) = bb;
+    } else if (is_decode) {
+      bf16* dst = q_dec + static_cast<size_t>(b) * ld + head * d;
+      *reinterpret_cast<uint4*>(dst + j8) = a;
+      *reinterpret_cast<uint4*>(dst + half + j8) = bb;
+    }
+  } else {
+    const int c = idx - n_rope;
+    if (c >= (kvh * d) >> 3) return;
+    const uint4 v = *reinterpret_cast<const uint4*>(row + (nh + kvh) * d + c * 8);
+    const int head = (c * 8) / d, off = (c * 8) % d;
+    *reinterpret_cast<uint4*>(cv.row(true, b, head, pos) + off) = v;
+  }
+}
+
+// out[cu_q[b], :] = out_dec[b, :] for the decode rows
+__global__ void append_scatter_decode_kernel(const bf16* __restrict__ out_dec, bf16* __restrict__ out, const int* __restrict__ cu_q,
+                                             const int* __restrict__ dec_len, int width, int64_t ldo) {
+  const int b = blockIdx.x;
+  if (dec_len[b] < 0) return;
+  const uint4* src = reinterpret_cast<const uint4*>(out_dec + static_cast<size_t>(b) * width);
+  uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(cu_q[b]) * ldo);
+  for (int c = threadIdx.x; c < width / 8; c += blockDim.x) dst[c] = src[c];
+}
+}  // namespace gen
+}  // namespace b200
+
+extern "C" int64_t b200_append_attention_workspace_bytes(int64_t B, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim,
+                                                         int64_t num_splits) {
+  // dense decode-row q buffer [B, (nh + 2 kvh) d] bf16 | decode outputs [B, nh d] bf16 | decode lengths [B] int32 (padded) |
+  // split-KV partials of the decode kernel
+  const int64_t ld = (num_heads + 2 * num_kv_heads) * head_dim;
+  return B * ld * 2 + B * num_heads * head_dim * 2 + ((B * 4 + 255) / 256) * 256 +
+         (num_splits > 1 ? b200_decode_attention_workspace_bytes(B, num_heads, num_splits) : 0);
+}
+
+extern "C" int b200_append_attention(void* qkv, void* key_cache, void* value_cache, const int32_t* seq_lens_encoder,
+                                     const int32_t* seq_lens_decoder, const int32_t* seq_lens_this_time,
+                                     const int32_t* cu_seqlens_q, const int32_t* block_tables, const float* cos_table,
+                                     const float* sin_table, void* out, void* workspace, int64_t B, int64_t token_num,
+                                     int64_t max_q_len, int64_t num_heads, int64_t num_kv_heads, int64_t head_dim,
+                                     int64_t num_blocks, int64_t block_size, int64_t max_blocks_per_seq, int64_t rope_positions,
+                                     int64_t ldq, int64_t ldo, float softmax_scale, int64_t num_splits, cudaStream_t stream) {
+  using namespace b200;
+  B200_CHECK_ARG(qkv && key_cache && value_cache && seq_lens_encoder && seq_lens_decoder && seq_lens_this_time && cu_seqlens_q &&
+                     block_tables && cos_table && sin_table && out && workspace,
+                 "append_attention: null pointer");
+  B200_CHECK_ARG(head_dim == 128, "append_attention: head_dim must be 128 (got %lld)", (long long)head_dim);
+  B200_CHECK_ARG(block_size == 32 || block_size == 64 || block_size == 128, "append_attention: block_size must be 32, 64 or 128");
+  B200_CHECK_ARG(B > 0 && token_num > 0 && max_q_len > 0 && num_heads % num_kv_heads == 0 && ldq % 8 == 0 && ldo % 8 == 0 &&
+                     num_splits >= 1 && num_splits <= 64,
+                 "append_attention: bad shape");
+  const int64_t ld = (num_heads + 2 * num_kv_heads) * head_dim;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  bf16* q_dec = reinterpret_cast<bf16*>(ws);
+  bf16* out_dec = reinterpret_cast<bf16*>(ws + B * ld * 2);
+  int32_t* dec_len = reinterpret_cast<int32_t*>(ws + B * ld * 2 + B * num_heads * head_dim * 2);
+  void* dec_ws = ws + B * ld * 2 + B * num_heads * head_dim * 2 + ((B * 4 + 255) / 256) * 256;
+  gen::CacheView cv = {};
+  cv.k = static_cast<bf16*>(key_cache);
+  cv.v = static_cast<bf16*>(value_cache);
+  cv.block_tables = block_tables;
+  cv.max_blocks = (int)max_blocks_per_seq; cv.block_size = (int)block_size;
+  cv.kvh = (int)num_kv_heads; cv.max_len = (int)(max_blocks_per_seq * block_size); cv.d = (int)head_dim;
+  const int threads = static_cast<int>(((num_heads + num_kv_heads) * (head_dim / 16) + (num_kv_heads * head_dim) / 8 + 31) / 32 * 32);
+  B200_CHECK_ARG(threads <= 1024, "append_attention: too many heads");
+  gen::append_rope_write_kernel<<<static_cast<unsigned>(token_num), threads, 0, stream>>>(
+      static_cast<bf16*>(qkv), cv, cos_table, sin_table, cu_seqlens_q, seq_lens_encoder, seq_lens_decoder, seq_lens_this_time, q_dec,
+      dec_len, (int)B, (int)num_heads, (int)rope_positions, ldq);
+  int rc = check_launch("append_attention(rope + cache write)");
+  if (rc) return rc;
+  rc = launch_fa_prefill_paged(qkv, key_cache, value_cache, out, cu_seqlens_q, seq_lens_encoder, seq_lens_decoder,
+                               seq_lens_this_time, block_tables, B, token_num, max_q_len, num_heads, num_kv_heads, num_blocks,
+                               block_size, max_blocks_per_seq, ldq, ldo, softmax_scale, stream);
+  if (rc) return rc;
+  rc = b200_decode_attention_paged(q_dec, key_cache, value_cache, block_tables, dec_len, out_dec, num_splits > 1 ? dec_ws : nullptr, B,
+                                   num_heads, num_kv_heads, head_dim, num_blocks, block_size, max_blocks_per_seq, ld, softmax_scale,
+                                   num_splits, stream);
+  if (rc) return rc;
+  gen::append_scatter_decode_kernel<<<static_cast<unsigned>(B), 128, 0, stream>>>(out_dec, static_cast<bf16*>(out), cu_seqlens_q,
+                                                                                 dec_len, (int)(num_heads * head_dim), ldo);
+  return check_launch("append_attention(scatter)");
+}

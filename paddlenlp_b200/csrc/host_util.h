@@ -27,6 +27,12 @@ int launch_fa_bwd2(const void* q, const void* k, const void* v, const void* o, c
                    void* dk, void* dv, void* workspace, int64_t B, int64_t S, int64_t num_heads, int64_t num_kv_heads,
                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv,
                    float softmax_scale, cudaStream_t stream);
+// fa_fwd2.cu, PAGED instantiation: prefill half of b200_append_attention
+int launch_fa_prefill_paged(const void* qkv, const void* key_cache, const void* value_cache, void* out, const int32_t* cu_seqlens_q,
+                            const int32_t* seq_lens_encoder, const int32_t* seq_lens_decoder, const int32_t* seq_lens_this_time,
+                            const int32_t* block_tables, int64_t B, int64_t token_num, int64_t max_q_len, int64_t num_heads,
+                            int64_t num_kv_heads, int64_t num_blocks, int64_t block_size, int64_t max_blocks_per_seq, int64_t ldq,
+                            int64_t ldo, float softmax_scale, cudaStream_t stream);
 bool pdl_enabled();   // b200_set_pdl(): launch GEMMs with programmatic dependent launch (decode-step kernel chains)
 
 // Launch `kern` on `stream`; when PDL is enabled the launch carries the programmatic-stream-serialization attribute, so the

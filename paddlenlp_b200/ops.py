@@ -611,6 +611,35 @@ def fused_get_rotary_embedding(input_ids, position_ids, head_dim_shape_tensor, p
     return out
 
 
+def append_attention(qkv, key_cache, value_cache, seq_lens_encoder, seq_lens_decoder, seq_lens_this_time, cu_seqlens_q,
+                     block_tables, cos, sin, nh: int, max_q_len: int, softmax_scale=None, out=None, num_splits: int = 0):
+    """append_attention of the reference (csrc/gpu/append_attention.cu:428-851) for a mixed batch over the paged cache: RoPE +
+    cache append for every new token row of the packed projection qkv [token_num, (nh + 2 kvh) d] (modified in place), then
+    attention of every row over its sequence's pages — prompts / prompt chunks and decode rows in one call.
+    Returns out [token_num, nh * d]."""
+    _chk(qkv, "qkv"); _chk(cos, "cos", torch.float32); _chk(sin, "sin", torch.float32)
+    for name, t in (("seq_lens_encoder", seq_lens_encoder), ("seq_lens_decoder", seq_lens_decoder),
+                    ("seq_lens_this_time", seq_lens_this_time), ("cu_seqlens_q", cu_seqlens_q)):
+        _chk(t, name, torch.int32)
+        assert t.is_contiguous()
+    nb, kvh, bs, d, mb = _paged_geom(key_cache, value_cache, block_tables)
+    token_num, ld = qkv.shape
+    B = seq_lens_this_time.numel()
+    assert qkv.stride(1) == 1 and ld == (nh + 2 * kvh) * d and block_tables.shape[0] == B and cu_seqlens_q.numel() >= B
+    if out is None:
+        out = torch.empty(token_num, nh * d, dtype=BF16, device=qkv.device)
+    if softmax_scale is None:
+        softmax_scale = 1.0 / math.sqrt(d)
+    if num_splits <= 0:
+        num_splits = max(1, min((mb * bs + 127) // 128, (3 * 148 + B * kvh - 1) // (B * kvh)))
+    ws = _workspace(_lib.load().b200_append_attention_workspace_bytes(B, nh, kvh, d, num_splits), qkv.device, "append_attn")
+    call("b200_append_attention", ptr(qkv), ptr(key_cache), ptr(value_cache), ptr(seq_lens_encoder), ptr(seq_lens_decoder),
+         ptr(seq_lens_this_time), ptr(cu_seqlens_q), ptr(block_tables), ptr(cos), ptr(sin), ptr(out), ptr(ws), B, token_num,
+         int(max_q_len), nh, kvh, d, nb, bs, mb, cos.shape[0], qkv.stride(0), out.stride(0), float(softmax_scale), num_splits,
+         stream_ptr())
+    return out
+
+
 def get_padding_offset(input_ids, cum_offsets, token_num, seq_lens):
     """get_padding_offset_v2: returns (x_remove_padding, cum_offsets_out, padding_offset, cu_seqlens_q, cu_seqlens_k)."""
     bsz, max_len = input_ids.shape

@@ -616,3 +616,78 @@ def test_streaming_token_output():
     torch.cuda.synchronize()
     with pytest.raises(Exception):
         stream3.get_output(False)
+
+
+@pytest.mark.parametrize("block_size", [64, 32])
+def test_append_attention_mixed_batch(block_size):
+    """append_attention (csrc/gpu/append_attention.cu:428-851): ONE call serves a mixed batch over the paged cache — a fresh prompt,
+    a prompt CHUNK on top of a cached prefix (chunked prefill), a decode row, a one-token prompt and an idle slot — with RoPE and
+    the cache append inside the op.  Checked against the oracle's full causal attention of every sequence at absolute positions,
+    and the appended cache rows against the oracle's rotated k / raw v; two chunked calls equal one whole-prompt call."""
+    from paddlenlp_b200 import ops
+
+    nh, kvh, d = 4, 2, 128
+    ld = (nh + 2 * kvh) * d
+    B, max_len = 5, 640
+    mb = max_len // block_size
+    num_blocks = B * mb + 3
+    g = torch.Generator().manual_seed(7)
+    perm = torch.randperm(num_blocks, generator=g)[: B * mb].to(torch.int32)          # scattered physical pages
+    block_tables = perm.view(B, mb).contiguous().to(DEV)
+    cos, sin = ops.rope_tables(d, max_len, 10000.0, DEV)
+    rcos, rsin = R.rope_tables(d, max_len, 10000.0)
+
+    totals = [300, 350, 78, 1, 0]                      # final lengths of the five sequences
+    seqs = [torch.randn(L, ld, generator=g).to(torch.bfloat16) for L in totals]       # pre-RoPE packed projections
+
+    def oracle(seq):
+        L = seq.shape[0]
+        x = seq.float()
+        q = x[:, : nh * d].view(1, L, nh, d)
+        k = x[:, nh * d:(nh + kvh) * d].view(1, L, kvh, d)
+        v = x[:, (nh + kvh) * d:].view(1, L, kvh, d)
+        qr, kr = R.apply_rope(q, rcos, rsin, "bf16"), R.apply_rope(k, rcos, rsin, "bf16")
+        return R.attention(qr, kr, v, "fp32")[0], kr[0], v[0]          # [L, nh*d], [L, kvh, d], [L, kvh, d]
+
+    def call(chunks, key_cache, value_cache):
+        """chunks: per sequence (start, stop) rows of its projection to append in this call (stop == start: idle)."""
+        rows = [seqs[b][s:e] for b, (s, e) in enumerate(chunks)]
+        n = [e - s for s, e in chunks]
+        qkv = torch.cat([r for r in rows if r.shape[0]], 0).to(DEV).contiguous()
+        cu = torch.tensor([0] + list(torch.tensor(n).cumsum(0)), dtype=torch.int32, device=DEV)
+        enc = torch.tensor([ni if (ni > 1 or s == 0) and ni > 0 else 0 for ni, (s, e) in zip(n, chunks)], dtype=torch.int32, device=DEV)
+        dec = torch.tensor([s for s, e in chunks], dtype=torch.int32, device=DEV)
+        this = torch.tensor(n, dtype=torch.int32, device=DEV)
+        out = ops.append_attention(qkv, key_cache, value_cache, enc, dec, this, cu, block_tables, cos, sin, nh, max_q_len=max(n))
+        return out.float().cpu(), cu.cpu().tolist()
+
+    def caches():
+        return (torch.zeros(num_blocks, kvh, block_size, d, dtype=torch.bfloat16, device=DEV),
+                torch.zeros(num_blocks, kvh, block_size, d, dtype=torch.bfloat16, device=DEV))
+
+    kc, vc = caches()
+    # call 1: build the cached prefixes (seq 1: first 150 rows, seq 2: first 77 rows), seq 0 / 3 / 4 idle
+    call([(0, 0), (0, 150), (0, 77), (0, 0), (0, 0)], kc, vc)
+    # call 2: the mixed batch
+    out, cu = call([(0, 300), (150, 350), (77, 78), (0, 1), (0, 0)], kc, vc)
+    refs = [oracle(s) if s.shape[0] else None for s in seqs]
+    starts = [0, 150, 77, 0, 0]
+    for b in range(4):
+        ref_out = refs[b][0][starts[b]:]
+        got = out[cu[b]:cu[b + 1]]
+        e = ((got - ref_out).abs().max() / ref_out.abs().max()).item()
+        assert e < 2e-2, (b, e)
+    # the appended cache rows: rotated k and raw v at every position of every sequence
+    kc_c, vc_c, bt = kc.float().cpu(), vc.float().cpu(), block_tables.cpu()
+    for b in range(4):
+        _, kr, v = refs[b]
+        for pos in (0, totals[b] // 2, totals[b] - 1):
+            phys, off = int(bt[b, pos // block_size]), pos % block_size
+            assert torch.equal(kc_c[phys, :, off], kr[pos]), (b, pos)
+            assert torch.equal(vc_c[phys, :, off], v[pos]), (b, pos)
+    # chunked prefill == whole prompt: sequence 1 appended in one call gives the rows of the two-call run
+    kc2, vc2 = caches()
+    whole, cu2 = call([(0, 0), (0, 350), (0, 0), (0, 0), (0, 0)], kc2, vc2)
+    two_step = out[cu[1]:cu[2]]
+    one_step = whole[cu2[1]:cu2[2]][150:]
+    assert ((two_step - one_step).abs().max() / one_step.abs().max()).item() < 1e-2
