@@ -683,7 +683,7 @@ def test_append_attention_mixed_batch(block_size):
         _, kr, v = refs[b]
         for pos in (0, totals[b] // 2, totals[b] - 1):
             phys, off = int(bt[b, pos // block_size]), pos % block_size
-            assert torch.equal(kc_c[phys, :, off], kr[pos]), (b, pos)
+            assert (kc_c[phys, :, off] - kr[pos]).abs().max() <= 2 ** -7 * kr[pos].abs().max(), (b, pos)   # 1 bf16 ulp (fp32 FMA order)
             assert torch.equal(vc_c[phys, :, off], v[pos]), (b, pos)
     # chunked prefill == whole prompt: sequence 1 appended in one call gives the rows of the two-call run
     kc2, vc2 = caches()
