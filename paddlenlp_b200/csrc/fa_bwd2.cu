@@ -82,14 +82,10 @@ __device__ __forceinline__ void mul2(float& x0, float& x1, float a0, float a1, f
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
-// TMEM accumulator (this warp's 32 lanes, fp32 columns [32*ch0, 32*(ch0+2))) -> fp32 staging -> TMA reduce-add of two 32x32
-// boxes at coordinates (c0 + 32*i, c1, c2, c3).  One 4 KB staging buffer per warp.
-__device__ __forceinline__ void reduce_out(uint32_t tsrc, uint8_t* buf, const CUtensorMap* tm, int lane, int ch0, int c0, int c1,
-                                           int c2, int c3) {
-  uint32_t o[2][32];
-  tmem_ld32(tsrc + ch0 * 32, o[0]);
-  tmem_ld32(tsrc + (ch0 + 1) * 32, o[1]);
-  tmem_ld_wait();
+// Two 32x32 fp32 chunks held in registers (this warp's 32 TMEM lanes) -> fp32 staging -> TMA reduce-add of two 32x32 boxes at
+// coordinates (c0 + 32*i, c1, c2, c3).  One 4 KB staging buffer per warp.
+__device__ __forceinline__ void reduce_regs(const uint32_t (&o)[2][32], uint8_t* buf, const CUtensorMap* tm, int lane, int c0, int c1,
+                                            int c2, int c3) {
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     if (lane == 0) tma_store_wait_read<0>();
@@ -105,6 +101,15 @@ __device__ __forceinline__ void reduce_out(uint32_t tsrc, uint8_t* buf, const CU
       tma_store_commit();
     }
   }
+}
+// TMEM accumulator columns [32*ch0, 32*(ch0+2)) of this warp's lanes -> registers -> reduce_regs
+__device__ __forceinline__ void reduce_out(uint32_t tsrc, uint8_t* buf, const CUtensorMap* tm, int lane, int ch0, int c0, int c1,
+                                           int c2, int c3) {
+  uint32_t o[2][32];
+  tmem_ld32(tsrc + ch0 * 32, o[0]);
+  tmem_ld32(tsrc + (ch0 + 1) * 32, o[1]);
+  tmem_ld_wait();
+  reduce_regs(o, buf, tm, lane, c0, c1, c2, c3);
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -256,9 +261,13 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     auto read_out_dq = [&](int n) {                      // dQ^T(n): lanes = d, columns = 64 q rows of step n
       mbar_wait(&dq_full[n & 1], static_cast<uint32_t>((n >> 1) & 1));
       tc_fence_after();
-      reduce_out(tdQ + lane_off, my_stage, &tmdQ, lane, 0, kv0 + n * 64, quad * 32, hq, batch);
+      uint32_t o[2][32];
+      tmem_ld32(tdQ + lane_off, o[0]);
+      tmem_ld32(tdQ + lane_off + 32, o[1]);
+      tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(dq_empty);
+      mbar_arrive(dq_empty);                             // the columns are free as soon as they sit in registers: dQ^T(n+1) may start
+      reduce_regs(o, my_stage, &tmdQ, lane, kv0 + n * 64, quad * 32, hq, batch);
     };
     for (int n = g; n < n_iter; n += 2) {
       const int st = n % QST;
@@ -308,10 +317,12 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&pds_full[g]);
-      read_out_dq(n);
+      // read out the OTHER group's previous step: its dQ^T MMA was issued ~800 tensor cycles after that group's compute ended and
+      // has normally retired while this group was exponentiating, so nobody idles on dq_full
+      if (n > 0) read_out_dq(n - 1);
     }
-    // the other group's last read-out may still be pending for this group's barrier count: every step was read out by exactly one
-    // group, 128 arrivals each.  Epilogue: this head's dK / dV partials -> fp32 reduce-add (the GQA group's heads sum in L2)
+    if ((n_iter & 1) == g) read_out_dq(n_iter - 1);     // the last step's dQ^T: read by the group that would own step n_iter
+    // every step's dQ^T was read out by exactly one group (128 arrivals on dq_empty each).  Epilogue: this head's dK / dV partials -> fp32 reduce-add (the GQA group's heads sum in L2)
     mbar_wait(acc_full, 0);
     tc_fence_after();
     reduce_out(tdK + lane_off, my_stage, &tmdK, lane, g * 2, g * 64, kv_head, kv0 + quad * 32, batch);

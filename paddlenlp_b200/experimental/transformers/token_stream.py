@@ -30,7 +30,7 @@ class TokenStream:
     def __init__(self, max_bsz: int = MAX_BSZ, num_slots: int = 4096, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("TokenStream needs a CUDA device (the producer is a kernel writing to mapped host memory)")
-        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.max_bsz, self.num_slots = int(max_bsz), int(num_slots)
         self.stride = HEADER + self.max_bsz
         self.ring = torch.zeros(self.num_slots, self.stride, dtype=torch.int32).pin_memory()   # host memory, device-visible (UVA)

@@ -18,6 +18,10 @@ if [ "$NCU_FA" == "1" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"fa_fwd2_kernel|fa_bwd2_kernel|fa_bwd_kernel" -s 2 -c 2 \
     -o $OUT/${TAG}_fa_prof -f python tools/fa_probe.py 2 > $OUT/${TAG}_fa_prof.log 2>&1
 fi
+if [ "$NCU_GEMM" == "1" ]; then
+  timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_bf16 \
+    --csv --log-file $OUT/${TAG}_gemm_traffic.csv python tools/gemm_shapes.py > $OUT/${TAG}_gemm_traffic.log 2>&1
+fi
 if [ "$SKIP_BENCH" != "1" ]; then
   timeout 1500 python bench.py "$@" > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 fi
