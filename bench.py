@@ -220,6 +220,7 @@ def run_reference(args):
 # kernel family of every C-ABI entry point the training step calls (for `breakdown`)
 FAMILY = {
     "b200_gemm_bf16_ex": "gemm (tcgen05)", "b200_gemm_bf16": "gemm (tcgen05)",
+    "b200_gemm_swiglu_bf16": "gemm + swiglu epilogue (tcgen05)", "b200_gemm_swiglu_bwd_bf16": "gemm + swiglu-bwd epilogue (tcgen05)",
     "b200_fa_fwd_flashmask": "attention fwd (tcgen05)", "b200_fa_fwd": "attention fwd (tcgen05)",
     "b200_fa_bwd_flashmask": "attention bwd (tcgen05)", "b200_fa_bwd": "attention bwd (tcgen05)",
     "b200_rmsnorm_fwd": "rmsnorm", "b200_rmsnorm_bwd": "rmsnorm", "b200_rope_inplace": "rope",
@@ -357,12 +358,18 @@ def run_native(args):
 
     @contextlib.contextmanager
     def hook(name, a):
-        if name == "b200_gemm_bf16_ex":
+        if name in ("b200_gemm_bf16_ex", "b200_gemm_swiglu_bf16", "b200_gemm_swiglu_bwd_bf16"):
+            if name == "b200_gemm_bf16_ex":
+                M, N, K = int(a[5]), int(a[6]), int(a[7])
+            elif name == "b200_gemm_swiglu_bf16":          # (X, W, GU, M_out, M, I, K, ...): N = 2 I
+                M, N, K = int(a[4]), 2 * int(a[5]), int(a[6])
+            else:                                          # (dY, Wdown, GU, DGU, M, I, K, ...): N = I
+                M, N, K = int(a[4]), int(a[5]), int(a[6])
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             yield
             e1.record()
-            gemm_events.append((e0, e1, 2.0 * a[5] * a[6] * a[7], (int(a[5]), int(a[6]), int(a[7]))))
+            gemm_events.append((e0, e1, 2.0 * M * N * K, (M, N, K)))
         else:
             yield
 
