@@ -24,6 +24,8 @@
 // Replaces Paddle-core flash_attn_grad (reference: fusion_ops.py:240-246 backward; csrc/gpu/flash_attn_bwd.cc:22-92).
 #include "../../include/b200nlp.h"
 #include "common.cuh"
+#include <type_traits>
+
 #include "host_util.h"
 
 namespace b200 {
@@ -46,7 +48,8 @@ constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 struct Params {
   int S, Spad, B, nh, kvh;
   float scale, scale_log2;
-  const float2* stats;   // [B, nh, Spad] (-lse*log2e, -delta*scale); padding rows hold (-inf, 0)
+  const float2* stats;   // [B, nh, Spad] x 2 floats: -lse*log2e ("nl") and -delta*scale ("nd"), stored per 64-row block as
+                         // (nl(2c), nl(2c+1), nd(2c), nd(2c+1)) for c = 0..31; padding rows hold (-inf, 0)
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -112,7 +115,7 @@ __device__ __forceinline__ void reduce_out(uint32_t tsrc, uint8_t* buf, const CU
   reduce_regs(o, buf, tm, lane, c0, c1, c2, c3);
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(200)
 fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdK,
@@ -181,9 +184,22 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tma_load_4d(&tmV, kv_full, sV, 0, kv_head, kv0, batch);
       tma_load_4d(&tmV, kv_full, sV + KV_HALF, 64, kv_head, kv0, batch);
       const float2* stat_row = p.stats + (static_cast<size_t>(batch) * p.nh + hq) * p.Spad;
+      // The 3-stage ring gives a Q / dO tile about one step (~1500 tensor cycles) between its slot becoming free and its first
+      // MMA: enough for an L2 hit, not for a DRAM miss (ncu r02d: the compute groups spent 27 % of their time waiting for S^T).
+      // So every tile is requested into L2 PF_AHEAD steps before its shared-memory load.
+      constexpr int PF_AHEAD = 4;
+      for (int n = 0; n < min(PF_AHEAD, n_iter); ++n) {
+        tma_prefetch_l2_4d(&tmQ, 0, hq, kv0 + n * 64, batch);  tma_prefetch_l2_4d(&tmQ, 64, hq, kv0 + n * 64, batch);
+        tma_prefetch_l2_4d(&tmdO, 0, hq, kv0 + n * 64, batch); tma_prefetch_l2_4d(&tmdO, 64, hq, kv0 + n * 64, batch);
+      }
       for (int n = 0; n < n_iter; ++n) {
         const int st = n % QST;
         const int q0 = kv0 + n * 64;
+        if (n + PF_AHEAD < n_iter) {
+          const int qp = q0 + PF_AHEAD * 64;
+          tma_prefetch_l2_4d(&tmQ, 0, hq, qp, batch);  tma_prefetch_l2_4d(&tmQ, 64, hq, qp, batch);
+          tma_prefetch_l2_4d(&tmdO, 0, hq, qp, batch); tma_prefetch_l2_4d(&tmdO, 64, hq, qp, batch);
+        }
         mbar_wait(&qdo_empty[st], static_cast<uint32_t>((n / QST) & 1) ^ 1u);
         mbar_arrive_expect_tx(&qdo_full[st], 2 * Q_TILE_BYTES + STAT_BYTES);
         tma_load_4d(&tmQ, &qdo_full[st], sQ + st * Q_TILE_BYTES, 0, hq, q0, batch);
@@ -286,25 +302,30 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       tc_fence_before();
       mbar_arrive(dp_free);
-      const float4* stat = reinterpret_cast<const float4*>(sStat + st * STAT_BYTES);   // (nl0, nd0, nl1, nd1) per q pair
+      const uint32_t stat_a = smem_u32(sStat + st * STAT_BYTES);      // per q pair: (nl0, nl1, nd0, nd1)
       const int diag_shift = n * 64;                     // column c is visible to kv row r iff r <= c + 64 n
-      const bool diag = diag_shift < 128;
       uint32_t pk[32], dk[32];
+      auto body = [&](auto diag_tag) {
+        constexpr bool DIAG = decltype(diag_tag)::value;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float4 s4 = stat[c];                       // warp-uniform address: one broadcast LDS.128
-        float x0, x1, t0, t1, p0, p1, d0, d1;
-        fma2v(x0, x1, __uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1]), p.scale_log2, s4.x, s4.z);
-        p0 = fast_exp2(x0); p1 = fast_exp2(x1);
-        if (diag) {
-          if (r > 2 * c + diag_shift) p0 = 0.f;
-          if (r > 2 * c + 1 + diag_shift) p1 = 0.f;
+        for (int c = 0; c < 32; ++c) {
+          const uint4 su = ld_shared_v4(stat_a + c * 16);  // warp-uniform address: one broadcast LDS.128
+          float x0, x1, t0, t1, p0, p1, d0, d1;
+          fma2v(x0, x1, __uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1]), p.scale_log2, __uint_as_float(su.x),
+                __uint_as_float(su.y));
+          p0 = fast_exp2(x0); p1 = fast_exp2(x1);
+          if constexpr (DIAG) {
+            if (r > 2 * c + diag_shift) p0 = 0.f;
+            if (r > 2 * c + 1 + diag_shift) p1 = 0.f;
+          }
+          fma2v(t0, t1, __uint_as_float(dv[2 * c]), __uint_as_float(dv[2 * c + 1]), p.scale, __uint_as_float(su.z),
+                __uint_as_float(su.w));
+          mul2(d0, d1, p0, p1, t0, t1);
+          pk[c] = pack_bf16x2(p0, p1);
+          dk[c] = pack_bf16x2(d0, d1);
         }
-        fma2v(t0, t1, __uint_as_float(dv[2 * c]), __uint_as_float(dv[2 * c + 1]), p.scale, s4.y, s4.w);
-        mul2(d0, d1, p0, p1, t0, t1);
-        pk[c] = pack_bf16x2(p0, p1);
-        dk[c] = pack_bf16x2(d0, d1);
-      }
+      };
+      if (diag_shift < 128) body(std::true_type{}); else body(std::false_type{});
       {
         uint32_t(*a)[16] = reinterpret_cast<uint32_t(*)[16]>(pk);
         tmem_st16(tS, a[0]); tmem_st16(tS + 16, a[1]);   // P^T: 64 q as 32 packed columns over the start of S^T[g]
@@ -372,7 +393,11 @@ __global__ void fa_bwd2_stats_kernel(const bf16* __restrict__ o, const bf16* __r
       v.x = -INFINITY;
       v.y = 0.f;
     }
-    stats[(static_cast<size_t>(b) * nh + h) * Spad + s] = v;
+    // layout per 64-row block: for the q pair (2c, 2c+1): nl(2c), nl(2c+1), nd(2c), nd(2c+1) — the pairs the f32x2 FMAs consume
+    float* blk = reinterpret_cast<float*>(stats + (static_cast<size_t>(b) * nh + h) * Spad + (s & ~63));
+    const int c = (s & 63) >> 1, e = s & 1;
+    blk[c * 4 + e] = v.x;
+    blk[c * 4 + 2 + e] = v.y;
   }
 }
 

@@ -13,6 +13,14 @@ fi
 timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_ops_gpu.py::test_flash_attention_fwd_bwd \
   --deselect tests/test_ops_gpu.py::test_flash_attention_bench_shapes -rf 2>&1 | grep -v "^loss: \|^PASSED" > $OUT/${TAG}_tests_full.log
 tail -60 $OUT/${TAG}_tests_full.log > $OUT/${TAG}_tests.log
+if [ "$PARITY_PRINTS" == "1" ]; then
+  timeout 900 python -m pytest tests/test_model_gpu.py -q -s -k "two_layer or reorder or bench_shape or full_width or logits_loss" 2>&1 | grep "^\[" > $OUT/${TAG}_parity_prints.log
+fi
+if [ "$NCU_DECODE" == "1" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 400 --csv --log-file $OUT/${TAG}_launches_decode.csv \
+    python tools/gen_bench.py --gen 16 > $OUT/${TAG}_decode_ncu.log 2>&1
+  timeout 600 python tools/gen_bench.py > $OUT/${TAG}_gen_bench.log 2>&1
+fi
 timeout 600 python tools/fa_bench.py > $OUT/${TAG}_fa_bench.log 2>&1
 if [ "$NCU_FA" == "1" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"fa_fwd2_kernel|fa_bwd2_kernel|fa_bwd_kernel" -s 2 -c 2 \
