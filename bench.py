@@ -40,26 +40,31 @@ PER_GPU_BATCH = 8
 METRIC = "tokens/sec Llama-3-8B seq4096 bf16 pretrain step (global, all GPUs)"
 
 
-def gemm_traffic_from_profile():
-    """Average DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
-    capture of the same kernel family at the bench shapes (profiles/r01_ncu_summary.md); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_summary.md")
+def gemm_traffic_from_profile(per_shape=None):
+    """DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture of every GEMM
+    shape of the step (profiles/r02_gemm_traffic.json, written by tools/gemm_shapes.py --summarise: cold L2, one launch per
+    shape).  Returns (mean bytes per launch weighted by this run's launch counts, mean algorithmic bytes, per-shape table) or
+    (None, None, None) if the profile is absent."""
+    path = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
     try:
-        tot, n, section = 0.0, 0, ""
-        for line in open(path):
-            if line.startswith("| **"):
-                section = line
-            if "prof_top" not in section or "gemm_bf16_kernel" not in line:
-                continue
-            cells = [c.strip() for c in line.strip().strip("|").split("|")]
-            vals = []
-            for c in cells[2:4]:                       # dram rd, dram wr
-                num, unit = c.split()[0], c.split()[1]
-                vals.append(float(num) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit])
-            tot += sum(vals); n += 1
-        return (tot / n) if n else None
+        shapes = json.load(open(path))["shapes"]
     except Exception:
-        return None
+        return None, None, None
+    table = {(s["M"], s["N"], s["K"]): s for s in shapes}
+    if not per_shape:
+        n = len(shapes)
+        return sum(s["dram_bytes"] for s in shapes) / n, sum(s["algorithmic_bytes"] for s in shapes) / n, None
+    tot = alg = cnt = 0.0
+    rows = {}
+    for shp, v in per_shape.items():
+        s = table.get(tuple(shp))
+        if s is None:
+            continue
+        tot += s["dram_bytes"] * v[0]; alg += s["algorithmic_bytes"] * v[0]; cnt += v[0]
+        rows[f"{shp[0]}x{shp[1]}x{shp[2]}"] = {"dram_bytes": s["dram_bytes"], "algorithmic_bytes": s["algorithmic_bytes"], "ratio": s["ratio"]}
+    if not cnt:
+        return None, None, None
+    return tot / cnt, alg / cnt, rows
 
 
 def load_peaks():
@@ -433,7 +438,7 @@ def run_native(args):
     hbm_peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
     out = None
     if rank == 0:
-        traffic = gemm_traffic_from_profile()
+        traffic, traffic_alg, traffic_rows = gemm_traffic_from_profile(per_shape)
         out = {
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -463,7 +468,11 @@ def run_native(args):
                          "frac": (gemm_tf / peaks["bf16_sustained"]) if gemm_tf else None, "peak_source": peaks["source"] + ", sustained",
                          "launches_timed": n_gemm, "avg_launch_ms": gemm_ms / max(1, n_gemm), "share_of_step": gemm_ms / ms,
                          "algorithmic_flops_per_launch": gemm_flops / max(1, n_gemm),
-                         "traffic": traffic, "traffic_unit": "bytes/launch (ncu --set full, profiles/r01_ncu_summary.md)",
+                         "traffic": traffic, "traffic_algorithmic": traffic_alg,
+                         "traffic_ratio": (traffic / traffic_alg) if traffic and traffic_alg else None,
+                         "traffic_unit": "DRAM bytes/launch, mean over this run's launches; per shape from the committed ncu capture "
+                                         "profiles/r02_gemm_traffic.json (cold L2)",
+                         "traffic_per_shape": traffic_rows,
                          "per_shape_MNK": {f"{k[0]}x{k[1]}x{k[2]}": {"launches": v[0], "ms_per_launch": round(v[1] / v[0], 4),
                                                                        "tflops": round(v[2] / (v[1] / 1e3) / 1e12, 1)}
                                            for k, v in sorted(per_shape.items(), key=lambda kv: -kv[1][1])}},
