@@ -115,7 +115,9 @@ __device__ __forceinline__ void reduce_out(uint32_t tsrc, uint8_t* buf, const CU
   reduce_regs(o, buf, tm, lane, c0, c1, c2, c3);
 }
 
-__global__ void __maxnreg__(200)
+// 10 warps = 3 on one SM sub-partition (16 K registers each): 16384 / (3 * 32) = 170 registers per thread is the hardware limit for this
+// block shape (a 200-register build fails to launch), which is what __launch_bounds__(320, 1) makes ptxas target
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdK,

@@ -78,7 +78,9 @@ __device__ __forceinline__ void add2(float& acc0, float& acc1, float a0, float a
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 template <bool PAGED>
-__global__ void __maxnreg__(200)
+// 10 warps = 3 on one SM sub-partition (16 K registers each): 16384 / (3 * 32) = 170 registers per thread is the hardware limit for this
+// block shape (a 200-register build fails to launch), which is what __launch_bounds__(320, 1) makes ptxas target
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const Params p) {
   extern __shared__ uint8_t smem_raw[];
