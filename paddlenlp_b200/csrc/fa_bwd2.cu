@@ -213,31 +213,46 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow, barrier waits and descriptor arithmetic; one elected lane issues the
+    // tcgen05 instructions.  Inside `if (lane == 0) { ... }` the compiler treats every value as divergent and rebuilds each
+    // descriptor in vector registers, then moves it to the uniform registers UTCHMMA reads (ELECT + R2UR.BROADCAST loops): ~19
+    // SASS instructions and ~120 cycles per MMA against 32-64 tensor cycles per MMA (ncu r02e: the issuing thread was busy 77 %
+    // of the time, the tensor pipe 36 %).  Descriptors are therefore built once per operand and ADVANCED by adding the k-step's
+    // byte offset (>> 4) to the 64-bit value, all in convergent code.
+    {
+      const bool leader = elect_one();
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform by construction: lets it live in a UR
+      const uint32_t uST = tbase, udP = tbase + 128, udQ = tbase + 192, udV = tbase + 256, udK = tbase + 384;
       constexpr uint32_t id_st = umma_idesc_bf16(128, 64, false, false);    // S^T / dP^T : A = K|V (K-major), B = Q|dO (K-major), N = 64
       constexpr uint32_t id_dv = umma_idesc_bf16(128, 128, false, true);    // dV : A = P^T (TMEM), B = dO (MN-major)
       constexpr uint32_t id_dk = umma_idesc_bf16(128, 128, false, true);    // dK : A = dS^T (smem, K-major), B = Q (MN-major)
       constexpr uint32_t id_dq = umma_idesc_bf16(128, 64, true, true);      // dQ^T: A = K^T (MN-major), B = dS^T (MN-major), N = 64
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      auto kmaj = [](uint32_t base, int kk, uint32_t half_bytes) {   // K-major operand over head_dim, k-step kk (16 of the 128 d)
-        return umma_desc_sw128(base + (kk >> 2) * half_bytes + (kk & 3) * 32, 16, 1024);
-      };
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ0 = smem_u32(sQ), adO0 = smem_u32(sdO), adS0 = smem_u32(sdS);
+      const uint64_t dK_k = umma_desc_sw128(aK, 16, 1024), dV_k = umma_desc_sw128(aV, 16, 1024);   // K-major over head_dim
+      const uint64_t dK_mn = umma_desc_sw128(aK, KV_HALF, 1024);                                      // K^T: MN-major over head_dim
+      // byte offset of k-step kk (16 of the 128 head_dim columns) in a K-major tile stored as two 64-column halves
+      auto koff = [](int kk, uint32_t half_bytes) { return static_cast<uint64_t>(((kk >> 2) * half_bytes + (kk & 3) * 32) >> 4); };
       auto issue_st_dp = [&](int n, bool first_wait) {
         const int st = n % QST;
-        const uint32_t aQ = smem_u32(sQ + st * Q_TILE_BYTES), adO = smem_u32(sdO + st * Q_TILE_BYTES);
         mbar_wait(&qdo_full[st], static_cast<uint32_t>((n / QST) & 1));
         tc_fence_after();
-        const uint32_t tS = tST + static_cast<uint32_t>((n & 1) * 64);
+        const uint64_t dQ_k = umma_desc_sw128(aQ0 + st * Q_TILE_BYTES, 16, 1024);
+        const uint64_t ddO_k = umma_desc_sw128(adO0 + st * Q_TILE_BYTES, 16, 1024);
+        const uint32_t tS = uST + static_cast<uint32_t>((n & 1) * 64);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tS, kmaj(aK, kk, KV_HALF), kmaj(aQ, kk, Q_HALF), id_st, kk > 0);     // S^T = K Q^T
-        umma_commit(&s_full[n & 1]);
+          for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tS, dK_k + koff(kk, KV_HALF), dQ_k + koff(kk, Q_HALF), id_st, kk > 0);   // S^T = K Q^T
+          umma_commit(&s_full[n & 1]);
+        }
         if (first_wait) {
           mbar_wait(dp_free, static_cast<uint32_t>((n - 1) & 1));       // compute(n-1) holds dP^T(n-1) in registers
           tc_fence_after();
         }
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tdP, kmaj(aV, kk, KV_HALF), kmaj(adO, kk, Q_HALF), id_st, kk > 0);   // dP^T = V dO^T
-        umma_commit(&dp_full[n & 1]);
+          for (int kk = 0; kk < 8; ++kk) umma_ss<1>(udP, dV_k + koff(kk, KV_HALF), ddO_k + koff(kk, Q_HALF), id_st, kk > 0);  // dP^T = V dO^T
+          umma_commit(&dp_full[n & 1]);
+        }
       };
       mbar_wait(kv_full, 0);
       issue_st_dp(0, false);
@@ -246,28 +261,33 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (n + 1 < n_iter) issue_st_dp(n + 1, true);
         mbar_wait(&pds_full[n & 1], static_cast<uint32_t>((n >> 1) & 1));
         tc_fence_after();
-        const uint32_t aQ = smem_u32(sQ + st * Q_TILE_BYTES), adO = smem_u32(sdO + st * Q_TILE_BYTES);
-        const uint32_t adS = smem_u32(sdS + (n & 1) * DS_BYTES);
-        const uint32_t tP = tST + static_cast<uint32_t>((n & 1) * 64);
+        const uint64_t dQ_mn = umma_desc_sw128(aQ0 + st * Q_TILE_BYTES, Q_HALF, 1024);      // Q / dO as MN-major B (k-step = 16 rows = 2 KB)
+        const uint64_t ddO_mn = umma_desc_sw128(adO0 + st * Q_TILE_BYTES, Q_HALF, 1024);
+        const uint64_t ddS_k = umma_desc_sw128(adS0 + (n & 1) * DS_BYTES, 16, 1024);         // dS^T K-major A (k-step = 32 bytes)
+        const uint32_t tP = uST + static_cast<uint32_t>((n & 1) * 64);
+        const uint32_t acc0 = n > 0 ? 1u : 0u;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)     // dV += P^T dO : K = 64 q;  A k-step = 8 TMEM columns, B k-step = 16 dO rows (2 KB)
-          umma_ts(tdV, tP + kk * 8, umma_desc_sw128(adO + kk * 2048, Q_HALF, 1024), id_dv, (n > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk)     // dV += P^T dO : K = 64 q;  A k-step = 8 TMEM columns, B k-step = 16 dO rows
+            umma_ts(udV, tP + kk * 8, ddO_mn + static_cast<uint64_t>(kk * 128), id_dv, kk > 0 ? 1u : acc0);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)     // dK += dS^T Q : A k-step = 32 bytes along the 128-byte q row, B k-step = 16 Q rows
-          umma_ss<1>(tdK, umma_desc_sw128(adS + kk * 32, 16, 1024), umma_desc_sw128(aQ + kk * 2048, Q_HALF, 1024), id_dk,
-                     (n > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&qdo_empty[st]);       // Q / dO / stats of this step are not read again
+          for (int kk = 0; kk < 4; ++kk)     // dK += dS^T Q : A k-step = 32 bytes along the 128-byte q row, B k-step = 16 Q rows
+            umma_ss<1>(udK, ddS_k + static_cast<uint64_t>(kk * 2), dQ_mn + static_cast<uint64_t>(kk * 128), id_dk, kk > 0 ? 1u : acc0);
+          umma_commit(&qdo_empty[st]);       // Q / dO / stats of this step are not read again
+        }
         if (n > 0) {
           mbar_wait(dq_empty, (n - 1) & 1);
           tc_fence_after();
         }
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)     // dQ^T = K^T dS^T : K = 128 kv;  A k-step = 16 K rows (2 KB), B k-step = 16 dS^T rows (2 KB)
-          umma_ss<1>(tdQ, umma_desc_sw128(aK + kk * 2048, KV_HALF, 1024), umma_desc_sw128(adS + kk * 2048, 16, 1024), id_dq,
-                     kk > 0);
-        umma_commit(&dq_full[n & 1]);
+          for (int kk = 0; kk < 8; ++kk)     // dQ^T = K^T dS^T : K = 128 kv;  A k-step = 16 K rows (2 KB), B k-step = 16 dS^T rows (2 KB)
+            umma_ss<1>(udQ, dK_mn + static_cast<uint64_t>(kk * 128), ddS_k + static_cast<uint64_t>(kk * 128), id_dq, kk > 0);
+          umma_commit(&dq_full[n & 1]);
+        }
       }
-      umma_commit(acc_full);
+      if (leader) umma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     // ------------------------------- compute groups: one thread per kv row -------------------------------

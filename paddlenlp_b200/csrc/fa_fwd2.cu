@@ -209,31 +209,40 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    // Convergent code: the whole warp runs the control flow, the barrier waits and the descriptor arithmetic, one elected lane
+    // issues.  (Inside `if (lane == 0)` every descriptor is rebuilt in vector registers and moved to the uniform registers
+    // UTCHMMA reads through ELECT / R2UR.BROADCAST loops: ~19 SASS instructions, ~120 cycles per MMA against 64 tensor cycles —
+    // the first version of this kernel was bound by that, tensor pipe 50 %.)  Descriptors are built once per tile and advanced
+    // by adding the k-step's byte offset >> 4.
+    {
+      const bool leader = elect_one();
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);   // A = Q (smem, K-major), B = K (K-major)
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, false, true);    // A = P (TMEM), B = V (MN-major)
+      const uint32_t sQ_a = smem_u32(sQ), sKV_a = smem_u32(sKV);
       auto wait_kv = [&](int it) { mbar_wait(&kv_full[it % NST], static_cast<uint32_t>(it / NST) & 1u); };
-      auto free_kv = [&](int it) { umma_commit(&kv_empty[it % NST]); };
+      auto free_kv = [&](int it) { if (leader) umma_commit(&kv_empty[it % NST]); };
+      auto koff = [](int kk) { return static_cast<uint64_t>(((kk >> 2) * HALF_BYTES + (kk & 3) * 32) >> 4); };
       auto issue_qk = [&](int t, int j) {          // S_t = Q_t K_j^T
-        const uint32_t sQ_a = smem_u32(sQ + t * TILE_BYTES);
-        const uint32_t sK_a = smem_u32(sKV + ((2 * j) % NST) * TILE_BYTES);
-        const uint32_t tS = tmem_base + static_cast<uint32_t>(t * 128);
+        const uint64_t dQ = umma_desc_sw128(sQ_a + t * TILE_BYTES, 16, 1024);
+        const uint64_t dK = umma_desc_sw128(sKV_a + ((2 * j) % NST) * TILE_BYTES, 16, 1024);
+        const uint32_t tS = tbase + static_cast<uint32_t>(t * 128);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
-          umma_ss<1>(tS, umma_desc_sw128(sQ_a + off, 16, 1024), umma_desc_sw128(sK_a + off, 16, 1024), idesc_qk,
-                     kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk) umma_ss<1>(tS, dQ + koff(kk), dK + koff(kk), idesc_qk, kk > 0 ? 1u : 0u);
+          umma_commit(&s_full[t]);
         }
-        umma_commit(&s_full[t]);
       };
       auto issue_pv = [&](int t, int j) {          // O_t (+)= P_t V_j ; P_t = packed bf16 in the first 64 columns of S_t
-        const uint32_t sV_a = smem_u32(sKV + ((2 * j + 1) % NST) * TILE_BYTES);
-        const uint32_t tP = tmem_base + static_cast<uint32_t>(t * 128);
-        const uint32_t tO = tmem_base + 256u + static_cast<uint32_t>(t * 128);
+        const uint64_t dV = umma_desc_sw128(sKV_a + ((2 * j + 1) % NST) * TILE_BYTES, HALF_BYTES, 1024);
+        const uint32_t tP = tbase + static_cast<uint32_t>(t * 128);
+        const uint32_t tO = tbase + 256u + static_cast<uint32_t>(t * 128);
+        const uint32_t acc0 = j > 0 ? 1u : 0u;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 128 / 16; ++kk)
-          umma_ts(tO, tP + kk * 8, umma_desc_sw128(sV_a + kk * 2048, HALF_BYTES, 1024), idesc_pv,
-                  (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 128 / 16; ++kk)
+            umma_ts(tO, tP + kk * 8, dV + static_cast<uint64_t>(kk * 128), idesc_pv, kk > 0 ? 1u : acc0);
+        }
       };
       mbar_wait(&q_full[0], 0);
       wait_kv(0);
@@ -258,7 +267,7 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               wait_kv(2 * j + 2);
               tc_fence_after();
               issue_qk(t, j + 1);
-            } else {
+            } else if (leader) {
               umma_commit(&o_full[t]);
             }
           }
@@ -267,6 +276,7 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         free_kv(2 * j + 1);
         if (j + 1 < n_kv) free_kv(2 * j + 2);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------- softmax / epilogue: one thread per q row -------------------------------

@@ -38,6 +38,7 @@ class FusedMultiTransformerConfig:
     qkv_bias: bool = False
     nranks: int = 1
     trans_qkvw: bool = True
+    append_attn: bool = False                # FusedBlockMultiTransformer: route attention through the unified append_attention op
 
     def __post_init__(self):
         if self.kv_num_heads <= 0:
@@ -162,7 +163,7 @@ class FusedMultiTransformerBase:
         decode = time_step is not None
         residual = src
         ln_out, _ = ops.add_rmsnorm(src, None, self.ln_scales[0], eps, want_residual=False)   # compute_layernorm_before_qkv
-        fused = decode and src.shape[0] <= self.SKINNY_M
+        fused = decode and src.shape[0] <= self.SKINNY_M and not getattr(self.config, "append_attn", False)
         for i in range(self.L):
             if fused:
                 # decode step: the split-K GEMMs leave fp32 sums that the next kernel rounds once (same rounding points,
@@ -229,3 +230,25 @@ class FusedBlockMultiTransformer(FusedMultiTransformerBase):
 
     def _attend(self, qkv, caches, i, seq_lens_decoder, kw):
         return ops.decode_attention_paged(qkv, caches[2 * i], caches[2 * i + 1], self._tables(kw), seq_lens_decoder, self.nh)
+
+    # ---- config.append_attn (fused_transformer_layers.py:2215-2262): ONE op does RoPE + cache append + attention for the prompt
+    # rows and the decode rows alike; the padded [B, S] prefill layout is the packed layout with cu_seqlens_q[b] = b * S ----
+    def _append(self, qkv, caches, i, B, S, enc, dec, this_time, kw):
+        cos, sin = self.rope
+        cu = torch.arange(0, (B + 1) * S, S, dtype=torch.int32, device=qkv.device)
+        return ops.append_attention(qkv, caches[2 * i], caches[2 * i + 1], enc, dec, this_time, cu, self._tables(kw), cos, sin,
+                                    self.nh, max_q_len=S)
+
+    def compute_fmha(self, qkv, caches, i, B, S, seq_lens_encoder, kw):
+        if not self.config.append_attn:
+            return super().compute_fmha(qkv, caches, i, B, S, seq_lens_encoder, kw)
+        enc = (seq_lens_encoder if seq_lens_encoder is not None
+               else torch.full((B,), S, dtype=torch.int32, device=qkv.device)).to(torch.int32)
+        return self._append(qkv, caches, i, B, S, enc, torch.zeros_like(enc), enc, kw)
+
+    def compute_mmha(self, qkv, caches, i, seq_lens_decoder, kw):
+        if not self.config.append_attn:
+            return super().compute_mmha(qkv, caches, i, seq_lens_decoder, kw)
+        B = qkv.shape[0]
+        one = torch.ones(B, dtype=torch.int32, device=qkv.device)
+        return self._append(qkv, caches, i, B, 1, torch.zeros_like(one), seq_lens_decoder, one, kw)

@@ -15,9 +15,12 @@ BF16 = torch.bfloat16
 
 
 class LlamaForCausalLMInferenceModel(GenerationInferenceModel):
-    def __init__(self, config, device=None, block_attn: bool = False, block_size: int = 64):
+    def __init__(self, config, device=None, block_attn: bool = False, block_size: int = 64, append_attn: bool = False):
         """block_attn=True selects the paged KV cache (`--block_attn` of llm/predict/predictor.py:1507-1520:
-        LlamaBlockInferenceModel on FusedBlockMultiTransformer)."""
+        LlamaBlockInferenceModel on FusedBlockMultiTransformer); append_attn=True (`--append_attn`) additionally routes prefill
+        and decode attention through the unified append_attention op."""
+        if append_attn and not block_attn:
+            raise ValueError("append_attn needs block_attn=True (the op works on the paged cache)")
         self.config = config
         self.block_attn = bool(block_attn)
         self.block_size = int(block_size)
@@ -28,7 +31,7 @@ class LlamaForCausalLMInferenceModel(GenerationInferenceModel):
             embed_dim=c.hidden_size, num_heads=c.num_attention_heads, dim_feedforward=c.intermediate_size,
             kv_num_heads=c.num_key_value_heads, num_layers=c.num_hidden_layers, epsilon=c.rms_norm_eps,
             rope_theta=c.rope_theta, max_position_embeddings=max(int(getattr(c, "max_position_embeddings", 4096)), 128),
-            qkv_bias=(c.model_type == "qwen2"))
+            qkv_bias=(c.model_type == "qwen2"), append_attn=bool(append_attn))
         self.transformer_block = (FusedBlockMultiTransformer if self.block_attn else FusedMultiTransformerBase)(fcfg, device)
         self.device = self.transformer_block.device
         self.embed_tokens = torch.zeros(c.vocab_size, c.hidden_size, dtype=BF16, device=self.device)
