@@ -221,12 +221,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (is_leader && lane == 0) {
+    // The leader CTA's whole warp runs the (warp-uniform) loop, waits and descriptor arithmetic; one elected lane issues.  Inside
+    // `if (lane == 0)` the compiler rebuilds every descriptor in vector registers and moves it to the uniform registers UTCHMMA
+    // reads through ELECT / R2UR.BROADCAST sequences (~19 SASS instructions per MMA, measured on the attention kernels); here a
+    // stage's descriptors are built once and advanced by adding the k-step's byte offset >> 4.
+    if (is_leader) {
+      const bool leader = elect_one();
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, A_MN, B_MN);
       // K-major  : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.       K advance = 32 B
       // MN-major : 64-element chunks along M/N 8 KB apart (LBO), 8-k groups 1024 B.  K advance = 16 rows = 2 KB
       constexpr uint32_t a_lbo = A_MN ? 64 * BK * 2 : 16, a_adv = A_MN ? UK * 128 : UK * 2;
       constexpr uint32_t b_lbo = B_MN ? 64 * BK * 2 : 16, b_adv = B_MN ? UK * 128 : UK * 2;
+      const uint32_t smem_a0 = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -234,25 +241,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int t = pair_id; t < num_tiles; t += num_pairs) {
         mbar_wait(&tmem_empty[as], aphase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        const uint32_t tmem_d = tbase + static_cast<uint32_t>(as * BN);
         const int kb0 = (t % p.split_k) * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + C::A_BYTES;
+          const uint32_t sa = smem_a0 + stage * C::STAGE_BYTES;
+          const uint64_t da0 = umma_desc_sw128(sa, a_lbo, 1024);
+          const uint64_t db0 = umma_desc_sw128(sa + C::A_BYTES, b_lbo, 1024);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t da = umma_desc_sw128(sa + k * a_adv, a_lbo, 1024);
-            const uint64_t db = umma_desc_sw128(sb + k * b_adv, b_lbo, 1024);
-            umma_ss<CG>(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UK; ++k)
+              umma_ss<CG>(tmem_d, da0 + static_cast<uint64_t>((k * a_adv) >> 4), db0 + static_cast<uint64_t>((k * b_adv) >> 4), idesc,
+                          (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           }
-          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        if constexpr (CG == 2) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
+        if (leader) {
+          if constexpr (CG == 2) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
+        }
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
+      __syncwarp();
     }
   } else {
     // ===================================== epilogue =====================================
