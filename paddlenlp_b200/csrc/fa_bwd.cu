@@ -146,42 +146,54 @@ fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: convergent code, one elected lane issues, descriptors advanced by byte offsets >> 4 (see fa_bwd2.cu)
+    {
+      const bool leader = elect_one();
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t uS = tb, udP = tb + 128, udV = tb + 256, udK = tb + 384;
       constexpr uint32_t id_kk = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t id_mm = umma_idesc_bf16(128, 128, true, true);
       constexpr uint32_t id_km = umma_idesc_bf16(128, 128, false, true);
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO), aP = smem_u32(sP),
                      adS = smem_u32(sdS);
-      auto kmaj = [](uint32_t base, int kk) {   // K-major operand, k-step kk (16 elements of the contiguous dim)
-        return umma_desc_sw128(base + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
-      };
-      auto mnmaj = [](uint32_t base, int kk) {  // MN-major operand, k-step kk (16 rows of the tile)
-        return umma_desc_sw128(base + kk * 2048, HALF_BYTES, 1024);
-      };
+      // K-major operand (k-step = 16 of the contiguous dim) / MN-major operand (k-step = 16 rows = 2 KB) base descriptors
+      const uint64_t kQ = umma_desc_sw128(aQ, 16, 1024), kK = umma_desc_sw128(aK, 16, 1024), kdO = umma_desc_sw128(adO, 16, 1024),
+                     kV = umma_desc_sw128(aV, 16, 1024), kdS = umma_desc_sw128(adS, 16, 1024);
+      const uint64_t mP = umma_desc_sw128(aP, HALF_BYTES, 1024), mdO = umma_desc_sw128(adO, HALF_BYTES, 1024),
+                     mdS = umma_desc_sw128(adS, HALF_BYTES, 1024), mQ = umma_desc_sw128(aQ, HALF_BYTES, 1024),
+                     mK = umma_desc_sw128(aK, HALF_BYTES, 1024);
+      auto koff = [](int kk) { return static_cast<uint64_t>(((kk >> 2) * HALF_BYTES + (kk & 3) * 32) >> 4); };
+      auto moff = [](int kk) { return static_cast<uint64_t>(kk * 128); };
       mbar_wait(kv_full, 0);
       for (int n = 0; n < n_iter; ++n) {
         mbar_wait(qdo_full, n & 1);
         tc_fence_after();
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tS, kmaj(aQ, kk), kmaj(aK, kk), id_kk, kk > 0);      // S = Q K^T
+          for (int kk = 0; kk < 8; ++kk) umma_ss<1>(uS, kQ + koff(kk), kK + koff(kk), id_kk, kk > 0);      // S = Q K^T
+        }
         mbar_wait(dq_empty, (n & 1) ^ 1u);     // dP|dQ columns drained by the previous iteration's dQ read-out
         tc_fence_after();
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tdP, kmaj(adO, kk), kmaj(aV, kk), id_kk, kk > 0);    // dP = dO V^T
-        umma_commit(s_full);
+          for (int kk = 0; kk < 8; ++kk) umma_ss<1>(udP, kdO + koff(kk), kV + koff(kk), id_kk, kk > 0);    // dP = dO V^T
+          umma_commit(s_full);
+        }
         mbar_wait(pds_full, n & 1);
         tc_fence_after();
+        const uint32_t acc0 = n > 0 ? 1u : 0u;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)                                                                  // dV += P^T dO
-          umma_ss<1>(tdV, mnmaj(aP, kk), mnmaj(adO, kk), id_mm, (n > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk) umma_ss<1>(udV, mP + moff(kk), mdO + moff(kk), id_mm, kk > 0 ? 1u : acc0);   // dV += P^T dO
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)                                                                  // dK += dS^T Q
-          umma_ss<1>(tdK, mnmaj(adS, kk), mnmaj(aQ, kk), id_mm, (n > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(qdo_empty);                // Q / dO are not read by the dQ GEMM: the next tiles can be loaded now
+          for (int kk = 0; kk < 8; ++kk) umma_ss<1>(udK, mdS + moff(kk), mQ + moff(kk), id_mm, kk > 0 ? 1u : acc0);   // dK += dS^T Q
+          umma_commit(qdo_empty);                // Q / dO are not read by the dQ GEMM: the next tiles can be loaded now
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tdP, kmaj(adS, kk), mnmaj(aK, kk), id_km, kk > 0);    // dQ = dS K
-        umma_commit(dq_full);
+          for (int kk = 0; kk < 8; ++kk) umma_ss<1>(udP, kdS + koff(kk), mK + moff(kk), id_km, kk > 0);    // dQ = dS K
+          umma_commit(dq_full);
+        }
       }
+      __syncwarp();
     }
   } else {
     const int quad = warp & 3;                 // TMEM lane quadrant (warps w and w+4 share the rows of a quadrant)

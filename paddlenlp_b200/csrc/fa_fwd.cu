@@ -120,22 +120,27 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    // convergent code, one elected lane issues, descriptors advanced by adding byte offsets >> 4 (see fa_fwd2.cu: inside
+    // `if (lane == 0)` every UTCHMMA costs ~19 SASS instructions of descriptor rebuilding and R2UR traffic)
+    {
+      const bool leader = elect_one();
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t uS0 = tb, uO = tb + 256;
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);   // A=Q K-major, B=K K-major
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, false, true);    // A=P K-major, B=V MN-major
-      const uint32_t sQ_a = smem_u32(sQ), sP_a = smem_u32(sP);
+      const uint32_t sK_a0 = smem_u32(sK), sV_a0 = smem_u32(sV);
+      const uint64_t dQ = umma_desc_sw128(smem_u32(sQ), 16, 1024), dP = umma_desc_sw128(smem_u32(sP), 16, 1024);
+      auto koff = [](int kk) { return static_cast<uint64_t>(((kk >> 2) * HALF_BYTES + (kk & 3) * 32) >> 4); };
       auto issue_qk = [&](int j) {
         const int st = j & 1;
-        const uint32_t sK_a = smem_u32(sK + st * TILE_BYTES);
-        const uint32_t tS = tS0 + static_cast<uint32_t>((j & 1) * 128);
+        const uint64_t dK = umma_desc_sw128(sK_a0 + st * TILE_BYTES, 16, 1024);
+        const uint32_t tS = uS0 + static_cast<uint32_t>((j & 1) * 128);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;
-          umma_ss<1>(tS, umma_desc_sw128(sQ_a + off, 16, 1024), umma_desc_sw128(sK_a + off, 16, 1024), idesc_qk,
-                     kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk) umma_ss<1>(tS, dQ + koff(kk), dK + koff(kk), idesc_qk, kk > 0 ? 1u : 0u);
+          umma_commit(&k_empty[st]);
+          umma_commit(&s_full[j & 1]);
         }
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[j & 1]);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
@@ -154,17 +159,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mbar_wait(&v_full[st], (j >> 1) & 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t sV_a = smem_u32(sV + st * TILE_BYTES);
+        const uint64_t dV = umma_desc_sw128(sV_a0 + st * TILE_BYTES, HALF_BYTES, 1024);
+        const uint32_t acc0 = j > 0 ? 1u : 0u;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint32_t a_off = (kk >> 2) * HALF_BYTES + (kk & 3) * 32;   // P: kv along K (K-major)
-          const uint32_t b_off = kk * 16 * 128;                            // V: 16 kv rows = 2 KB (MN-major)
-          umma_ss<1>(tO, umma_desc_sw128(sP_a + a_off, 16, 1024), umma_desc_sw128(sV_a + b_off, HALF_BYTES, 1024),
-                     idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < BKV / 16; ++kk)     // P: kv along K (K-major);  V: 16 kv rows = 2 KB per k-step (MN-major)
+            umma_ss<1>(uO, dP + koff(kk), dV + static_cast<uint64_t>(kk * 128), idesc_pv, kk > 0 ? 1u : acc0);
+          umma_commit(&v_empty[st]);
+          umma_commit(pv_done);
         }
-        umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------- softmax / epilogue -------------------------------
