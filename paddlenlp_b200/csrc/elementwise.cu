@@ -86,13 +86,27 @@ __global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __re
 #pragma unroll
     for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(wi[j]); wf[2 * j] = f.x; wf[2 * j + 1] = f.y; }
   }
+  // software pipeline: the next row's x / dy / dres loads are in flight while this row's CTA-wide reduction (two barriers) runs
+  uint4 xv_n = make_uint4(0u, 0u, 0u, 0u), dv_n = xv_n, rv_n = xv_n;
+  float rs_n = 0.f;
+  auto issue = [&](int row) {
+    if (row < rows) {
+      rs_n = rstd[row];
+      if (active) {
+        xv_n = ld_nc_v4(reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * h) + t);
+        dv_n = ld_nc_v4(reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * h) + t);
+        if (dres != nullptr) rv_n = ld_nc_v4(reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * h) + t);
+      }
+    }
+  };
+  issue(blockIdx.x);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     float xh[8], g[8];
     float dot = 0.f;
-    const float rs = rstd[row];
+    const float rs = rs_n;
+    const uint4 xv = xv_n, dv = dv_n, rv = rv_n;
+    issue(row + gridDim.x);
     if (active) {
-      const uint4 xv = ld_nc_v4(reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * h) + t);
-      const uint4 dv = ld_nc_v4(reinterpret_cast<const uint4*>(dy + static_cast<size_t>(row) * h) + t);
       const uint32_t* xi = reinterpret_cast<const uint32_t*>(&xv);
       const uint32_t* di = reinterpret_cast<const uint32_t*>(&dv);
 #pragma unroll
@@ -119,7 +133,6 @@ __global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __re
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = rs * (g[j] - xh[j] * mean);
       if (dres != nullptr) {
-        const uint4 rv = ld_nc_v4(reinterpret_cast<const uint4*>(dres + static_cast<size_t>(row) * h) + t);
         const uint32_t* ri = reinterpret_cast<const uint32_t*>(&rv);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(ri[j]); r[2 * j] += f.x; r[2 * j + 1] += f.y; }

@@ -19,6 +19,8 @@
 //   Operand majors: both K-major (contraction dim contiguous) and MN-major operands are fed straight from their
 //   row-major global layout through TMA; no transposes are materialised.
 #include "../../include/b200nlp.h"
+#include <cstring>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -63,6 +65,8 @@ struct Params {
   int b_prefetch;          // PDL: issue the first stages' B (weight) loads before griddepcontrol.wait
   int l2_prefetch_kb;      // PDL: ... and L2-prefetch this many further B k-blocks of the CTA's first work item
   const float* bias;       // [N] fp32 or nullptr
+  const void* aux = nullptr;   // mode 5: the saved gate|up projection [M, 2I] bf16 (read with plain loads, one row per thread)
+  int64_t ld_aux = 0;      //         its leading dimension in elements
 };
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
@@ -131,6 +135,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // first column of this CTA's c-th 64-column chunk of the B tile (MN-major B).  Mode 4: chunk g of the 256-column tile is
+      // g = 0,1: gate channels [128 n_blk, +128), g = 2,3: the up columns of the same channels (at column I + ...), so the stored
+      // [h, 2I] weight needs no interleaved copy
+      auto b_col64 = [&](int n_blk, int c) {
+        if (p.epi_mode == 4) {
+          const int g = static_cast<int>(cta_rank) * (C::B_COLS / 64) + c;
+          return n_blk * 128 + (g & 1) * 64 + (g >> 1) * p.swiglu_inter;
+        }
+        return n_blk * BN + static_cast<int>(cta_rank) * C::B_COLS + c * 64;
+      };
       // With PDL (p.b_prefetch): the B operand (weights) of the first stages does not depend on the previous kernel, so
       // its TMA loads are issued before griddepcontrol.wait; the A loads (activations) follow after the wait.
       int prefetched = 0;
@@ -150,7 +164,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           };
           if constexpr (B_MN) {
 #pragma unroll
-            for (int c = 0; c < C::B_COLS / 64; ++c) load(&tmB, sb + c * (64 * BK * 2), n0 + c * 64, k0);
+            for (int c = 0; c < C::B_COLS / 64; ++c) load(&tmB, sb + c * (64 * BK * 2), b_col64(n_blk, c), k0);
           } else {
 #pragma unroll
             for (int c = 0; c < C::B_COLS / 128; ++c) load(&tmB, sb + c * (128 * BK * 2), k0, n0 + c * 128);
@@ -163,7 +177,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int k0 = (kb0 + s) * BK;
           if constexpr (B_MN) {
 #pragma unroll
-            for (int c = 0; c < C::B_COLS / 64; ++c) tma_prefetch_l2_2d(&tmB, n0 + c * 64, k0);
+            for (int c = 0; c < C::B_COLS / 64; ++c) tma_prefetch_l2_2d(&tmB, b_col64(n_blk, c), k0);
           } else {
 #pragma unroll
             for (int c = 0; c < C::B_COLS / 128; ++c) tma_prefetch_l2_2d(&tmB, k0, n0 + c * 128);
@@ -197,19 +211,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (!b_done) {
             if constexpr (B_MN) {
-              if (p.epi_mode == 4) {
-                // 64-column chunk g of the 256-column tile: chunks 0,1 = gate channels [128 n_blk, +128), chunks 2,3 = the up
-                // columns of the same channels (at column I + ...) — no interleaved weight layout needed
 #pragma unroll
-                for (int c = 0; c < C::B_COLS / 64; ++c) {
-                  const int g = static_cast<int>(cta_rank) * (C::B_COLS / 64) + c;
-                  const int col = n_blk * 128 + (g & 1) * 64 + (g >> 1) * p.swiglu_inter;
-                  load(&tmB, sb + c * (64 * BK * 2), col, k0);
-                }
-              } else {
-#pragma unroll
-                for (int c = 0; c < C::B_COLS / 64; ++c) load(&tmB, sb + c * (64 * BK * 2), n0 + c * 64, k0);
-              }
+              for (int c = 0; c < C::B_COLS / 64; ++c) load(&tmB, sb + c * (64 * BK * 2), b_col64(n_blk, c), k0);
             } else {
 #pragma unroll
               for (int c = 0; c < C::B_COLS / 128; ++c) load(&tmB, sb + c * (128 * BK * 2), k0, n0 + c * 128);
@@ -275,6 +278,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int as = 0;
     uint32_t aphase = 0;
     int buf = 0;
+    uint4 gpf[8], upf[8];                          // mode 5: the next slab's saved gate / up values of this thread's row
+    bool pf_valid = false;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) gpf[ch] = upf[ch] = make_uint4(0u, 0u, 0u, 0u);
     for (int t = pair_id; t < num_tiles; t += num_pairs) {
       int m_blk, n_blk;
       tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
@@ -304,6 +311,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (row0 < p.M) {
 #pragma unroll
             for (int which = 0; which < 3; ++which) {       // 0: gate -> C, 1: up -> C (+I), 2: m -> tmR's tensor
+              if (which < 2 && p.aux == nullptr) continue;  // inference: only m is wanted
               if (lane == 0) tma_store_wait_read<1>();
               __syncwarp();
               const uint32_t row_s = my_buf_s + buf * EPI_BUF_BYTES + lane * 128;
@@ -345,40 +353,53 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (p.epi_mode == 5) {
         // d(m) = dY W_down^T  ->  d(gate) = d(m) * up * silu'(gate),  d(up) = d(m) * silu(gate)     (swiglu backward, elementwise.cu)
-        // gate / up tiles come in through the two staging buffers (TMA loads), the results leave through the same buffers.
+        // One thread = one token row; a slab = 64 channels.  The saved gate / up values of a slab are 128 contiguous bytes per row
+        // each: they are fetched into REGISTERS one slab ahead (the first slab of the next tile while this tile's last slab is
+        // processed, i.e. also across the accumulator wait), so no load latency sits between tcgen05.ld and the TMA stores.
+        const uint8_t* gu_base = static_cast<const uint8_t*>(p.aux);
+        auto fetch = [&](int row, int c, uint4 (&g)[8], uint4 (&u)[8]) {
+          if (row < p.M && c < p.N) {
+            const uint8_t* gp = gu_base + (static_cast<int64_t>(row) * p.ld_aux + c) * 2;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              g[ch] = ld_nc_v4(gp + ch * 16);
+              u[ch] = ld_nc_v4(gp + static_cast<int64_t>(p.swiglu_inter) * 2 + ch * 16);
+            }
+          }
+        };
+        if (!pf_valid) { fetch(row0 + lane, col0, gpf, upf); pf_valid = true; }
 #pragma unroll 1
         for (int slab = 0; slab < BN / EPI_BOX_COLS; ++slab) {
           const int c0 = col0 + slab * EPI_BOX_COLS;
           const bool live = (row0 < p.M) && (c0 < p.N);
-          if (lane == 0) tma_store_wait_read<0>();          // both buffers are about to be overwritten by the loads
-          __syncwarp();
-          if (live && lane == 0) {
-            mbar_arrive_expect_tx(&epi_bar[q], 2 * EPI_BUF_BYTES);
-            tma_load_2d(&tmR, &epi_bar[q], my_buf, c0, row0);
-            tma_load_2d(&tmR, &epi_bar[q], my_buf + EPI_BUF_BYTES, c0 + p.swiglu_inter, row0);
-          }
           uint32_t v0[32], v1[32];
           tmem_ld32(taddr + slab * EPI_BOX_COLS, v0);
           tmem_ld32(taddr + slab * EPI_BOX_COLS + 32, v1);
           tmem_ld_wait();
+          uint4 gc[8], uc[8];
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) { gc[ch] = gpf[ch]; uc[ch] = upf[ch]; }
           if (slab == BN / EPI_BOX_COLS - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+            const int tn = t + num_pairs;                   // next tile of this CTA pair: its first slab
+            if (tn < num_tiles) {
+              int m2, n2;
+              tile_coords(tn / p.split_k, p.num_m_tiles, p.num_n_tiles, m2, n2);
+              fetch(m2 * (BM * CG) + static_cast<int>(cta_rank) * BM + q * 32 + lane, n2 * BN, gpf, upf);
+            }
+          } else {
+            fetch(row0 + lane, c0 + EPI_BOX_COLS, gpf, upf);
           }
           if (live) {
-            mbar_wait(&epi_bar[q], ephase);
-            ephase ^= 1u;
-            const uint32_t row_s = my_buf_s + lane * 128;
+            uint4 og[8], ou[8];
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
-              const uint32_t addr = row_s + ((ch ^ (lane & 7)) << 4);
-              const uint4 gq = ld_shared_v4(addr), uq = ld_shared_v4(addr + EPI_BUF_BYTES);
-              const uint32_t* gi = reinterpret_cast<const uint32_t*>(&gq);
-              const uint32_t* ui = reinterpret_cast<const uint32_t*>(&uq);
-              uint4 og, ou;
-              uint32_t* ogi = reinterpret_cast<uint32_t*>(&og);
-              uint32_t* oui = reinterpret_cast<uint32_t*>(&ou);
+              const uint32_t* gi = reinterpret_cast<const uint32_t*>(&gc[ch]);
+              const uint32_t* ui = reinterpret_cast<const uint32_t*>(&uc[ch]);
+              uint32_t* ogi = reinterpret_cast<uint32_t*>(&og[ch]);
+              uint32_t* oui = reinterpret_cast<uint32_t*>(&ou[ch]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int idx = ch * 8 + 2 * j;
@@ -392,15 +413,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 ogi[j] = pack_bf16x2(d0 * uf.x * ds0, d1 * uf.y * ds1);
                 oui[j] = pack_bf16x2(d0 * silu0, d1 * silu1);
               }
-              st_shared_v4(addr, og);
-              st_shared_v4(addr + EPI_BUF_BYTES, ou);
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmC, my_buf, c0, row0);
-              tma_store_2d(&tmC, my_buf + EPI_BUF_BYTES, c0 + p.swiglu_inter, row0);
-              tma_store_commit();
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {       // 0: d(gate) -> buffer 0, 1: d(up) -> buffer 1
+              if (lane == 0) tma_store_wait_read<1>();        // the store issued from THIS buffer one slab ago has read it
+              __syncwarp();
+              const uint32_t row_s = my_buf_s + which * EPI_BUF_BYTES + lane * 128;
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch) st_shared_v4(row_s + ((ch ^ (lane & 7)) << 4), which ? ou[ch] : og[ch]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmC, my_buf + which * EPI_BUF_BYTES, c0 + which * p.swiglu_inter, row0);
+                tma_store_commit();
+              }
             }
           }
         }
@@ -547,7 +573,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   Params pp = p;
   pp.b_prefetch = 0;
   pp.l2_prefetch_kb = 0;
-  if (pdl_enabled() && p.epi_mode != 4) {     // (the early weight prefetch does not know mode 4's column mapping)
+  if (pdl_enabled()) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
@@ -650,7 +676,7 @@ extern "C" int b200_gemm_swiglu_bf16(const void* X, const void* W, void* GU, voi
                                      int64_t ldx, int64_t ldw, int64_t ldgu, int64_t ldm, int cta_group, cudaStream_t stream) {
   using namespace b200;
   using namespace b200::gemm;
-  B200_CHECK_ARG(X && W && GU && Mout, "gemm_swiglu: null pointer");
+  B200_CHECK_ARG(X && W && Mout, "gemm_swiglu: null pointer");     // GU may be null: gate|up are then not written (inference)
   B200_CHECK_ARG(M > 0 && inter > 0 && K > 0 && inter % 128 == 0, "gemm_swiglu: intermediate size must be a multiple of 128 (got %lld)",
                  (long long)inter);
   B200_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0 && ldgu % 8 == 0 && ldm % 8 == 0, "gemm_swiglu: leading dimensions must be multiples of 8");
@@ -672,7 +698,11 @@ extern "C" int b200_gemm_swiglu_bf16(const void* X, const void* W, void* GU, voi
   {
     uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)}, strides[1] = {static_cast<uint64_t>(ldgu) * 2};
     uint32_t box[2] = {EPI_BOX_COLS, EPI_BOX_ROWS};
-    if ((rc = encode_tmap_bf16(&tmC, GU, 2, dims, strides, box)) != 0) return rc;
+    if (GU) {
+      if ((rc = encode_tmap_bf16(&tmC, GU, 2, dims, strides, box)) != 0) return rc;
+    } else {
+      memset(&tmC, 0, sizeof(tmC));
+    }
     dims[0] = static_cast<uint64_t>(inter);
     strides[0] = static_cast<uint64_t>(ldm) * 2;
     if ((rc = encode_tmap_bf16(&tmM, Mout, 2, dims, strides, box)) != 0) return rc;
@@ -684,6 +714,7 @@ extern "C" int b200_gemm_swiglu_bf16(const void* X, const void* W, void* GU, voi
   p.num_m_tiles = static_cast<int>((M + BM * cta_group - 1) / (BM * cta_group));
   p.num_n_tiles = static_cast<int>(inter / 128);
   p.epi_mode = 4;
+  p.aux = GU;
   p.split_k = 1;
   p.kb_per_split = static_cast<int>((K + BK - 1) / BK);
   p.bias = nullptr;
@@ -732,6 +763,8 @@ extern "C" int b200_gemm_swiglu_bwd_bf16(const void* dY, const void* Wdown, cons
   p.num_m_tiles = static_cast<int>((M + BM * cta_group - 1) / (BM * cta_group));
   p.num_n_tiles = static_cast<int>((inter + BN - 1) / BN);
   p.epi_mode = 5;
+  p.aux = GU;
+  p.ld_aux = ldgu;
   p.split_k = 1;
   p.kb_per_split = static_cast<int>((K + BK - 1) / BK);
   p.bias = nullptr;

@@ -12,6 +12,7 @@ Layer loop (:1126-1174): the output norm of layer i is fused with the residual a
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -80,6 +81,7 @@ class FusedMultiTransformerBase:
         self.ffn2_weights = [z(self.I, self.h) for _ in range(self.L)]
         self._bias_f32 = [None] * self.L
         self.fuse_ffn1_swiglu = False       # see the measurement note in forward()
+        self.ffn1_epilogue_swiglu = os.environ.get("B200_DECODE_FFN1_SWIGLU", "1") != "0"
         self._ffn1_il: List[Optional[torch.Tensor]] = [None] * self.L   # decode-step copy of ffn1_weight, columns interleaved per 64
         self.rope = ops.rope_tables(self.d, c.max_position_embeddings, float(c.rope_theta), self.device)
 
@@ -177,7 +179,11 @@ class FusedMultiTransformerBase:
                 # alternatives in the same chain (tools/decode_ablation.py, B200_FFN1=skinny|fused; profiles/
                 # r01_decode_ablation_ffn1_fused.log): swapped-operand kernel + swiglu_fwd_f32 — equal; ffn1 + SwiGLU fused in
                 # the swapped-operand epilogue (ops.gemm_swiglu_skinny) — 1.2 % SLOWER (scattered 2-byte stores in the tail)
-                if self.fuse_ffn1_swiglu and ln_out.shape[0] <= 64 and self.I % 64 == 0:
+                if self.ffn1_epilogue_swiglu and self.I % 128 == 0:
+                    # SwiGLU in the ffn1 epilogue of the persistent kernel: the 256-column tile pairs 128 gate columns with the
+                    # 128 up columns of the same channels straight from the reference-layout weight; only the activation is stored
+                    _, act = ops.gemm_swiglu(ln_out, self.ffn1_weights[i], cta_group=1, store_gate_up=False)
+                elif self.fuse_ffn1_swiglu and ln_out.shape[0] <= 64 and self.I % 64 == 0:
                     act = ops.gemm_swiglu_skinny(ln_out, self._ffn1_interleaved(i))
                 else:
                     ffn1 = self._mm(ln_out, self.ffn1_weights[i])

@@ -88,9 +88,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, *
 
 
 def gemm_swiglu(x: torch.Tensor, w_gate_up: torch.Tensor, gate_up: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None, cta_group: int = 2):
+                out: Optional[torch.Tensor] = None, cta_group: int = 2, store_gate_up: bool = True):
     """(gate_up [M, 2I], m [M, I]) = fused gate|up projection + SwiGLU (one tcgen05 GEMM; the epilogue holds gate and up of the
-    same channels).  w_gate_up is the reference-layout fused weight [K, 2I] (gate | up).  Requires I % 128 == 0."""
+    same channels).  w_gate_up is the reference-layout fused weight [K, 2I] (gate | up).  Requires I % 128 == 0.
+    store_gate_up=False (inference): only m is written and (None, m) is returned."""
     _chk(x, "x"); _chk(w_gate_up, "w_gate_up")
     assert x.dim() == 2 and w_gate_up.dim() == 2 and x.stride(1) == 1 and w_gate_up.stride(1) == 1
     M, K = x.shape
@@ -98,13 +99,13 @@ def gemm_swiglu(x: torch.Tensor, w_gate_up: torch.Tensor, gate_up: Optional[torc
     if K != Kw or two_i % 2:
         raise ValueError(f"gemm_swiglu: shapes {tuple(x.shape)} x {tuple(w_gate_up.shape)}")
     inter = two_i // 2
-    if gate_up is None:
+    if gate_up is None and store_gate_up:
         gate_up = torch.empty(M, two_i, dtype=BF16, device=x.device)
     if out is None:
         out = torch.empty(M, inter, dtype=BF16, device=x.device)
-    call("b200_gemm_swiglu_bf16", ptr(x), ptr(w_gate_up), ptr(gate_up), ptr(out), M, inter, K, x.stride(0), w_gate_up.stride(0),
-         gate_up.stride(0), out.stride(0), cta_group, stream_ptr())
-    return gate_up, out
+    call("b200_gemm_swiglu_bf16", ptr(x), ptr(w_gate_up), ptr(gate_up) if store_gate_up else 0, ptr(out), M, inter, K, x.stride(0),
+         w_gate_up.stride(0), gate_up.stride(0) if store_gate_up else two_i, out.stride(0), cta_group, stream_ptr())
+    return (gate_up if store_gate_up else None), out
 
 
 def gemm_swiglu_bwd(dy: torch.Tensor, w_down: torch.Tensor, gate_up: torch.Tensor, dgate_up: Optional[torch.Tensor] = None,
