@@ -48,6 +48,11 @@ int b200_set_fa_fwd_impl(int impl);
  * S^T double-buffered, P^T kept in tensor memory (csrc/fa_bwd2.cu); 1 = csrc/fa_bwd.cu (also every FlashMask call).
  * Environment override: B200_FA_BWD_IMPL. */
 int b200_set_fa_bwd_impl(int impl);
+/* Share of the forward softmax exponentials (generation-2 kernel) evaluated by a degree-3 polynomial on the FMA pipe instead of
+ * MUFU.EX2 (the MUFU's 16 ex2/clk/SM equals the tensor time of a kv step): 0 = none, 1 (default) = a quarter, 2 = half.
+ * Relative error of the polynomial 7.5e-5, below the bf16 rounding P receives.  Environment override: B200_FA_EXP_POLY.
+ * Returns the previous setting. */
+int b200_set_fa_exp_poly(int mode);
 /* Which kernel serves b200_gemm_bf16_splitk for M <= 128 with a row-major A (returns the previous setting; NOT an error
  * code): 1 (default) = the swapped-operand, two-CTA-per-SM weight-streaming kernel (csrc/gemm_skinny.cu), 2 = its stream-K
  * variant (M <= 64), 0 = the persistent 128x256 kernel in split-K mode.  Same results up to fp32 summation order; kept switchable

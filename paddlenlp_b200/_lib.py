@@ -27,6 +27,7 @@ _SIGNATURES = {
     "b200_set_skinny_gemm": [I],
     "b200_set_fa_fwd_impl": [I],
     "b200_set_fa_bwd_impl": [I],
+    "b200_set_fa_exp_poly": [I],
     "b200_gemm_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I, I, I, P],
     "b200_gemm_bf16_ex": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I, I, I, I, I, P],
     "b200_gemm_swiglu_bf16": [P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I, P],

@@ -49,6 +49,9 @@ int fa_fwd_impl() { return g_fa_fwd_impl; }
 // backward 2 = transposed tiles, software-pipelined (fa_bwd2.cu), 1 = fa_bwd.cu
 static int g_fa_bwd_impl = env_int("B200_FA_BWD_IMPL", 2);
 int fa_bwd_impl() { return g_fa_bwd_impl; }
+// share of the forward softmax exponentials evaluated by a polynomial on the FMA pipe (fa_fwd2.cu exp2_poly2): 0, 1 (1/4), 2 (1/2)
+static int g_fa_exp_poly = env_int("B200_FA_EXP_POLY", 1);
+int fa_exp_poly() { return g_fa_exp_poly; }
 
 int sm_count() {
   static int cached[64];
@@ -135,6 +138,12 @@ int b200_set_pdl(int enable) {
 int b200_set_fa_fwd_impl(int impl) {
   int old = b200::g_fa_fwd_impl;
   b200::g_fa_fwd_impl = impl == 1 ? 1 : 2;
+  return old;
+}
+
+int b200_set_fa_exp_poly(int mode) {
+  int old = b200::g_fa_exp_poly;
+  b200::g_fa_exp_poly = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
   return old;
 }
 

@@ -370,6 +370,54 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Packed fp32x2 arithmetic (FMUL2 / FADD2 / FFMA2: one issue slot for two IEEE round-to-nearest results, bit-identical to the
+// scalar .rn instructions and never re-associated or contracted by the compiler).
+struct f32x2 { float x, y; };
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}" : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}" : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+
+// SwiGLU backward for two adjacent channels (llama/modeling.py:632-652 swiglu, backward of silu(g) * u):
+//   sg = sigmoid(g) ; d(gate) = d * u * sg * (1 + g (1 - sg)) ; d(up) = d * g * sg          (fp32, results rounded once to bf16)
+// sigmoid = rcp.approx(1 + ex2.approx(-g log2 e)): two SFU operations (a few fp32 ulp, far inside the bf16 rounding of the
+// outputs) instead of an IEEE division.  The ONE definition used by b200_swiglu_bwd and by the GEMM epilogue that fuses it
+// (gemm_tcgen05.cu mode 5): the operation order is pinned by the packed instructions, so both produce the same bits.
+__device__ __forceinline__ void swiglu_bwd_pair(uint32_t g2, uint32_t u2, float d0, float d1, uint32_t& dg2, uint32_t& du2) {
+  const float2 gf = unpack_bf16x2(g2), uf = unpack_bf16x2(u2);
+  const f32x2 g{gf.x, gf.y}, u{uf.x, uf.y}, d{d0, d1}, one{1.f, 1.f};
+  const f32x2 t = f2_mul(g, f32x2{-1.4426950408889634f, -1.4426950408889634f});
+  const f32x2 a = f2_add(f32x2{fast_exp2(t.x), fast_exp2(t.y)}, one);
+  const f32x2 sg{fast_rcp(a.x), fast_rcp(a.y)};
+  const f32x2 silu = f2_mul(g, sg);
+  const f32x2 om = f2_fma(sg, f32x2{-1.f, -1.f}, one);           // 1 - sg
+  const f32x2 ds = f2_mul(sg, f2_fma(g, om, one));               // sg (1 + g (1 - sg))
+  const f32x2 dgv = f2_mul(f2_mul(d, u), ds);
+  const f32x2 duv = f2_mul(d, silu);
+  dg2 = pack_bf16x2(dgv.x, dgv.y);
+  du2 = pack_bf16x2(duv.x, duv.y);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128) rmsnorm_fwd_kernel(const bf16* __restrict
 // One CTA per row-slice, thread t owns columns [8t, 8t+8): the per-thread dw partial lives in 8 registers across
 // the CTA's rows; partials go to a [gridDim.x, h] fp32 workspace reduced by rmsnorm_dw_reduce_kernel.
 // ------------------------------------------------------------------------------------------------
-__global__ void rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(1024) rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                    const bf16* __restrict__ w, const float* __restrict__ rstd,
                                    const bf16* __restrict__ dres, bf16* __restrict__ dx,
                                    float* __restrict__ dw_partial, int rows, int h) {
@@ -323,14 +323,8 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __res
     uint32_t* oui = reinterpret_cast<uint32_t*>(&ou);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 gf = unpack_bf16x2(gi[j]);
-      const float2 uf = unpack_bf16x2(ui[j]);
       const float2 df = unpack_bf16x2(di[j]);
-      const float sg0 = 1.f / (1.f + __expf(-gf.x)), sg1 = 1.f / (1.f + __expf(-gf.y));
-      const float silu0 = gf.x * sg0, silu1 = gf.y * sg1;
-      const float ds0 = sg0 * (1.f + gf.x * (1.f - sg0)), ds1 = sg1 * (1.f + gf.y * (1.f - sg1));
-      ogi[j] = pack_bf16x2(df.x * uf.x * ds0, df.y * uf.y * ds1);
-      oui[j] = pack_bf16x2(df.x * silu0, df.y * silu1);
+      swiglu_bwd_pair(gi[j], ui[j], df.x, df.y, ogi[j], oui[j]);
     }
     uint4* orow = reinterpret_cast<uint4*>(dgu + r * 2 * inter);
     st_na_v4(orow + c, og);

@@ -232,26 +232,19 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint64_t dK_mn = umma_desc_sw128(aK, KV_HALF, 1024);                                      // K^T: MN-major over head_dim
       // byte offset of k-step kk (16 of the 128 head_dim columns) in a K-major tile stored as two 64-column halves
       auto koff = [](int kk, uint32_t half_bytes) { return static_cast<uint64_t>(((kk >> 2) * half_bytes + (kk & 3) * 32) >> 4); };
-      // Issue order.  Group g = n & 1 can start step n+2 once S^T(n+2) and dP^T(n+2) exist, and S^T(n+2) overwrites the columns
-      // P^T(n) is read from by dV(n).  So after P^T(n) / dS^T(n) arrive the order is dV(n), S^T(n+2), dP^T(n+2) and only then
-      // dK(n), dQ^T(n): the group's next step waits for 1024 tensor cycles instead of the 1920 of the natural order, and
-      // dK / dQ^T run while that group is already exponentiating.
-      auto issue_s = [&](int n) {
+      auto issue_st_dp = [&](int n, bool first_wait) {
         const int st = n % QST;
         mbar_wait(&qdo_full[st], static_cast<uint32_t>((n / QST) & 1));
         tc_fence_after();
         const uint64_t dQ_k = umma_desc_sw128(aQ0 + st * Q_TILE_BYTES, 16, 1024);
+        const uint64_t ddO_k = umma_desc_sw128(adO0 + st * Q_TILE_BYTES, 16, 1024);
         const uint32_t tS = uST + static_cast<uint32_t>((n & 1) * 64);
         if (leader) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) umma_ss<1>(tS, dK_k + koff(kk, KV_HALF), dQ_k + koff(kk, Q_HALF), id_st, kk > 0);   // S^T = K Q^T
           umma_commit(&s_full[n & 1]);
         }
-      };
-      auto issue_dp = [&](int n) {
-        const int st = n % QST;
-        const uint64_t ddO_k = umma_desc_sw128(adO0 + st * Q_TILE_BYTES, 16, 1024);
-        if (n > 0) {
+        if (first_wait) {
           mbar_wait(dp_free, static_cast<uint32_t>((n - 1) & 1));       // compute(n-1) holds dP^T(n-1) in registers
           tc_fence_after();
         }
@@ -262,11 +255,10 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       };
       mbar_wait(kv_full, 0);
-      issue_s(0);
-      issue_dp(0);
-      if (n_iter > 1) { issue_s(1); issue_dp(1); }
+      issue_st_dp(0, false);
       for (int n = 0; n < n_iter; ++n) {
         const int st = n % QST;
+        if (n + 1 < n_iter) issue_st_dp(n + 1, true);
         mbar_wait(&pds_full[n & 1], static_cast<uint32_t>((n >> 1) & 1));
         tc_fence_after();
         const uint64_t dQ_mn = umma_desc_sw128(aQ0 + st * Q_TILE_BYTES, Q_HALF, 1024);      // Q / dO as MN-major B (k-step = 16 rows = 2 KB)
@@ -278,9 +270,6 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)     // dV += P^T dO : K = 64 q;  A k-step = 8 TMEM columns, B k-step = 16 dO rows
             umma_ts(udV, tP + kk * 8, ddO_mn + static_cast<uint64_t>(kk * 128), id_dv, kk > 0 ? 1u : acc0);
-        }
-        if (n + 2 < n_iter) { issue_s(n + 2); issue_dp(n + 2); }
-        if (leader) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)     // dK += dS^T Q : A k-step = 32 bytes along the 128-byte q row, B k-step = 16 Q rows
             umma_ss<1>(udK, ddS_k + static_cast<uint64_t>(kk * 2), dQ_mn + static_cast<uint64_t>(kk * 128), id_dk, kk > 0 ? 1u : acc0);
@@ -294,7 +283,7 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)     // dQ^T = K^T dS^T : K = 128 kv;  A k-step = 16 K rows (2 KB), B k-step = 16 dS^T rows (2 KB)
             umma_ss<1>(udQ, dK_mn + static_cast<uint64_t>(kk * 128), ddS_k + static_cast<uint64_t>(kk * 128), id_dq, kk > 0);
-          umma_commit(&dq_full[n & 1]);      // also: dS^T(n) in smem buffer n & 1 is free (group n & 1 waits for it before step n+2's store)
+          umma_commit(&dq_full[n & 1]);
         }
       }
       if (leader) umma_commit(acc_full);
@@ -363,8 +352,6 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t(*a)[16] = reinterpret_cast<uint32_t(*)[16]>(pk);
         tmem_st16(tS, a[0]); tmem_st16(tS + 16, a[1]);   // P^T: 64 q as 32 packed columns over the start of S^T[g]
       }
-      // dS^T(n-2) of this group's buffer was last read by dQ^T(n-2), which (unlike in program order) may still be in flight
-      if (n >= 2) mbar_wait(&dq_full[g], static_cast<uint32_t>(((n - 2) >> 1) & 1));
       const uint32_t row_s = smem_u32(sdS + g * DS_BYTES) + r * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c)

@@ -24,6 +24,8 @@
 // Rounding points are those of fa_fwd.cu (and of the reference's flash path): S and the softmax in
 // fp32 with the scale applied to S, P rounded to bf16 before P@V, O accumulated in fp32 and rounded to bf16 once.
 // Replaces F.scaled_dot_product_attention(is_causal=True) (paddlenlp/transformers/llama/fusion_ops.py:240-246).
+#include <type_traits>
+
 #include "../../include/b200nlp.h"
 #include "common.cuh"
 #include "host_util.h"
@@ -55,6 +57,7 @@ struct Params {
   int max_blocks, block_size;
   bf16* out;          // [token_num, ldo]
   int64_t ldo;
+  int exp_poly;       // 0 / 1 / 2: none / a quarter / half of the exponentials on the FMA pipe (exp2_poly2)
 };
 
 // (x0, x1) = (a0, a1) * s + c    on the packed fp32x2 pipe
@@ -77,6 +80,39 @@ __device__ __forceinline__ void add2(float& acc0, float& acc1, float a0, float a
 }
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
+// 2^x for a pair of non-positive arguments on the FMA pipe instead of the MUFU (16 ex2/clk/SM: the 32768 exponentials of one kv
+// step of the two q tiles occupy it for 2048 cycles, exactly the tensor time of that step, so the softmax of a tile is
+// MUFU-paced).  x = xr + xf with xr = round(x) taken from the low mantissa bits of x + 1.5*2^23, 2^xf by a degree-3 minimax
+// polynomial on [-0.5, 0.5] (relative error 7.5e-5, far below the bf16 rounding P gets anyway), 2^xr by adding xr to the exponent
+// field.  Arguments are clamped at -125 so that the exponent add cannot wrap (2^-125 instead of 0 for masked / far-away scores).
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float& p1) {
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  uint32_t t0, t1, r0, r1;
+  asm("{\n\t.reg .b64 rx, rt, rr, rf, rp, rc;\n\t"
+      "mov.b64 rx, {%4, %5};\n\t"
+      "mov.b64 rc, {%6, %6};\n\t"
+      "add.rn.f32x2 rt, rx, rc;\n\t"          // t = x + 1.5 * 2^23
+      "mov.b64 {%2, %3}, rt;\n\t"
+      "mov.b64 rc, {%7, %7};\n\t"
+      "add.rn.f32x2 rr, rt, rc;\n\t"          // xr = t - 1.5 * 2^23 = round(x)
+      "mov.b64 rc, {%8, %8};\n\t"
+      "fma.rn.f32x2 rf, rr, rc, rx;\n\t"      // xf = x - xr
+      "mov.b64 rp, {%9, %9};\n\t"
+      "mov.b64 rc, {%10, %10};\n\t"
+      "fma.rn.f32x2 rp, rp, rf, rc;\n\t"      // c3 xf + c2
+      "mov.b64 rc, {%11, %11};\n\t"
+      "fma.rn.f32x2 rp, rp, rf, rc;\n\t"      // ... xf + c1
+      "mov.b64 rc, {%12, %12};\n\t"
+      "fma.rn.f32x2 rp, rp, rf, rc;\n\t"      // ... xf + c0
+      "mov.b64 {%0, %1}, rp;\n\t}"
+      : "=r"(r0), "=r"(r1), "=r"(t0), "=r"(t1)
+      : "f"(x0), "f"(x1), "f"(12582912.f), "f"(-12582912.f), "f"(-1.f), "f"(0.055171649903059006f), "f"(0.2426111251115799f),
+        "f"(0.6932609677314758f), "f"(0.9999280571937561f));
+  p0 = __uint_as_float(r0 + (t0 << 23));
+  p1 = __uint_as_float(r1 + (t1 << 23));
+}
+
 template <bool PAGED>
 // 10 warps = 3 on one SM sub-partition (16 K registers each): 16384 / (3 * 32) = 170 registers per thread is the hardware limit for this
 // block shape (a 200-register build fails to launch), which is what __launch_bounds__(320, 1) makes ptxas target
@@ -92,8 +128,8 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* kv_full = bars + 2;                // [NST]
   uint64_t* kv_empty = bars + 2 + NST;         // [NST]
   uint64_t* s_full = bars + 2 + 2 * NST;       // [2]  MMA -> softmax: S_t(j) complete (and every earlier MMA)
-  uint64_t* p_full = s_full + 2;               // [2]  softmax -> MMA: P_t(j) in TMEM, O_t rescaled
-  uint64_t* o_full = p_full + 2;               // [2]  MMA -> softmax: last PV of tile t complete
+  uint64_t* p_full = s_full + 2;               // [2][2] softmax -> MMA: half h (64 kv columns) of P_t(j) in TMEM, O_t rescaled
+  uint64_t* o_full = p_full + 4;               // [2]  MMA -> softmax: last PV of tile t complete
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,7 +164,8 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[2 * i], 128);
+      mbar_init(&p_full[2 * i + 1], 128);
       mbar_init(&o_full[i], 1);
     }
     for (int i = 0; i < NST; ++i) {
@@ -233,15 +270,23 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           umma_commit(&s_full[t]);
         }
       };
-      auto issue_pv = [&](int t, int j) {          // O_t (+)= P_t V_j ; P_t = packed bf16 in the first 64 columns of S_t
+      // O_t (+)= P_t V_j ; P_t = packed bf16 in the first 64 columns of S_t.  The softmax warps publish P in two halves of 64 kv
+      // columns: the first four k-steps run while the second half is still being exponentiated.
+      auto issue_pv = [&](int t, int j) {
         const uint64_t dV = umma_desc_sw128(sKV_a + ((2 * j + 1) % NST) * TILE_BYTES, HALF_BYTES, 1024);
         const uint32_t tP = tbase + static_cast<uint32_t>(t * 128);
         const uint32_t tO = tbase + 256u + static_cast<uint32_t>(t * 128);
         const uint32_t acc0 = j > 0 ? 1u : 0u;
-        if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < 128 / 16; ++kk)
-            umma_ts(tO, tP + kk * 8, dV + static_cast<uint64_t>(kk * 128), idesc_pv, kk > 0 ? 1u : acc0);
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&p_full[2 * t + h], j & 1);
+          if (h == 0) wait_kv(2 * j + 1);
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int kk = 4 * h; kk < 4 * h + 4; ++kk)
+              umma_ts(tO, tP + kk * 8, dV + static_cast<uint64_t>(kk * 128), idesc_pv, kk > 0 ? 1u : acc0);
+          }
         }
       };
       mbar_wait(&q_full[0], 0);
@@ -259,9 +304,6 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int t = 0; t < 2; ++t) {
           const int nt = t == 0 ? nA : nB;
           if (j < nt) {
-            mbar_wait(&p_full[t], j & 1);
-            wait_kv(2 * j + 1);
-            tc_fence_after();
             issue_pv(t, j);
             if (j + 1 < nt) {
               wait_kv(2 * j + 2);
@@ -334,36 +376,59 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         const bool rescale = __any_sync(0xffffffffu, need);
         const float neg_m = -m_used;
-        uint32_t pk[64];
+        // P over the first 64 columns of this row's S (every S value of the row is already in registers), published in two halves
+        // of 64 kv columns so that the first four PV k-steps run under the second half's exponentials
+        auto half = [&](auto mode_tag, auto half_tag, bool publish) {
+          constexpr int MODE = decltype(mode_tag)::value;   // share of the exponentials evaluated on the FMA pipe: 0, 1/4, 1/2
+          constexpr int H = decltype(half_tag)::value;
+          uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          float x0, x1;
-          fma2(x0, x1, __uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1]), p.scale_log2, neg_m);
-          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-          add2(l0, l1, p0, p1);
-          pk[c] = pack_bf16x2(p0, p1);
-        }
-        // P over the first 64 columns of this row's S (every S value of the row is already in registers)
-        {
-          uint32_t(*c)[32] = reinterpret_cast<uint32_t(*)[32]>(pk);
-          tmem_st32(tS, c[0]); tmem_st32(tS + 32, c[1]);
-        }
-        if (rescale) {
-          // s_full(j) tracks every MMA issued before QK_t(j), PV_t(j-1) included, and PV_t(j) waits for the arrive below:
-          // the O accumulator of this tile is quiescent here
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t o[32];
-            tmem_ld32(tO + ch * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
-            tmem_st32(tO + ch * 32, o);
+          for (int c = 0; c < 32; ++c) {
+            float x0, x1, p0, p1;
+            fma2(x0, x1, __uint_as_float(sv[64 * H + 2 * c]), __uint_as_float(sv[64 * H + 2 * c + 1]), p.scale_log2, neg_m);
+            if ((MODE == 1 && (c & 3) == 3) || (MODE == 2 && (c & 1) == 1)) {
+              exp2_poly2(x0, x1, p0, p1);
+            } else {
+              p0 = fast_exp2(x0); p1 = fast_exp2(x1);
+            }
+            add2(l0, l1, p0, p1);
+            pk[c] = pack_bf16x2(p0, p1);
           }
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[t]);
+          tmem_st32(tS + 32 * H, pk);
+          if (publish) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_full[2 * t + H]);
+          }
+        };
+        auto both = [&](auto mode_tag) {
+          if (!rescale) {
+            half(mode_tag, std::integral_constant<int, 0>{}, true);
+            half(mode_tag, std::integral_constant<int, 1>{}, true);
+          } else {
+            // (rare: the row max of some row grew by more than 2^8)  O must be rescaled before ANY PV k-step of this kv tile:
+            // both halves of P first (the scores leave the registers), then O, then both halves are published together.
+            // s_full(j) tracks every MMA issued before QK_t(j), PV_t(j-1) included: the O accumulator of this tile is quiescent
+            half(mode_tag, std::integral_constant<int, 0>{}, false);
+            half(mode_tag, std::integral_constant<int, 1>{}, false);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t o[32];
+              tmem_ld32(tO + ch * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
+              tmem_st32(tO + ch * 32, o);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_full[2 * t]);
+            mbar_arrive(&p_full[2 * t + 1]);
+          }
+        };
+        if (p.exp_poly == 2) both(std::integral_constant<int, 2>{});
+        else if (p.exp_poly == 1) both(std::integral_constant<int, 1>{});
+        else both(std::integral_constant<int, 0>{});
       }
       // epilogue: O / l -> bf16 -> swizzled smem (this tile's Q buffer) -> TMA store ; LSE
       const float l = l0 + l1;
@@ -468,6 +533,7 @@ int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* 
   dim3 grid(static_cast<unsigned>((S + 255) / 256), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
   p.cu_q = p.seq_dec = p.seq_this = p.seq_enc = p.block_tables = nullptr;
   p.max_blocks = p.block_size = 0; p.out = nullptr; p.ldo = 0;
+  p.exp_poly = fa_exp_poly();
   fa_fwd2_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   return check_launch("fa_fwd2");
 }
@@ -515,6 +581,7 @@ int launch_fa_prefill_paged(const void* qkv, const void* key_cache, const void* 
   p.block_tables = block_tables;
   p.max_blocks = static_cast<int>(max_blocks_per_seq); p.block_size = static_cast<int>(block_size);
   p.out = static_cast<bf16*>(out); p.ldo = ldo;
+  p.exp_poly = fa_exp_poly();
   dim3 grid(static_cast<unsigned>((max_q_len + 255) / 256), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
   fa_fwd2_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmQ, p);
   return check_launch("fa_prefill_paged");

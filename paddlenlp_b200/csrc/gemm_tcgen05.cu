@@ -191,6 +191,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb0 = (t % p.split_k) * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         const int m0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM;   // this CTA's A rows
         const int n0 = n_blk * BN + static_cast<int>(cta_rank) * C::B_COLS;   // this CTA's B columns
+        if (p.epi_mode == 5) {
+          // the saved gate / up values this tile's epilogue will read (one mainloop from now): pull them into L2 so that the
+          // epilogue's row-wise loads do not pay a DRAM round trip each while the operand stream keeps HBM busy
+#pragma unroll 1
+          for (int r = 0; r < BM && m0 + r < p.M; r += EPI_BOX_ROWS) {
+#pragma unroll
+            for (int c = 0; c < BN; c += EPI_BOX_COLS) {
+              if (n_blk * BN + c < p.N) {
+                tma_prefetch_l2_2d(&tmR, n_blk * BN + c, m0 + r);
+                tma_prefetch_l2_2d(&tmR, n_blk * BN + c + p.swiglu_inter, m0 + r);
+              }
+            }
+          }
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const bool b_done = (t == pair_id) && (kb - kb0 < prefetched);     // B tile (and expect_tx) already issued
           if (!b_done) mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -403,15 +417,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int idx = ch * 8 + 2 * j;
-                const float d0 = bf16_round(__uint_as_float(idx < 32 ? v0[idx] : v1[idx - 32]));          // d(m): the GEMM's own
-                const float d1 = bf16_round(__uint_as_float(idx + 1 < 32 ? v0[idx + 1] : v1[idx + 1 - 32]));  // bf16 output rounding
-                const float2 gf = unpack_bf16x2(gi[j]);
-                const float2 uf = unpack_bf16x2(ui[j]);
-                const float sg0 = 1.f / (1.f + __expf(-gf.x)), sg1 = 1.f / (1.f + __expf(-gf.y));
-                const float silu0 = gf.x * sg0, silu1 = gf.y * sg1;
-                const float ds0 = sg0 * (1.f + gf.x * (1.f - sg0)), ds1 = sg1 * (1.f + gf.y * (1.f - sg1));
-                ogi[j] = pack_bf16x2(d0 * uf.x * ds0, d1 * uf.y * ds1);
-                oui[j] = pack_bf16x2(d0 * silu0, d1 * silu1);
+                // d(m) with the GEMM's own bf16 output rounding (one packed convert + unpack per pair)
+                const float2 dr = unpack_bf16x2(pack_bf16x2(__uint_as_float(idx < 32 ? v0[idx] : v1[idx - 32]),
+                                                            __uint_as_float(idx + 1 < 32 ? v0[idx + 1] : v1[idx + 1 - 32])));
+                swiglu_bwd_pair(gi[j], ui[j], dr.x, dr.y, ogi[j], oui[j]);
               }
             }
 #pragma unroll

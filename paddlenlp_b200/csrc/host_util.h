@@ -21,6 +21,7 @@ int fa_fwd_impl();         // b200_set_fa_fwd_impl(): 2 = two-q-tile kernel (fa_
 int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* lse, int64_t B, int64_t S, int64_t num_heads,
                    int64_t num_kv_heads, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float softmax_scale,
                    cudaStream_t stream);
+int fa_exp_poly();        // b200_set_fa_exp_poly(): 0 / 1 / 2 = none / a quarter / half of the forward exponentials on the FMA pipe
 int fa_bwd_impl();         // b200_set_fa_bwd_impl(): 2 = transposed pipelined kernel (fa_bwd2.cu, plain causal), 1 = fa_bwd.cu
 // fa_bwd2.cu: plain-causal backward (same argument meaning as b200_fa_bwd)
 int launch_fa_bwd2(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq,

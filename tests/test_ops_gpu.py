@@ -82,8 +82,8 @@ def test_gemm_residual_epilogue():
     assert mism < 0.02 and maxerr(out, ref) < 2 ** -7           # only fp32 accumulation-order ties may differ
 
 
+@pytest.mark.parametrize("cg", [2, 1])
 @pytest.mark.parametrize("M,inter,K", [(520, 384, 328), (8192, 14336, 4096), (300, 128, 64), (64, 14336, 4096)])
-@pytest.mark.parametrize("M,inter,K", [(520, 384, 328), (8192, 14336, 4096), (300, 128, 64)])
 def test_gemm_swiglu_fused_epilogue(M, inter, K, cg):
     """gate|up projection + SwiGLU in one tcgen05 GEMM (tile = 128 gate columns | the 128 up columns of the same channels) is
     bit-identical to GEMM followed by the SwiGLU kernel: same accumulation order per element, same rounding points."""
