@@ -83,7 +83,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
-                       const uint64_t* strides, const uint32_t* box);
+                       const uint64_t* strides, const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                      const uint32_t* box) {
@@ -93,9 +93,13 @@ int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t
                     const uint32_t* box) {
   return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides, box);
 }
+int encode_tmap_bf16_linear(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                            const uint32_t* box) {
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
 
 static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
-                       const uint64_t* strides, const uint32_t* box) {
+                       const uint64_t* strides, const uint32_t* box, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail_arg("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -112,7 +116,7 @@ static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* 
   for (int i = 0; i < rank - 1; ++i)
     if (gstr[i] % 16 != 0) return fail_arg("tensor map stride %llu not a multiple of 16 bytes", (unsigned long long)gstr[i]);
   CUresult r = fn(out, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
-                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail_arg("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu] box=[%u,%u]", (int)r, rank,

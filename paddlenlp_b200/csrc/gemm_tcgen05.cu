@@ -46,7 +46,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (CG == 2) ? 6 : 4;
   static constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;  // 32 KB
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
@@ -96,7 +96,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * C::STAGES;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint64_t* epi_bar = tmem_empty + 2;              // [EPI_WARPS]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_bar + EPI_WARPS);
+  uint64_t* epi_ld_bar = epi_bar + EPI_WARPS;      // [EPI_WARPS][4]  mode 5: gate|up slab loads of each epilogue warp
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_ld_bar + 4 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,6 +123,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_empty[i], CG * EPI_WARPS);
     }
     for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&epi_bar[i], 1);
+    for (int i = 0; i < 4 * EPI_WARPS; ++i) mbar_init(&epi_ld_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<CG>(tmem_ptr_smem, TMEM_COLS);
@@ -191,20 +193,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb0 = (t % p.split_k) * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         const int m0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM;   // this CTA's A rows
         const int n0 = n_blk * BN + static_cast<int>(cta_rank) * C::B_COLS;   // this CTA's B columns
-        if (p.epi_mode == 5) {
-          // the saved gate / up values this tile's epilogue will read (one mainloop from now): pull them into L2 so that the
-          // epilogue's row-wise loads do not pay a DRAM round trip each while the operand stream keeps HBM busy
-#pragma unroll 1
-          for (int r = 0; r < BM && m0 + r < p.M; r += EPI_BOX_ROWS) {
-#pragma unroll
-            for (int c = 0; c < BN; c += EPI_BOX_COLS) {
-              if (n_blk * BN + c < p.N) {
-                tma_prefetch_l2_2d(&tmR, n_blk * BN + c, m0 + r);
-                tma_prefetch_l2_2d(&tmR, n_blk * BN + c + p.swiglu_inter, m0 + r);
-              }
-            }
-          }
-        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const bool b_done = (t == pair_id) && (kb - kb0 < prefetched);     // B tile (and expect_tx) already issued
           if (!b_done) mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -292,10 +280,91 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int as = 0;
     uint32_t aphase = 0;
     int buf = 0;
-    uint4 gpf[8], upf[8];                          // mode 5: the next slab's saved gate / up values of this thread's row
-    bool pf_valid = false;
+    if (p.epi_mode == 5) {
+      // ---- down-proj dX GEMM + SwiGLU backward (llama/modeling.py:632-652) ----
+      // acc = d(m) tile;  d(gate) = d(m) * up * silu'(gate),  d(up) = d(m) * silu(gate)   (swiglu_bwd_pair, common.cuh)
+      // One thread = one token row; a slab = 16 channels.  The saved gate / up values of a slab come in by TMA (boxes of 32 rows
+      // x 32 bytes, no swizzle) into one of FOUR 2 KB buffer pairs of this warp, two slabs ahead of their use and across tile
+      // boundaries; the results overwrite them in place and leave by TMA store.  Nothing in this loop waits for a memory round
+      // trip: the load of slab g+2 is issued when the store of slab g-2 has released its pair (one slab old).  (Earlier versions —
+      // TMA load and use in the same slab, then per-thread 128-byte global loads one slab ahead — left the epilogue slower than the
+      // 256x256x4096 mainloop it has to hide under: profiles/r02_swiglu_bwd_epilogue.md.)
+      constexpr int SL = 16, NSL = BN / SL, SLAB_BYTES = EPI_BOX_ROWS * SL * 2;     // 1 KB per operand and slab
+      uint64_t* ld_bar = epi_ld_bar + q * 4;
+      int it_t = pair_id, it_s = 0;                  // next slab to request
+      uint32_t n_issued = 0, n_done = 0;
+      auto issue_next = [&]() {
+        int m2 = 0, n2 = 0, c0 = 0;
+        while (it_t < num_tiles) {
+          tile_coords(it_t / p.split_k, p.num_m_tiles, p.num_n_tiles, m2, n2);
+          c0 = n2 * BN + it_s * SL;
+          if (c0 < p.N) break;
+          it_s = 0;                                  // N % 64 == 0: the dead slabs of a tile are its tail
+          it_t += num_pairs;
+        }
+        if (it_t >= num_tiles) return;
+        const uint32_t pr = n_issued & 3u;
+        if (lane == 0) {
+          const int r0 = m2 * (BM * CG) + static_cast<int>(cta_rank) * BM + q * 32;   // fully out-of-range boxes read zeros
+          mbar_arrive_expect_tx(&ld_bar[pr], 2 * SLAB_BYTES);
+          tma_load_2d(&tmR, &ld_bar[pr], my_buf + pr * 2 * SLAB_BYTES, c0, r0);
+          tma_load_2d(&tmR, &ld_bar[pr], my_buf + pr * 2 * SLAB_BYTES + SLAB_BYTES, c0 + p.swiglu_inter, r0);
+        }
+        ++n_issued;
+        if (++it_s == NSL) { it_s = 0; it_t += num_pairs; }
+      };
+      issue_next();
+      issue_next();
+      for (int t = pair_id; t < num_tiles; t += num_pairs) {
+        int m_blk, n_blk;
+        tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
+        const int row0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM + q * 32;
+        const int col0 = n_blk * BN;
+        const int n_live = min(NSL, (p.N - col0) / SL);
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+        for (int sl = 0; sl < n_live; ++sl) {
+          const int c0 = col0 + sl * SL;
+          if (lane == 0) tma_store_wait_read<1>();   // every store but the previous slab's has read its pair: slab n_done-2's is free
+          __syncwarp();
+          issue_next();
+          uint32_t v[16];
+          tmem_ld16(taddr + sl * SL, v);
+          tmem_ld_wait();
+          if (sl == n_live - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+          }
+          const uint32_t pr = n_done & 3u;
+          mbar_wait(&ld_bar[pr], (n_done >> 2) & 1u);
+          const uint32_t ga = my_buf_s + pr * 2 * SLAB_BYTES + lane * (SL * 2), ua = ga + SLAB_BYTES;
+          uint4 gv[2], uv[2], og[2], ou[2];
+          gv[0] = ld_shared_v4(ga); gv[1] = ld_shared_v4(ga + 16);
+          uv[0] = ld_shared_v4(ua); uv[1] = ld_shared_v4(ua + 16);
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) gpf[ch] = upf[ch] = make_uint4(0u, 0u, 0u, 0u);
+          for (int j = 0; j < 8; ++j) {
+            // d(m) with the GEMM's own bf16 output rounding (one packed convert + unpack per pair)
+            const float2 dr = unpack_bf16x2(pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
+            swiglu_bwd_pair(reinterpret_cast<const uint32_t*>(&gv[j >> 2])[j & 3], reinterpret_cast<const uint32_t*>(&uv[j >> 2])[j & 3],
+                            dr.x, dr.y, reinterpret_cast<uint32_t*>(&og[j >> 2])[j & 3], reinterpret_cast<uint32_t*>(&ou[j >> 2])[j & 3]);
+          }
+          st_shared_v4(ga, og[0]); st_shared_v4(ga + 16, og[1]);
+          st_shared_v4(ua, ou[0]); st_shared_v4(ua + 16, ou[1]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, my_buf + pr * 2 * SLAB_BYTES, c0, row0);
+            tma_store_2d(&tmC, my_buf + pr * 2 * SLAB_BYTES + SLAB_BYTES, c0 + p.swiglu_inter, row0);
+            tma_store_commit();
+          }
+          ++n_done;
+        }
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    } else
     for (int t = pair_id; t < num_tiles; t += num_pairs) {
       int m_blk, n_blk;
       tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
@@ -359,83 +428,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_store_commit();
               }
               buf ^= 1;
-            }
-          }
-        }
-        if (++as == 2) { as = 0; aphase ^= 1u; }
-        continue;
-      }
-      if (p.epi_mode == 5) {
-        // d(m) = dY W_down^T  ->  d(gate) = d(m) * up * silu'(gate),  d(up) = d(m) * silu(gate)     (swiglu backward, elementwise.cu)
-        // One thread = one token row; a slab = 64 channels.  The saved gate / up values of a slab are 128 contiguous bytes per row
-        // each: they are fetched into REGISTERS one slab ahead (the first slab of the next tile while this tile's last slab is
-        // processed, i.e. also across the accumulator wait), so no load latency sits between tcgen05.ld and the TMA stores.
-        const uint8_t* gu_base = static_cast<const uint8_t*>(p.aux);
-        auto fetch = [&](int row, int c, uint4 (&g)[8], uint4 (&u)[8]) {
-          if (row < p.M && c < p.N) {
-            const uint8_t* gp = gu_base + (static_cast<int64_t>(row) * p.ld_aux + c) * 2;
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              g[ch] = ld_nc_v4(gp + ch * 16);
-              u[ch] = ld_nc_v4(gp + static_cast<int64_t>(p.swiglu_inter) * 2 + ch * 16);
-            }
-          }
-        };
-        if (!pf_valid) { fetch(row0 + lane, col0, gpf, upf); pf_valid = true; }
-#pragma unroll 1
-        for (int slab = 0; slab < BN / EPI_BOX_COLS; ++slab) {
-          const int c0 = col0 + slab * EPI_BOX_COLS;
-          const bool live = (row0 < p.M) && (c0 < p.N);
-          uint32_t v0[32], v1[32];
-          tmem_ld32(taddr + slab * EPI_BOX_COLS, v0);
-          tmem_ld32(taddr + slab * EPI_BOX_COLS + 32, v1);
-          tmem_ld_wait();
-          uint4 gc[8], uc[8];
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) { gc[ch] = gpf[ch]; uc[ch] = upf[ch]; }
-          if (slab == BN / EPI_BOX_COLS - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
-            const int tn = t + num_pairs;                   // next tile of this CTA pair: its first slab
-            if (tn < num_tiles) {
-              int m2, n2;
-              tile_coords(tn / p.split_k, p.num_m_tiles, p.num_n_tiles, m2, n2);
-              fetch(m2 * (BM * CG) + static_cast<int>(cta_rank) * BM + q * 32 + lane, n2 * BN, gpf, upf);
-            }
-          } else {
-            fetch(row0 + lane, c0 + EPI_BOX_COLS, gpf, upf);
-          }
-          if (live) {
-            uint4 og[8], ou[8];
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              const uint32_t* gi = reinterpret_cast<const uint32_t*>(&gc[ch]);
-              const uint32_t* ui = reinterpret_cast<const uint32_t*>(&uc[ch]);
-              uint32_t* ogi = reinterpret_cast<uint32_t*>(&og[ch]);
-              uint32_t* oui = reinterpret_cast<uint32_t*>(&ou[ch]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int idx = ch * 8 + 2 * j;
-                // d(m) with the GEMM's own bf16 output rounding (one packed convert + unpack per pair)
-                const float2 dr = unpack_bf16x2(pack_bf16x2(__uint_as_float(idx < 32 ? v0[idx] : v1[idx - 32]),
-                                                            __uint_as_float(idx + 1 < 32 ? v0[idx + 1] : v1[idx + 1 - 32])));
-                swiglu_bwd_pair(gi[j], ui[j], dr.x, dr.y, ogi[j], oui[j]);
-              }
-            }
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {       // 0: d(gate) -> buffer 0, 1: d(up) -> buffer 1
-              if (lane == 0) tma_store_wait_read<1>();        // the store issued from THIS buffer one slab ago has read it
-              __syncwarp();
-              const uint32_t row_s = my_buf_s + which * EPI_BUF_BYTES + lane * 128;
-#pragma unroll
-              for (int ch = 0; ch < 8; ++ch) st_shared_v4(row_s + ((ch ^ (lane & 7)) << 4), which ? ou[ch] : og[ch]);
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(&tmC, my_buf + which * EPI_BUF_BYTES, c0 + which * p.swiglu_inter, row0);
-                tma_store_commit();
-              }
             }
           }
         }
@@ -760,10 +752,10 @@ extern "C" int b200_gemm_swiglu_bwd_bf16(const void* dY, const void* Wdown, cons
   }
   {
     uint64_t dims[2] = {static_cast<uint64_t>(2 * inter), static_cast<uint64_t>(M)}, strides[1] = {static_cast<uint64_t>(lddgu) * 2};
-    uint32_t box[2] = {EPI_BOX_COLS, EPI_BOX_ROWS};
-    if ((rc = encode_tmap_bf16(&tmC, DGU, 2, dims, strides, box)) != 0) return rc;
+    uint32_t box[2] = {16, EPI_BOX_ROWS};            // the mode-5 epilogue works on slabs of 16 channels: 32 rows x 32 bytes, unswizzled
+    if ((rc = encode_tmap_bf16_linear(&tmC, DGU, 2, dims, strides, box)) != 0) return rc;
     strides[0] = static_cast<uint64_t>(ldgu) * 2;
-    if ((rc = encode_tmap_bf16(&tmG, GU, 2, dims, strides, box)) != 0) return rc;
+    if ((rc = encode_tmap_bf16_linear(&tmG, GU, 2, dims, strides, box)) != 0) return rc;
   }
   Params p;
   p.M = static_cast<int>(M);
