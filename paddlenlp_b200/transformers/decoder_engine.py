@@ -61,10 +61,10 @@ class DecoderEngine:
         # SwiGLU fused into the gate|up GEMM epilogue (needs 128-channel tiles); B200_FUSE_SWIGLU=0 selects GEMM + swiglu kernel
         import os as _os
         self.fuse_swiglu = (self.I % 128 == 0) and _os.environ.get("B200_FUSE_SWIGLU", "1") != "0"
-        # the backward twin (SwiGLU backward in the down-proj dX epilogue) is bit-identical but measured SLOWER in the step than
-        # GEMM + swiglu_bwd kernel (0.997 vs 0.718 + 0.24 ms per layer micro-batch, profiles/r02_bench_swiglu_fusion.md: the
-        # epilogue waits for its gate|up tile loads slab by slab): opt-in only
-        self.fuse_swiglu_bwd = (self.I % 64 == 0) and _os.environ.get("B200_FUSE_SWIGLU_BWD", "0") == "1"
+        # the backward twin: SwiGLU backward in the down-proj dX epilogue (bit-identical to GEMM + swiglu_bwd kernel).  The epilogue
+        # streams the saved gate|up tile through a 4-deep TMA pipeline of 16-channel slabs: 0.70 ms against 0.61 ms for the bare GEMM
+        # and 0.88 ms for GEMM + kernel (tools/epilogue_bench.py, profiles/r02_swiglu_bwd_epilogue.md).  B200_FUSE_SWIGLU_BWD=0 unfuses
+        self.fuse_swiglu_bwd = (self.I % 64 == 0) and _os.environ.get("B200_FUSE_SWIGLU_BWD", "1") != "0"
         # recompute (llama/modeling.py:1706-1733 `recompute_training_full`): keep only each layer's input and re-run the
         # layer forward inside backward.  Only the "full" granularity exists here (the "full_attn" / "core_attn" splits
         # exist to trade memory against the reference's unfused attention; the fused attention keeps no S x S tensor).
