@@ -369,8 +369,8 @@ extern "C" int b200_fa_bwd_flashmask(const void* q, const void* k, const void* v
   B200_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 &&
                      lddk % 8 == 0 && lddv % 8 == 0,
                  "fa_bwd: token strides must be multiples of 8");
-  if (mask_start_rows == nullptr && fa_bwd_impl() == 2)    // plain causal: transposed, software-pipelined kernel (fa_bwd2.cu)
-    return launch_fa_bwd2(q, k, v, o, dout, lse, dq, dk, dv, workspace, B, S, num_heads, num_kv_heads, ldq, ldk, ldv, ldo, lddo,
+  if (fa_bwd_impl() == 2)    // transposed, software-pipelined kernel (fa_bwd2.cu); plain causal or FlashMask start rows
+    return launch_fa_bwd2(q, k, v, o, dout, lse, mask_start_rows, dq, dk, dv, workspace, B, S, num_heads, num_kv_heads, ldq, ldk, ldv, ldo, lddo,
                           lddq, lddk, lddv, softmax_scale, stream);
   float* dq_acc = static_cast<float*>(workspace);
   float* dk_acc = dq_acc + B * S * num_heads * 128;

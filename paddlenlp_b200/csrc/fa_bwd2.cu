@@ -50,6 +50,10 @@ struct Params {
   float scale, scale_log2;
   const float2* stats;   // [B, nh, Spad] x 2 floats: -lse*log2e ("nl") and -delta*scale ("nd"), stored per 64-row block as
                          // (nl(2c), nl(2c+1), nd(2c), nd(2c+1)) for c = 0..31; padding rows hold (-inf, 0)
+  // FlashMask, causal lower-triangular form (see fa_fwd.cu): mask_start[b, c] = first query row that may NOT see key column c,
+  // non-decreasing in c and > c; nullptr = plain causal.  Here a compute thread owns one kv ROW of the transposed tiles, i.e. one
+  // key column c: its start row is a per-thread scalar, and the mask is one more comparison in the steps that need it.
+  const int* mask_start;
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -153,7 +157,15 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int hq = blockIdx.y, batch = blockIdx.z;
   const int kv_head = hq / (p.nh / p.kvh);
   const int kv0 = jt * 128;
-  const int n_iter = (p.S - kv0 + 63) / 64;        // 64-row q sub-tiles kv0, kv0+64, ... (q >= kv0: causal)
+  // 64-row q sub-tiles kv0, kv0+64, ... (q >= kv0: causal).  With a document mask the steps past the end of the document(s) of
+  // this kv tile are skipped: the last column has the largest start row (non-decreasing), no column is seen from that row on.
+  int q_end = p.S, start_min = 0x7fffffff;
+  if (p.mask_start != nullptr) {
+    const int* ms = p.mask_start + static_cast<size_t>(batch) * p.S;
+    q_end = min(p.S, __ldg(ms + min(kv0 + 127, p.S - 1)));
+    start_min = __ldg(ms + kv0);                   // the first column's document ends first: steps below it need no mask
+  }
+  const int n_iter = max(1, (q_end - kv0 + 63) / 64);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
@@ -296,6 +308,10 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int r = quad * 32 + lane;                      // kv row within the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     uint8_t* my_stage = sStage + (warp - 2) * 4096;
+    // q rows (relative to kv0) this thread's key column is visible to: [r, vis_end)
+    int vis_end = 0x7fffffff;
+    if (p.mask_start != nullptr && kv0 + r < p.S)
+      vis_end = __ldg(p.mask_start + static_cast<size_t>(batch) * p.S + kv0 + r) - kv0;
     auto read_out_dq = [&](int n) {                      // dQ^T(n): lanes = d, columns = 64 q rows of step n
       mbar_wait(&dq_full[n & 1], static_cast<uint32_t>((n >> 1) & 1));
       tc_fence_after();
@@ -337,8 +353,9 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 __uint_as_float(su.y));
           p0 = fast_exp2(x0); p1 = fast_exp2(x1);
           if constexpr (DIAG) {
-            if (r > 2 * c + diag_shift) p0 = 0.f;
-            if (r > 2 * c + 1 + diag_shift) p1 = 0.f;
+            const int qr = 2 * c + diag_shift;               // q row of column 2c, relative to kv0
+            if (r > qr || qr >= vis_end) p0 = 0.f;
+            if (r > qr + 1 || qr + 1 >= vis_end) p1 = 0.f;
           }
           fma2v(t0, t1, __uint_as_float(dv[2 * c]), __uint_as_float(dv[2 * c + 1]), p.scale, __uint_as_float(su.z),
                 __uint_as_float(su.w));
@@ -347,7 +364,8 @@ fa_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           dk[c] = pack_bf16x2(d0, d1);
         }
       };
-      if (diag_shift < 128) body(std::true_type{}); else body(std::false_type{});
+      // masked steps: the two that touch the diagonal, and (FlashMask) those that reach the end of this tile's first document
+      if (diag_shift < 128 || kv0 + diag_shift + 63 >= start_min) body(std::true_type{}); else body(std::false_type{});
       {
         uint32_t(*a)[16] = reinterpret_cast<uint32_t(*)[16]>(pk);
         tmem_st16(tS, a[0]); tmem_st16(tS + 16, a[1]);   // P^T: 64 q as 32 packed columns over the start of S^T[g]
@@ -488,10 +506,10 @@ static int make_dqT_map(CUtensorMap* tm, const void* base, int64_t B, int64_t Sp
 
 }  // namespace fab2
 
-// Plain-causal backward through the transposed, pipelined kernel; called by b200_fa_bwd_flashmask (fa_bwd.cu) when no mask is
-// given.  Workspace layout: dQ^T accumulation [B, nh, 128, Spad] | dK acc | dV acc | stats [B, nh, Spad] float2.
-int launch_fa_bwd2(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq,
-                   void* dk, void* dv, void* workspace, int64_t B, int64_t S, int64_t num_heads, int64_t num_kv_heads,
+// Causal (optionally FlashMask start rows) backward through the transposed, pipelined kernel; called by b200_fa_bwd_flashmask
+// (fa_bwd.cu).  Workspace layout: dQ^T accumulation [B, nh, 128, Spad] | dK acc | dV acc | stats [B, nh, Spad] float2.
+int launch_fa_bwd2(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                   const int32_t* mask_start_rows, void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t S, int64_t num_heads, int64_t num_kv_heads,
                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv,
                    float softmax_scale, cudaStream_t stream) {
   using namespace fab2;
@@ -535,6 +553,7 @@ int launch_fa_bwd2(const void* q, const void* k, const void* v, const void* o, c
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.stats = stats;
+  p.mask_start = mask_start_rows;
   dim3 grid(static_cast<unsigned>((S + 127) / 128), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
   fa_bwd2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p);
   if ((rc = check_launch("fa_bwd2")) != 0) return rc;

@@ -346,8 +346,8 @@ extern "C" int b200_fa_fwd_flashmask(const void* q, const void* k, const void* v
                  "fa_fwd: bad shape B=%lld S=%lld nh=%lld kvh=%lld", (long long)B, (long long)S, (long long)num_heads,
                  (long long)num_kv_heads);
   B200_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "fa_fwd: token strides must be multiples of 8");
-  if (mask_start_rows == nullptr && fa_fwd_impl() == 2)     // plain causal: two q tiles per CTA, P in TMEM (fa_fwd2.cu)
-    return launch_fa_fwd2(q, k, v, o, lse, B, S, num_heads, num_kv_heads, ldq, ldk, ldv, ldo, softmax_scale, stream);
+  if (fa_fwd_impl() == 2)     // two q tiles per CTA, P in TMEM (fa_fwd2.cu); plain causal or FlashMask start rows
+    return launch_fa_fwd2(q, k, v, o, lse, mask_start_rows, B, S, num_heads, num_kv_heads, ldq, ldk, ldv, ldo, softmax_scale, stream);
   CUtensorMap tmQ, tmK, tmV, tmO;
   int rc;
   if ((rc = make_map(&tmQ, q, B, S, num_heads, ldq)) != 0) return rc;

@@ -58,6 +58,10 @@ struct Params {
   bf16* out;          // [token_num, ldo]
   int64_t ldo;
   int exp_poly;       // 0 / 1 / 2: none / a quarter / half of the exponentials on the FMA pipe (exp2_poly2)
+  // MASK instantiation — FlashMask, causal lower-triangular form (fusion_ops.py:218-231 -> F.flashmask_attention(
+  // startend_row_indices, causal=True)): mask_start[b, c] = first query row that may NOT see key column c (the end of c's packed
+  // document), non-decreasing in c and > c.  Row i sees column c iff c <= i < mask_start[b, c].
+  const int* mask_start;
 };
 
 // (x0, x1) = (a0, a1) * s + c    on the packed fp32x2 pipe
@@ -113,7 +117,7 @@ __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float&
   p1 = __uint_as_float(r1 + (t1 << 23));
 }
 
-template <bool PAGED>
+template <bool PAGED, bool MASK>
 // 10 warps = 3 on one SM sub-partition (16 K registers each): 16384 / (3 * 32) = 170 registers per thread is the hardware limit for this
 // block shape (a 200-register build fails to launch), which is what __launch_bounds__(320, 1) makes ptxas target
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -156,6 +160,22 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     b_active = (q0 + 128) < p.S;
     nA = 2 * qb + 1;                   // kv tiles 0 .. 2qb     (diagonal = last)
     nB = b_active ? 2 * qb + 2 : 0;    // kv tiles 0 .. 2qb+1   (diagonal = last)
+  }
+  // With a document mask the leading kv tiles whose every column belongs to a document that ended at or before a q tile's first
+  // row are skipped (mask_start is non-decreasing, so they form a prefix; the diagonal tile is never empty).  Tile B starts
+  // 128 rows later than tile A and may skip more: the CTA's kv stream starts at tile A's first tile `lo`, tile B joins at
+  // relative tile loB.  From here on kv tile indices are RELATIVE to lo (ring items 2j = K_{lo+j}, 2j+1 = V_{lo+j}).
+  int lo = 0, loB = 0;
+  if constexpr (MASK) {
+    const int* ms = p.mask_start + static_cast<size_t>(batch) * p.S;
+    while (lo < nA - 1 && __ldg(ms + min(lo * 128 + 127, p.S - 1)) <= q0) ++lo;
+    if (b_active) {
+      loB = lo;
+      while (loB < nB - 1 && __ldg(ms + min(loB * 128 + 127, p.S - 1)) <= q0 + 128) ++loB;
+      loB -= lo;
+    }
+    nA -= lo;
+    if (b_active) nB -= lo;
   }
   const int n_kv = b_active ? nB : nA;
 
@@ -238,7 +258,7 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mbar_arrive_expect_tx(&kv_full[st], TILE_BYTES);
           uint8_t* dst = sKV + st * TILE_BYTES;
           const CUtensorMap* tm = (it & 1) ? &tmV : &tmK;
-          const int row = (it >> 1) * 128;
+          const int row = (lo + (it >> 1)) * 128;
           tma_load_4d(tm, &kv_full[st], dst, 0, kv_head, row, batch);
           tma_load_4d(tm, &kv_full[st], dst + HALF_BYTES, 64, kv_head, row, batch);
         }
@@ -272,14 +292,14 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       };
       // O_t (+)= P_t V_j ; P_t = packed bf16 in the first 64 columns of S_t.  The softmax warps publish P in two halves of 64 kv
       // columns: the first four k-steps run while the second half is still being exponentiated.
-      auto issue_pv = [&](int t, int j) {
+      auto issue_pv = [&](int t, int j, int jl) {   // jl = j - (first kv tile of q tile t): phase and accumulate flag
         const uint64_t dV = umma_desc_sw128(sKV_a + ((2 * j + 1) % NST) * TILE_BYTES, HALF_BYTES, 1024);
         const uint32_t tP = tbase + static_cast<uint32_t>(t * 128);
         const uint32_t tO = tbase + 256u + static_cast<uint32_t>(t * 128);
-        const uint32_t acc0 = j > 0 ? 1u : 0u;
+        const uint32_t acc0 = jl > 0 ? 1u : 0u;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mbar_wait(&p_full[2 * t + h], j & 1);
+          mbar_wait(&p_full[2 * t + h], jl & 1);
           if (h == 0) wait_kv(2 * j + 1);
           tc_fence_after();
           if (leader) {
@@ -293,7 +313,7 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       wait_kv(0);
       tc_fence_after();
       issue_qk(0, 0);
-      if (b_active) {
+      if (b_active && loB == 0) {
         mbar_wait(&q_full[1], 0);
         tc_fence_after();
         issue_qk(1, 0);
@@ -303,8 +323,9 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int nt = t == 0 ? nA : nB;
-          if (j < nt) {
-            issue_pv(t, j);
+          const int lt = t == 0 ? 0 : loB;
+          if (j >= lt && j < nt) {
+            issue_pv(t, j, j - lt);
             if (j + 1 < nt) {
               wait_kv(2 * j + 2);
               tc_fence_after();
@@ -312,6 +333,11 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             } else if (leader) {
               umma_commit(&o_full[t]);
             }
+          } else if (MASK && t == 1 && b_active && j + 1 == lt) {   // tile B joins the stream at its first visible kv tile
+            mbar_wait(&q_full[1], 0);
+            wait_kv(2 * j + 2);
+            tc_fence_after();
+            issue_qk(1, j + 1);
           }
         }
         // both tiles have issued everything that reads V_j and K_{j+1}: hand the stages back when those MMAs retire
@@ -324,6 +350,7 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // ------------------------------- softmax / epilogue: one thread per q row -------------------------------
     const int t = (warp - 2) >> 2;                        // 0: tile A, 1: tile B
     const int nt = t == 0 ? nA : nB;
+    const int lt = t == 0 ? 0 : loB;
     if (nt > 0) {
       const int quad = warp & 3;                          // TMEM lane quadrant this warp may touch
       const int r = quad * 32 + lane;                     // row within the tile == TMEM lane
@@ -332,8 +359,8 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint32_t tO = tmem_base + lane_off + 256u + static_cast<uint32_t>(t * 128);
       const int q0t = q0 + t * 128;
       float m_used = -INFINITY, l0 = 0.f, l1 = 0.f;
-      for (int j = 0; j < nt; ++j) {
-        mbar_wait(&s_full[t], j & 1);
+      for (int j = lt; j < nt; ++j) {
+        mbar_wait(&s_full[t], (j - lt) & 1);
         tc_fence_after();
         uint32_t sv[128];
         {
@@ -355,6 +382,24 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int c = 0; c < 128; ++c)
             if (c > r) sv[c] = 0xff800000u;               // -inf
         }
+        if constexpr (MASK) {
+          // columns whose document ended at or before this row: start rows are non-decreasing, so they are the first `hid`
+          // columns of the tile, hid = #{c : mask_start[c] <= row} by bisection (7 L1-resident loads, only in tiles where some
+          // document ends at or before the q tile's last row)
+          const int col0 = (lo + j) * 128;
+          const int* ms = p.mask_start + static_cast<size_t>(batch) * p.S + col0;
+          if (__ldg(ms) <= q0t + 127) {
+            const int row = q0t + r;
+            int a = 0, b = min(128, p.S - col0);
+            while (a < b) {
+              const int mid = (a + b) >> 1;
+              if (__ldg(ms + mid) <= row) a = mid + 1; else b = mid;
+            }
+#pragma unroll
+            for (int c = 0; c < 128; ++c)
+              if (c < a) sv[c] = 0xff800000u;             // -inf
+          }
+        }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 128; c += 8) {
@@ -366,7 +411,7 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const float rowmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;   // scale > 0
         bool need = false;
         float factor = 1.f;
-        if (j == 0) {
+        if (j == lt) {
           m_used = rowmax;
         } else if (rowmax > m_used + RESCALE_THRESHOLD) {
           need = true;
@@ -375,7 +420,8 @@ fa_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           m_used = rowmax;
         }
         const bool rescale = __any_sync(0xffffffffu, need);
-        const float neg_m = -m_used;
+        // with documents a row can be fully masked in its first tiles: (-inf) * scale - (-inf) must not be evaluated
+        const float neg_m = (MASK && m_used == -INFINITY) ? 0.f : -m_used;
         // P over the first 64 columns of this row's S (every S value of the row is already in registers), published in two halves
         // of 64 kv columns so that the first four PV k-steps run under the second half's exponentials
         auto half = [&](auto mode_tag, auto half_tag, bool publish) {
@@ -505,8 +551,8 @@ static int make_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S, int
 
 }  // namespace fa2
 
-// Plain-causal forward through the two-tile kernel; called by b200_fa_fwd_flashmask (fa_fwd.cu) when no mask is given.
-int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* lse, int64_t B, int64_t S, int64_t num_heads,
+// Causal forward (optionally with FlashMask start rows) through the two-tile kernel; called by b200_fa_fwd_flashmask (fa_fwd.cu).
+int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* lse, const int32_t* mask_start_rows, int64_t B, int64_t S, int64_t num_heads,
                    int64_t num_kv_heads, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float softmax_scale,
                    cudaStream_t stream) {
   using namespace fa2;
@@ -518,7 +564,9 @@ int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* 
   if ((rc = make_map(&tmO, o, B, S, num_heads, ldo)) != 0) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fa_fwd2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) {
       set_last_error("fa_fwd2 smem attr: %s", cudaGetErrorString(e));
       return static_cast<int>(e);
@@ -534,7 +582,9 @@ int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* 
   p.cu_q = p.seq_dec = p.seq_this = p.seq_enc = p.block_tables = nullptr;
   p.max_blocks = p.block_size = 0; p.out = nullptr; p.ldo = 0;
   p.exp_poly = fa_exp_poly();
-  fa_fwd2_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  p.mask_start = mask_start_rows;
+  if (mask_start_rows != nullptr) fa_fwd2_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
+  else fa_fwd2_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmO, p);
   return check_launch("fa_fwd2");
 }
 
@@ -565,7 +615,7 @@ int launch_fa_prefill_paged(const void* qkv, const void* key_cache, const void* 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) {
       set_last_error("fa_prefill_paged smem attr: %s", cudaGetErrorString(e));
       return static_cast<int>(e);
@@ -582,8 +632,9 @@ int launch_fa_prefill_paged(const void* qkv, const void* key_cache, const void* 
   p.max_blocks = static_cast<int>(max_blocks_per_seq); p.block_size = static_cast<int>(block_size);
   p.out = static_cast<bf16*>(out); p.ldo = ldo;
   p.exp_poly = fa_exp_poly();
+  p.mask_start = nullptr;
   dim3 grid(static_cast<unsigned>((max_q_len + 255) / 256), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
-  fa_fwd2_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmQ, p);
+  fa_fwd2_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmQ, p);
   return check_launch("fa_prefill_paged");
 }
 

@@ -16,16 +16,16 @@ int check_launch(const char* what);  // cudaGetLastError() -> return code
 
 int sm_count();  // multiprocessors of the current device (cached per device)
 int skinny_gemm_impl();   // b200_set_skinny_gemm(): 1 = swapped-operand two-CTA/SM kernel (gemm_skinny.cu), 0 = the 128x256 persistent kernel
-int fa_fwd_impl();         // b200_set_fa_fwd_impl(): 2 = two-q-tile kernel (fa_fwd2.cu, plain causal), 1 = fa_fwd.cu for everything
-// fa_fwd2.cu: plain-causal forward (same argument meaning as b200_fa_fwd)
-int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* lse, int64_t B, int64_t S, int64_t num_heads,
+int fa_fwd_impl();         // b200_set_fa_fwd_impl(): 2 = two-q-tile kernel (fa_fwd2.cu), 1 = fa_fwd.cu
+// fa_fwd2.cu: causal forward, optional FlashMask start rows (same argument meaning as b200_fa_fwd_flashmask)
+int launch_fa_fwd2(const void* q, const void* k, const void* v, void* o, float* lse, const int32_t* mask_start_rows, int64_t B, int64_t S, int64_t num_heads,
                    int64_t num_kv_heads, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float softmax_scale,
                    cudaStream_t stream);
 int fa_exp_poly();        // b200_set_fa_exp_poly(): 0 / 1 / 2 = none / a quarter / half of the forward exponentials on the FMA pipe
-int fa_bwd_impl();         // b200_set_fa_bwd_impl(): 2 = transposed pipelined kernel (fa_bwd2.cu, plain causal), 1 = fa_bwd.cu
-// fa_bwd2.cu: plain-causal backward (same argument meaning as b200_fa_bwd)
-int launch_fa_bwd2(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse, void* dq,
-                   void* dk, void* dv, void* workspace, int64_t B, int64_t S, int64_t num_heads, int64_t num_kv_heads,
+int fa_bwd_impl();         // b200_set_fa_bwd_impl(): 2 = transposed pipelined kernel (fa_bwd2.cu), 1 = fa_bwd.cu
+// fa_bwd2.cu: causal backward, optional FlashMask start rows (same argument meaning as b200_fa_bwd_flashmask)
+int launch_fa_bwd2(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                   const int32_t* mask_start_rows, void* dq, void* dk, void* dv, void* workspace, int64_t B, int64_t S, int64_t num_heads, int64_t num_kv_heads,
                    int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq, int64_t lddk, int64_t lddv,
                    float softmax_scale, cudaStream_t stream);
 // fa_fwd2.cu, PAGED instantiation: prefill half of b200_append_attention

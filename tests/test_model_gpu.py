@@ -186,9 +186,7 @@ def test_flashmask_packing_invariance(model_type, request):
     from paddlenlp_b200.datasets import ZeroPaddingMapDataset
 
     # the "same tiles, same order -> same bits" property below compares packed (FlashMask) and one-by-one (plain causal) runs
-    # of the SAME attention kernel generation: pin the plain-causal forward to fa_fwd.cu, where the FlashMask instantiation lives
-    old_impl = _lib.load().b200_set_fa_fwd_impl(1)
-    request.addfinalizer(lambda: _lib.load().b200_set_fa_fwd_impl(old_impl))
+    # of the SAME attention kernel generation: both instantiations live in fa_fwd2.cu (the default)
     cfg = tiny_cfg(model_type)
     w = make_weights(cfg)
     model = build(cfg, w)

@@ -336,13 +336,16 @@ def _doc_mask(doc_lens, S):
 
 
 @pytest.mark.parametrize("S,nh,kvh,docs", [(384, 2, 1, [[100, 284], [128, 128, 128]]), (1024, 4, 2, [[1, 700, 323]]),
-                                           (200, 2, 2, [[7, 57, 136]]), (640, 1, 1, [[256, 1, 383], [640]])])
-@pytest.mark.parametrize("fa_fwd_impl", [1], indirect=True)
+                                           (200, 2, 2, [[7, 57, 136]]), (640, 1, 1, [[256, 1, 383], [640]]),
+                                           (1024, 2, 1, [[300, 724], [130, 126, 256, 512], [257, 255, 129, 383]]),
+                                           (1536, 4, 4, [[640, 40, 856], [2, 1300, 234]]),
+                                           (900, 2, 2, [[513, 387], [128, 600, 172]])])
+@pytest.mark.parametrize("fa_fwd_impl", [2, 1], indirect=True)
 def test_flash_attention_flashmask(S, nh, kvh, docs, fa_fwd_impl):
     """Packed-document (FlashMask causal-LT) attention, forward and backward, vs the oracle's masked softmax; a row of
-    [S]*S start rows is plain causal.  Document boundaries on and off the 128-row tile grid, 1-token documents.
-    (The bit-equality properties below compare masked and unmasked runs of the SAME kernel generation: the FlashMask
-    instantiation lives in fa_fwd.cu, so the plain-causal runs are pinned to that generation here.)"""
+    [S]*S start rows is plain causal.  Document boundaries on and off the 128-row tile grid (and off the 256-row block grid of
+    the two-q-tile forward: its second tile can join the kv stream later than the first), 1-token documents, ragged S.
+    The bit-equality properties below compare masked and unmasked runs of the SAME kernel generation."""
     o = ops()
     B, d = len(docs), 128
     ms = torch.stack([_doc_mask(dl, S) for dl in docs])
@@ -372,6 +375,34 @@ def test_flash_attention_flashmask(S, nh, kvh, docs, fa_fwd_impl):
     a, la = o.flash_attn_fwd(q, k, v, mask_start=full)
     b, lb = o.flash_attn_fwd(q, k, v)
     assert torch.equal(a, b) and torch.equal(la, lb)
+
+
+@pytest.mark.parametrize("fa_fwd_impl", [2, 1], indirect=True)
+@pytest.mark.parametrize("S,pads", [(512, [200, 0]), (700, [129, 511]), (384, [300, 1])])
+def test_flash_attention_left_padding_start_rows(S, pads, fa_fwd_impl):
+    """Left-padded batches in start-row form (llama/modeling.py `_mask_rows_from_padding_mask`: a padding column is a one-token
+    document, start = c + 1; real columns keep S): the real rows reproduce the un-padded sequence, forward and backward."""
+    o = ops()
+    B, nh, kvh, d = len(pads), 2, 1, 128
+    ms = torch.full((B, S), S, dtype=torch.int32)
+    for b, pad in enumerate(pads):
+        ms[b, :pad] = torch.arange(1, pad + 1, dtype=torch.int32)
+    qkv = rand_bf16(B, S, (nh + 2 * kvh) * d, seed=41).to(DEV)
+    q = qkv[:, :, : nh * d].view(B, S, nh, d)
+    k = qkv[:, :, nh * d: (nh + kvh) * d].view(B, S, kvh, d)
+    v = qkv[:, :, (nh + kvh) * d:].view(B, S, kvh, d)
+    out, lse = o.flash_attn_fwd(q, k, v, mask_start=ms.to(DEV))
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    dout = rand_bf16(B, S, nh, d, seed=42).to(DEV)
+    dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+    o.flash_attn_bwd(q, k, v, out, dout, lse, dq, dk, dv, mask_start=ms.to(DEV))
+    for b, pad in enumerate(pads):
+        qf, kf, vf = (t[b:b + 1, pad:].float().detach().requires_grad_(True) for t in (q, k, v))
+        ref = R.attention(qf, kf, vf, "fp32")
+        assert maxerr(out[b:b + 1, pad:].reshape(1, S - pad, -1), ref.detach()) < 1.5e-2
+        ref.backward(dout[b:b + 1, pad:].float().reshape(1, S - pad, -1))
+        for name, a, r in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+            assert relerr(a[b:b + 1, pad:], r) < 2e-2, (name, b, relerr(a[b:b + 1, pad:], r))
 
 
 @pytest.mark.parametrize("fa_fwd_impl", [2, 1], indirect=True)
