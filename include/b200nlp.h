@@ -142,11 +142,11 @@ int b200_swiglu_fwd(const void* gate_up, void* out, int64_t rows, int64_t inter,
  * re-zeroed): the decode step's ffn1 -> fused_bias_act("swiglu") pair (fused_transformer_layers.py:100-168). */
 int b200_swiglu_fwd_f32(float* gate_up_f32_ws, void* out, int64_t rows, int64_t inter, cudaStream_t stream);
 /* Decode-step ffn1 + SwiGLU in one kernel (M <= 64 token rows): act[M, inter] = bf16(silu(g) * u) with g|u = bf16(X W).
- * W [K, 2*inter] is the ffn1 weight with its columns interleaved per 64 channels — columns [128j, 128j+64) = gate channels
- * [64j, 64j+64), columns [128j+64, 128j+128) = the matching up channels — so that one 128-feature tile of the swapped-operand
- * weight-streaming kernel holds both halves (fused_transformer_layers.py:100-168 fused_bias_act("swiglu") after ffn1). */
-int b200_gemm_swiglu_skinny(const void* X, const void* W_interleaved, void* act, int64_t M, int64_t inter, int64_t K,
-                            int64_t ldx, int64_t ldw, cudaStream_t stream);
+ * W [K, 2*inter] is the reference-layout fused ffn1 weight (gate | up): one 128-feature tile of the swapped-operand
+ * weight-streaming kernel is fed by two 64-column TMA boxes, gate channels [64j, 64j+64) and the up columns of the same channels
+ * (fused_transformer_layers.py:100-168 fused_bias_act("swiglu") after ffn1).  inter % 64 == 0; ldact = row stride of act. */
+int b200_gemm_swiglu_skinny(const void* X, const void* W_gate_up, void* act, int64_t M, int64_t inter, int64_t K,
+                            int64_t ldx, int64_t ldw, int64_t ldact, cudaStream_t stream);
 int b200_swiglu_bwd(const void* gate_up, const void* dout, void* dgate_up, int64_t rows, int64_t inter,
                     cudaStream_t stream);
 

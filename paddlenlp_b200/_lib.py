@@ -42,7 +42,7 @@ _SIGNATURES = {
     "b200_rope_inplace": [P, P, P, P, I64, I64, I64, I64, I64, I, P],
     "b200_swiglu_fwd": [P, P, I64, I64, P],
     "b200_swiglu_fwd_f32": [P, P, I64, I64, P],
-    "b200_gemm_swiglu_skinny": [P, P, P, I64, I64, I64, I64, I64, P],
+    "b200_gemm_swiglu_skinny": [P, P, P, I64, I64, I64, I64, I64, I64, P],
     "b200_swiglu_bwd": [P, P, P, I64, I64, P],
     "b200_embedding_fwd": [P, P, P, I64, I64, I64, P],
     "b200_embedding_bwd": [P, P, P, I64, I64, I64, P],

@@ -399,6 +399,21 @@ __device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
   return r;
 }
 
+// SwiGLU forward for two adjacent channels (llama/modeling.py:38-45, 648-650): m = bf16(silu(g) * u) from the bf16-rounded gate and
+// up projections.  sigmoid = rcp.approx(1 + ex2.approx(-g log2 e)) like the backward below (two SFU operations; an IEEE division
+// plus expf costs ~35 instructions per element, which made the fused ffn1 epilogue of the decode step 6 us long).  The ONE
+// definition used by b200_swiglu_fwd / _f32 and by the GEMM epilogues that fuse it (gemm_tcgen05.cu mode 4, gemm_skinny.cu
+// SWIGLU): the operation order is pinned by the packed instructions, so all of them produce the same bits.
+__device__ __forceinline__ uint32_t swiglu_fwd_pair(uint32_t g2, uint32_t u2) {
+  const float2 gf = unpack_bf16x2(g2), uf = unpack_bf16x2(u2);
+  const f32x2 g{gf.x, gf.y}, u{uf.x, uf.y}, one{1.f, 1.f};
+  const f32x2 t = f2_mul(g, f32x2{-1.4426950408889634f, -1.4426950408889634f});
+  const f32x2 a = f2_add(f32x2{fast_exp2(t.x), fast_exp2(t.y)}, one);
+  const f32x2 sg{fast_rcp(a.x), fast_rcp(a.y)};
+  const f32x2 m = f2_mul(f2_mul(g, sg), u);
+  return pack_bf16x2(m.x, m.y);
+}
+
 // SwiGLU backward for two adjacent channels (llama/modeling.py:632-652 swiglu, backward of silu(g) * u):
 //   sg = sigmoid(g) ; d(gate) = d * u * sg * (1 + g (1 - sg)) ; d(up) = d * g * sg          (fp32, results rounded once to bf16)
 // sigmoid = rcp.approx(1 + ex2.approx(-g log2 e)): two SFU operations (a few fp32 ulp, far inside the bf16 rounding of the

@@ -16,8 +16,14 @@
 //   * 4 softmax warps, one thread per cache row: G scores per thread and tile, tile max / final sum reduced with
 //     shuffles + 4-way smem exchange, lazy rescale of the TMEM-resident O^T accumulator (threshold 8 in log2 units);
 //   * split-KV partials use the layout of decode_attention_merge_kernel (generation.cu).
-// Masked rows contribute P = 0; cache rows past the sequence length must hold finite values (the cache is allocated
-// zero-filled, as the reference does with paddle.zeros).
+//   * the last (partial) tile of a sequence is fetched in 32-row boxes, only as many as hold valid rows (at a context of ~1000
+//     tokens a full 128-row tail tile is 5-10 % of an item's bytes).
+// Masked rows contribute P = 0 (the shared-memory ring starts zero-filled, so the rows a partial tile does not fetch hold finite
+// values: zeros or an earlier tile).
+// Measured and NOT adopted (profiles/r02_decode_probe_attn_balanced_negative.log): cutting the launch's tiles into equal contiguous
+// runs per CTA (stream-K, pieces merged in-kernel through flags) instead of whole (b, kv head) items dealt round-robin — 512 items
+// on 296 CTAs look unbalanced (216 CTAs with two items), but the kernel is bound by the HBM stream, not by the longest CTA: the
+// balanced version was 4 % slower (51.8 vs 49.8 us at context 1048), the work it adds per segment is not paid back.
 #include "../../include/b200nlp.h"
 #include "common.cuh"
 #include "host_util.h"
@@ -87,7 +93,8 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 template <int G, bool PAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 decode_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                           const __grid_constant__ CUtensorMap tmV, const Params p) {
+                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmK32,
+                           const __grid_constant__ CUtensorMap tmV32, const Params p) {
   static_assert(G >= 1 && G <= 8, "group size");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -125,10 +132,9 @@ decode_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const int t = threadIdx.x - 64;
     *reinterpret_cast<uint4*>(sP + t * 32) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(sP + t * 32 + 16) = make_uint4(0, 0, 0, 0);
-    if constexpr (PAGED) {
-      // pages past the end of a sequence are not fetched: their smem rows must still be finite (P = 0 there, 0 * NaN = NaN)
-      for (int i = t; i < NSLOT * TILE_BYTES / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    }
+    // pages / 32-row boxes past the end of a sequence are not fetched: their smem rows must still be finite (P = 0 there, but
+    // 0 * NaN = NaN in the PV accumulation)
+    for (int i = t; i < NSLOT * TILE_BYTES / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -178,14 +184,27 @@ decode_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
               }
             }
           } else {
+            const int rows = it.t_end - t0;                  // valid cache rows of this tile (< 128 only in a sequence's last tile)
+            const int nbox = (rows + 31) >> 5;               // 32-row boxes that hold them
 #pragma unroll
             for (int kv = 0; kv < 2; ++kv, ++c) {
               const uint32_t slot = c % NSLOT;
               mbar_wait(&empty[slot], ((c / NSLOT) & 1u) ^ 1u);
-              mbar_arrive_expect_tx(&full[slot], TILE_BYTES);
-              const CUtensorMap* tm = kv ? &tmV : &tmK;
-              tma_load_3d(tm, &full[slot], smem + slot * TILE_BYTES, 0, t0, plane);
-              tma_load_3d(tm, &full[slot], smem + slot * TILE_BYTES + HALF_BYTES, 64, t0, plane);
+              uint8_t* dst = smem + slot * TILE_BYTES;
+              if (rows >= BKV) {
+                mbar_arrive_expect_tx(&full[slot], TILE_BYTES);
+                const CUtensorMap* tm = kv ? &tmV : &tmK;
+                tma_load_3d(tm, &full[slot], dst, 0, t0, plane);
+                tma_load_3d(tm, &full[slot], dst + HALF_BYTES, 64, t0, plane);
+              } else {
+                // a 32-row box = 4 KB per 64-column half = four 8-row swizzle atoms: same layout as the rows of the full box
+                mbar_arrive_expect_tx(&full[slot], static_cast<uint32_t>(nbox) * 8192u);
+                const CUtensorMap* tm = kv ? &tmV32 : &tmK32;
+                for (int bx = 0; bx < nbox; ++bx) {
+                  tma_load_3d(tm, &full[slot], dst + bx * 4096, 0, t0 + bx * 32, plane);
+                  tma_load_3d(tm, &full[slot], dst + HALF_BYTES + bx * 4096, 64, t0 + bx * 32, plane);
+                }
+              }
             }
           }
         }
@@ -395,8 +414,9 @@ namespace b200 {
 namespace dtc {
 
 template <bool PAGED>
-static int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const Params& p, int G, void* out,
-                  int64_t B, int64_t num_heads, int64_t num_splits, cudaStream_t stream) {
+static int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmK32,
+                  const CUtensorMap& tmV32, const Params& p, int G, void* out, int64_t B, int64_t num_heads, int64_t num_splits,
+                  cudaStream_t stream) {
   const int max_ctas = 2 * sm_count();      // two co-resident CTAs per SM: item prologues/epilogues of one overlap the other's stream
   const unsigned grid = static_cast<unsigned>(p.items < max_ctas ? p.items : max_ctas);
 #define B200_DTC(GG)                                                                                                 \
@@ -411,7 +431,8 @@ static int launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensor
       }                                                                                                              \
       attr_set = true;                                                                                               \
     }                                                                                                                \
-    launch_pdl(decode_attention_tc_kernel<GG, PAGED>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmQ, tmK, tmV, p); \
+    launch_pdl(decode_attention_tc_kernel<GG, PAGED>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, tmQ, tmK, tmV, tmK32, \
+               tmV32, p);                                                                                            \
   } break;
   switch (G) {
     B200_DTC(1) B200_DTC(2) B200_DTC(4) B200_DTC(7) B200_DTC(8)
@@ -445,17 +466,20 @@ extern "C" int b200_decode_attention_tc(const void* qkv, const void* cache, cons
   B200_CHECK_ARG(head_dim == 128, "decode_attention_tc: head_dim must be 128 (got %lld)", (long long)head_dim);
   B200_CHECK_ARG(B > 0 && num_kv_heads > 0 && num_heads % num_kv_heads == 0 && max_len > 0 && ld % 8 == 0,
                  "decode_attention_tc: bad shape");
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmK32, tmV32;
   int rc;
   if ((rc = make_q_map(&tmQ, qkv, B, num_heads, ld)) != 0) return rc;
   {
     uint64_t dims[3] = {128, static_cast<uint64_t>(max_len), static_cast<uint64_t>(B * num_kv_heads)};
     uint64_t strides[2] = {128 * 2, static_cast<uint64_t>(max_len) * 128 * 2};
     uint32_t box[3] = {64, BKV, 1};
+    uint32_t box32[3] = {64, 32, 1};           // a sequence's last, partial tile
     const bf16* kbase = static_cast<const bf16*>(cache);
+    const bf16* vbase = kbase + static_cast<size_t>(B) * num_kv_heads * max_len * 128;
     if ((rc = encode_tmap_bf16(&tmK, kbase, 3, dims, strides, box)) != 0) return rc;
-    if ((rc = encode_tmap_bf16(&tmV, kbase + static_cast<size_t>(B) * num_kv_heads * max_len * 128, 3, dims, strides, box)) != 0)
-      return rc;
+    if ((rc = encode_tmap_bf16(&tmV, vbase, 3, dims, strides, box)) != 0) return rc;
+    if ((rc = encode_tmap_bf16(&tmK32, kbase, 3, dims, strides, box32)) != 0) return rc;
+    if ((rc = encode_tmap_bf16(&tmV32, vbase, 3, dims, strides, box32)) != 0) return rc;
   }
   Params p = {};
   p.seq_lens = seq_lens;
@@ -465,7 +489,8 @@ extern "C" int b200_decode_attention_tc(const void* qkv, const void* cache, cons
   p.max_len = static_cast<int>(max_len); p.nsplit = static_cast<int>(num_splits);
   p.items = static_cast<int>(B * num_kv_heads * num_splits);
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  return launch<false>(tmQ, tmK, tmV, p, static_cast<int>(num_heads / num_kv_heads), out, B, num_heads, num_splits, stream);
+  return launch<false>(tmQ, tmK, tmV, tmK32, tmV32, p, static_cast<int>(num_heads / num_kv_heads), out, B, num_heads, num_splits,
+                       stream);
 }
 
 extern "C" int b200_decode_attention_paged(const void* qkv, const void* key_cache, const void* value_cache,
@@ -507,5 +532,5 @@ extern "C" int b200_decode_attention_paged(const void* qkv, const void* key_cach
   p.block_tables = block_tables;
   p.max_blocks = static_cast<int>(max_blocks_per_seq);
   p.block_size = static_cast<int>(block_size);
-  return launch<true>(tmQ, tmK, tmV, p, static_cast<int>(num_heads / num_kv_heads), out, B, num_heads, num_splits, stream);
+  return launch<true>(tmQ, tmK, tmV, tmK, tmV, p, static_cast<int>(num_heads / num_kv_heads), out, B, num_heads, num_splits, stream);
 }

@@ -264,12 +264,7 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
     uint4 o;
     uint32_t* oi = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 gf = unpack_bf16x2(gi[j]);
-      const float2 uf = unpack_bf16x2(ui[j]);
-      const float s0 = gf.x / (1.f + __expf(-gf.x)), s1 = gf.y / (1.f + __expf(-gf.y));
-      oi[j] = pack_bf16x2(s0 * uf.x, s1 * uf.y);
-    }
+    for (int j = 0; j < 4; ++j) oi[j] = swiglu_fwd_pair(gi[j], ui[j]);
     st_na_v4(reinterpret_cast<uint4*>(m + r * inter) + c, o);
   }
 }
@@ -294,12 +289,8 @@ __global__ void swiglu_fwd_f32_kernel(float* __restrict__ acc, bf16* __restrict_
     uint4 o;
     uint32_t* oi = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float ga = bf16_round(gv[2 * j]), gb = bf16_round(gv[2 * j + 1]);
-      const float ua = bf16_round(uv[2 * j]), ub = bf16_round(uv[2 * j + 1]);
-      const float s0 = ga / (1.f + __expf(-ga)), s1 = gb / (1.f + __expf(-gb));
-      oi[j] = pack_bf16x2(s0 * ua, s1 * ub);
-    }
+    for (int j = 0; j < 4; ++j)
+      oi[j] = swiglu_fwd_pair(pack_bf16x2(gv[2 * j], gv[2 * j + 1]), pack_bf16x2(uv[2 * j], uv[2 * j + 1]));
     st_na_v4(reinterpret_cast<uint4*>(m + r * inter) + c, o);
   }
 }

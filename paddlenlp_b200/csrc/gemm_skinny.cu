@@ -47,10 +47,12 @@ struct Params {
   int inter;
 };
 
-// SWIGLU (ffn1 of the decode step, no K split): the weight columns are interleaved per 64 channels — tile j holds
-// [gate 64j..64j+63 | up 64j..64j+63] — so accumulator lanes 0..63 are gate channels and lanes 64..127 the matching up channels;
-// the epilogue rounds both to bf16 (the Linear output rounding), exchanges the up half through the drained ring and writes
-// bf16(silu(g) * u) straight to act[M, inter]: no fp32 workspace, no separate activation kernel.
+// SWIGLU (ffn1 of the decode step, no K split): feature tile j pairs the gate columns [64j, 64j+64) with the up columns
+// [I + 64j, I + 64j + 64) of the reference-layout weight [K, 2I] (two 64-column TMA boxes per stage, no re-laid-out copy), so
+// accumulator lanes 0..63 are gate channels and lanes 64..127 the matching up channels.  The epilogue rounds both to bf16 (the Linear
+// output rounding), the gate warps and the up warps swap one half of their tokens through the drained ring so that all four warps
+// evaluate silu(g) * u (swiglu_fwd_pair, common.cuh), the [tokens x 64 channels] result is staged row-major in shared memory and
+// leaves as ONE TMA store into act[M, inter]: no fp32 workspace, no separate activation kernel, no 2-byte scattered stores.
 template <int NT, bool W_KMAJOR, bool SWIGLU = false>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
@@ -95,6 +97,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const int k0 = kb * BK;
         if constexpr (W_KMAJOR) {
           tma_load_2d(&tmW, &full_bar[s], sw, k0, f0);                      // [128 features x 64 k], k contiguous
+        } else if constexpr (SWIGLU) {
+          tma_load_2d(&tmW, &full_bar[s], sw, f_tile * 64, k0);                         // 64 gate columns
+          tma_load_2d(&tmW, &full_bar[s], sw + 64 * BK * 2, p.inter + f_tile * 64, k0);  // the up columns of the same channels
         } else {
           tma_load_2d(&tmW, &full_bar[s], sw, f0, k0);                      // two [64 k x 64 features] boxes
           tma_load_2d(&tmW, &full_bar[s], sw + 64 * BK * 2, f0 + 64, k0);
@@ -113,6 +118,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           const int k0 = (kb0 + s) * BK;
           if constexpr (W_KMAJOR) {
             tma_prefetch_l2_2d(&tmW, k0, f0);
+          } else if constexpr (SWIGLU) {
+            tma_prefetch_l2_2d(&tmW, f_tile * 64, k0);
+            tma_prefetch_l2_2d(&tmW, p.inter + f_tile * 64, k0);
           } else {
             tma_prefetch_l2_2d(&tmW, f0, k0);
             tma_prefetch_l2_2d(&tmW, f0 + 64, k0);
@@ -163,29 +171,38 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     if constexpr (SWIGLU) {
       static_assert(!SWIGLU || NT == 64, "SWIGLU epilogue: 64 token columns");
-      float* s_up = reinterpret_cast<float*>(smem);             // [64 tokens][64 channels] fp32
-      uint32_t v[2][32];
-      tmem_ld32(taddr, v[0]);
-      tmem_ld32(taddr + 32, v[1]);
-      tmem_ld_wait();
-      if (q >= 2) {
+      uint32_t* s_x = reinterpret_cast<uint32_t*>(smem);        // [32 token pairs][64 channels] bf16x2: the swapped halves (8 KB)
+      bf16* s_m = reinterpret_cast<bf16*>(smem + 8192);         // [64 tokens][64 channels] bf16, row-major = the TMA store box (8 KB)
+      uint32_t pk[32];                                          // this lane's channel, token pairs (2i, 2i+1), rounded to bf16
+      {
+        uint32_t v[2][32];
+        tmem_ld32(taddr, v[0]);
+        tmem_ld32(taddr + 32, v[1]);
+        tmem_ld_wait();
 #pragma unroll
-        for (int t = 0; t < 64; ++t) s_up[t * 64 + (q - 2) * 32 + lane] = __uint_as_float(v[t >> 5][t & 31]);
+        for (int i = 0; i < 32; ++i)
+          pk[i] = pack_bf16x2(__uint_as_float(v[i >> 4][(2 * i) & 31]), __uint_as_float(v[i >> 4][(2 * i + 1) & 31]));
       }
-      named_bar_sync(1, 128);
-      if (q < 2) {
-        const int ch = (f0 >> 1) + q * 32 + lane;               // channel of this lane's gate row
-        if (ch < p.inter) {
+      const bool is_gate = q < 2;
+      const int chl = (q & 1) * 32 + lane;                      // channel within the tile
+      // gate warps keep tokens 0..31 and hand their gates of tokens 32..63 to the up warps; the up warps do the opposite
 #pragma unroll
-          for (int t = 0; t < 64; ++t) {
-            if (t < p.M) {
-              const float g = bf16_round(__uint_as_float(v[t >> 5][t & 31]));
-              const float u = bf16_round(s_up[t * 64 + q * 32 + lane]);
-              const float sg = g / (1.f + __expf(-g));
-              p.act[static_cast<size_t>(t) * p.inter + ch] = __float2bfloat16_rn(sg * u);
-            }
-          }
-        }
+      for (int i = 0; i < 16; ++i) s_x[(is_gate ? 16 + i : i) * 64 + chl] = pk[is_gate ? 16 + i : i];
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int tp = is_gate ? i : 16 + i;                    // token pair
+        const uint32_t other = s_x[tp * 64 + chl];
+        const uint32_t m2 = is_gate ? swiglu_fwd_pair(pk[tp], other) : swiglu_fwd_pair(other, pk[tp]);
+        reinterpret_cast<unsigned short*>(s_m)[(2 * tp) * 64 + chl] = static_cast<unsigned short>(m2 & 0xffffu);
+        reinterpret_cast<unsigned short*>(s_m)[(2 * tp + 1) * 64 + chl] = static_cast<unsigned short>(m2 >> 16);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 64) {                                  // rows >= M are clipped by the tensor map
+        tma_store_2d(&tmF, s_m, f_tile * 64, 0);
+        tma_store_commit();
+        tma_store_wait<0>();
       }
     } else if (f0 + q * 32 < p.N) {
 #pragma unroll
@@ -529,18 +546,23 @@ int gemm_skinny_f32(const void* X, const void* W, void* workspace, int64_t M, in
   return w_kmajor ? launch<128, true>(tmW, tmX, tmF, p, items, stream) : launch<128, false>(tmW, tmX, tmF, p, items, stream);
 }
 
-// act[M, inter] = bf16(silu(g) * u), g|u = bf16(X W) with W [K, 2*inter] in the 64-interleaved column layout described above.
+// act[M, inter] = bf16(silu(g) * u), g|u = bf16(X W) with W the reference-layout fused weight [K, 2*inter] (gate | up).
 int gemm_swiglu_skinny(const void* X, const void* W, void* act, int64_t M, int64_t inter, int64_t K, int64_t ldx, int64_t ldw,
-                       cudaStream_t stream) {
-  if (!(M > 0 && M <= 64 && inter > 0 && inter % 64 == 0 && K > 0 && ldx % 8 == 0 && ldw % 8 == 0))
+                       int64_t ldact, cudaStream_t stream) {
+  if (!(M > 0 && M <= 64 && inter > 0 && inter % 64 == 0 && K > 0 && ldx % 8 == 0 && ldw % 8 == 0 && ldact % 8 == 0))
     return fail_arg("gemm_swiglu_skinny: need 0 < M <= 64, inter %% 64 == 0, leading dimensions %% 8 == 0");
   const int64_t N = 2 * inter;
-  CUtensorMap tmW, tmX;
+  CUtensorMap tmW, tmX, tmAct;
   int rc;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(K)}, strides[1] = {static_cast<uint64_t>(ldw) * 2};
     uint32_t box[2] = {64, BK};
     if ((rc = encode_tmap_bf16(&tmW, W, 2, dims, strides, box)) != 0) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(inter), static_cast<uint64_t>(M)}, strides[1] = {static_cast<uint64_t>(ldact) * 2};
+    uint32_t box[2] = {64, 64};
+    if ((rc = encode_tmap_bf16_linear(&tmAct, act, 2, dims, strides, box)) != 0) return rc;
   }
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
@@ -557,15 +579,15 @@ int gemm_swiglu_skinny(const void* X, const void* W, void* act, int64_t M, int64
   p.split_major = 0;
   p.act = static_cast<bf16*>(act);
   p.inter = static_cast<int>(inter);
-  return launch<64, false, true>(tmW, tmX, tmX, p, p.f_tiles, stream);    // the fp32 workspace map is unused
+  return launch<64, false, true>(tmW, tmX, tmAct, p, p.f_tiles, stream);  // tmF = the activation map
 }
 
 }  // namespace skinny
 }  // namespace b200
 
-extern "C" int b200_gemm_swiglu_skinny(const void* X, const void* W_interleaved, void* act, int64_t M, int64_t inter, int64_t K,
-                                       int64_t ldx, int64_t ldw, cudaStream_t stream) {
+extern "C" int b200_gemm_swiglu_skinny(const void* X, const void* W_gate_up, void* act, int64_t M, int64_t inter, int64_t K,
+                                       int64_t ldx, int64_t ldw, int64_t ldact, cudaStream_t stream) {
   using namespace b200;
-  B200_CHECK_ARG(X && W_interleaved && act, "gemm_swiglu_skinny: null pointer");
-  return skinny::gemm_swiglu_skinny(X, W_interleaved, act, M, inter, K, ldx, ldw, stream);
+  B200_CHECK_ARG(X && W_gate_up && act, "gemm_swiglu_skinny: null pointer");
+  return skinny::gemm_swiglu_skinny(X, W_gate_up, act, M, inter, K, ldx, ldw, ldact, stream);
 }

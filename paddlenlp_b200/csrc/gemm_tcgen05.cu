@@ -400,25 +400,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint32_t row_s = my_buf_s + buf * EPI_BUF_BYTES + lane * 128;
 #pragma unroll
               for (int ch = 0; ch < 8; ++ch) {
-                float f[8];
+                uint32_t o[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const int idx = ch * 8 + j;
-                  const float gv = __uint_as_float(idx < 32 ? g0[idx] : g1[idx - 32]);
-                  const float uv = __uint_as_float(idx < 32 ? u0[idx] : u1[idx - 32]);
-                  if (which == 0) f[j] = gv;
-                  else if (which == 1) f[j] = uv;
-                  else {
-                    const float gb = bf16_round(gv), ub = bf16_round(uv);
-                    f[j] = gb / (1.f + __expf(-gb)) * ub;
-                  }
+                for (int j = 0; j < 4; ++j) {
+                  const int idx = ch * 8 + 2 * j;
+                  const uint32_t gp = idx < 32 ? pack_bf16x2(__uint_as_float(g0[idx]), __uint_as_float(g0[idx + 1]))
+                                               : pack_bf16x2(__uint_as_float(g1[idx - 32]), __uint_as_float(g1[idx - 31]));
+                  const uint32_t up = idx < 32 ? pack_bf16x2(__uint_as_float(u0[idx]), __uint_as_float(u0[idx + 1]))
+                                               : pack_bf16x2(__uint_as_float(u1[idx - 32]), __uint_as_float(u1[idx - 31]));
+                  o[j] = which == 0 ? gp : (which == 1 ? up : swiglu_fwd_pair(gp, up));
                 }
-                uint4 o;
-                o.x = pack_bf16x2(f[0], f[1]);
-                o.y = pack_bf16x2(f[2], f[3]);
-                o.z = pack_bf16x2(f[4], f[5]);
-                o.w = pack_bf16x2(f[6], f[7]);
-                st_shared_v4(row_s + ((ch ^ (lane & 7)) << 4), o);
+                st_shared_v4(row_s + ((ch ^ (lane & 7)) << 4), make_uint4(o[0], o[1], o[2], o[3]));
               }
               fence_proxy_async_smem();
               __syncwarp();

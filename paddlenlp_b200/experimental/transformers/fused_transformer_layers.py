@@ -80,9 +80,9 @@ class FusedMultiTransformerBase:
         self.ffn1_weights = [z(self.h, 2 * self.I) for _ in range(self.L)]
         self.ffn2_weights = [z(self.I, self.h) for _ in range(self.L)]
         self._bias_f32 = [None] * self.L
-        self.fuse_ffn1_swiglu = False       # see the measurement note in forward()
-        self.ffn1_epilogue_swiglu = os.environ.get("B200_DECODE_FFN1_SWIGLU", "1") != "0"
-        self._ffn1_il: List[Optional[torch.Tensor]] = [None] * self.L   # decode-step copy of ffn1_weight, columns interleaved per 64
+        # decode-step ffn1 + SwiGLU (see the measurement note in forward()): "persistent" = 128x256-tile kernel with the SwiGLU
+        # epilogue, "skinny" = swapped-operand two-CTA/SM kernel with the SwiGLU epilogue, "unfused" = GEMM + SwiGLU kernel
+        self.ffn1_impl = os.environ.get("B200_DECODE_FFN1", "skinny")
         self.rope = ops.rope_tables(self.d, c.max_position_embeddings, float(c.rope_theta), self.device)
 
     def ensure_rope(self, positions: int):
@@ -99,16 +99,8 @@ class FusedMultiTransformerBase:
             self._bias_f32[i] = self.qkv_biases[i].float()
         return self._bias_f32[i]
 
-    def _ffn1_interleaved(self, i):
-        """ffn1_weight with its gate / up columns interleaved per 64 channels (ops.interleave_gate_up): the layout of the fused
-        ffn1 + SwiGLU decode kernel.  Built on first use from the reference-layout weight, which prefill keeps using."""
-        if self._ffn1_il[i] is None:
-            self._ffn1_il[i] = ops.interleave_gate_up(self.ffn1_weights[i])
-        return self._ffn1_il[i]
-
     def weights_changed(self):
         """Call after editing the weight tensors in place (set_state_dict does): derived copies are rebuilt lazily."""
-        self._ffn1_il = [None] * self.L
         self._bias_f32 = [None] * self.L
 
     SKINNY_M = 128     # at or below this many token rows the GEMMs are weight-streaming bound: split-K kernel
@@ -175,16 +167,18 @@ class FusedMultiTransformerBase:
                 attn = self._attend(qkv, caches, i, seq_lens_decoder, kw)
                 acc = ops.gemm_skinny_f32(attn, self.linear_weights[i], tag="splitk_h")
                 ln_out, residual = ops.add_rmsnorm_f32(acc, residual, self.ffn_ln_scales[i], eps)
-                # ffn1 [h, 2I] has enough 256-wide column tiles to stream at ~5.5 TB/s from the persistent kernel.  Measured
-                # alternatives in the same chain (tools/decode_ablation.py, B200_FFN1=skinny|fused; profiles/
-                # r01_decode_ablation_ffn1_fused.log): swapped-operand kernel + swiglu_fwd_f32 — equal; ffn1 + SwiGLU fused in
-                # the swapped-operand epilogue (ops.gemm_swiglu_skinny) — 1.2 % SLOWER (scattered 2-byte stores in the tail)
-                if self.ffn1_epilogue_swiglu and self.I % 128 == 0:
+                # ffn1 + SwiGLU, measured in the 32-layer chain at context 1024 (tools/decode_ablation.py B200_FFN1=fused|epi|plain,
+                # profiles/r02_decode_ablation_ffn1.log): swapped-operand kernel with the SwiGLU epilogue 4.458 ms, persistent
+                # 128x256-tile kernel with the SwiGLU epilogue 4.533 ms, GEMM + SwiGLU kernel 4.630 ms.  (Both epilogues use
+                # swiglu_fwd_pair: with an IEEE division + expf per element the persistent epilogue alone took 6.5 us per layer.)
+                if self.ffn1_impl == "skinny" and ln_out.shape[0] <= 64 and self.I % 64 == 0:
+                    # swapped-operand kernel, tile = 64 gate columns + the 64 up columns of the same channels, straight from the
+                    # reference-layout weight; the activation leaves as one TMA store per tile
+                    act = ops.gemm_swiglu_skinny(ln_out, self.ffn1_weights[i])
+                elif self.ffn1_impl != "unfused" and self.I % 128 == 0:
                     # SwiGLU in the ffn1 epilogue of the persistent kernel: the 256-column tile pairs 128 gate columns with the
                     # 128 up columns of the same channels straight from the reference-layout weight; only the activation is stored
                     _, act = ops.gemm_swiglu(ln_out, self.ffn1_weights[i], cta_group=1, store_gate_up=False)
-                elif self.fuse_ffn1_swiglu and ln_out.shape[0] <= 64 and self.I % 64 == 0:
-                    act = ops.gemm_swiglu_skinny(ln_out, self._ffn1_interleaved(i))
                 else:
                     ffn1 = self._mm(ln_out, self.ffn1_weights[i])
                     act = ops.swiglu_fwd(ffn1)

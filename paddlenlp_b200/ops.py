@@ -293,27 +293,18 @@ def swiglu_fwd_f32(acc_f32: torch.Tensor, out: Optional[torch.Tensor] = None):
     return out
 
 
-def interleave_gate_up(w_gate_up: torch.Tensor, block: int = 64) -> torch.Tensor:
-    """[K, 2I] (gate | up) -> the per-64-channel interleaved layout gemm_swiglu_skinny consumes:
-    columns [128j, 128j+64) = gate channels [64j, 64j+64), columns [128j+64, 128j+128) = up channels [64j, 64j+64)."""
-    K, two_i = w_gate_up.shape
-    inter = two_i // 2
-    assert inter % block == 0
-    g = w_gate_up[:, :inter].reshape(K, inter // block, block)
-    u = w_gate_up[:, inter:].reshape(K, inter // block, block)
-    return torch.stack([g, u], dim=2).reshape(K, two_i).contiguous()
-
-
-def gemm_swiglu_skinny(x: torch.Tensor, w_interleaved: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Decode-step ffn1 + SwiGLU (M <= 64 token rows) in one weight-streaming kernel; see interleave_gate_up."""
-    _chk(x, "x"); _chk(w_interleaved, "w_interleaved")
+def gemm_swiglu_skinny(x: torch.Tensor, w_gate_up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decode-step ffn1 + SwiGLU (M <= 64 token rows) in one weight-streaming kernel (two CTAs per SM, swapped operands);
+    w_gate_up is the reference-layout fused weight [K, 2I] (gate | up), I % 64 == 0."""
+    _chk(x, "x"); _chk(w_gate_up, "w_gate_up")
     M, K = x.shape
-    inter = w_interleaved.shape[1] // 2
-    assert w_interleaved.shape[0] == K and x.stride(1) == 1 and w_interleaved.stride(1) == 1
+    inter = w_gate_up.shape[1] // 2
+    assert w_gate_up.shape[0] == K and x.stride(1) == 1 and w_gate_up.stride(1) == 1
     if out is None:
         out = torch.empty(M, inter, dtype=BF16, device=x.device)
-    call("b200_gemm_swiglu_skinny", ptr(x), ptr(w_interleaved), ptr(out), M, inter, K, x.stride(0), w_interleaved.stride(0),
-         stream_ptr())
+    assert out.shape == (M, inter) and out.stride(1) == 1
+    call("b200_gemm_swiglu_skinny", ptr(x), ptr(w_gate_up), ptr(out), M, inter, K, x.stride(0), w_gate_up.stride(0),
+         out.stride(0), stream_ptr())
     return out
 
 

@@ -152,14 +152,12 @@ def test_gemm_skinny_alternative_kernels(impl):
 
 @pytest.mark.parametrize("M,inter,K", [(64, 14336, 4096), (5, 192, 328), (33, 18944, 3584)])
 def test_gemm_swiglu_skinny(M, inter, K):
-    """Decode ffn1 + SwiGLU in one kernel == GEMM (bf16 output) followed by the SwiGLU kernel, on the interleaved weight."""
+    """Decode ffn1 + SwiGLU in one swapped-operand kernel == GEMM (bf16 output) followed by the SwiGLU kernel, straight from the
+    reference-layout [K, 2I] weight."""
     o = ops()
     x = rand_bf16(M, K, seed=51).to(DEV)
     w = rand_bf16(K, 2 * inter, seed=52, scale=0.05).to(DEV)
-    wil = o.interleave_gate_up(w)
-    assert torch.equal(wil[:, :64], w[:, :64]) and torch.equal(wil[:, 64:128], w[:, inter:inter + 64])
-    assert torch.equal(wil[:, 128:192], w[:, 64:128])
-    got = o.gemm_swiglu_skinny(x, wil)
+    got = o.gemm_swiglu_skinny(x, w)
     want = o.swiglu_fwd(o.gemm(x, w, cta_group=1))
     ref = R.swiglu(R.linear(x.float().cpu(), w[:, :inter].float().cpu(), None, "bf16"),
                    R.linear(x.float().cpu(), w[:, inter:].float().cpu(), None, "bf16"), "bf16")

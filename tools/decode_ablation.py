@@ -22,7 +22,6 @@ def main():
     o_w = [rnd(nh * d, h) for _ in range(L)]
     f1_w = [rnd(h, 2 * I) for _ in range(L)]
     f2_w = [rnd(I, h) for _ in range(L)]
-    f1_il = [ops.interleave_gate_up(w) for w in f1_w] if os.environ.get("B200_FFN1", "plain") == "fused" else None
     ln = torch.ones(h, dtype=BF, device=dev)
     caches = [torch.zeros(2, B, kvh, max_len, d, dtype=BF, device=dev) for _ in range(L)]
     cos, sin = ops.rope_tables(d, max_len, 500000.0, dev)
@@ -52,7 +51,9 @@ def main():
                 act = fix_act
             else:
                 if os.environ.get("B200_FFN1", "plain") == "fused":
-                    act = ops.gemm_swiglu_skinny(ln_out if "norm" not in skip else fix_ln, f1_il[i])
+                    act = ops.gemm_swiglu_skinny(ln_out if "norm" not in skip else fix_ln, f1_w[i])
+                elif os.environ.get("B200_FFN1", "plain") == "epi":
+                    _, act = ops.gemm_swiglu(ln_out if "norm" not in skip else fix_ln, f1_w[i], cta_group=1, store_gate_up=False)
                 elif os.environ.get("B200_FFN1", "plain") == "skinny":
                     acc1 = ops.gemm_skinny_f32(ln_out if "norm" not in skip else fix_ln, f1_w[i], tag="splitk_ffn1")
                     act = fix_act if "swiglu" in skip else ops.swiglu_fwd_f32(acc1)
