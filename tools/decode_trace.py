@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--prompt", type=int, default=1024)
     ap.add_argument("--gen", type=int, default=24)
+    ap.add_argument("--timeline", action="store_true", help="also print start / end (us) of every kernel of two middle layers of the last step")
     a = ap.parse_args()
     cfg = T.LlamaConfig.llama3_8b()
     m = LlamaForCausalLMInferenceModel(cfg)
@@ -71,11 +72,22 @@ def main():
             # adds to the step
             v[2] += max(0.0, e.time_range.end - prev_end)
             prev_end = max(prev_end, e.time_range.end)
+    timeline = None
+    if a.timeline:
+        lo, hi = steps[-1]
+        seg = evs[lo:hi]
+        per_layer = max(1, (len(seg) - 4) // cfg.num_hidden_layers)
+        first = 1 + 15 * per_layer                      # kernel 0 is the embedding, then per_layer kernels per layer
+        t0 = seg[first].time_range.start
+        timeline = [{"kernel": e.name.split("(")[0][-48:], "start_us": round(e.time_range.start - t0, 2),
+                     "end_us": round(e.time_range.end - t0, 2)} for e in seg[first:first + 2 * per_layer]]
     n = len(steps)
     out = {"context": a.prompt + a.gen, "steps": n, "step_span_us": sum(spans) / n, "gpu_busy_us": sum(busy) / n,
            "kernels": {k: {"per_step": v[0] / n, "mean_us": v[1] / v[0], "sum_us_per_step": v[1] / n,
                            "exclusive_us_per_step": v[2] / n, "exclusive_us_per_launch": v[2] / v[0]} for k, v in agg.items()}}
     out["sum_of_kernel_durations_us"] = sum(v["sum_us_per_step"] for v in out["kernels"].values())
+    if timeline is not None:
+        out["timeline_two_layers"] = timeline
     print(json.dumps(out, indent=1))
 
 
