@@ -149,6 +149,27 @@ int b200_gemm_swiglu_skinny(const void* X, const void* W_gate_up, void* act, int
                             int64_t ldx, int64_t ldw, int64_t ldact, cudaStream_t stream);
 int b200_swiglu_bwd(const void* gate_up, const void* dout, void* dgate_up, int64_t rows, int64_t inter,
                     cudaStream_t stream);
+/* The GEMM chain of one decode-step layer (M <= 64 token rows) as ONE persistent kernel of two CTAs per SM whose six steps are
+ * separated by grid-wide barriers instead of kernel boundaries, the weight stream running ahead across them
+ * (fused_transformer_layers.py:895-896 out-linear, :937-949 ffn layernorm, :100-168 ffn1 + swiglu, ffn2, :976-999 residual +
+ * next layernorm, :843-856 the NEXT layer's qkv projection):
+ *   acc_h += attn @ W_o ; residual += bf16(acc_h), ln = rmsnorm(residual) * w_ffn_ln ; act = swiglu(bf16(ln @ W_ffn1)) ;
+ *   acc_h += act @ W_ffn2 ; residual += bf16(acc_h), ln = rmsnorm(residual) * w_next_ln ; acc_qkv += ln @ W_next_qkv^T
+ * attn bf16 [M, attn_width]; W_o [attn_width, h], W_ffn1 [h, 2*inter] (gate | up), W_ffn2 [inter, h], W_next_qkv [qkv_n, h] (the
+ * reference layouts); residual bf16 [M, h] in/out; ln_buf [M, h] and act_buf [M, inter] bf16 scratch; acc_h fp32 [M, h] and
+ * acc_qkv fp32 [M, qkv_n]: zero on entry, acc_h zero again on exit, acc_qkv holds the projection sums (same contract as
+ * b200_gemm_bf16_splitk's workspace: the RoPE-append consumer rounds and re-zeroes).  w_next_ln / w_next_qkv NULL (last layer):
+ * the chain ends with the residual update.  sync_ws: b200_decode_layer_chain_workspace_bytes() bytes, zero before the first call
+ * (handed back zeroed).  Same rounding points and summation structure as the unfused kernels. */
+int64_t b200_decode_layer_chain_workspace_bytes(void);
+/* Debugging aid (tools/decode_probe.py chain): stamps = device buffer of 2 * 6 * 8 bytes per CTA (2 x SM count CTAs) that the next
+ * launches fill with %globaltimer values — [cta][phase][0] = the producer saw the phase's inputs, [1] = the CTA published the
+ * phase; NULL switches it off. */
+int b200_decode_layer_chain_debug(void* stamps);
+int b200_decode_layer_chain(const void* attn, const void* w_o, const void* w_ffn_ln, const void* w_ffn1, const void* w_ffn2,
+                            const void* w_next_ln, const void* w_next_qkv, void* residual, void* ln_buf, void* act_buf, float* acc_h,
+                            float* acc_qkv, void* sync_ws, int64_t M, int64_t h, int64_t attn_width, int64_t inter, int64_t qkv_n,
+                            float eps, cudaStream_t stream);
 
 /* ---- Embedding gather / scatter-add (nn.Embedding, llama/modeling.py:1465-1468, 1634). ids are int64. */
 int b200_embedding_fwd(const int64_t* ids, const void* table, void* out, int64_t tokens, int64_t h, int64_t vocab,

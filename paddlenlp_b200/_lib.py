@@ -44,6 +44,9 @@ _SIGNATURES = {
     "b200_swiglu_fwd_f32": [P, P, I64, I64, P],
     "b200_gemm_swiglu_skinny": [P, P, P, I64, I64, I64, I64, I64, I64, P],
     "b200_swiglu_bwd": [P, P, P, I64, I64, P],
+    "b200_decode_layer_chain_workspace_bytes": [],
+    "b200_decode_layer_chain_debug": [P],
+    "b200_decode_layer_chain": [P, P, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, F, P],
     "b200_embedding_fwd": [P, P, P, I64, I64, I64, P],
     "b200_embedding_bwd": [P, P, P, I64, I64, I64, P],
     "b200_fa_fwd": [P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, I64, I64, F, P],
@@ -96,6 +99,7 @@ _RESTYPE = {
     "b200_fa_bwd_workspace_bytes": c_int64,
     "b200_append_attention_workspace_bytes": c_int64,
     "b200_grad_sqnorm_workspace_bytes": c_int64,
+    "b200_decode_layer_chain_workspace_bytes": c_int64,
 }
 
 

@@ -83,6 +83,11 @@ class FusedMultiTransformerBase:
         # decode-step ffn1 + SwiGLU (see the measurement note in forward()): "persistent" = 128x256-tile kernel with the SwiGLU
         # epilogue, "skinny" = swapped-operand two-CTA/SM kernel with the SwiGLU epilogue, "unfused" = GEMM + SwiGLU kernel
         self.ffn1_impl = os.environ.get("B200_DECODE_FFN1", "skinny")
+        # decode step: out-linear .. next layer's qkv as ONE persistent kernel per layer (ops.decode_layer_chain) instead of six
+        # programmatically chained launches.  OFF by default: measured 108 us against 89 us per layer for the six kernels
+        # (tools/decode_probe.py chain, profiles/r02_decode_chain_probe.log) — the grid barriers are cheap (0.25 us) but the two
+        # norm phases take 8 us each under the weight-prefetch traffic, and the chained launches already overlap their prologues
+        self.layer_chain = os.environ.get("B200_DECODE_CHAIN", "0") != "0"
         self.rope = ops.rope_tables(self.d, c.max_position_embeddings, float(c.rope_theta), self.device)
 
     def ensure_rope(self, positions: int):
@@ -158,6 +163,19 @@ class FusedMultiTransformerBase:
         residual = src
         ln_out, _ = ops.add_rmsnorm(src, None, self.ln_scales[0], eps, want_residual=False)   # compute_layernorm_before_qkv
         fused = decode and src.shape[0] <= self.SKINNY_M and not getattr(self.config, "append_attn", False)
+        if (fused and self.layer_chain and src.shape[0] <= 64 and self.I % 64 == 0 and self.h % 128 == 0 and self.h <= 8192
+                and self.qkv_n % 128 == 0):
+            # one persistent kernel per layer for everything between two attention calls; the residual stream lives in one buffer
+            residual = src.clone()
+            acc = ops.gemm_skinny_f32(ln_out, self.qkv_weights[0], trans_b=True, tag="splitk_qkv")
+            for i in range(self.L):
+                qkv = self._rope_append(None, acc, caches, i, seq_lens_decoder, kw)
+                attn = self._attend(qkv, caches, i, seq_lens_decoder, kw)
+                last = i == self.L - 1
+                acc = ops.decode_layer_chain(attn, self.linear_weights[i], self.ffn_ln_scales[i], self.ffn1_weights[i],
+                                             self.ffn2_weights[i], None if last else self.ln_scales[i + 1],
+                                             None if last else self.qkv_weights[i + 1], residual, eps)
+            return residual
         for i in range(self.L):
             if fused:
                 # decode step: the split-K GEMMs leave fp32 sums that the next kernel rounds once (same rounding points,

@@ -308,6 +308,39 @@ def gemm_swiglu_skinny(x: torch.Tensor, w_gate_up: torch.Tensor, out: Optional[t
     return out
 
 
+def decode_layer_chain(attn: torch.Tensor, w_o: torch.Tensor, w_ffn_ln: torch.Tensor, w_ffn1: torch.Tensor, w_ffn2: torch.Tensor,
+                       w_next_ln: Optional[torch.Tensor], w_next_qkv: Optional[torch.Tensor], residual: torch.Tensor, eps: float,
+                       qkv_tag: str = "splitk_qkv"):
+    """One persistent kernel for the GEMM chain of a decode layer (M <= 64 rows): out-linear, residual + ffn RMSNorm, ffn1 +
+    SwiGLU, ffn2, residual + the next layer's RMSNorm, the next layer's QKV projection (see b200_decode_layer_chain).
+    `residual` [M, h] is updated IN PLACE.  Returns the fp32 QKV accumulation [M, qkv_n] of the next layer (the workspace
+    decode_rope_append_f32 consumes and re-zeroes) or None for the last layer (w_next_qkv None)."""
+    for t, n in ((attn, "attn"), (w_o, "w_o"), (w_ffn_ln, "w_ffn_ln"), (w_ffn1, "w_ffn1"), (w_ffn2, "w_ffn2"), (residual, "residual")):
+        _chk(t, n)
+    M, aw = attn.shape
+    h = w_o.shape[1]
+    inter = w_ffn2.shape[0]
+    assert w_o.shape == (aw, h) and w_ffn1.shape == (h, 2 * inter) and w_ffn2.shape == (inter, h) and residual.shape == (M, h)
+    assert all(t.is_contiguous() for t in (attn, w_o, w_ffn1, w_ffn2, residual))
+    dev = attn.device
+    ln_buf = _workspace(M * h * 2, dev, "chain_ln")
+    act_buf = _workspace(M * inter * 2, dev, "chain_act")
+    acc_h = _zero_workspace(M * h * 4, dev, "chain_h")
+    sync = _zero_workspace(_lib.load().b200_decode_layer_chain_workspace_bytes(), dev, "chain_sync")
+    acc_qkv, qkv_n = None, 0
+    if w_next_qkv is not None:
+        _chk(w_next_qkv, "w_next_qkv"); _chk(w_next_ln, "w_next_ln")
+        qkv_n = w_next_qkv.shape[0]
+        assert w_next_qkv.shape == (qkv_n, h) and w_next_qkv.is_contiguous()
+        acc_qkv = _zero_workspace(M * qkv_n * 4, dev, qkv_tag)
+    call("b200_decode_layer_chain", ptr(attn), ptr(w_o), ptr(w_ffn_ln), ptr(w_ffn1), ptr(w_ffn2), ptr(w_next_ln), ptr(w_next_qkv),
+         ptr(residual), ptr(ln_buf), ptr(act_buf), ptr(acc_h), ptr(acc_qkv), ptr(sync), M, h, aw, inter, qkv_n, float(eps),
+         stream_ptr())
+    if acc_qkv is None:
+        return None
+    return acc_qkv[: M * qkv_n * 4].view(torch.float32).view(M, qkv_n)
+
+
 def swiglu_bwd(gate_up: torch.Tensor, dout: torch.Tensor, dgate_up: Optional[torch.Tensor] = None):
     _chk(gate_up, "gate_up"); _chk(dout, "dout")
     rows, two_i = gate_up.shape

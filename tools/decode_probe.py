@@ -12,7 +12,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from paddlenlp_b200 import ops  # noqa: E402
+from paddlenlp_b200 import _lib, ops  # noqa: E402
 
 dev = "cuda:0"
 BF = torch.bfloat16
@@ -75,6 +75,50 @@ def main():
                 print(json.dumps(dict(probe=f"skinny gemm {name}", K=K, N=N, split_k=split_k, us=us, tb_s=K * N * 2 / us / 1e6)),
                       flush=True)
             del ws
+    if "chain" in which:
+        # the six kernels between two attention calls of a layer (out-linear .. next qkv) against ops.decode_layer_chain
+        h, inter, qn = 4096, 14336, 6144
+        Ws = [dict(o=rnd(h, h), f1=rnd(h, 2 * inter), f2=rnd(inter, h), q=rnd(qn, h)) for _ in range(ROT)]
+        ln_w = torch.ones(h, dtype=BF, device=dev)
+        attn, res = rnd(M, h), rnd(M, h)
+
+        def unfused(w):
+            acc = ops.gemm_skinny_f32(attn, w["o"], tag="p_h")
+            ln, r = ops.add_rmsnorm_f32(acc, res, ln_w, 1e-5)
+            act = ops.gemm_swiglu_skinny(ln, w["f1"])
+            acc = ops.gemm_skinny_f32(act, w["f2"], tag="p_h")
+            ln, r = ops.add_rmsnorm_f32(acc, r, ln_w, 1e-5)
+            ops.gemm_skinny_f32(ln, w["q"], trans_b=True, tag="p_q")
+
+        def chained(w):
+            ops.decode_layer_chain(attn, w["o"], ln_w, w["f1"], w["f2"], ln_w, w["q"], res, 1e-5, qkv_tag="p_q2")
+
+        lib = _lib.load()
+        for pdl in (0, 1):
+            lib.b200_set_pdl(pdl)
+            us_u = graph_time([(lambda w=w: unfused(w)) for w in Ws])
+            us_c = graph_time([(lambda w=w: chained(w)) for w in Ws])
+            print(json.dumps(dict(probe="layer chain: 6 kernels vs one persistent kernel", pdl=pdl, unfused_us=us_u, chained_us=us_c,
+                                  weights_mb=(h * h + 3 * h * inter + qn * h) * 2 / 1e6)), flush=True)
+        lib.b200_set_pdl(0)
+        # per-phase stamps of one launch
+        n_cta = 2 * torch.cuda.get_device_properties(0).multi_processor_count
+        stamps = torch.zeros(n_cta, 6, 2, dtype=torch.int64, device=dev)
+        lib.b200_decode_layer_chain_debug(stamps.data_ptr())
+        for w in Ws[:3]:
+            chained(w)
+        torch.cuda.synchronize()
+        lib.b200_decode_layer_chain_debug(None)
+        st = stamps.cpu().double()
+        t0 = st[st > 0].min()
+        rows = []
+        for ph in range(6):
+            rdy, pub = st[:, ph, 0], st[:, ph, 1]
+            rows.append(dict(phase=ph, ready_first_us=float((rdy[rdy > 0].min() - t0) / 1e3) if (rdy > 0).any() else None,
+                             ready_last_us=float((rdy.max() - t0) / 1e3) if (rdy > 0).any() else None,
+                             pub_first_us=float((pub[pub > 0].min() - t0) / 1e3), pub_last_us=float((pub.max() - t0) / 1e3)))
+        print(json.dumps(dict(probe="layer chain phase stamps (us from the first stamp; ready = inputs seen by a producer, pub = CTA "
+                                    "published the phase)", phases=rows)), flush=True)
     if "attn" in which:
         B, nh, kvh, d, max_len = 64, 32, 8, 128, 2048
         caches = [torch.randn(2, B, kvh, max_len, d, device=dev).to(BF) for _ in range(ROT)]
