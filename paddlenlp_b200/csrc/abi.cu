@@ -50,6 +50,8 @@ int fa_fwd_impl() { return g_fa_fwd_impl; }
 static int g_fa_bwd_impl = env_int("B200_FA_BWD_IMPL", 2);
 int fa_bwd_impl() { return g_fa_bwd_impl; }
 // share of the forward softmax exponentials evaluated by a polynomial on the FMA pipe (fa_fwd2.cu exp2_poly2): 0, 1 (1/4), 2 (1/2)
+static int g_l2_prefetch_mb = env_int("B200_L2_PREFETCH_MB", 64);
+int l2_prefetch_mb() { return g_l2_prefetch_mb < 0 ? 0 : g_l2_prefetch_mb; }
 static int g_fa_exp_poly = env_int("B200_FA_EXP_POLY", 1);
 int fa_exp_poly() { return g_fa_exp_poly; }
 

@@ -444,7 +444,7 @@ static int launch_streamk(const CUtensorMap& tmW, const CUtensorMap& tmX, const 
   }
   p.w_prefetch = pdl_enabled() ? 1 : 0;
   const long long per_kb = static_cast<long long>(W_BYTES) * grid;
-  const long long kbs = (64ll << 20) / per_kb;
+  const long long kbs = (static_cast<long long>(l2_prefetch_mb()) << 20) / per_kb;
   p.l2_prefetch_kb = p.w_prefetch ? static_cast<int>(kbs > 64 ? 64 : kbs) : 0;
   cudaError_t e = launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(NUM_THREADS), SKCfg::SMEM_BYTES, stream, tmW, tmX, tmF, p);
   if (e != cudaSuccess) {
@@ -471,7 +471,7 @@ static int launch(const CUtensorMap& tmW, const CUtensorMap& tmX, const CUtensor
   p.w_prefetch = pdl_enabled() ? 1 : 0;
   // at most ~64 MB of weights parked in L2 ahead of the loads
   const long long per_kb = static_cast<long long>(W_BYTES) * items;
-  const long long kbs = (64ll << 20) / per_kb;
+  const long long kbs = (static_cast<long long>(l2_prefetch_mb()) << 20) / per_kb;
   p.l2_prefetch_kb = p.w_prefetch ? static_cast<int>(kbs > 64 ? 64 : kbs) : 0;
   cudaError_t e = launch_pdl(kern, dim3(static_cast<unsigned>(items)), dim3(NUM_THREADS), C::SMEM_BYTES, stream, tmW, tmX, tmF, p);
   if (e != cudaSuccess) {

@@ -573,7 +573,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     pp.b_prefetch = 1;
     // at most ~64 MB of weights resident in L2 ahead of the loads (the L2 is 126 MB and also holds the activations)
     const long long per_kb = static_cast<long long>(C::B_COLS) * BK * 2 * pairs * CG;
-    long long kbs = (64ll << 20) / per_kb;
+    long long kbs = (static_cast<long long>(l2_prefetch_mb()) << 20) / per_kb;
     pp.l2_prefetch_kb = static_cast<int>(kbs > 64 ? 64 : kbs);
   }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, pp);
