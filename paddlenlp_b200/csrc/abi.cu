@@ -50,7 +50,11 @@ int fa_fwd_impl() { return g_fa_fwd_impl; }
 static int g_fa_bwd_impl = env_int("B200_FA_BWD_IMPL", 2);
 int fa_bwd_impl() { return g_fa_bwd_impl; }
 // share of the forward softmax exponentials evaluated by a polynomial on the FMA pipe (fa_fwd2.cu exp2_poly2): 0, 1 (1/4), 2 (1/2)
-static int g_l2_prefetch_mb = env_int("B200_L2_PREFETCH_MB", 64);
+// Weight bytes a decode-step GEMM requests into L2 (beyond its shared-memory ring) before griddepcontrol.wait.  Round 1 used 64 MB;
+// with every kernel of the step launched programmatically the flood delays the small row-wise kernels that run meanwhile more than
+// it shortens the GEMM: generation 12.8 / 13.2 / 13.5 k tokens/s at 128 / 64 / 16 MB and 13.96 / 14.05 / 14.03 k at 16 / 8 / 0 MB
+// (profiles/r02_gen_bench_l2_prefetch_sweep.log).
+static int g_l2_prefetch_mb = env_int("B200_L2_PREFETCH_MB", 8);
 int l2_prefetch_mb() { return g_l2_prefetch_mb < 0 ? 0 : g_l2_prefetch_mb; }
 static int g_fa_exp_poly = env_int("B200_FA_EXP_POLY", 1);
 int fa_exp_poly() { return g_fa_exp_poly; }

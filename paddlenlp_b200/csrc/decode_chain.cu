@@ -539,7 +539,7 @@ extern "C" int b200_decode_layer_chain(const void* attn, const void* w_o, const 
   p.nph = n;
   p.counter = static_cast<unsigned*>(sync_ws);
   p.exit_counter = p.counter + MAX_PHASES * 32;                      // its own 128-byte line
-  p.l2_kb = 16;
+  p.l2_kb = static_cast<int>((static_cast<long long>(l2_prefetch_mb()) << 20) / (static_cast<long long>(W_BYTES) * slots));
   p.dbg = g_chain_dbg;
   static bool attr_set = false;
   if (!attr_set) {
