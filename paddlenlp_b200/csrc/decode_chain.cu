@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "host_util.h"
+#include "norm_row.cuh"
 
 namespace b200 {
 namespace chain {
@@ -354,60 +355,7 @@ decode_chain_kernel(const __grid_constant__ Maps maps, const Params p) {
         if (static_cast<int>(blockIdx.x) < p.M) {
           if (et == 0) grid_wait(p.counter + (ph - 1) * 32, G);
           named_bar_sync(1, 128);
-          const int row = blockIdx.x;
-          const int nchunk = P.h >> 3;               // 8-element chunks; thread et owns chunks et, et + 128, ...
-          float4* xf = reinterpret_cast<float4*>(P.x_f32 + static_cast<size_t>(row) * P.h);
-          uint4* rr = reinterpret_cast<uint4*>(P.res + static_cast<size_t>(row) * P.h);
-          float ss = 0.f;
-          constexpr int MAXV = 8;                    // h <= 8192
-          uint4 v[MAXV];
-#pragma unroll
-          for (int i = 0; i < MAXV; ++i) {
-            const int c = et + 128 * i;
-            if (c < nchunk) {
-              const float4 a = __ldcg(xf + 2 * c), b = __ldcg(xf + 2 * c + 1);
-              const uint4 r = __ldcg(rr + c);
-              v[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
-              uint32_t* vi = reinterpret_cast<uint32_t*>(&v[i]);
-              const uint32_t* ri = reinterpret_cast<const uint32_t*>(&r);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 x = unpack_bf16x2(vi[j]), y = unpack_bf16x2(ri[j]);
-                vi[j] = pack_bf16x2(x.x + y.x, x.y + y.y);
-                const float2 s = unpack_bf16x2(vi[j]);
-                ss += s.x * s.x + s.y * s.y;
-              }
-              xf[2 * c] = make_float4(0.f, 0.f, 0.f, 0.f);
-              xf[2 * c + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-              rr[c] = v[i];
-            }
-          }
-          ss = warp_sum(ss);
-          if (lane == 0) s_part[q] = ss;
-          named_bar_sync(1, 128);
-          ss = s_part[0] + s_part[1] + s_part[2] + s_part[3];
-          if (P.normed != nullptr) {
-            const float rstd = rsqrtf(ss / static_cast<float>(P.h) + P.eps);
-            const uint4* wr = reinterpret_cast<const uint4*>(P.w);
-            uint4* yr = reinterpret_cast<uint4*>(P.normed + static_cast<size_t>(row) * P.h);
-#pragma unroll
-            for (int i = 0; i < MAXV; ++i) {
-              const int c = et + 128 * i;
-              if (c < nchunk) {
-                const uint4 wv = __ldg(wr + c);
-                uint4 o;
-                const uint32_t* xi = reinterpret_cast<const uint32_t*>(&v[i]);
-                const uint32_t* wi = reinterpret_cast<const uint32_t*>(&wv);
-                uint32_t* oi = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 x = unpack_bf16x2(xi[j]), w2 = unpack_bf16x2(wi[j]);
-                  oi[j] = pack_bf16x2(bf16_round(x.x * rstd) * w2.x, bf16_round(x.y * rstd) * w2.y);
-                }
-                yr[c] = o;
-              }
-            }
-          }
+          add_rmsnorm_row_128(P.x_f32, P.res, P.res, P.w, P.normed, static_cast<int>(blockIdx.x), P.h, P.eps, et, s_part, 1);
           fence_proxy_async_all();                 // ln / the zeroed workspace are read / added to by other CTAs' TMA
           __threadfence();
         }
