@@ -441,18 +441,20 @@ __global__ void fa_bwd2_stats_kernel(const bf16* __restrict__ o, const bf16* __r
   }
 }
 
-// dq[b, s, h, :] (bf16, token stride lddq) = bf16(accT[b, h, :, s])  — 32 q rows x 128 d per block, through shared memory
+// dq[b, s, h, :] (bf16, token stride lddq) = bf16(accT[b, h, :, s])  — 64 q rows x 128 d per block, through shared memory
+// (64 consecutive floats = 256 contiguous bytes per d row: with 32-row blocks the reads were 128-byte pieces 16 KB apart and the
+// kernel ran at 2.7 TB/s)
 __global__ void __launch_bounds__(256) fa_bwd2_dq_finish_kernel(const float* __restrict__ accT, bf16* __restrict__ dq, int S, int Spad,
                                                                int nh, int64_t lddq) {
-  __shared__ float tile[128][33];
-  const int s0 = blockIdx.x * 32, h = blockIdx.y, b = blockIdx.z;
+  __shared__ float tile[128][65];
+  const int s0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
   const float* src = accT + (static_cast<size_t>(b) * nh + h) * 128 * Spad;
-  for (int i = threadIdx.x; i < 128 * 32; i += 256) {
-    const int d = i >> 5, s = i & 31;
-    tile[d][s] = src[static_cast<size_t>(d) * Spad + s0 + s];      // 32 consecutive floats per d row: coalesced
+  for (int i = threadIdx.x; i < 128 * 64; i += 256) {
+    const int d = i >> 6, s = i & 63;
+    tile[d][s] = src[static_cast<size_t>(d) * Spad + s0 + s];      // 64 consecutive floats per d row: coalesced
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 32 * 16; i += 256) {
+  for (int i = threadIdx.x; i < 64 * 16; i += 256) {
     const int s = i >> 4, c = i & 15;                              // 16 chunks of 8 d per token
     if (s0 + s < S) {
       uint4 o;
@@ -558,7 +560,7 @@ int launch_fa_bwd2(const void* q, const void* k, const void* v, const void* o, c
   fa_bwd2_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p);
   if ((rc = check_launch("fa_bwd2")) != 0) return rc;
   {
-    dim3 g2(static_cast<unsigned>(Spad / 32), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
+    dim3 g2(static_cast<unsigned>(Spad / 64), static_cast<unsigned>(num_heads), static_cast<unsigned>(B));
     fa_bwd2_dq_finish_kernel<<<g2, 256, 0, stream>>>(dq_acc, static_cast<bf16*>(dq), (int)S, (int)Spad, (int)num_heads, lddq);
     if ((rc = check_launch("fa_bwd2(dq finish)")) != 0) return rc;
     const int64_t tokens = B * S;
