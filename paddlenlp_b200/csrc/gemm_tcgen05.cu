@@ -19,6 +19,7 @@
 //   Operand majors: both K-major (contraction dim contiguous) and MN-major operands are fed straight from their
 //   row-major global layout through TMA; no transposes are materialised.
 #include "../../include/b200nlp.h"
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -60,6 +61,7 @@ struct Params {
                            // 5: down-proj dX GEMM + SwiGLU backward: acc = d(m) tile; tmR's tensor = saved gate|up [M, 2I];
                            //    C = [d(gate) | d(up)] [M, 2I]
   int swiglu_inter;        // modes 4, 5: I (the up half starts at column I)
+  int gm;                  // m-tiles per raster group (tile_coords)
   int split_k;             // work items per output tile (K is cut into split_k ranges of kb_per_split k-blocks)
   int kb_per_split;
   int b_prefetch;          // PDL: issue the first stages' B (weight) loads before griddepcontrol.wait
@@ -69,10 +71,9 @@ struct Params {
   int64_t ld_aux = 0;      //         its leading dimension in elements
 };
 
-__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk, int GM) {
   // Grouped ordering: GM consecutive m-tiles share each n-tile column so that concurrently running CTAs reuse
-  // A and B tiles out of L2.
-  constexpr int GM = 8;
+  // A and B tiles out of L2.  GM is chosen per shape by the host (Params::gm).
   const int per_group = GM * num_n;
   const int g = t / per_group;
   const int first_m = g * GM;
@@ -152,7 +153,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int prefetched = 0;
       if (p.b_prefetch && pair_id < num_tiles) {
         int m_blk, n_blk;
-        tile_coords(pair_id / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
+        tile_coords(pair_id / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk, p.gm);
         const int kb0 = (pair_id % p.split_k) * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         const int n0 = n_blk * BN + static_cast<int>(cta_rank) * C::B_COLS;
         prefetched = min(C::STAGES, kb1 - kb0);
@@ -189,7 +190,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       pdl_wait();
       for (int t = pair_id; t < num_tiles; t += num_pairs) {
         int m_blk, n_blk;
-        tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
+        tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk, p.gm);
         const int kb0 = (t % p.split_k) * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
         const int m0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM;   // this CTA's A rows
         const int n0 = n_blk * BN + static_cast<int>(cta_rank) * C::B_COLS;   // this CTA's B columns
@@ -296,7 +297,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       auto issue_next = [&]() {
         int m2 = 0, n2 = 0, c0 = 0;
         while (it_t < num_tiles) {
-          tile_coords(it_t / p.split_k, p.num_m_tiles, p.num_n_tiles, m2, n2);
+          tile_coords(it_t / p.split_k, p.num_m_tiles, p.num_n_tiles, m2, n2, p.gm);
           c0 = n2 * BN + it_s * SL;
           if (c0 < p.N) break;
           it_s = 0;                                  // N % 64 == 0: the dead slabs of a tile are its tail
@@ -317,7 +318,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       issue_next();
       for (int t = pair_id; t < num_tiles; t += num_pairs) {
         int m_blk, n_blk;
-        tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
+        tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk, p.gm);
         const int row0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM + q * 32;
         const int col0 = n_blk * BN;
         const int n_live = min(NSL, (p.N - col0) / SL);
@@ -367,7 +368,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else
     for (int t = pair_id; t < num_tiles; t += num_pairs) {
       int m_blk, n_blk;
-      tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk);
+      tile_coords(t / p.split_k, p.num_m_tiles, p.num_n_tiles, m_blk, n_blk, p.gm);
       const int row0 = m_blk * (BM * CG) + static_cast<int>(cta_rank) * BM + q * 32;
       const int col0 = n_blk * BN;
       mbar_wait(&tmem_full[as], aphase);
@@ -564,6 +565,15 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   Params pp = p;
+  // Raster group: the tiles of GM consecutive m-tiles are walked n-column by n-column, so the group's A panels (GM x BM*CG x K
+  // elements) are re-used out of L2 by every wave while the B panels stream through once per group: DRAM traffic ~ A + B * (m-tiles /
+  // GM).  GM = 16 halves the B re-reads as long as the group's A panels stay resident (<= ~36 MB of the 126 MB L2, i.e. K <= 4608:
+  // the forward projections and the K = 4096 dX GEMMs); the K-long shapes keep 8, where a wave of 74 CTA pairs is closest to square.
+  // Full-step sweep of a FIXED value: 8 -> 1460-1467 ms, 16 -> 1455, 4 -> 1512, 32 -> 1522; per-shape choice against fixed 8 on
+  // another box: 1381.9 / 1374.6 ms against 1387.5 / 1385.7 (profiles/r02_bench_gemm_raster_gm_sweep.log).
+  static const int gm_env = []() { const char* e = getenv("B200_GEMM_GM"); return e ? atoi(e) : 0; }();
+  if (gm_env > 0) pp.gm = gm_env;
+  else pp.gm = (16ll * BM * CG * p.K * 2 <= (36ll << 20)) ? 16 : 8;   // (52 / 72 / 120 MB measured within noise of 36)
   pp.b_prefetch = 0;
   pp.l2_prefetch_kb = 0;
   if (pdl_enabled()) {
