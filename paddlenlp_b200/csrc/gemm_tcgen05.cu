@@ -573,7 +573,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   // another box: 1381.9 / 1374.6 ms against 1387.5 / 1385.7 (profiles/r02_bench_gemm_raster_gm_sweep.log).
   static const int gm_env = []() { const char* e = getenv("B200_GEMM_GM"); return e ? atoi(e) : 0; }();
   if (gm_env > 0) pp.gm = gm_env;
-  else pp.gm = (16ll * BM * CG * p.K * 2 <= (36ll << 20)) ? 16 : 8;   // (52 / 72 / 120 MB measured within noise of 36)
+  else pp.gm = (16ll * BM * CG * p.K * 2 <= (36ll << 20) || p.N > 65536 || p.K > 65536) ? 16 : 8;
+  // (thresholds of 52 / 72 / 120 MB measured within noise of 36; the vocabulary-sized lm_head GEMMs take 16 by measurement:
+  //  per-shape DRAM bytes and times for GM = 4 ... 32 in profiles/r02_gemm_traffic_gm_sweep.txt)
   pp.b_prefetch = 0;
   pp.l2_prefetch_kb = 0;
   if (pdl_enabled()) {
